@@ -1,0 +1,210 @@
+/*
+ * atm_b200.h -- C ABI of the Blackwell (sm_100a) back-end for the ATM Meta-Force per-step hot path.
+ *
+ * One shared library (libatm_b200.so) replaces the reference's four kernel back-ends
+ * (platforms/common, platforms/cuda, platforms/hip, platforms/opencl).  Every entry point is
+ * `extern "C"`, takes plain pointers and sizes, returns an int status (0 = ok) and never throws.
+ * Device pointers are BORROWED (owned by the caller, e.g. by OpenMM's ComputeContext) unless stated;
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  No entry point
+ * synchronises the device unless its comment says so.  One handle per OpenMM Context; calls on one
+ * handle must be serialised by the caller (OpenMM contexts are single-threaded), different handles
+ * are independent.
+ *
+ * "ref:" comments cite the reference interface each entry point replaces (paths relative to the
+ * reference repository root, Gallicchio-Lab/openmm-atmmetaforce-plugin v0.3.1).
+ *
+ * Two tiers:
+ *   Tier 1 -- drop-in replacements of the reference's two device kernels and its host scalar stage;
+ *             OpenMM's inner contexts still evaluate U1,F1 / U2,F2.
+ *   Tier 2 -- the fused Blackwell path: the library evaluates the direct-space NonbondedForce of BOTH
+ *             inner states itself (one launch, env-env pairs shared), keeps U1/U2/u/W/dW/du on the
+ *             device and merges the forces, batched over R replicas that share one System.
+ */
+#ifndef ATM_B200_H_
+#define ATM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATM_B200_VERSION "0.3.1-b200.1"
+
+typedef struct atm_handle atm_handle;
+
+enum atm_status {
+    ATM_OK = 0,
+    ATM_ERR_INVALID = 1,      /* bad argument (message in atm_last_error) */
+    ATM_ERR_CUDA = 2,         /* a CUDA runtime call failed */
+    ATM_ERR_STATE = 3,        /* call sequence error (e.g. step before nb_setup) */
+    ATM_ERR_UNSUPPORTED = 4,  /* valid request this build does not implement (e.g. triclinic box) */
+    ATM_ERR_NOMEM = 5
+};
+
+/* ref: platform property "Precision" (example/abfe/abfe.py:109-110); decides the element type of posq:
+ * single/mixed -> float4 (+ float4 posqCorrection in mixed), double -> double4. */
+enum atm_precision { ATM_PREC_SINGLE = 0, ATM_PREC_MIXED = 1, ATM_PREC_DOUBLE = 2 };
+
+/* Index of each global parameter in a `double p[9]` block.
+ * ref: openmmapi/include/ATMMetaForce.h:151-218 (the nine Context parameter names). */
+enum atm_param {
+    ATM_LAMBDA1 = 0, ATM_LAMBDA2 = 1, ATM_ALPHA = 2, ATM_U0 = 3, ATM_W0 = 4,
+    ATM_UMAX = 5, ATM_UBCORE = 6, ATM_ACORE = 7, ATM_DIRECTION = 8, ATM_NUM_PARAMS = 9
+};
+
+/* Slots of the per-replica energy record kept on the device (doubles). */
+enum atm_energy_slot {
+    ATM_E_U1 = 0,      /* state-1 energy of the variable force groups (direct space + external part) */
+    ATM_E_U2 = 1,      /* state-2 energy */
+    ATM_E_U = 2,       /* raw perturbation energy, +-(U2-U1) by direction, formed from the state-specific pairs only */
+    ATM_E_USC = 3,     /* soft-core perturbation energy == ATMMetaForce::getPerturbationEnergy() */
+    ATM_E_EBIAS = 4,   /* W(u_sc) */
+    ATM_E_ENERGY = 5,  /* e0 + W : what calcForcesAndEnergy returns */
+    ATM_E_SP = 6,      /* weight of F2 in the merged force */
+    ATM_E_NPAIRS = 7,  /* pairs inside the cutoff evaluated by the last nb2 launch (diagnostic) */
+    ATM_NUM_ENERGY_SLOTS = 8
+};
+
+typedef struct {
+    int32_t num_particles;        /* N = force.getNumParticles() (ref: CommonATMMetaForceKernels.cpp:80) */
+    int32_t padded_num_particles; /* P = cc.getPaddedNumAtoms(); 0 -> 32*ceil(N/32) (ref: :83) */
+    int32_t precision;            /* enum atm_precision */
+    int32_t num_replicas;         /* R >= 1 coordinate sets sharing this System (Tier 2 batches them) */
+    int32_t device;               /* CUDA device ordinal; -1 = current device */
+} atm_config;
+
+/* Thread-local message of the last failing call on this thread. */
+const char *atm_last_error(void);
+const char *atm_version(void);
+
+/* ref: CudaATMMetaForceKernelFactory::createKernelImpl (platforms/cuda/src/CudaATMMetaForceKernelFactory.cpp:38-43)
+ *      + CommonCalcATMMetaForceKernel ctor/dtor.  Allocates only library-owned scratch. */
+int atm_create(const atm_config *cfg, atm_handle **out);
+int atm_destroy(atm_handle *h);
+
+/* Builds and uploads the float4 displacement table in device (slot) order.
+ *   atom_index : [N] slot -> atom (cc.getAtomIndex()); NULL = identity
+ *   dxyz       : [N][3] displacement of ATOM a in nm (entry i of the force is atom i; the 'particle'
+ *                field is ignored exactly as the reference does)
+ * ref: CommonCalcATMMetaForceKernel::initialize (platforms/common/src/CommonATMMetaForceKernels.cpp:78-109),
+ *      ReorderListener::execute (:53-72), copyParametersToContext (:229-251).
+ * Also (Tier 2) re-derives the displacement groups.  Asynchronous on `stream` (host staging is copied). */
+int atm_set_displacements(atm_handle *h, const int32_t *atom_index, const double *dxyz, void *stream);
+
+/* The nine global parameters of one replica (replica = -1: all).
+ * ref: context.getParameter(...) reads in execute (CommonATMMetaForceKernels.cpp:164-178). */
+int atm_set_parameters(atm_handle *h, int32_t replica, const double p[ATM_NUM_PARAMS]);
+int atm_get_parameters(atm_handle *h, int32_t replica, double p[ATM_NUM_PARAMS]);
+
+/* ------------------------------------------------------------------ Tier 1 */
+
+/* posq1 = posq, posq2 = posq + displ (component-wise in `real`, .w gets + 0), corrections copied verbatim.
+ * Element type per cfg.precision.  posq_corr/posq1_corr/posq2_corr may be NULL (single, double).
+ * Only slots i < N are written.  One sweep, one launch.
+ * ref: kernel CopyState (platforms/common/src/kernels/atmmetaforce.cc:19-52), launched from
+ *      CommonCalcATMMetaForceKernel::copyState (CommonATMMetaForceKernels.cpp:206-212). */
+int atm_copy_state(atm_handle *h, const void *posq, const void *posq_corr, void *posq1, void *posq1_corr,
+                   void *posq2, void *posq2_corr, void *stream);
+
+/* Optional extra (north_star "with periodic wrap"): posq2w = posq2 wrapped into [0,L) per axis of a
+ * rectangular box; posq2 itself stays the bit-exact unwrapped value.  float4 only. */
+int atm_wrap_positions(atm_handle *h, const void *posq_in, void *posq_out, const double box[9], void *stream);
+
+/* force[c*P+i] += llrint(sp*f2[c*P+i] + (1-sp)*f1[c*P+i]), c = 0..2, i < N, on the 2^32 fixed-point
+ * SoA buffers; blend in double.
+ * ref: kernel HybridForce (platforms/common/src/kernels/atmmetaforce.cc:1-17). */
+int atm_hybrid_force(atm_handle *h, int64_t *force, const int64_t *force_state1, const int64_t *force_state2,
+                     double sp, void *stream);
+
+/* Host scalar stage: out = {u_sc, fp, ebias, bfp, energy, sp, bfp*fp}.
+ * ref: SoftCoreF + softplus in CommonCalcATMMetaForceKernel::execute (CommonATMMetaForceKernels.cpp:19-30,182-199). */
+int atm_softcore_softplus(const double p[ATM_NUM_PARAMS], double state1_energy, double state2_energy, double out[7]);
+
+/* The reference's execute(): scalar stage on the host from the replica's parameters, then the
+ * hybrid-force launch.  *energy = includeEnergy ? e0 + ebias : 0; the perturbation energy is cached.
+ * ref: CommonCalcATMMetaForceKernel::execute (CommonATMMetaForceKernels.cpp:154-204). */
+int atm_execute(atm_handle *h, int32_t replica, double state1_energy, double state2_energy, int64_t *force,
+                const int64_t *force_state1, const int64_t *force_state2, int32_t include_energy, double *energy,
+                void *stream);
+
+/* ref: CalcATMMetaForceKernel::getPerturbationEnergy (openmmapi/include/ATMMetaForceKernels.h:57). */
+int atm_get_perturbation_energy(atm_handle *h, int32_t replica, double *u_sc);
+
+/* ------------------------------------------------------------------ Tier 2 */
+
+/* What the inner contexts evaluate for the variable force groups: the NonbondedForce direct space.
+ * ref: ATMMetaForceImpl::copysystem / initialize (openmmapi/src/ATMMetaForceImpl.cpp:51-65,75-81) decide
+ * which forces make up U1/U2; the arithmetic itself is OpenMM's NonbondedForce (external to the reference). */
+typedef struct {
+    const double *charge;            /* [N] e, by atom */
+    const double *sigma;             /* [N] nm */
+    const double *epsilon;           /* [N] kJ/mol */
+    int32_t num_exclusions;
+    const int32_t *exclusions;       /* [num_exclusions][2] atom pairs, each once */
+    int32_t num_exceptions;
+    const int32_t *exception_pairs;  /* [num_exceptions][2], subset of the exclusions */
+    const double *exception_params;  /* [num_exceptions][3] chargeProd (e^2), sigma (nm), epsilon (kJ/mol) */
+    double cutoff;                   /* nm */
+    double ewald_alpha;              /* 1/nm; 0 = plain Coulomb inside the cutoff */
+    double skin;                     /* nm, neighbour-list padding (list radius = cutoff + skin) */
+} atm_nonbonded_desc;
+
+int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
+
+/* Box vectors (row-major a,b,c in nm) of one replica (-1 = all).  Rectangular boxes only in this build.
+ * ref: the box mirror in copyState (CommonATMMetaForceKernels.cpp:214-219). */
+int atm_set_box(atm_handle *h, int32_t replica, const double box[9]);
+
+/* (Re)builds the cluster pair list of every replica for both coordinate states from
+ * posq ([R][P] float4, slot order).  Must be called before the first atm_step and whenever any atom has
+ * moved by more than skin/2 since the last rebuild, and after atm_set_displacements / reordering. */
+int atm_nb_rebuild(atm_handle *h, const void *posq, void *stream);
+
+typedef struct {
+    const void *posq;          /* [R][P] float4 positions+charge, slot order (borrowed) */
+    const void *posq_corr;     /* [R][P] float4 or NULL */
+    int64_t *force;            /* [R][3P] outer-context force buffers the merged force is ADDED to */
+    /* optional per-state contributions computed elsewhere (e.g. OpenMM's PME reciprocal in the inner contexts): */
+    const int64_t *force_state1_ext; /* [R][3P] or NULL */
+    const int64_t *force_state2_ext; /* [R][3P] or NULL */
+    const double *energy_ext;        /* device [R][2] {U1_ext, U2_ext} or NULL */
+    /* optional inner-context coordinate outputs (exactly what atm_copy_state writes), or NULL: */
+    void *posq1, *posq1_corr, *posq2, *posq2_corr;
+    int32_t include_energy;    /* also evaluate the shared (env-env) pair energies so that U1,U2,E are valid;
+                                  0 = forces and u only (u, u_sc, W, sp remain exact) */
+} atm_step_io;
+
+/* One pass of the hot path for all R replicas: copy-state -> two-state direct space -> device scalar
+ * stage -> merge.  No host synchronisation; safe to capture into a CUDA graph.
+ * ref: ATMMetaForceImpl::calcForcesAndEnergy (openmmapi/src/ATMMetaForceImpl.cpp:90-128). */
+int atm_step(atm_handle *h, const atm_step_io *io, void *stream);
+
+/* Device pointer to the [R][ATM_NUM_ENERGY_SLOTS] energy records (valid after atm_step completes). */
+int atm_energies_device(atm_handle *h, const double **dev_ptr);
+/* Copies the records to the host; SYNCHRONISES `stream`. */
+int atm_get_energies(atm_handle *h, double *out, void *stream);
+
+/* Diagnostics of the last rebuild: out = {sites per replica, clusters of replica 0, list entries per replica (mean),
+ * env list capacity, ligand/ghost list capacity, displaced atoms M, displacement groups G, xy columns}. */
+int atm_nb_stats(atm_handle *h, int64_t out[8]);
+
+/* ------------------------------------------------------------------ Hamiltonian replica exchange (host) */
+
+/* Deterministic Metropolis sweep over neighbouring lambda-states, identical on every rank.
+ *   state_params  : [num_states][9]
+ *   u12           : [num_replicas][2] {U1, U2} of every replica's current coordinates (all-gathered)
+ *   replica_state : [num_replicas] in/out, state index held by each replica (a permutation when
+ *                   num_replicas == num_states)
+ *   beta          : 1/kT in mol/kJ;  (seed, cycle) key the counter-based RNG
+ * No reference counterpart (the reference has no replica exchange). */
+int atm_hrex_sweep(int32_t num_states, const double *state_params, int32_t num_replicas, const double *u12,
+                   int32_t *replica_state, double beta, uint64_t seed, uint64_t cycle, int32_t *num_accepted);
+
+/* Reduced energy beta*E_s(x) of coordinates with energies (U1,U2) under state parameters p (host). */
+double atm_hrex_reduced_energy(const double p[ATM_NUM_PARAMS], double U1, double U2, double beta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATM_B200_H_ */

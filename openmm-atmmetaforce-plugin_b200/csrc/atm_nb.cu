@@ -1,0 +1,1175 @@
+// atm_nb.cu -- Tier 2: the fused two-state direct-space NonbondedForce path for sm_100a.
+//
+// What it evaluates (DESIGN.md "Two-state direct space"): the reference runs two complete inner-context
+// evaluations per step, U1,F1 at x and U2,F2 at x+d (openmmapi/src/ATMMetaForceImpl.cpp:113,116).  Only pairs
+// that involve a displaced atom differ between the two states, so this back-end evaluates
+//     C  : pairs whose two atoms move together (env-env, same displacement group)      -> both states
+//     S1 : pairs between differently displaced atoms at the state-1 coordinates (x)     -> state 1 only
+//     S2 : the same atom pairs at the state-2 coordinates (x+d), via "ghost" sites      -> state 2 only
+// in ONE launch:  F1 = C + S1, F2 = C + S2, U2 - U1 = U(S2) - U(S1) (formed from the few thousand
+// state-specific pairs only, so it does not suffer the cancellation of two 1e5 kJ/mol totals).
+//
+// Layout: "sites" = N atoms + M ghosts (displaced atoms at x+d).  Sites are binned (xy columns for the
+// environment, one bin per displacement group for ligand atoms and for their ghosts), z-sorted inside a
+// bin and cut into clusters of 8.  Every cluster owns a list of individual partner sites inside
+// cutoff+skin of its bounding box.  The force kernel gives one warp a (cluster, list chunk): each LANE
+// holds one partner site j, the 8 cluster atoms are broadcast from registers, so the inner loop has no
+// shuffles and no shared-memory traffic; f_j goes out with three 64-bit fixed-point RED.ADDs per lane per
+// 8 pairs, f_i is reduced by a 27-shuffle transpose-reduction once per work item.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "atm_common.cuh"
+
+namespace atm {
+
+constexpr int CL = 8;            // sites per cluster
+constexpr int ITEM_STEPS = 8;    // 32-entry list steps per work item
+constexpr int NB_THREADS = 256;  // force kernel block size (8 warps)
+constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
+constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
+constexpr int EACC_SLOTS = 4;                  // Uc, U(S1), U(S2), pairs in cutoff
+
+struct NbDev {  // everything the kernels need, passed by value
+    int N, P, R, M, G, U;
+    int nx, ny, ncol, nbins;
+    int Smax, Cmax, CLmax, CXmax, CenvMax;
+    int capC, capX;
+    float cutoff2, rlist, alpha, two_alpha_over_sqrtpi;
+    // static, by atom
+    const float *qp_atom;
+    const float2 *par_atom;
+    const int *excl_start, *excl_list;
+    const int *group_of_atom, *ghost_atom, *ghost_of_atom, *slot_of_atom, *atom_of_slot;
+    const float4 *displ;  // slot order (handle)
+    const float4 *box, *invbox;  // [R]
+    // per rebuild
+    unsigned long long *keys;
+    int *vals;
+    int *bin_count, *bin_site_start, *bin_cluster_start, *nclusters;
+    int *slot_site, *site_slot, *slot_src;
+    float *slot_qp;
+    float4 *xs;
+    float2 *par;
+    float4 *cc, *ch;
+    int *cmeta;
+    unsigned int *jlist;
+    int *list_nsteps;
+    int *flags;
+    // accumulators
+    unsigned long long *buf;
+    unsigned long long *eacc;
+    double *energies;
+    const double *params;
+};
+
+struct NbState {
+    bool ready = false, list_valid = false, groups_valid = false;
+    atm_nonbonded_desc desc{};
+    std::vector<float> h_qp;
+    std::vector<float2> h_par;
+    std::vector<int> h_excl_start, h_excl_list;
+    std::vector<int2> h_excl_pairs, h_exc_pairs;
+    std::vector<float4> h_exc_par;
+    std::vector<int> h_group_of_atom, h_ghost_atom, h_ghost_of_atom;
+    std::vector<double> h_box;  // [R][3]
+    bool box_set = false, box_dirty = true;
+    NbDev d{};
+    // owned device memory (freed in nb_destroy)
+    std::vector<void *> owned;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    unsigned long long *keys_alt = nullptr;
+    int *vals_alt = nullptr;
+    int2 *d_excl_pairs = nullptr, *d_exc_pairs = nullptr;
+    float4 *d_exc_par = nullptr;
+    int n_excl = 0, n_exc = 0;
+    int parity = 0;
+    int sort_bits = 64;
+    size_t jlist_entries = 0;
+    int64_t stats[8] = {0};
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int class_kind(int cls, int G) { return cls == 0 ? 0 : (cls <= G ? 1 : 2); }
+__device__ __forceinline__ int class_group(int cls, int G) { return cls == 0 ? 0 : (cls <= G ? cls : cls - G); }
+
+__device__ __forceinline__ int pair_target(int ca, int cb, int G) {
+    const int ka = class_kind(ca, G), kb = class_kind(cb, G);
+    if (ka == 0 && kb == 0) return TGT_C;
+    if ((ka == 1 && kb == 2) || (ka == 2 && kb == 1)) return TGT_SKIP;
+    const bool same = class_group(ca, G) == class_group(cb, G);
+    if (ka == 2 || kb == 2) return (ka == 2 && kb == 2 && same) ? TGT_SKIP : TGT_S2;
+    if (ka == 1 && kb == 1) return same ? TGT_C : TGT_S1;
+    return TGT_S1;
+}
+
+__device__ __forceinline__ float wrap_delta(float d, float L, float invL) { return d - L * rintf(d * invL); }
+
+__device__ __forceinline__ void red_add_fixed(unsigned long long *addr, float f) {
+    long long v = __float2ll_rn(f * 4294967296.0f);
+    atomicAdd(addr, (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rebuild step 1: sort keys (replica, bin, z) for every site; per-bin histogram.
+// ------------------------------------------------------------------------------------------------
+__global__ void nl_keys_kernel(NbDev d, const float4 *__restrict__ posq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.R * d.U) return;
+    const int r = t / d.U, u = t - r * d.U;
+    const bool ghost = u >= d.N;
+    const int a = ghost ? d.ghost_atom[u - d.N] : u;
+    const int slot = d.slot_of_atom[a];
+    float4 p = __ldg(posq + (size_t)r * d.P + slot);
+    if (ghost) {
+        const float4 dd = __ldg(d.displ + slot);
+        p.x = __fadd_rn(p.x, dd.x);
+        p.y = __fadd_rn(p.y, dd.y);
+        p.z = __fadd_rn(p.z, dd.z);
+    }
+    const float4 L = d.box[r], iL = d.invbox[r];
+    float wx = p.x - L.x * floorf(p.x * iL.x), wy = p.y - L.y * floorf(p.y * iL.y), wz = p.z - L.z * floorf(p.z * iL.z);
+    const int g = d.group_of_atom[a];
+    int bin;
+    if (g == 0) {
+        int ix = min(max((int)(wx * iL.x * d.nx), 0), d.nx - 1);
+        int iy = min(max((int)(wy * iL.y * d.ny), 0), d.ny - 1);
+        bin = ix * d.ny + iy;
+    } else {
+        bin = d.ncol + (ghost ? d.G : 0) + g - 1;
+    }
+    const int zq = min(max((int)(wz * iL.z * 65536.0f), 0), 65535);
+    d.keys[t] = ((unsigned long long)(r * d.nbins + bin) << 16) | (unsigned long long)zq;
+    d.vals[t] = u;
+    atomicAdd(&d.bin_count[r * d.nbins + bin], 1);
+}
+
+// Rebuild step 2: per replica exclusive scans of the bin populations (sites and 8-padded clusters).
+__global__ void nl_scan_kernel(NbDev d) {
+    const int r = blockIdx.x;
+    __shared__ int s_sites[1024], s_clusters[1024];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (d.nbins + nt - 1) / nt;
+    const int b0 = min(tid * per, d.nbins), b1 = min(b0 + per, d.nbins);
+    int ns = 0, nc = 0;
+    for (int b = b0; b < b1; b++) {
+        int c = d.bin_count[r * d.nbins + b];
+        ns += c;
+        nc += (c + CL - 1) / CL;
+    }
+    s_sites[tid] = ns;
+    s_clusters[tid] = nc;
+    __syncthreads();
+    if (tid == 0) {
+        int as = 0, ac = 0;
+        for (int i = 0; i < nt; i++) {
+            int ts = s_sites[i], tc = s_clusters[i];
+            s_sites[i] = as;
+            s_clusters[i] = ac;
+            as += ts;
+            ac += tc;
+        }
+        d.nclusters[r] = ac;
+        d.bin_site_start[r * (d.nbins + 1) + d.nbins] = as;
+        d.bin_cluster_start[r * (d.nbins + 1) + d.nbins] = ac;
+    }
+    __syncthreads();
+    ns = s_sites[tid];
+    nc = s_clusters[tid];
+    for (int b = b0; b < b1; b++) {
+        int c = d.bin_count[r * d.nbins + b];
+        d.bin_site_start[r * (d.nbins + 1) + b] = ns;
+        d.bin_cluster_start[r * (d.nbins + 1) + b] = nc;
+        ns += c;
+        nc += (c + CL - 1) / CL;
+    }
+}
+
+// Rebuild step 3: sorted position -> padded slot; static per-slot gather info.
+__global__ void nl_place_kernel(NbDev d, const unsigned long long *__restrict__ keys_sorted,
+                                const int *__restrict__ vals_sorted) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.R * d.U) return;
+    const int r = t / d.U, idx = t - r * d.U;
+    const int u = vals_sorted[t];
+    const int bin = (int)(keys_sorted[t] >> 16) - r * d.nbins;
+    const int rank = idx - d.bin_site_start[r * (d.nbins + 1) + bin];
+    const int slot = CL * d.bin_cluster_start[r * (d.nbins + 1) + bin] + rank;
+    const bool ghost = u >= d.N;
+    const int a = ghost ? d.ghost_atom[u - d.N] : u;
+    const size_t rs = (size_t)r * d.Smax + slot;
+    d.slot_site[rs] = u;
+    d.site_slot[(size_t)r * d.U + u] = slot;
+    d.slot_src[rs] = (r * d.P + d.slot_of_atom[a]) | (ghost ? 0x80000000 : 0);
+    d.slot_qp[rs] = d.qp_atom[a];
+    d.par[rs] = d.par_atom[a];
+}
+
+// Every step: gather current coordinates into cluster order; ghosts get posq + displ (the same float add as
+// CopyState, so a ghost sits exactly at the reference's posq2).
+__global__ void nb_pack_kernel(NbDev d, const float4 *__restrict__ posq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (t >= CL * d.nclusters[r]) return;
+    const size_t rs = (size_t)r * d.Smax + t;
+    const int src = d.slot_src[rs];
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.slot_site[rs] >= 0) {
+        const int idx = src & 0x7fffffff;
+        p = __ldg(posq + idx);
+        if (src < 0) {
+            const float4 dd = __ldg(d.displ + (idx - r * d.P));
+            p.x = __fadd_rn(p.x, dd.x);
+            p.y = __fadd_rn(p.y, dd.y);
+            p.z = __fadd_rn(p.z, dd.z);
+        }
+        p.w = d.slot_qp[rs];
+    }
+    d.xs[rs] = p;
+}
+
+// Rebuild step 4: cluster bounding boxes (centre, half extent) in the frame of the first member, class, valid mask.
+__global__ void nl_bbox_kernel(NbDev d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= d.nclusters[r]) return;
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const size_t base = (size_t)r * d.Smax + (size_t)c * CL;
+    float3 lo = make_float3(0, 0, 0), hi = make_float3(0, 0, 0), x0 = make_float3(0, 0, 0);
+    int valid = 0, cls = 0;
+    for (int k = 0; k < CL; k++) {
+        const int u = d.slot_site[base + k];
+        if (u < 0) continue;
+        const float4 p = d.xs[base + k];
+        if (!valid) {
+            x0 = make_float3(p.x, p.y, p.z);
+            const int a = u >= d.N ? d.ghost_atom[u - d.N] : u;
+            const int g = d.group_of_atom[a];
+            cls = g == 0 ? 0 : (u >= d.N ? d.G + g : g);
+        }
+        const float dx = wrap_delta(p.x - x0.x, L.x, iL.x), dy = wrap_delta(p.y - x0.y, L.y, iL.y),
+                    dz = wrap_delta(p.z - x0.z, L.z, iL.z);
+        lo.x = fminf(lo.x, dx); lo.y = fminf(lo.y, dy); lo.z = fminf(lo.z, dz);
+        hi.x = fmaxf(hi.x, dx); hi.y = fmaxf(hi.y, dy); hi.z = fmaxf(hi.z, dz);
+        valid |= 1 << k;
+    }
+    const size_t rc = (size_t)r * d.Cmax + c;
+    d.cc[rc] = make_float4(x0.x + 0.5f * (lo.x + hi.x), x0.y + 0.5f * (lo.y + hi.y), x0.z + 0.5f * (lo.z + hi.z), 0.f);
+    d.ch[rc] = make_float4(0.5f * (hi.x - lo.x), 0.5f * (hi.y - lo.y), 0.5f * (hi.z - lo.z), 0.f);
+    d.cmeta[rc] = cls | (valid << 16);
+    // the per-step image shift of a partner relative to the cluster centre needs half extent + list radius <= L/2
+    const float hmax_x = 0.5f * (hi.x - lo.x) + d.rlist, hmax_y = 0.5f * (hi.y - lo.y) + d.rlist,
+                hmax_z = 0.5f * (hi.z - lo.z) + d.rlist;
+    if (hmax_x > 0.5f * L.x || hmax_y > 0.5f * L.y || hmax_z > 0.5f * L.z) atomicOr(&d.flags[0], 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rebuild step 5: one warp per list.  List l of replica r:
+//   l <  Cmax            : primary list of cluster l   (env cluster -> C, ligand cluster -> S1, ghost cluster -> S2)
+//   l >= Cmax            : secondary list (same-group pairs, target C) of ligand cluster firstL + (l - Cmax)
+// ------------------------------------------------------------------------------------------------
+struct ListInfo {
+    int cluster, target, cap;
+    size_t offset;
+    bool valid;
+};
+
+__device__ __forceinline__ ListInfo decode_list(const NbDev &d, int r, int l) {
+    ListInfo li;
+    const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
+    const int nenv = bcs[d.ncol], firstG = bcs[d.ncol + d.G], ncl = d.nclusters[r];
+    const size_t per_replica = (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)d.CLmax * d.capC;
+    const size_t rbase = (size_t)r * per_replica;
+    li.valid = false;
+    li.cluster = 0; li.target = TGT_C; li.cap = d.capC; li.offset = rbase;
+    if (l < d.Cmax) {
+        if (l >= ncl) return li;
+        li.cluster = l;
+        if (l < nenv) {
+            li.target = TGT_C;
+            li.cap = d.capC;
+            li.offset = rbase + (size_t)l * d.capC;
+        } else {
+            li.target = l < firstG ? TGT_S1 : TGT_S2;
+            li.cap = d.capX;
+            li.offset = rbase + (size_t)d.CenvMax * d.capC + (size_t)(l - nenv) * d.capX;
+        }
+        li.valid = true;
+    } else {
+        const int k = l - d.Cmax;
+        if (k >= firstG - nenv) return li;
+        li.cluster = nenv + k;
+        li.target = TGT_C;
+        li.cap = d.capC;
+        li.offset = rbase + (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)k * d.capC;
+        li.valid = true;
+    }
+    return li;
+}
+
+__global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int r = blockIdx.y;
+    const int nlists = d.Cmax + d.CLmax;
+    if (l >= nlists) return;
+    const ListInfo li = decode_list(d, r, l);
+    int *nsteps_out = d.list_nsteps + (size_t)r * nlists + l;
+    if (!li.valid) {
+        if (lane == 0) *nsteps_out = 0;
+        return;
+    }
+    const int A = li.cluster;
+    const size_t rcA = (size_t)r * d.Cmax + A;
+    const float4 cA = d.cc[rcA], hA = d.ch[rcA];
+    const int metaA = d.cmeta[rcA];
+    const int clsA = metaA & 0xffff, validA = (metaA >> 16) & 0xff;
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const float rl2 = d.rlist * d.rlist;
+    const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
+    const int nenv = bcs[d.ncol], ncl = d.nclusters[r];
+    unsigned int *out = d.jlist + li.offset;
+    int count = 0;
+    bool overflow = false;
+
+    // candidate cluster ranges: env columns near A (only when env clusters can be partners), then all ligand/ghost clusters
+    const float cwx = cA.x - L.x * floorf(cA.x * iL.x), cwy = cA.y - L.y * floorf(cA.y * iL.y);
+    const float colw_x = L.x / d.nx, colw_y = L.y / d.ny;
+    int ix_lo = (int)floorf((cwx - hA.x - d.rlist) / colw_x), ix_hi = (int)floorf((cwx + hA.x + d.rlist) / colw_x);
+    int iy_lo = (int)floorf((cwy - hA.y - d.rlist) / colw_y), iy_hi = (int)floorf((cwy + hA.y + d.rlist) / colw_y);
+    if (ix_hi - ix_lo + 1 >= d.nx) { ix_lo = 0; ix_hi = d.nx - 1; }
+    if (iy_hi - iy_lo + 1 >= d.ny) { iy_lo = 0; iy_hi = d.ny - 1; }
+    const bool env_partners = pair_target(clsA, 0, d.G) == li.target;  // does this list take env sites at all?
+    const int n_ix = env_partners ? ix_hi - ix_lo + 1 : 0;
+    // iy range may wrap: split into up to two contiguous bin segments
+    int seg_lo[2], seg_hi[2], nseg = 0;
+    if (iy_lo >= 0 && iy_hi < d.ny) { seg_lo[0] = iy_lo; seg_hi[0] = iy_hi; nseg = 1; }
+    else if (iy_lo < 0) { seg_lo[0] = 0; seg_hi[0] = iy_hi; seg_lo[1] = iy_lo + d.ny; seg_hi[1] = d.ny - 1; nseg = 2; }
+    else { seg_lo[0] = iy_lo; seg_hi[0] = d.ny - 1; seg_lo[1] = 0; seg_hi[1] = iy_hi - d.ny; nseg = 2; }
+
+    const int n_ranges = n_ix * nseg + 1;
+    for (int rg = 0; rg < n_ranges; rg++) {
+        int c_begin, c_end;
+        if (rg < n_ix * nseg) {
+            int ix = ix_lo + rg / nseg;
+            ix = ((ix % d.nx) + d.nx) % d.nx;
+            const int sgi = rg % nseg;
+            c_begin = bcs[ix * d.ny + seg_lo[sgi]];
+            c_end = bcs[ix * d.ny + seg_hi[sgi] + 1];
+        } else {
+            c_begin = nenv;
+            c_end = ncl;
+        }
+        for (int base = c_begin; base < c_end; base += 32) {
+            const int B = base + lane;
+            bool pass = false;
+            if (B < c_end) {
+                const size_t rcB = (size_t)r * d.Cmax + B;
+                const int clsB = d.cmeta[rcB] & 0xffff;
+                bool owner;
+                if (clsA == clsB) owner = (A == B) || (((A + B) & 1) ? (A < B) : (A > B));
+                else owner = clsA > clsB;
+                if (owner && pair_target(clsA, clsB, d.G) == li.target) {
+                    const float4 cB = d.cc[rcB], hB = d.ch[rcB];
+                    const float dx = fmaxf(fabsf(wrap_delta(cB.x - cA.x, L.x, iL.x)) - hA.x - hB.x, 0.f);
+                    const float dy = fmaxf(fabsf(wrap_delta(cB.y - cA.y, L.y, iL.y)) - hA.y - hB.y, 0.f);
+                    const float dz = fmaxf(fabsf(wrap_delta(cB.z - cA.z, L.z, iL.z)) - hA.z - hB.z, 0.f);
+                    pass = dx * dx + dy * dy + dz * dz <= rl2;
+                }
+            }
+            unsigned int cmask = __ballot_sync(0xffffffffu, pass);
+            while (cmask) {
+                // next (up to) four passing clusters, 8 lanes each
+                const int grp = lane >> 3, k = lane & 7;
+                const int nset = __popc(cmask);
+                int bit = grp < nset ? __fns(cmask, 0, grp + 1) : -1;
+                bool take = false;
+                unsigned int entry = 0;
+                if (bit >= 0) {
+                    const int B2 = base + bit;
+                    const int j = B2 * CL + k;
+                    const size_t rs = (size_t)r * d.Smax + j;
+                    const int u = d.slot_site[rs];
+                    if (u >= 0) {
+                        const float4 p = d.xs[rs];
+                        const float dx = fmaxf(fabsf(wrap_delta(p.x - cA.x, L.x, iL.x)) - hA.x, 0.f);
+                        const float dy = fmaxf(fabsf(wrap_delta(p.y - cA.y, L.y, iL.y)) - hA.y, 0.f);
+                        const float dz = fmaxf(fabsf(wrap_delta(p.z - cA.z, L.z, iL.z)) - hA.z, 0.f);
+                        if (dx * dx + dy * dy + dz * dz <= rl2) {
+                            unsigned int m = (~validA) & 0xff;
+                            if (B2 == A) m |= (0xffu << k) & 0xff;  // within a cluster: pairs (i<j) once
+                            const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
+                            for (int e = d.excl_start[aj]; e < d.excl_start[aj + 1]; e++) {
+                                const int b = d.excl_list[e];
+                                const int s_real = d.site_slot[(size_t)r * d.U + b];
+                                if ((s_real >> 3) == A) m |= 1u << (s_real & 7);
+                                const int gm = d.ghost_of_atom[b];
+                                if (gm >= 0) {
+                                    const int s_gh = d.site_slot[(size_t)r * d.U + d.N + gm];
+                                    if ((s_gh >> 3) == A) m |= 1u << (s_gh & 7);
+                                }
+                            }
+                            if (m != 0xff) {
+                                take = true;
+                                entry = ((unsigned int)j << 8) | m;
+                            }
+                        }
+                    }
+                }
+                const unsigned int tmask = __ballot_sync(0xffffffffu, take);
+                if (take) {
+                    const int pos = count + __popc(tmask & ((1u << lane) - 1));
+                    if (pos < li.cap) out[pos] = entry;
+                }
+                count += __popc(tmask);
+                if (count > li.cap) overflow = true;
+                // clear the (up to) four consumed bits
+                for (int q = 0; q < 4 && cmask; q++) cmask &= cmask - 1;
+            }
+        }
+    }
+    if (overflow) {
+        if (lane == 0) {
+            atomicOr(&d.flags[0], 1);
+            atomicMax(&d.flags[1], count);
+            *nsteps_out = 0;
+        }
+        return;
+    }
+    // pad the tail of the last 32-entry step with masked sentinels
+    const int nsteps = (count + 31) >> 5;
+    for (int p = count + lane; p < nsteps * 32; p += 32) out[p] = 0xffu;
+    if (lane == 0) {
+        *nsteps_out = nsteps;
+        atomicAdd((unsigned long long *)&d.flags[2], (unsigned long long)count);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The force kernel.
+// ------------------------------------------------------------------------------------------------
+// erfc(x) = t (a0 + a1 t + ... + a6 t^6) exp(-x^2), t = 1/(1 + p x); max relative error 6.8e-8 on [0, 4.2]
+// (fit: DESIGN.md "erfc"); evaluated in fp32 the rounding error (~4e-7) dominates.
+#define ERFC_P 0.357431514f
+#define ERFC_A0 1.9957954259e-01f
+#define ERFC_A1 2.2717719300e-01f
+#define ERFC_A2 5.6467497521e-02f
+#define ERFC_A3 5.3674605718e-01f
+#define ERFC_A4 -4.8585730230e-01f
+#define ERFC_A5 6.4534500206e-01f
+#define ERFC_A6 -1.7945805777e-01f
+
+struct PairOut {
+    float fscale, energy;
+};
+
+// One pair.  qq = q_i q_j k_e (charges are stored pre-multiplied by sqrt(k_e)); sig = (s_i+s_j)/2; eps4 = 4 sqrt(e_i e_j).
+__device__ __forceinline__ PairOut pair_interaction(float r2, float qq, float sig, float eps4, float alpha,
+                                                   float two_alpha_over_sqrtpi) {
+    float rinv = rsqrtf(r2);
+    rinv = rinv * (1.5f - 0.5f * r2 * rinv * rinv);  // one Newton step: MUFU.RSQ is ~2^-22, forces need better
+    const float rinv2 = rinv * rinv;
+    const float r = r2 * rinv;
+    const float s2 = sig * sig * rinv2;
+    const float s6 = s2 * s2 * s2;
+    const float es6 = eps4 * s6;
+    const float elj = es6 * (s6 - 1.0f);
+    const float flj = es6 * (12.0f * s6 - 6.0f);
+    const float ar = alpha * r;
+    const float t = __fdividef(1.0f, fmaf(ERFC_P, ar, 1.0f));
+    const float ex = __expf(-ar * ar);
+    float poly = fmaf(ERFC_A6, t, ERFC_A5);
+    poly = fmaf(poly, t, ERFC_A4);
+    poly = fmaf(poly, t, ERFC_A3);
+    poly = fmaf(poly, t, ERFC_A2);
+    poly = fmaf(poly, t, ERFC_A1);
+    poly = fmaf(poly, t, ERFC_A0);
+    const float erfc_ar = poly * t * ex;
+    const float qr = qq * rinv;
+    const float ec = qr * erfc_ar;
+    const float fc = fmaf(qr * r * two_alpha_over_sqrtpi, ex, ec);
+    PairOut o;
+    o.fscale = (flj + fc) * rinv2;
+    o.energy = elj + ec;
+    return o;
+}
+
+__global__ void __launch_bounds__(NB_THREADS) nb2_kernel(NbDev d, int parity) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
+    const int r = blockIdx.y;
+    // item -> (list, chunk)
+    const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
+    const int nlists = d.Cmax + d.CLmax;
+    const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
+    const int nenv = bcs[d.ncol], ncl = d.nclusters[r];
+    int l, chunk;
+    {
+        const int itemsEnv = nenv * chunksC, itemsX = (ncl - nenv) * chunksX;
+        if (warp < itemsEnv) { l = warp / chunksC; chunk = warp - l * chunksC; }
+        else if (warp < itemsEnv + itemsX) { const int w = warp - itemsEnv; l = nenv + w / chunksX; chunk = w % chunksX; }
+        else { const int w = warp - itemsEnv - itemsX; l = d.Cmax + w / chunksC; chunk = w % chunksC; if (l >= nlists) return; }
+    }
+    const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
+    const int step0 = chunk * ITEM_STEPS;
+    if (step0 >= nsteps_total) return;
+    const int nst = min(ITEM_STEPS, nsteps_total - step0);
+    const ListInfo li = decode_list(d, r, l);
+    const int A = li.cluster;
+    const size_t rsite = (size_t)r * d.Smax;
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const float4 cA = d.cc[(size_t)r * d.Cmax + A];
+
+    // the 8 cluster atoms, broadcast-loaded into every lane's registers, shifted next to the cluster centre
+    float4 xi[CL];
+    float2 pi[CL];
+    float fix[CL], fiy[CL], fiz[CL];
+#pragma unroll
+    for (int k = 0; k < CL; k++) {
+        xi[k] = __ldg(d.xs + rsite + (size_t)A * CL + k);
+        pi[k] = __ldg(d.par + rsite + (size_t)A * CL + k);
+        xi[k].x -= L.x * rintf((xi[k].x - cA.x) * iL.x);
+        xi[k].y -= L.y * rintf((xi[k].y - cA.y) * iL.y);
+        xi[k].z -= L.z * rintf((xi[k].z - cA.z) * iL.z);
+        fix[k] = fiy[k] = fiz[k] = 0.f;
+    }
+    const unsigned int *list = d.jlist + li.offset + (size_t)step0 * 32;
+    unsigned long long *buf = d.buf + (size_t)li.target * 3 * d.R * d.Smax + rsite;
+    const size_t comp_stride = (size_t)d.R * d.Smax;
+    double e_acc = 0.0;
+    int npairs = 0;
+
+    for (int st = 0; st < nst; st++) {
+        const unsigned int e = __ldg(list + st * 32 + lane);
+        const int j = e >> 8;
+        const unsigned int m = e & 0xff;
+        float4 xj = __ldg(d.xs + rsite + j);
+        const float2 pj = __ldg(d.par + rsite + j);
+        xj.x -= L.x * rintf((xj.x - cA.x) * iL.x);
+        xj.y -= L.y * rintf((xj.y - cA.y) * iL.y);
+        xj.z -= L.z * rintf((xj.z - cA.z) * iL.z);
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
+#pragma unroll
+        for (int k = 0; k < CL; k++) {
+            const float dx = xi[k].x - xj.x, dy = xi[k].y - xj.y, dz = xi[k].z - xj.z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const bool in = (r2 < d.cutoff2) && !((m >> k) & 1u);
+            const PairOut o = pair_interaction(r2, xi[k].w * xj.w, pi[k].x + pj.x, pi[k].y * pj.y, d.alpha,
+                                               d.two_alpha_over_sqrtpi);
+            const float fs = in ? o.fscale : 0.f;
+            e_step += in ? o.energy : 0.f;
+            npairs += in ? 1 : 0;
+            fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
+            fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
+        }
+        e_acc += (double)e_step;
+        if (m != 0xff) {
+            red_add_fixed(buf + j, fjx);
+            red_add_fixed(buf + comp_stride + j, fjy);
+            red_add_fixed(buf + 2 * comp_stride + j, fjz);
+        }
+    }
+
+    // transpose-reduce the 24 i-force accumulators: after three halving exchanges lane (l&7) owns atom l&7
+    {
+        const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+        float w[4][3];
+#pragma unroll
+        for (int mm = 0; mm < 4; mm++) {
+            const float kx = b0 ? fix[2 * mm + 1] : fix[2 * mm], sx = b0 ? fix[2 * mm] : fix[2 * mm + 1];
+            const float ky = b0 ? fiy[2 * mm + 1] : fiy[2 * mm], sy = b0 ? fiy[2 * mm] : fiy[2 * mm + 1];
+            const float kz = b0 ? fiz[2 * mm + 1] : fiz[2 * mm], sz = b0 ? fiz[2 * mm] : fiz[2 * mm + 1];
+            w[mm][0] = kx + __shfl_xor_sync(0xffffffffu, sx, 1);
+            w[mm][1] = ky + __shfl_xor_sync(0xffffffffu, sy, 1);
+            w[mm][2] = kz + __shfl_xor_sync(0xffffffffu, sz, 1);
+        }
+        float x2[2][3];
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float kk = b1 ? w[2 * mm + 1][c] : w[2 * mm][c], ss = b1 ? w[2 * mm][c] : w[2 * mm + 1][c];
+                x2[mm][c] = kk + __shfl_xor_sync(0xffffffffu, ss, 2);
+            }
+        float y[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float kk = b2 ? x2[1][c] : x2[0][c], ss = b2 ? x2[0][c] : x2[1][c];
+            y[c] = kk + __shfl_xor_sync(0xffffffffu, ss, 4);
+            y[c] += __shfl_xor_sync(0xffffffffu, y[c], 8);
+            y[c] += __shfl_xor_sync(0xffffffffu, y[c], 16);
+        }
+        // lane l (< 8) now holds atom index (b0 + 2 b1 + 4 b2) = l
+        if (lane < CL) {
+            const int i = A * CL + lane;
+            red_add_fixed(buf + i, y[0]);
+            red_add_fixed(buf + comp_stride + i, y[1]);
+            red_add_fixed(buf + 2 * comp_stride + i, y[2]);
+        }
+    }
+    // energies: warp sum in double, one fixed-point atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        e_acc += __shfl_xor_sync(0xffffffffu, e_acc, off);
+        npairs += __shfl_xor_sync(0xffffffffu, npairs, off);
+    }
+    if (lane == 0) {
+        unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
+        atomicAdd(ea + li.target, (unsigned long long)__double2ll_rn(e_acc * ENERGY_SCALE));
+        atomicAdd(ea + 3, (unsigned long long)npairs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Excluded pairs (Ewald correction -qq erf(ar)/r, minimum image) and 1-4 exceptions (plain Coulomb + LJ, no image).
+// One thread per (replica, pair).  Pairs whose atoms move together go to C, others are evaluated in both states.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add_pair_force(const NbDev &d, int r, int target, int si, int sj, float fx, float fy, float fz) {
+    unsigned long long *buf = d.buf + (size_t)target * 3 * d.R * d.Smax + (size_t)r * d.Smax;
+    const size_t cs = (size_t)d.R * d.Smax;
+    red_add_fixed(buf + si, fx); red_add_fixed(buf + cs + si, fy); red_add_fixed(buf + 2 * cs + si, fz);
+    red_add_fixed(buf + sj, -fx); red_add_fixed(buf + cs + sj, -fy); red_add_fixed(buf + 2 * cs + sj, -fz);
+}
+
+__global__ void nb_special_pairs_kernel(NbDev d, int parity, const int2 *__restrict__ excl, int n_excl,
+                                        const int2 *__restrict__ exc, const float4 *__restrict__ exc_par, int n_exc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double e_tgt[3] = {0.0, 0.0, 0.0};
+    if (t < n_excl + n_exc) {
+        const bool is_exc = t >= n_excl;
+        const int2 pr = is_exc ? exc[t - n_excl] : excl[t];
+        const int ga = d.group_of_atom[pr.x], gb = d.group_of_atom[pr.y];
+        const float4 L = d.box[r], iL = d.invbox[r];
+        const int nstate = (ga == gb) ? 1 : 2;
+        for (int s = 0; s < nstate; s++) {
+            const int target = (ga == gb) ? TGT_C : (s == 0 ? TGT_S1 : TGT_S2);
+            int si = d.site_slot[(size_t)r * d.U + pr.x], sj = d.site_slot[(size_t)r * d.U + pr.y];
+            if (s == 1) {
+                if (ga != 0) si = d.site_slot[(size_t)r * d.U + d.N + d.ghost_of_atom[pr.x]];
+                if (gb != 0) sj = d.site_slot[(size_t)r * d.U + d.N + d.ghost_of_atom[pr.y]];
+            }
+            const float4 a = d.xs[(size_t)r * d.Smax + si], b = d.xs[(size_t)r * d.Smax + sj];
+            float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+            float fs, en;
+            if (!is_exc) {
+                dx = wrap_delta(dx, L.x, iL.x); dy = wrap_delta(dy, L.y, iL.y); dz = wrap_delta(dz, L.z, iL.z);
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float qq = a.w * b.w;
+                if (r2 > 0.f && qq != 0.f && d.alpha > 0.f) {
+                    const float rinv = 1.0f / sqrtf(r2), rr = r2 * rinv, ar = d.alpha * rr;
+                    const float erf_ar = erff(ar);
+                    en = -qq * rinv * erf_ar;
+                    fs = -qq * rinv * (erf_ar - ar * expf(-ar * ar) * 1.1283791670955126f) * rinv * rinv;
+                } else { en = 0.f; fs = 0.f; }
+            } else {
+                const float4 pp = exc_par[t - n_excl];  // ke*chargeProd, sigma, 4 eps
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float rinv = 1.0f / sqrtf(r2), rinv2 = rinv * rinv;
+                const float s2 = pp.y * pp.y * rinv2, s6 = s2 * s2 * s2;
+                en = pp.z * s6 * (s6 - 1.0f) + pp.x * rinv;
+                fs = (pp.z * s6 * (12.0f * s6 - 6.0f) + pp.x * rinv) * rinv2;
+            }
+            add_pair_force(d, r, target, si, sj, dx * fs, dy * fs, dz * fs);
+            e_tgt[target] += (double)en;
+        }
+    }
+    // block reduction of the three energies (warp shuffle, then one atomic per warp)
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double v = e_tgt[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && v != 0.0) {
+            unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
+            atomicAdd(ea + k, (unsigned long long)__double2ll_rn(v * ENERGY_SCALE));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused scalar stage + merge.  Per replica: u = U(S2) - U(S1), soft-core, softplus, sp (double, once per block),
+// then  F[slot] += C + (1-sp) S1 + sp S2  gathered from cluster order, accumulators zeroed behind the read.
+// Semantics: CommonATMMetaForceKernels.cpp:182-201 + kernels/atmmetaforce.cc:8-16, blend in double.
+// ------------------------------------------------------------------------------------------------
+constexpr int MERGE2_THREADS = 256;
+
+__global__ void __launch_bounds__(MERGE2_THREADS)
+nb_merge_kernel(NbDev d, int parity, long long *__restrict__ force, const long long *__restrict__ f1_ext,
+                const long long *__restrict__ f2_ext, const double *__restrict__ energy_ext, int include_energy) {
+    const int r = blockIdx.y;
+    __shared__ double s_sp;
+    if (threadIdx.x == 0) {
+        const unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
+        const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
+                     u2 = (double)(long long)ea[2] / ENERGY_SCALE;
+        double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
+        if (energy_ext) {
+            U1 += energy_ext[2 * r];
+            U2 += energy_ext[2 * r + 1];
+            du += energy_ext[2 * r + 1] - energy_ext[2 * r];
+        }
+        const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
+        s_sp = s.sp;
+        if (blockIdx.x == 0) {
+            double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
+            e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
+            e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp; e[ATM_E_NPAIRS] = (double)ea[3];
+            // zero the accumulators the NEXT step will use (nobody reads them during this launch)
+            unsigned long long *eo = d.eacc + ((size_t)(parity ^ 1) * d.R + r) * EACC_SLOTS;
+            eo[0] = eo[1] = eo[2] = eo[3] = 0ull;
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * MERGE2_THREADS + threadIdx.x;
+    if (i >= d.N) return;
+    const double sp = s_sp, sp1 = 1.0 - s_sp;
+    const int a = d.atom_of_slot[i];
+    const int s = d.site_slot[(size_t)r * d.U + a];
+    const int gm = d.ghost_of_atom[a];
+    const int gs = gm >= 0 ? d.site_slot[(size_t)r * d.U + d.N + gm] : -1;
+    const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
+    long long *bufC = (long long *)d.buf + rsite, *buf1 = bufC + 3 * cs, *buf2 = bufC + 6 * cs;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const long long fc = bufC[c * cs + s];
+        long long fa = buf1[c * cs + s], fb = buf2[c * cs + s];
+        bufC[c * cs + s] = 0; buf1[c * cs + s] = 0; buf2[c * cs + s] = 0;
+        if (gs >= 0) { fb += buf2[c * cs + gs]; buf2[c * cs + gs] = 0; }
+        const size_t fo = (size_t)r * 3 * d.P + (size_t)c * d.P + i;
+        if (f1_ext) fa += f1_ext[fo];
+        if (f2_ext) fb += f2_ext[fo];
+        const double v = __dadd_rn(__dmul_rn(sp, (double)fb), __dmul_rn(sp1, (double)fa));
+        force[fo] += fc + __double2ll_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(NbState *nb, T **ptr, size_t count) {
+    void *p = nullptr;
+    cudaError_t err = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (err != cudaSuccess) {
+        set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(err));
+        return ATM_ERR_NOMEM;
+    }
+    nb->owned.push_back(p);
+    *ptr = (T *)p;
+    return ATM_OK;
+}
+
+template <typename T>
+static int dev_upload(NbState *nb, T **ptr, const std::vector<T> &v, cudaStream_t stream) {
+    int rc = dev_alloc(nb, ptr, v.size());
+    if (rc) return rc;
+    if (!v.empty()) ATM_CUDA_CHECK(cudaMemcpyAsync(*ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return ATM_OK;
+}
+
+void nb_destroy(atm_handle *h) {
+    if (!h->nb) return;
+    for (void *p : h->nb->owned) cudaFree(p);
+    delete h->nb;
+    h->nb = nullptr;
+}
+
+// displacement groups: atoms with the same non-zero float-rounded displacement vector move together
+static int derive_groups(atm_handle *h) {
+    NbState *nb = h->nb;
+    const int N = h->N;
+    nb->h_group_of_atom.assign(N, 0);
+    nb->h_ghost_atom.clear();
+    nb->h_ghost_of_atom.assign(N, -1);
+    std::map<std::array<uint32_t, 3>, int> groups;
+    for (int a = 0; a < N; a++) {
+        float f[3] = {(float)h->displ_by_atom[3 * (size_t)a], (float)h->displ_by_atom[3 * (size_t)a + 1],
+                      (float)h->displ_by_atom[3 * (size_t)a + 2]};
+        if (f[0] == 0.f && f[1] == 0.f && f[2] == 0.f) continue;
+        std::array<uint32_t, 3> key;
+        memcpy(key.data(), f, 12);
+        auto it = groups.find(key);
+        int g;
+        if (it == groups.end()) {
+            g = (int)groups.size() + 1;
+            groups[key] = g;
+        } else {
+            g = it->second;
+        }
+        nb->h_group_of_atom[a] = g;
+        nb->h_ghost_of_atom[a] = (int)nb->h_ghost_atom.size();
+        nb->h_ghost_atom.push_back(a);
+    }
+    ATM_REQUIRE(groups.size() <= 100, ATM_ERR_UNSUPPORTED,
+                "more than 100 distinct displacement vectors (%zu) are not supported", groups.size());
+    nb->d.M = (int)nb->h_ghost_atom.size();
+    nb->d.G = (int)groups.size();
+    return ATM_OK;
+}
+
+static int nb_allocate(atm_handle *h, cudaStream_t stream);
+
+int nb_on_displacements_changed(atm_handle *h, cudaStream_t stream) {
+    if (!h->nb || !h->nb->ready) return ATM_OK;
+    // the site layout depends on the displacement groups and on the slot order: reallocate and require a rebuild
+    h->nb->list_valid = false;
+    return nb_allocate(h, stream);
+}
+
+static void free_owned(NbState *nb) {
+    for (void *p : nb->owned) cudaFree(p);
+    nb->owned.clear();
+    nb->sort_tmp = nullptr;
+}
+
+static int nb_allocate(atm_handle *h, cudaStream_t stream) {
+    NbState *nb = h->nb;
+    ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    free_owned(nb);
+    int rc = derive_groups(h);
+    if (rc) return rc;
+    NbDev &d = nb->d;
+    const int N = h->N, R = h->R;
+    d.N = N; d.P = h->P; d.R = R;
+    d.U = N + d.M;
+    d.cutoff2 = (float)(nb->desc.cutoff * nb->desc.cutoff);
+    d.rlist = (float)(nb->desc.cutoff + nb->desc.skin);
+    d.alpha = (float)nb->desc.ewald_alpha;
+    d.two_alpha_over_sqrtpi = (float)(2.0 * nb->desc.ewald_alpha / sqrt(M_PI));
+    d.displ = h->d_displ;
+    d.params = h->d_params;
+
+    // column grid from the first replica's box and the mean density: cubes holding ~8 atoms
+    ATM_REQUIRE(nb->box_set, ATM_ERR_STATE, "atm_set_box must be called before the neighbour structure is allocated");
+    const double Lx = nb->h_box[0], Ly = nb->h_box[1], Lz = nb->h_box[2];
+    const double edge = cbrt((double)CL * Lx * Ly * Lz / std::max(1, N));
+    d.nx = std::max(1, (int)floor(Lx / edge + 0.5));
+    d.ny = std::max(1, (int)floor(Ly / edge + 0.5));
+    d.ncol = d.nx * d.ny;
+    d.nbins = d.ncol + 2 * d.G;
+    std::vector<int> group_count(d.G + 1, 0);
+    for (int a = 0; a < N; a++) group_count[nb->h_group_of_atom[a]]++;
+    d.CLmax = 0;
+    for (int g = 1; g <= d.G; g++) d.CLmax += (group_count[g] + CL - 1) / CL;
+    d.CXmax = 2 * d.CLmax;
+    d.CenvMax = (N - d.M + CL - 1) / CL + d.ncol;
+    d.Cmax = d.CenvMax + d.CXmax;
+    d.Smax = d.Cmax * CL;
+    // list capacities from the expected partner count of an 8-atom cube (half list for env, full for ligand/ghost)
+    {
+        const double rho = (double)N / (Lx * Ly * Lz);
+        const double a = edge, rl = d.rlist;
+        const double vol = a * a * a + 6 * a * a * rl + 3 * M_PI * a * rl * rl + 4.0 / 3.0 * M_PI * rl * rl * rl;
+        const double full = vol * rho;
+        if (d.capC == 0) d.capC = 32 * (int)ceil(0.5 * full * 1.6 / 32.0 + 2);
+        if (d.capX == 0) d.capX = 32 * (int)ceil(full * 2.0 / 32.0 + 2);
+    }
+    ATM_REQUIRE((long long)d.Smax < (1ll << 24), ATM_ERR_UNSUPPORTED, "more than 2^24 sites per replica");
+
+    // static by-atom arrays
+    float *qp; float2 *par; int *es, *el, *goa, *ga, *gof, *soa, *aos;
+    if ((rc = dev_upload(nb, &qp, nb->h_qp, stream))) return rc;
+    if ((rc = dev_upload(nb, &par, nb->h_par, stream))) return rc;
+    if ((rc = dev_upload(nb, &es, nb->h_excl_start, stream))) return rc;
+    if ((rc = dev_upload(nb, &el, nb->h_excl_list, stream))) return rc;
+    if ((rc = dev_upload(nb, &goa, nb->h_group_of_atom, stream))) return rc;
+    if ((rc = dev_upload(nb, &ga, nb->h_ghost_atom, stream))) return rc;
+    if ((rc = dev_upload(nb, &gof, nb->h_ghost_of_atom, stream))) return rc;
+    std::vector<int> slot_of_atom(N);
+    for (int s = 0; s < N; s++) slot_of_atom[h->atom_index[s]] = s;
+    if ((rc = dev_upload(nb, &soa, slot_of_atom, stream))) return rc;
+    if ((rc = dev_upload(nb, &aos, h->atom_index, stream))) return rc;
+    d.qp_atom = qp; d.par_atom = par; d.excl_start = es; d.excl_list = el; d.group_of_atom = goa;
+    d.ghost_atom = ga; d.ghost_of_atom = gof; d.slot_of_atom = soa; d.atom_of_slot = aos;
+    if ((rc = dev_upload(nb, &nb->d_excl_pairs, nb->h_excl_pairs, stream))) return rc;
+    if ((rc = dev_upload(nb, &nb->d_exc_pairs, nb->h_exc_pairs, stream))) return rc;
+    if ((rc = dev_upload(nb, &nb->d_exc_par, nb->h_exc_par, stream))) return rc;
+    nb->n_excl = (int)nb->h_excl_pairs.size();
+    nb->n_exc = (int)nb->h_exc_pairs.size();
+
+    float4 *box, *invbox;
+    if ((rc = dev_alloc(nb, &box, R))) return rc;
+    if ((rc = dev_alloc(nb, &invbox, R))) return rc;
+    d.box = box; d.invbox = invbox;
+    nb->box_dirty = true;
+
+    const size_t RU = (size_t)R * d.U, RS = (size_t)R * d.Smax, RC = (size_t)R * d.Cmax;
+    if ((rc = dev_alloc(nb, &d.keys, RU))) return rc;
+    if ((rc = dev_alloc(nb, &nb->keys_alt, RU))) return rc;
+    if ((rc = dev_alloc(nb, &d.vals, RU))) return rc;
+    if ((rc = dev_alloc(nb, &nb->vals_alt, RU))) return rc;
+    if ((rc = dev_alloc(nb, &d.bin_count, (size_t)R * d.nbins))) return rc;
+    if ((rc = dev_alloc(nb, &d.bin_site_start, (size_t)R * (d.nbins + 1)))) return rc;
+    if ((rc = dev_alloc(nb, &d.bin_cluster_start, (size_t)R * (d.nbins + 1)))) return rc;
+    if ((rc = dev_alloc(nb, &d.nclusters, R))) return rc;
+    if ((rc = dev_alloc(nb, &d.slot_site, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.site_slot, RU))) return rc;
+    if ((rc = dev_alloc(nb, &d.slot_src, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.slot_qp, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.xs, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.par, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.cc, RC))) return rc;
+    if ((rc = dev_alloc(nb, &d.ch, RC))) return rc;
+    if ((rc = dev_alloc(nb, &d.cmeta, RC))) return rc;
+    const size_t per_replica = (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)d.CLmax * d.capC;
+    nb->jlist_entries = per_replica * R;
+    if ((rc = dev_alloc(nb, &d.jlist, nb->jlist_entries))) return rc;
+    if ((rc = dev_alloc(nb, &d.list_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
+    if ((rc = dev_alloc(nb, &d.flags, 8))) return rc;
+    if ((rc = dev_alloc(nb, &d.buf, 9 * RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.eacc, (size_t)2 * R * EACC_SLOTS))) return rc;
+    if ((rc = dev_alloc(nb, &d.energies, (size_t)R * ATM_NUM_ENERGY_SLOTS))) return rc;
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.buf, 0, 9 * RS * sizeof(unsigned long long), stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.eacc, 0, (size_t)2 * R * EACC_SLOTS * sizeof(unsigned long long), stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.energies, 0, (size_t)R * ATM_NUM_ENERGY_SLOTS * sizeof(double), stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.list_nsteps, 0, (size_t)R * (d.Cmax + d.CLmax) * sizeof(int), stream));
+    nb->parity = 0;
+
+    // radix sort scratch
+    int key_bits = 16;
+    while ((1ull << (key_bits - 16)) < (unsigned long long)R * d.nbins) key_bits++;
+    nb->sort_bits = std::min(64, key_bits);
+    nb->sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, nb->sort_tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, (int)RU, 0,
+                                    nb->sort_bits, stream);
+    char *tmp;
+    if ((rc = dev_alloc(nb, &tmp, nb->sort_tmp_bytes))) return rc;
+    nb->sort_tmp = tmp;
+    ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return ATM_OK;
+}
+
+static int upload_box_if_dirty(atm_handle *h, cudaStream_t stream) {
+    NbState *nb = h->nb;
+    if (!nb->box_dirty) return ATM_OK;
+    std::vector<float4> b(h->R), ib(h->R);
+    for (int r = 0; r < h->R; r++) {
+        b[r] = make_float4((float)nb->h_box[3 * r], (float)nb->h_box[3 * r + 1], (float)nb->h_box[3 * r + 2], 0.f);
+        ib[r] = make_float4(1.0f / b[r].x, 1.0f / b[r].y, 1.0f / b[r].z, 0.f);
+    }
+    ATM_CUDA_CHECK(cudaMemcpyAsync((void *)nb->d.box, b.data(), sizeof(float4) * h->R, cudaMemcpyHostToDevice, stream));
+    ATM_CUDA_CHECK(cudaMemcpyAsync((void *)nb->d.invbox, ib.data(), sizeof(float4) * h->R, cudaMemcpyHostToDevice, stream));
+    ATM_CUDA_CHECK(cudaStreamSynchronize(stream));  // the staging vectors die at return
+    nb->box_dirty = false;
+    return ATM_OK;
+}
+
+}  // namespace atm
+
+using namespace atm;
+
+extern "C" {
+
+int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && desc, ATM_ERR_INVALID, "atm_nb_setup: null argument");
+    ATM_REQUIRE(h->cfg.precision != ATM_PREC_DOUBLE, ATM_ERR_UNSUPPORTED,
+                "atm_nb_setup: the fused direct-space path computes in fp32 with fixed-point accumulation "
+                "(single/mixed); double precision is Tier 1 only");
+    ATM_REQUIRE(desc->charge && desc->sigma && desc->epsilon, ATM_ERR_INVALID, "atm_nb_setup: null parameter array");
+    ATM_REQUIRE(desc->cutoff > 0 && desc->skin >= 0 && desc->ewald_alpha >= 0, ATM_ERR_INVALID,
+                "atm_nb_setup: cutoff must be > 0, skin and ewald_alpha >= 0");
+    ATM_REQUIRE(desc->num_exclusions >= 0 && desc->num_exceptions >= 0, ATM_ERR_INVALID, "atm_nb_setup: negative count");
+    ATM_REQUIRE(h->N > 0, ATM_ERR_INVALID, "atm_nb_setup: empty system");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    const int N = h->N;
+    if (!h->nb) h->nb = new NbState();
+    NbState *nb = h->nb;
+    nb->ready = false;
+    nb->list_valid = false;
+    nb->desc = *desc;
+    nb->h_qp.resize(N);
+    nb->h_par.resize(N);
+    const double sq_ke = sqrt(ONE_4PI_EPS0);
+    for (int a = 0; a < N; a++) {
+        ATM_REQUIRE(desc->epsilon[a] >= 0 && desc->sigma[a] >= 0, ATM_ERR_INVALID, "atm_nb_setup: negative sigma/epsilon at atom %d", a);
+        nb->h_qp[a] = (float)(desc->charge[a] * sq_ke);
+        nb->h_par[a] = make_float2((float)(0.5 * desc->sigma[a]), (float)(2.0 * sqrt(desc->epsilon[a])));
+    }
+    // exclusions -> CSR (both directions) + pair list
+    nb->h_excl_start.assign(N + 1, 0);
+    nb->h_excl_pairs.resize(desc->num_exclusions);
+    for (int k = 0; k < desc->num_exclusions; k++) {
+        const int a = desc->exclusions[2 * k], b = desc->exclusions[2 * k + 1];
+        ATM_REQUIRE(a >= 0 && a < N && b >= 0 && b < N && a != b, ATM_ERR_INVALID, "atm_nb_setup: bad exclusion %d (%d,%d)", k, a, b);
+        nb->h_excl_pairs[k] = make_int2(a, b);
+        nb->h_excl_start[a + 1]++;
+        nb->h_excl_start[b + 1]++;
+    }
+    for (int a = 0; a < N; a++) nb->h_excl_start[a + 1] += nb->h_excl_start[a];
+    nb->h_excl_list.assign(nb->h_excl_start[N], 0);
+    {
+        std::vector<int> fill(N, 0);
+        for (int k = 0; k < desc->num_exclusions; k++) {
+            const int a = desc->exclusions[2 * k], b = desc->exclusions[2 * k + 1];
+            nb->h_excl_list[nb->h_excl_start[a] + fill[a]++] = b;
+            nb->h_excl_list[nb->h_excl_start[b] + fill[b]++] = a;
+        }
+    }
+    nb->h_exc_pairs.resize(desc->num_exceptions);
+    nb->h_exc_par.resize(desc->num_exceptions);
+    for (int k = 0; k < desc->num_exceptions; k++) {
+        const int a = desc->exception_pairs[2 * k], b = desc->exception_pairs[2 * k + 1];
+        ATM_REQUIRE(a >= 0 && a < N && b >= 0 && b < N && a != b, ATM_ERR_INVALID, "atm_nb_setup: bad exception %d", k);
+        nb->h_exc_pairs[k] = make_int2(a, b);
+        nb->h_exc_par[k] = make_float4((float)(ONE_4PI_EPS0 * desc->exception_params[3 * k]), (float)desc->exception_params[3 * k + 1],
+                                       (float)(4.0 * desc->exception_params[3 * k + 2]), 0.f);
+    }
+    // the desc pointers are not kept
+    nb->desc.charge = nb->desc.sigma = nb->desc.epsilon = nullptr;
+    nb->desc.exclusions = nb->desc.exception_pairs = nullptr;
+    nb->desc.exception_params = nullptr;
+    nb->d.capC = nb->d.capX = 0;
+    nb->ready = true;
+    if (nb->box_set) return nb_allocate(h, stream);
+    return ATM_OK;
+}
+
+int atm_set_box(atm_handle *h, int32_t replica, const double box[9]) {
+    ATM_REQUIRE(h && box, ATM_ERR_INVALID, "atm_set_box: null argument");
+    ATM_REQUIRE(replica >= -1 && replica < h->R, ATM_ERR_INVALID, "atm_set_box: replica %d out of range", replica);
+    ATM_REQUIRE(box[1] == 0 && box[2] == 0 && box[3] == 0 && box[5] == 0 && box[6] == 0 && box[7] == 0, ATM_ERR_UNSUPPORTED,
+                "atm_set_box: triclinic boxes are not supported by this build (rectangular only)");
+    ATM_REQUIRE(box[0] > 0 && box[4] > 0 && box[8] > 0, ATM_ERR_INVALID, "atm_set_box: non-positive box edge");
+    if (!h->nb) h->nb = new NbState();
+    NbState *nb = h->nb;
+    if (nb->h_box.empty()) nb->h_box.assign((size_t)3 * h->R, 0.0);
+    for (int r = 0; r < h->R; r++)
+        if (replica < 0 || replica == r) {
+            nb->h_box[3 * r] = box[0]; nb->h_box[3 * r + 1] = box[4]; nb->h_box[3 * r + 2] = box[8];
+        }
+    bool all = true;
+    for (int r = 0; r < h->R; r++) all = all && nb->h_box[3 * r] > 0;
+    const bool first = !nb->box_set && all;
+    nb->box_set = all;
+    nb->box_dirty = true;
+    if (first && nb->ready) {
+        ATM_CUDA_CHECK(cudaSetDevice(h->device));
+        return nb_allocate(h, 0);
+    }
+    return ATM_OK;
+}
+
+int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && posq_, ATM_ERR_INVALID, "atm_nb_rebuild: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->box_set, ATM_ERR_STATE, "atm_nb_rebuild: call atm_nb_setup and atm_set_box first");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    NbState *nb = h->nb;
+    const float4 *posq = (const float4 *)posq_;
+    int rc;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        NbDev &d = nb->d;
+        for (int r = 0; r < h->R; r++)
+            ATM_REQUIRE(2.0 * d.rlist < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
+                        "atm_nb_rebuild: box edge smaller than 2*(cutoff+skin)");
+        const int RU = d.R * d.U;
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
+        nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
+        nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
+        size_t tmp_bytes = nb->sort_tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
+        nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
+        nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq);
+        nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        const int nlists = d.Cmax + d.CLmax;
+        nl_build_kernel<<<dim3((nlists + 3) / 4, d.R), 128, 0, stream>>>(d);
+        ATM_CUDA_CHECK(cudaGetLastError());
+        int flags[8];
+        ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+        ATM_REQUIRE(!(flags[0] & 2), ATM_ERR_UNSUPPORTED,
+                    "atm_nb_rebuild: a cluster's extent + list radius exceeds half the box; box too small for this build");
+        if (flags[0] & 1) {
+            // a list overflowed its capacity: grow and retry
+            const int need = flags[1];
+            d.capC = std::max(d.capC, 32 * ((int)(need * 1.25) / 32 + 1));
+            d.capX = std::max(d.capX, 32 * ((int)(need * 1.25) / 32 + 1));
+            if ((rc = nb_allocate(h, stream))) return rc;
+            if ((rc = upload_box_if_dirty(h, stream))) return rc;
+            continue;
+        }
+        int ncl0 = 0;
+        ATM_CUDA_CHECK(cudaMemcpy(&ncl0, d.nclusters, sizeof(int), cudaMemcpyDeviceToHost));
+        unsigned long long entries = 0;
+        memcpy(&entries, &flags[2], 8);
+        nb->stats[0] = d.U; nb->stats[1] = ncl0; nb->stats[2] = (int64_t)(entries / d.R); nb->stats[3] = d.capC; nb->stats[4] = d.capX;
+        nb->stats[5] = d.M; nb->stats[6] = d.G; nb->stats[7] = d.ncol;
+        nb->list_valid = true;
+        return ATM_OK;
+    }
+    set_error("atm_nb_rebuild: neighbour list capacity could not be satisfied after 4 attempts");
+    return ATM_ERR_NOMEM;
+}
+
+int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && io, ATM_ERR_INVALID, "atm_step: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->list_valid, ATM_ERR_STATE, "atm_step: no valid neighbour structure (call atm_nb_rebuild)");
+    ATM_REQUIRE(io->posq && io->force, ATM_ERR_INVALID, "atm_step: posq and force are required");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    NbState *nb = h->nb;
+    NbDev &d = nb->d;
+    int rc;
+    if ((rc = upload_params_if_dirty(h, stream))) return rc;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    if (io->posq1 || io->posq2) {
+        ATM_REQUIRE(h->R == 1, ATM_ERR_UNSUPPORTED, "atm_step: inner-context coordinate outputs need num_replicas == 1");
+        if ((rc = atm_copy_state(h, io->posq, io->posq_corr, io->posq1, io->posq1_corr, io->posq2, io->posq2_corr, stream_))) return rc;
+    }
+    const int parity = nb->parity;
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
+    const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
+    const int items = d.CenvMax * chunksC + d.CXmax * chunksX + d.CLmax * chunksC;
+    const int warps_per_block = NB_THREADS / 32;
+    nb2_kernel<<<dim3((items + warps_per_block - 1) / warps_per_block, d.R), NB_THREADS, 0, stream>>>(d, parity);
+    const int nsp = nb->n_excl + nb->n_exc;
+    if (nsp > 0)
+        nb_special_pairs_kernel<<<dim3((nsp + 127) / 128, d.R), 128, 0, stream>>>(d, parity, nb->d_excl_pairs, nb->n_excl, nb->d_exc_pairs,
+                                                                                 nb->d_exc_par, nb->n_exc);
+    nb_merge_kernel<<<dim3((d.N + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
+        d, parity, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext,
+        io->energy_ext, io->include_energy);
+    ATM_CUDA_CHECK(cudaGetLastError());
+    nb->parity ^= 1;
+    return ATM_OK;
+}
+
+int atm_energies_device(atm_handle *h, const double **dev_ptr) {
+    ATM_REQUIRE(h && dev_ptr, ATM_ERR_INVALID, "atm_energies_device: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->d.energies, ATM_ERR_STATE, "atm_energies_device: Tier 2 not set up");
+    *dev_ptr = h->nb->d.energies;
+    return ATM_OK;
+}
+
+int atm_get_energies(atm_handle *h, double *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && out, ATM_ERR_INVALID, "atm_get_energies: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->d.energies, ATM_ERR_STATE, "atm_get_energies: Tier 2 not set up");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    ATM_CUDA_CHECK(cudaMemcpyAsync(out, h->nb->d.energies, sizeof(double) * (size_t)h->R * ATM_NUM_ENERGY_SLOTS, cudaMemcpyDeviceToHost, stream));
+    ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int r = 0; r < h->R; r++) h->pert_energy[r] = out[(size_t)r * ATM_NUM_ENERGY_SLOTS + ATM_E_USC];
+    return ATM_OK;
+}
+
+int atm_nb_stats(atm_handle *h, int64_t out[8]) {
+    ATM_REQUIRE(h && out, ATM_ERR_INVALID, "atm_nb_stats: null argument");
+    ATM_REQUIRE(h->nb && h->nb->list_valid, ATM_ERR_STATE, "atm_nb_stats: no neighbour structure");
+    memcpy(out, h->nb->stats, sizeof(int64_t) * 8);
+    return ATM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,9 @@
+"""atmmetaforce -- Python face of the Blackwell ATM Meta-Force back-end.
+
+Same module name and public names as the reference's SWIG module (python/atmmetaforceplugin.i:1,35-36,66-124):
+ATMMetaForce, ATMMetaForceUtils, ATMMETAFORCE_VERSION.  The compute path is libatm_b200.so (CUDA, sm_100a).
+"""
+from ._capi import ATMError, LIB_PATH  # noqa: F401
+from .backend import ATMBackend, softcore_softplus, hrex_sweep, hrex_reduced_energy  # noqa: F401
+
+ATMMETAFORCE_VERSION = "0.3.1"  # reference openmmapi/include/ATMMetaForceVersion.h:4

@@ -1,0 +1,174 @@
+"""Thin object wrapper over the C ABI that takes torch CUDA tensors as borrowed device buffers.
+
+torch is plumbing only (device memory + the current stream); every kernel is in libatm_b200.so.
+Mirrors the reference's kernel seam CalcATMMetaForceKernel (openmmapi/include/ATMMetaForceKernels.h:15-59):
+initialize -> __init__/set_displacements, copyState -> copy_state, execute -> execute,
+copyParametersToContext -> set_displacements, getPerturbationEnergy -> get_perturbation_energy.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import ATMError, check
+
+_PREC = {"single": _capi.PREC_SINGLE, "mixed": _capi.PREC_MIXED, "double": _capi.PREC_DOUBLE}
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _dptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ATMError("expected a CUDA tensor (this back-end has no CPU path)")
+    if not t.is_contiguous():
+        raise ATMError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class ATMBackend:
+    """One handle == one OpenMM Context (or R batched replicas of one System)."""
+
+    def __init__(self, num_particles, padded_num_particles=0, precision="mixed", num_replicas=1, device=-1):
+        self._h = C.c_void_p()
+        cfg = _capi.Config(int(num_particles), int(padded_num_particles), _PREC[precision], int(num_replicas), int(device))
+        check(_capi.lib().atm_create(C.byref(cfg), C.byref(self._h)))
+        self.N = int(num_particles)
+        self.P = int(padded_num_particles) if padded_num_particles else 32 * ((self.N + 31) // 32)
+        self.R = int(num_replicas)
+        self.precision = precision
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            _capi.lib().atm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- displacement table / parameters ---------------------------------------------------------
+    def set_displacements(self, dxyz, atom_index=None, stream=None):
+        d = _np(dxyz, np.float64).reshape(self.N, 3)
+        ai = _np(atom_index, np.int32) if atom_index is not None else None
+        check(_capi.lib().atm_set_displacements(self._h, ai.ctypes.data_as(C.c_void_p) if ai is not None else None,
+                                                d.ctypes.data_as(C.c_void_p), _stream_ptr(stream)))
+
+    def set_parameters(self, p, replica=-1):
+        p = _np(p, np.float64)
+        assert p.size == _capi.NUM_PARAMS
+        check(_capi.lib().atm_set_parameters(self._h, int(replica), p.ctypes.data_as(C.c_void_p)))
+
+    def get_parameters(self, replica=0):
+        p = np.zeros(_capi.NUM_PARAMS)
+        check(_capi.lib().atm_get_parameters(self._h, int(replica), p.ctypes.data_as(C.c_void_p)))
+        return p
+
+    # -- Tier 1 -------------------------------------------------------------------------------------
+    def copy_state(self, posq, posq1, posq2, posq_corr=None, posq1_corr=None, posq2_corr=None, stream=None):
+        check(_capi.lib().atm_copy_state(self._h, _dptr(posq), _dptr(posq_corr), _dptr(posq1), _dptr(posq1_corr),
+                                         _dptr(posq2), _dptr(posq2_corr), _stream_ptr(stream)))
+
+    def wrap_positions(self, posq_in, posq_out, box, stream=None):
+        b = _np(box, np.float64).reshape(9)
+        check(_capi.lib().atm_wrap_positions(self._h, _dptr(posq_in), _dptr(posq_out), b.ctypes.data_as(C.c_void_p),
+                                             _stream_ptr(stream)))
+
+    def hybrid_force(self, force, f1, f2, sp, stream=None):
+        check(_capi.lib().atm_hybrid_force(self._h, _dptr(force), _dptr(f1), _dptr(f2), float(sp), _stream_ptr(stream)))
+
+    def execute(self, U1, U2, force, f1, f2, include_energy=True, replica=0, stream=None):
+        e = C.c_double()
+        check(_capi.lib().atm_execute(self._h, int(replica), float(U1), float(U2), _dptr(force), _dptr(f1), _dptr(f2),
+                                      1 if include_energy else 0, C.byref(e), _stream_ptr(stream)))
+        return e.value
+
+    def get_perturbation_energy(self, replica=0):
+        u = C.c_double()
+        check(_capi.lib().atm_get_perturbation_energy(self._h, int(replica), C.byref(u)))
+        return u.value
+
+    # -- Tier 2 -------------------------------------------------------------------------------------
+    def nb_setup(self, charge, sigma, epsilon, cutoff, ewald_alpha, skin=0.1, exclusions=None, exception_pairs=None,
+                 exception_params=None, stream=None):
+        q, s, e = _np(charge, np.float64), _np(sigma, np.float64), _np(epsilon, np.float64)
+        assert q.size == self.N and s.size == self.N and e.size == self.N
+        ex = _np(exclusions if exclusions is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        xp = _np(exception_pairs if exception_pairs is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        xq = _np(exception_params if exception_params is not None else np.zeros((0, 3)), np.float64).reshape(-1, 3)
+        assert xp.shape[0] == xq.shape[0]
+        d = _capi.NonbondedDesc(q.ctypes.data, s.ctypes.data, e.ctypes.data, ex.shape[0], ex.ctypes.data, xp.shape[0],
+                                xp.ctypes.data, xq.ctypes.data, float(cutoff), float(ewald_alpha), float(skin))
+        check(_capi.lib().atm_nb_setup(self._h, C.byref(d), _stream_ptr(stream)))
+
+    def set_box(self, box, replica=-1):
+        b = np.asarray(box, np.float64)
+        if b.size == 3:
+            b = np.diag(b)
+        b = _np(b, np.float64).reshape(9)
+        check(_capi.lib().atm_set_box(self._h, int(replica), b.ctypes.data_as(C.c_void_p)))
+
+    def rebuild(self, posq, stream=None):
+        check(_capi.lib().atm_nb_rebuild(self._h, _dptr(posq), _stream_ptr(stream)))
+
+    def step(self, posq, force, posq_corr=None, f1_ext=None, f2_ext=None, energy_ext=None, posq1=None, posq1_corr=None,
+             posq2=None, posq2_corr=None, include_energy=True, stream=None):
+        def v(t):
+            p = _dptr(t)
+            return p.value if p is not None else None
+        io = _capi.StepIO(v(posq), v(posq_corr), v(force), v(f1_ext), v(f2_ext), v(energy_ext), v(posq1), v(posq1_corr),
+                          v(posq2), v(posq2_corr), 1 if include_energy else 0)
+        check(_capi.lib().atm_step(self._h, C.byref(io), _stream_ptr(stream)))
+
+    def energies_device_ptr(self):
+        p = C.c_void_p()
+        check(_capi.lib().atm_energies_device(self._h, C.byref(p)))
+        return p.value
+
+    def get_energies(self, stream=None):
+        """Synchronises.  Returns an [R][8] array (see _capi.E_* slots)."""
+        out = np.zeros((self.R, _capi.NUM_ENERGY_SLOTS))
+        check(_capi.lib().atm_get_energies(self._h, out.ctypes.data_as(C.c_void_p), _stream_ptr(stream)))
+        return out
+
+    def nb_stats(self):
+        out = np.zeros(8, np.int64)
+        check(_capi.lib().atm_nb_stats(self._h, out.ctypes.data_as(C.c_void_p)))
+        keys = ("sites", "clusters", "list_entries", "cap_env", "cap_lig", "displaced_atoms", "groups", "columns")
+        return dict(zip(keys, (int(x) for x in out)))
+
+
+def softcore_softplus(params, U1, U2):
+    """Host scalar stage of the library (same math the device runs)."""
+    p = _np(params, np.float64)
+    out = np.zeros(7)
+    check(_capi.lib().atm_softcore_softplus(p.ctypes.data_as(C.c_void_p), float(U1), float(U2), out.ctypes.data_as(C.c_void_p)))
+    keys = ("u_sc", "fp", "ebias", "bfp", "energy", "sp", "sp_ref")
+    return dict(zip(keys, out))
+
+
+def hrex_sweep(state_params, u12, replica_state, beta, seed, cycle):
+    sp = _np(state_params, np.float64).reshape(-1, _capi.NUM_PARAMS)
+    u = _np(u12, np.float64).reshape(-1, 2)
+    rs = np.array(replica_state, dtype=np.int32, copy=True)
+    acc = C.c_int32()
+    check(_capi.lib().atm_hrex_sweep(sp.shape[0], sp.ctypes.data_as(C.c_void_p), u.shape[0], u.ctypes.data_as(C.c_void_p),
+                                     rs.ctypes.data_as(C.c_void_p), float(beta), int(seed), int(cycle), C.byref(acc)))
+    return rs, acc.value
+
+
+def hrex_reduced_energy(params, U1, U2, beta):
+    p = _np(params, np.float64)
+    return _capi.lib().atm_hrex_reduced_energy(p.ctypes.data_as(C.c_void_p), float(U1), float(U2), float(beta))

@@ -1,0 +1,58 @@
+"""Developer timing probe (not the bench contract): times atm_step / rebuild for a synthetic system."""
+import argparse, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "openmm-atmmetaforce-plugin_b200", "python"))
+import numpy as np
+import torch
+import atmmetaforce as atm
+from atmmetaforce import synthetic
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--system", default="config3")
+ap.add_argument("--replicas", type=int, default=1)
+ap.add_argument("--steps", type=int, default=50)
+ap.add_argument("--skin", type=float, default=0.1)
+ap.add_argument("--natoms", type=int, default=25000)
+args = ap.parse_args()
+
+s = synthetic.config3() if args.system == "config3" else (synthetic.config4() if args.system == "config4" else synthetic.water_box(args.natoms))
+n = s["pos"].shape[0]
+R = args.replicas
+be = atm.ATMBackend(n, precision="mixed", num_replicas=R)
+P = be.P
+be.set_displacements(s["displ"])
+be.set_box(s["box"])
+sched = synthetic.atm_schedule_22()
+for r in range(R):
+    be.set_parameters(sched[r % 22], replica=r)
+be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin, exclusions=s["excl"])
+posq = np.zeros((R, P, 4), np.float32)
+rng = np.random.default_rng(0)
+for r in range(R):
+    posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.002, (n, 3)) * (r > 0)
+    posq[r, :n, 3] = s["charge"]
+posq = torch.from_numpy(posq).cuda()
+force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+t0 = time.time(); be.rebuild(posq); torch.cuda.synchronize(); t_first = time.time() - t0
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+ev[0].record()
+for _ in range(5):
+    be.rebuild(posq)
+ev[1].record()
+for _ in range(5):
+    be.step(posq, force)
+torch.cuda.synchronize()
+ev[2].record()
+for _ in range(args.steps):
+    be.step(posq, force)
+ev[3].record()
+torch.cuda.synchronize()
+en = be.get_energies()
+st = be.nb_stats()
+ms_step = ev[2].elapsed_time(ev[3]) / args.steps
+ms_rebuild = ev[0].elapsed_time(ev[1]) / 5
+pairs = en[:, 7].sum()
+print(f"system={args.system} N={n} R={R} skin={args.skin} stats={st}")
+print(f"first rebuild {t_first*1e3:.1f} ms; rebuild {ms_rebuild:.3f} ms; step {ms_step*1e3:.1f} us; pairs in cutoff/step {pairs:.3e}; "
+      f"listed pair slots {st['list_entries']*8*R:.3e}; fill {pairs/(st['list_entries']*8*R):.3f}; "
+      f"Gpairs/s {pairs/ms_step/1e6:.2f}; u[0]={en[0,2]:.3f} U1[0]={en[0,0]:.2f}")
