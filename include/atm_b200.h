@@ -147,7 +147,8 @@ typedef struct {
     const double *exception_params;  /* [num_exceptions][3] chargeProd (e^2), sigma (nm), epsilon (kJ/mol) */
     double cutoff;                   /* nm */
     double ewald_alpha;              /* 1/nm; 0 = plain Coulomb inside the cutoff */
-    double skin;                     /* nm, neighbour-list padding (list radius = cutoff + skin) */
+    double skin;                     /* nm, padding of the pruned (inner) pair list used every step */
+    double skin_outer;               /* nm, padding of the outer list the inner one is pruned from (0 = same as skin) */
 } atm_nonbonded_desc;
 
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
@@ -156,10 +157,16 @@ int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
  * ref: the box mirror in copyState (CommonATMMetaForceKernels.cpp:214-219). */
 int atm_set_box(atm_handle *h, int32_t replica, const double box[9]);
 
-/* (Re)builds the cluster pair list of every replica for both coordinate states from
- * posq ([R][P] float4, slot order).  Must be called before the first atm_step and whenever any atom has
- * moved by more than skin/2 since the last rebuild, and after atm_set_displacements / reordering. */
+/* (Re)builds the cluster pair lists of every replica for both coordinate states from posq ([R][P] float4, slot
+ * order): spatial sort, clusters, the OUTER list (radius cutoff+skin_outer, with exclusion masks) and the pruned INNER
+ * list (radius cutoff+skin).  Must be called before the first atm_step, whenever any atom has moved by more than
+ * skin_outer/2 since the last rebuild, and after atm_set_displacements / reordering.  SYNCHRONISES `stream` once (it
+ * reads back the capacity check). */
 int atm_nb_rebuild(atm_handle *h, const void *posq, void *stream);
+
+/* Re-prunes the INNER list from the outer one at the current coordinates (cheap, asynchronous, capturable).
+ * Needed whenever any atom has moved by more than skin/2 since the last prune or rebuild. */
+int atm_nb_prune(atm_handle *h, const void *posq, void *stream);
 
 typedef struct {
     const void *posq;          /* [R][P] float4 positions+charge, slot order (borrowed) */
@@ -173,6 +180,7 @@ typedef struct {
     void *posq1, *posq1_corr, *posq2, *posq2_corr;
     int32_t include_energy;    /* also evaluate the shared (env-env) pair energies so that U1,U2,E are valid;
                                   0 = forces and u only (u, u_sc, W, sp remain exact) */
+    int32_t collect_stats;     /* also count the pairs inside the cutoff (ATM_E_NPAIRS); costs a few percent */
 } atm_step_io;
 
 /* One pass of the hot path for all R replicas: copy-state -> two-state direct space -> device scalar

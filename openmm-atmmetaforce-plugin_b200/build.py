@@ -33,15 +33,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: developer A/B builds (e.g. defines=["ATM_NO_NEWTON"], out="libatm_b200_exp.so")."""
+    lib = os.path.join(HERE, out) if out else LIB
+    if not force and not out and not needs_build():
         return LIB
+    tag = ("_" + out.replace(".so", "")) if out else ""
     objs = []
     procs = []
     for s in SOURCES:
-        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", s.replace(".cu", tag + ".o"))
         os.makedirs(os.path.dirname(obj), exist_ok=True)
-        cmd = [NVCC] + [f for f in FLAGS if f != "--shared"] + ["-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [NVCC] + [f for f in FLAGS if f != "--shared"] + ["-c", os.path.join(CSRC, s), "-o", obj] + ["-D" + x for x in defines]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -53,10 +56,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
         if verbose:
             sys.stdout.write(out)
-    cmd = [NVCC, "--shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
+    cmd = [NVCC, "--shared", "-ccbin", "/usr/bin/g++", "-o", lib] + objs
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

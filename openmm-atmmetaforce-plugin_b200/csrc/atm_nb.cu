@@ -17,6 +17,7 @@
 // shuffles and no shared-memory traffic; f_j goes out with three 64-bit fixed-point RED.ADDs per lane per
 // 8 pairs, f_i is reduced by a 27-shuffle transpose-reduction once per work item.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -28,8 +29,9 @@
 namespace atm {
 
 constexpr int CL = 8;            // sites per cluster
-constexpr int ITEM_STEPS = 8;    // 32-entry list steps per work item
-constexpr int NB_THREADS = 256;  // force kernel block size (8 warps)
+constexpr int ITEM_STEPS = 16;     // 32-entry list steps per work item
+constexpr int NB_THREADS = 128;    // force kernel block size (4 warps, one work item each)
+constexpr int NB_MIN_BLOCKS = 4;   // 16 warps / SM at <= 128 registers
 constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int EACC_SLOTS = 4;                  // Uc, U(S1), U(S2), pairs in cutoff
@@ -39,7 +41,7 @@ struct NbDev {  // everything the kernels need, passed by value
     int nx, ny, ncol, nbins;
     int Smax, Cmax, CLmax, CXmax, CenvMax;
     int capC, capX;
-    float cutoff2, rlist, alpha, two_alpha_over_sqrtpi;
+    float cutoff2, rlist, rlist_outer, alpha, two_alpha_over_sqrtpi;
     // static, by atom
     const float *qp_atom;
     const float2 *par_atom;
@@ -51,14 +53,15 @@ struct NbDev {  // everything the kernels need, passed by value
     unsigned long long *keys;
     int *vals;
     int *bin_count, *bin_site_start, *bin_cluster_start, *nclusters;
-    int *slot_site, *site_slot, *slot_src;
+    int *slot_site, *site_slot, *slot_src, *slot_out, *slot_ghost;
     float *slot_qp;
     float4 *xs;
     float2 *par;
     float4 *cc, *ch;
     int *cmeta;
-    unsigned int *jlist;
-    int *list_nsteps;
+    unsigned int *jlist, *jlist_outer;
+    int *list_nsteps, *outer_nsteps;
+    int2 *items;
     int *flags;
     // accumulators
     unsigned long long *buf;
@@ -91,6 +94,10 @@ struct NbState {
     int parity = 0;
     int sort_bits = 64;
     size_t jlist_entries = 0;
+    int *item_counts = nullptr, *item_offsets = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int n_items = 0, max_items = 0;
     int64_t stats[8] = {0};
 };
 
@@ -210,6 +217,17 @@ __global__ void nl_place_kernel(NbDev d, const unsigned long long *__restrict__ 
     d.slot_src[rs] = (r * d.P + d.slot_of_atom[a]) | (ghost ? 0x80000000 : 0);
     d.slot_qp[rs] = d.qp_atom[a];
     d.par[rs] = d.par_atom[a];
+    d.slot_out[rs] = ghost ? -1 : d.slot_of_atom[a];
+}
+
+// after every site has its slot: link each displaced atom's real slot to its ghost slot
+__global__ void nl_link_ghosts_kernel(NbDev d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.R * d.M) return;
+    const int r = t / d.M, m = t - r * d.M;
+    const int a = d.ghost_atom[m];
+    const int s_real = d.site_slot[(size_t)r * d.U + a], s_gh = d.site_slot[(size_t)r * d.U + d.N + m];
+    d.slot_ghost[(size_t)r * d.Smax + s_real] = s_gh;
 }
 
 // Every step: gather current coordinates into cluster order; ghosts get posq + displ (the same float add as
@@ -265,8 +283,8 @@ __global__ void nl_bbox_kernel(NbDev d) {
     d.ch[rc] = make_float4(0.5f * (hi.x - lo.x), 0.5f * (hi.y - lo.y), 0.5f * (hi.z - lo.z), 0.f);
     d.cmeta[rc] = cls | (valid << 16);
     // the per-step image shift of a partner relative to the cluster centre needs half extent + list radius <= L/2
-    const float hmax_x = 0.5f * (hi.x - lo.x) + d.rlist, hmax_y = 0.5f * (hi.y - lo.y) + d.rlist,
-                hmax_z = 0.5f * (hi.z - lo.z) + d.rlist;
+    const float hmax_x = 0.5f * (hi.x - lo.x) + d.rlist_outer, hmax_y = 0.5f * (hi.y - lo.y) + d.rlist_outer,
+                hmax_z = 0.5f * (hi.z - lo.z) + d.rlist_outer;
     if (hmax_x > 0.5f * L.x || hmax_y > 0.5f * L.y || hmax_z > 0.5f * L.z) atomicOr(&d.flags[0], 2);
 }
 
@@ -314,36 +332,65 @@ __device__ __forceinline__ ListInfo decode_list(const NbDev &d, int r, int l) {
     return li;
 }
 
-__global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
-    const int lane = threadIdx.x & 31;
-    const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+constexpr int BUILD_WARPS = 4;
+constexpr int TBL_CAP = 160;  // exclusion partners of one cluster kept in shared memory
+
+// OUTER list: every site inside (cutoff + outer skin) of the cluster's bounding box, with exclusion masks.
+// Built rarely; the per-step work uses the pruned INNER list (nl_prune_kernel).
+__global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
+    __shared__ int s_pass[BUILD_WARPS][32];
+    __shared__ int2 s_tbl[BUILD_WARPS][TBL_CAP];
+    __shared__ int s_tn[BUILD_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int l = blockIdx.x * BUILD_WARPS + w;
     const int r = blockIdx.y;
     const int nlists = d.Cmax + d.CLmax;
     if (l >= nlists) return;
     const ListInfo li = decode_list(d, r, l);
-    int *nsteps_out = d.list_nsteps + (size_t)r * nlists + l;
+    int *nsteps_out = d.outer_nsteps + (size_t)r * nlists + l;
     if (!li.valid) {
         if (lane == 0) *nsteps_out = 0;
         return;
     }
     const int A = li.cluster;
     const size_t rcA = (size_t)r * d.Cmax + A;
+    const size_t rsite = (size_t)r * d.Smax;
     const float4 cA = d.cc[rcA], hA = d.ch[rcA];
     const int metaA = d.cmeta[rcA];
     const int clsA = metaA & 0xffff, validA = (metaA >> 16) & 0xff;
     const float4 L = d.box[r], iL = d.invbox[r];
-    const float rl2 = d.rlist * d.rlist;
+    const float rl2 = d.rlist_outer * d.rlist_outer;
     const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
     const int nenv = bcs[d.ncol], ncl = d.nclusters[r];
-    unsigned int *out = d.jlist + li.offset;
+    unsigned int *out = d.jlist_outer + li.offset;
     int count = 0;
-    bool overflow = false;
+
+    // exclusion table of this cluster: (partner slot, bit of the member that excludes it)
+    if (lane == 0) s_tn[w] = 0;
+    __syncwarp();
+    if (lane < CL && ((validA >> lane) & 1)) {
+        const int u = d.slot_site[rsite + (size_t)A * CL + lane];
+        const int a = u >= d.N ? d.ghost_atom[u - d.N] : u;
+        for (int e = d.excl_start[a]; e < d.excl_start[a + 1]; e++) {
+            const int b = d.excl_list[e];
+            int idx = atomicAdd(&s_tn[w], 1);
+            if (idx < TBL_CAP) s_tbl[w][idx] = make_int2(d.site_slot[(size_t)r * d.U + b], 1 << lane);
+            const int gm = d.ghost_of_atom[b];
+            if (gm >= 0) {
+                idx = atomicAdd(&s_tn[w], 1);
+                if (idx < TBL_CAP) s_tbl[w][idx] = make_int2(d.site_slot[(size_t)r * d.U + d.N + gm], 1 << lane);
+            }
+        }
+    }
+    __syncwarp();
+    const int T = s_tn[w];
+    const bool tbl_ok = T <= TBL_CAP;
 
     // candidate cluster ranges: env columns near A (only when env clusters can be partners), then all ligand/ghost clusters
     const float cwx = cA.x - L.x * floorf(cA.x * iL.x), cwy = cA.y - L.y * floorf(cA.y * iL.y);
     const float colw_x = L.x / d.nx, colw_y = L.y / d.ny;
-    int ix_lo = (int)floorf((cwx - hA.x - d.rlist) / colw_x), ix_hi = (int)floorf((cwx + hA.x + d.rlist) / colw_x);
-    int iy_lo = (int)floorf((cwy - hA.y - d.rlist) / colw_y), iy_hi = (int)floorf((cwy + hA.y + d.rlist) / colw_y);
+    int ix_lo = (int)floorf((cwx - hA.x - d.rlist_outer) / colw_x), ix_hi = (int)floorf((cwx + hA.x + d.rlist_outer) / colw_x);
+    int iy_lo = (int)floorf((cwy - hA.y - d.rlist_outer) / colw_y), iy_hi = (int)floorf((cwy + hA.y + d.rlist_outer) / colw_y);
     if (ix_hi - ix_lo + 1 >= d.nx) { ix_lo = 0; ix_hi = d.nx - 1; }
     if (iy_hi - iy_lo + 1 >= d.ny) { iy_lo = 0; iy_hi = d.ny - 1; }
     const bool env_partners = pair_target(clsA, 0, d.G) == li.target;  // does this list take env sites at all?
@@ -368,6 +415,7 @@ __global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
             c_end = ncl;
         }
         for (int base = c_begin; base < c_end; base += 32) {
+            // stage 1: one candidate cluster per lane, box-box distance; passing clusters compacted (in order) to smem
             const int B = base + lane;
             bool pass = false;
             if (B < c_end) {
@@ -384,36 +432,44 @@ __global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
                     pass = dx * dx + dy * dy + dz * dz <= rl2;
                 }
             }
-            unsigned int cmask = __ballot_sync(0xffffffffu, pass);
-            while (cmask) {
-                // next (up to) four passing clusters, 8 lanes each
-                const int grp = lane >> 3, k = lane & 7;
-                const int nset = __popc(cmask);
-                int bit = grp < nset ? __fns(cmask, 0, grp + 1) : -1;
+            const unsigned int cmask = __ballot_sync(0xffffffffu, pass);
+            const int npass = __popc(cmask);
+            if (npass == 0) continue;
+            if (pass) s_pass[w][__popc(cmask & ((1u << lane) - 1))] = B;
+            __syncwarp();
+            // stage 2: one candidate SITE per lane (four clusters per sweep)
+            for (int q = 0; q < npass; q += 4) {
+                const int g = q + (lane >> 3), k = lane & 7;
                 bool take = false;
                 unsigned int entry = 0;
-                if (bit >= 0) {
-                    const int B2 = base + bit;
+                if (g < npass) {
+                    const int B2 = s_pass[w][g];
                     const int j = B2 * CL + k;
-                    const size_t rs = (size_t)r * d.Smax + j;
-                    const int u = d.slot_site[rs];
+                    const int u = d.slot_site[rsite + j];
                     if (u >= 0) {
-                        const float4 p = d.xs[rs];
-                        const float dx = fmaxf(fabsf(wrap_delta(p.x - cA.x, L.x, iL.x)) - hA.x, 0.f);
-                        const float dy = fmaxf(fabsf(wrap_delta(p.y - cA.y, L.y, iL.y)) - hA.y, 0.f);
-                        const float dz = fmaxf(fabsf(wrap_delta(p.z - cA.z, L.z, iL.z)) - hA.z, 0.f);
-                        if (dx * dx + dy * dy + dz * dz <= rl2) {
+                        const float4 p = __ldg(d.xs + rsite + j);
+                        const float bx = fmaxf(fabsf(wrap_delta(p.x - cA.x, L.x, iL.x)) - hA.x, 0.f);
+                        const float by = fmaxf(fabsf(wrap_delta(p.y - cA.y, L.y, iL.y)) - hA.y, 0.f);
+                        const float bz = fmaxf(fabsf(wrap_delta(p.z - cA.z, L.z, iL.z)) - hA.z, 0.f);
+                        if (bx * bx + by * by + bz * bz <= rl2) {
                             unsigned int m = (~validA) & 0xff;
                             if (B2 == A) m |= (0xffu << k) & 0xff;  // within a cluster: pairs (i<j) once
-                            const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
-                            for (int e = d.excl_start[aj]; e < d.excl_start[aj + 1]; e++) {
-                                const int b = d.excl_list[e];
-                                const int s_real = d.site_slot[(size_t)r * d.U + b];
-                                if ((s_real >> 3) == A) m |= 1u << (s_real & 7);
-                                const int gm = d.ghost_of_atom[b];
-                                if (gm >= 0) {
-                                    const int s_gh = d.site_slot[(size_t)r * d.U + d.N + gm];
-                                    if ((s_gh >> 3) == A) m |= 1u << (s_gh & 7);
+                            if (tbl_ok) {
+                                for (int t = 0; t < T; t++) {
+                                    const int2 te = s_tbl[w][t];
+                                    if (te.x == j) m |= te.y;
+                                }
+                            } else {  // rare: a cluster with more exclusion partners than the table holds
+                                const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
+                                for (int e = d.excl_start[aj]; e < d.excl_start[aj + 1]; e++) {
+                                    const int b = d.excl_list[e];
+                                    const int s_real = d.site_slot[(size_t)r * d.U + b];
+                                    if ((s_real >> 3) == A) m |= 1u << (s_real & 7);
+                                    const int gm = d.ghost_of_atom[b];
+                                    if (gm >= 0) {
+                                        const int s_gh = d.site_slot[(size_t)r * d.U + d.N + gm];
+                                        if ((s_gh >> 3) == A) m |= 1u << (s_gh & 7);
+                                    }
                                 }
                             }
                             if (m != 0xff) {
@@ -429,13 +485,11 @@ __global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
                     if (pos < li.cap) out[pos] = entry;
                 }
                 count += __popc(tmask);
-                if (count > li.cap) overflow = true;
-                // clear the (up to) four consumed bits
-                for (int q = 0; q < 4 && cmask; q++) cmask &= cmask - 1;
             }
+            __syncwarp();
         }
     }
-    if (overflow) {
+    if (count > li.cap) {
         if (lane == 0) {
             atomicOr(&d.flags[0], 1);
             atomicMax(&d.flags[1], count);
@@ -449,7 +503,93 @@ __global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
     if (lane == 0) {
         *nsteps_out = nsteps;
         atomicAdd((unsigned long long *)&d.flags[2], (unsigned long long)count);
+        atomicAdd(&d.flags[5], (nsteps + ITEM_STEPS - 1) / ITEM_STEPS);
     }
+}
+
+// INNER list: the outer entries that are inside (cutoff + inner skin) of at least one ATOM of the cluster at the
+// current coordinates.  Cheap (coalesced reads of the outer list, no exclusion work), run every few steps.
+__global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int r = blockIdx.y;
+    const int nlists = d.Cmax + d.CLmax;
+    if (l >= nlists) return;
+    const int nst_outer = d.outer_nsteps[(size_t)r * nlists + l];
+    int *nsteps_out = d.list_nsteps + (size_t)r * nlists + l;
+    if (nst_outer == 0) {
+        if (lane == 0) *nsteps_out = 0;
+        return;
+    }
+    const ListInfo li = decode_list(d, r, l);
+    const int A = li.cluster;
+    const size_t rcA = (size_t)r * d.Cmax + A;
+    const size_t rsite = (size_t)r * d.Smax;
+    const float4 cA = d.cc[rcA];
+    const int validA = (d.cmeta[rcA] >> 16) & 0xff;
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const float rl2 = d.rlist * d.rlist;
+    float xa[CL], ya[CL], za[CL];
+#pragma unroll
+    for (int k = 0; k < CL; k++) {
+        const float4 p = __ldg(d.xs + rsite + (size_t)A * CL + k);
+        const bool ok = (validA >> k) & 1;
+        xa[k] = ok ? cA.x + wrap_delta(p.x - cA.x, L.x, iL.x) : 1e18f;
+        ya[k] = ok ? cA.y + wrap_delta(p.y - cA.y, L.y, iL.y) : 1e18f;
+        za[k] = ok ? cA.z + wrap_delta(p.z - cA.z, L.z, iL.z) : 1e18f;
+    }
+    const unsigned int *in = d.jlist_outer + li.offset;
+    unsigned int *out = d.jlist + li.offset;
+    int count = 0;
+    unsigned int e = __ldg(in + lane);
+    for (int st = 0; st < nst_outer; st++) {
+        const unsigned int ec = e;
+        if (st + 1 < nst_outer) e = __ldg(in + (st + 1) * 32 + lane);
+        bool keep = false;
+        if ((ec & 0xffu) != 0xffu) {
+            const float4 p = __ldg(d.xs + rsite + (ec >> 8));
+            const float px = cA.x + wrap_delta(p.x - cA.x, L.x, iL.x), py = cA.y + wrap_delta(p.y - cA.y, L.y, iL.y),
+                        pz = cA.z + wrap_delta(p.z - cA.z, L.z, iL.z);
+            float d2min = 1e30f;
+#pragma unroll
+            for (int k = 0; k < CL; k++) {
+                const float ex = px - xa[k], ey = py - ya[k], ez = pz - za[k];
+                d2min = fminf(d2min, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+            }
+            keep = d2min <= rl2;
+        }
+        const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[count + __popc(kmask & ((1u << lane) - 1))] = ec;
+        count += __popc(kmask);
+    }
+    const int nsteps = (count + 31) >> 5;
+    for (int p = count + lane; p < nsteps * 32; p += 32) out[p] = 0xffu;
+    if (lane == 0) {
+        *nsteps_out = nsteps;
+        atomicAdd((unsigned long long *)&d.flags[6], (unsigned long long)count);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rebuild step 6: compact work items (replica, list, chunk of ITEM_STEPS steps), longest lists first.
+// ------------------------------------------------------------------------------------------------
+__global__ void nl_item_count_kernel(NbDev d, int *__restrict__ counts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nlists = d.Cmax + d.CLmax;
+    if (t >= d.R * nlists) return;
+    // reversed list order inside a replica: ligand/ghost lists (the long ones) get the lowest item indices
+    const int r = t / nlists, l = nlists - 1 - (t - r * nlists);
+    counts[t] = (d.list_nsteps[(size_t)r * nlists + l] + ITEM_STEPS - 1) / ITEM_STEPS;
+}
+
+__global__ void nl_item_fill_kernel(NbDev d, const int *__restrict__ counts, const int *__restrict__ offsets) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nlists = d.Cmax + d.CLmax;
+    if (t >= d.R * nlists) return;
+    const int r = t / nlists, l = nlists - 1 - (t - r * nlists);
+    const int n = counts[t], o = offsets[t];
+    for (int c = 0; c < n; c++) d.items[o + c] = make_int2(l | (r << 24), c);
+    if (t == d.R * nlists - 1) d.flags[4] = o + n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,25 +606,36 @@ __global__ void __launch_bounds__(128) nl_build_kernel(NbDev d) {
 #define ERFC_A5 6.4534500206e-01f
 #define ERFC_A6 -1.7945805777e-01f
 
-struct PairOut {
-    float fscale, energy;
+// MUFU wrappers without the denormal / range fix-up code the CUDA math library adds around them
+__device__ __forceinline__ float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// round to nearest integer for |x| < 2^22 without the (quarter-rate) FRND instruction
+__device__ __forceinline__ float fast_rint(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+
+struct PairConst {
+    float cutoff2;
+    float p_alpha;      // ERFC_P * alpha
+    float neg_a2_log2e; // -alpha^2 log2(e)
+    float two_a_sqrtpi; // 2 alpha / sqrt(pi)
 };
 
 // One pair.  qq = q_i q_j k_e (charges are stored pre-multiplied by sqrt(k_e)); sig = (s_i+s_j)/2; eps4 = 4 sqrt(e_i e_j).
-__device__ __forceinline__ PairOut pair_interaction(float r2, float qq, float sig, float eps4, float alpha,
-                                                   float two_alpha_over_sqrtpi) {
-    float rinv = rsqrtf(r2);
-    rinv = rinv * (1.5f - 0.5f * r2 * rinv * rinv);  // one Newton step: MUFU.RSQ is ~2^-22, forces need better
+// Returns F/r (fscale) and, when ENERGY, the pair energy.
+template <bool ENERGY>
+__device__ __forceinline__ float pair_interaction(float r2, float qq, float sig, float eps4, const PairConst &pc, float &energy) {
+    float rinv = mufu_rsqrt(r2);
+#ifndef ATM_NO_NEWTON
+    rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);  // one Newton step: MUFU.RSQ alone is ~2^-22.5
+#endif
     const float rinv2 = rinv * rinv;
     const float r = r2 * rinv;
     const float s2 = sig * sig * rinv2;
     const float s6 = s2 * s2 * s2;
     const float es6 = eps4 * s6;
-    const float elj = es6 * (s6 - 1.0f);
-    const float flj = es6 * (12.0f * s6 - 6.0f);
-    const float ar = alpha * r;
-    const float t = __fdividef(1.0f, fmaf(ERFC_P, ar, 1.0f));
-    const float ex = __expf(-ar * ar);
+    const float flj = es6 * fmaf(12.0f, s6, -6.0f);
+    const float t = mufu_rcp(fmaf(pc.p_alpha, r, 1.0f));
+    const float ex = mufu_ex2(pc.neg_a2_log2e * r2);
     float poly = fmaf(ERFC_A6, t, ERFC_A5);
     poly = fmaf(poly, t, ERFC_A4);
     poly = fmaf(poly, t, ERFC_A3);
@@ -492,40 +643,33 @@ __device__ __forceinline__ PairOut pair_interaction(float r2, float qq, float si
     poly = fmaf(poly, t, ERFC_A1);
     poly = fmaf(poly, t, ERFC_A0);
     const float erfc_ar = poly * t * ex;
-    const float qr = qq * rinv;
-    const float ec = qr * erfc_ar;
-    const float fc = fmaf(qr * r * two_alpha_over_sqrtpi, ex, ec);
-    PairOut o;
-    o.fscale = (flj + fc) * rinv2;
-    o.energy = elj + ec;
-    return o;
+    const float ec = qq * rinv * erfc_ar;
+    const float fc = fmaf(qq * pc.two_a_sqrtpi, ex, ec);
+    if (ENERGY) energy = fmaf(es6, s6, -es6) + ec;
+    return (flj + fc) * rinv2;
 }
 
-__global__ void __launch_bounds__(NB_THREADS) nb2_kernel(NbDev d, int parity) {
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
-    const int r = blockIdx.y;
-    // item -> (list, chunk)
-    const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
-    const int nlists = d.Cmax + d.CLmax;
-    const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
-    const int nenv = bcs[d.ncol], ncl = d.nclusters[r];
-    int l, chunk;
-    {
-        const int itemsEnv = nenv * chunksC, itemsX = (ncl - nenv) * chunksX;
-        if (warp < itemsEnv) { l = warp / chunksC; chunk = warp - l * chunksC; }
-        else if (warp < itemsEnv + itemsX) { const int w = warp - itemsEnv; l = nenv + w / chunksX; chunk = w % chunksX; }
-        else { const int w = warp - itemsEnv - itemsX; l = d.Cmax + w / chunksC; chunk = w % chunksC; if (l >= nlists) return; }
-    }
-    const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
-    const int step0 = chunk * ITEM_STEPS;
-    if (step0 >= nsteps_total) return;
-    const int nst = min(ITEM_STEPS, nsteps_total - step0);
-    const ListInfo li = decode_list(d, r, l);
-    const int A = li.cluster;
-    const size_t rsite = (size_t)r * d.Smax;
-    const float4 L = d.box[r], iL = d.invbox[r];
-    const float4 cA = d.cc[(size_t)r * d.Cmax + A];
+struct ItemCtx {
+    int r, A, target, nst;
+    const unsigned int *list;
+    size_t rsite, comp_stride;
+};
+
+template <bool ENERGY, bool STATS>
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int parity, int lane) {
+    const float4 L = d.box[it.r], iL = d.invbox[it.r];
+    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
+    PairConst pc;
+    pc.cutoff2 = d.cutoff2;
+    pc.p_alpha = ERFC_P * d.alpha;
+    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
+    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+
+    // software pipeline: list entries two steps ahead, partner coordinates one step ahead
+    unsigned int e_cur = __ldg(it.list + lane);
+    unsigned int e_nxt = it.nst > 1 ? __ldg(it.list + 32 + lane) : 0xffu;
+    float4 xj = __ldg(d.xs + it.rsite + (e_cur >> 8));
+    float2 pj = __ldg(d.par + it.rsite + (e_cur >> 8));
 
     // the 8 cluster atoms, broadcast-loaded into every lane's registers, shifted next to the cluster centre
     float4 xi[CL];
@@ -533,47 +677,55 @@ __global__ void __launch_bounds__(NB_THREADS) nb2_kernel(NbDev d, int parity) {
     float fix[CL], fiy[CL], fiz[CL];
 #pragma unroll
     for (int k = 0; k < CL; k++) {
-        xi[k] = __ldg(d.xs + rsite + (size_t)A * CL + k);
-        pi[k] = __ldg(d.par + rsite + (size_t)A * CL + k);
-        xi[k].x -= L.x * rintf((xi[k].x - cA.x) * iL.x);
-        xi[k].y -= L.y * rintf((xi[k].y - cA.y) * iL.y);
-        xi[k].z -= L.z * rintf((xi[k].z - cA.z) * iL.z);
+        xi[k] = __ldg(d.xs + it.rsite + (size_t)it.A * CL + k);
+        pi[k] = __ldg(d.par + it.rsite + (size_t)it.A * CL + k);
+        xi[k].x -= L.x * fast_rint((xi[k].x - cA.x) * iL.x);
+        xi[k].y -= L.y * fast_rint((xi[k].y - cA.y) * iL.y);
+        xi[k].z -= L.z * fast_rint((xi[k].z - cA.z) * iL.z);
         fix[k] = fiy[k] = fiz[k] = 0.f;
     }
-    const unsigned int *list = d.jlist + li.offset + (size_t)step0 * 32;
-    unsigned long long *buf = d.buf + (size_t)li.target * 3 * d.R * d.Smax + rsite;
-    const size_t comp_stride = (size_t)d.R * d.Smax;
+    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
     double e_acc = 0.0;
     int npairs = 0;
 
-    for (int st = 0; st < nst; st++) {
-        const unsigned int e = __ldg(list + st * 32 + lane);
+    for (int st = 0; st < it.nst; st++) {
+        const unsigned int e = e_cur;
+        const float4 xjc = xj;
+        const float2 pjc = pj;
+        // prefetch
+        e_cur = e_nxt;
+        if (st + 1 < it.nst) {
+            xj = __ldg(d.xs + it.rsite + (e_cur >> 8));
+            pj = __ldg(d.par + it.rsite + (e_cur >> 8));
+        }
+        e_nxt = (st + 2 < it.nst) ? __ldg(it.list + (st + 2) * 32 + lane) : 0xffu;
+
         const int j = e >> 8;
-        const unsigned int m = e & 0xff;
-        float4 xj = __ldg(d.xs + rsite + j);
-        const float2 pj = __ldg(d.par + rsite + j);
-        xj.x -= L.x * rintf((xj.x - cA.x) * iL.x);
-        xj.y -= L.y * rintf((xj.y - cA.y) * iL.y);
-        xj.z -= L.z * rintf((xj.z - cA.z) * iL.z);
+        const unsigned int m = e & 0xffu;
+        const float xjx = xjc.x - L.x * fast_rint((xjc.x - cA.x) * iL.x);
+        const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
+        const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
         float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
+        bool any = false;
 #pragma unroll
         for (int k = 0; k < CL; k++) {
-            const float dx = xi[k].x - xj.x, dy = xi[k].y - xj.y, dz = xi[k].z - xj.z;
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            const bool in = (r2 < d.cutoff2) && !((m >> k) & 1u);
-            const PairOut o = pair_interaction(r2, xi[k].w * xj.w, pi[k].x + pj.x, pi[k].y * pj.y, d.alpha,
-                                               d.two_alpha_over_sqrtpi);
-            const float fs = in ? o.fscale : 0.f;
-            e_step += in ? o.energy : 0.f;
-            npairs += in ? 1 : 0;
+            const float dx = xi[k].x - xjx, dy = xi[k].y - xjy, dz = xi[k].z - xjz;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
+            float en = 0.f;
+            const float fsc = pair_interaction<ENERGY>(r2, xi[k].w * xjc.w, pi[k].x + pjc.x, pi[k].y * pjc.y, pc, en);
+            const float fs = in ? fsc : 0.f;
+            if (ENERGY) e_step += in ? en : 0.f;
+            if (STATS) npairs += in ? 1 : 0;
+            any |= in;
             fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
             fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
         }
-        e_acc += (double)e_step;
-        if (m != 0xff) {
+        if (ENERGY) e_acc += (double)e_step;
+        if (any) {
             red_add_fixed(buf + j, fjx);
-            red_add_fixed(buf + comp_stride + j, fjy);
-            red_add_fixed(buf + 2 * comp_stride + j, fjz);
+            red_add_fixed(buf + it.comp_stride + j, fjy);
+            red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
         }
     }
 
@@ -608,23 +760,48 @@ __global__ void __launch_bounds__(NB_THREADS) nb2_kernel(NbDev d, int parity) {
         }
         // lane l (< 8) now holds atom index (b0 + 2 b1 + 4 b2) = l
         if (lane < CL) {
-            const int i = A * CL + lane;
+            const int i = it.A * CL + lane;
             red_add_fixed(buf + i, y[0]);
-            red_add_fixed(buf + comp_stride + i, y[1]);
-            red_add_fixed(buf + 2 * comp_stride + i, y[2]);
+            red_add_fixed(buf + it.comp_stride + i, y[1]);
+            red_add_fixed(buf + 2 * it.comp_stride + i, y[2]);
         }
     }
     // energies: warp sum in double, one fixed-point atomic per warp
+    if (ENERGY || STATS) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        e_acc += __shfl_xor_sync(0xffffffffu, e_acc, off);
-        npairs += __shfl_xor_sync(0xffffffffu, npairs, off);
+        for (int off = 16; off > 0; off >>= 1) {
+            if (ENERGY) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, off);
+            if (STATS) npairs += __shfl_xor_sync(0xffffffffu, npairs, off);
+        }
+        if (lane == 0) {
+            unsigned long long *ea = d.eacc + ((size_t)parity * d.R + it.r) * EACC_SLOTS;
+            if (ENERGY) atomicAdd(ea + it.target, (unsigned long long)__double2ll_rn(e_acc * ENERGY_SCALE));
+            if (STATS) atomicAdd(ea + 3, (unsigned long long)npairs);
+        }
     }
-    if (lane == 0) {
-        unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
-        atomicAdd(ea + li.target, (unsigned long long)__double2ll_rn(e_acc * ENERGY_SCALE));
-        atomicAdd(ea + 3, (unsigned long long)npairs);
-    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) nb2_kernel(NbDev d, int parity, int n_items, int energy_common) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
+    if (warp >= d.flags[4]) return;  // the pruned list's item count lives on the device (n_items is the outer bound)
+    const int2 item = __ldg(d.items + warp);
+    const int r = item.x >> 24, l = item.x & 0xffffff;
+    const int nlists = d.Cmax + d.CLmax;
+    const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
+    const int step0 = item.y * ITEM_STEPS;
+    const ListInfo li = decode_list(d, r, l);
+    ItemCtx it;
+    it.r = r;
+    it.A = li.cluster;
+    it.target = li.target;
+    it.nst = min(ITEM_STEPS, nsteps_total - step0);
+    it.list = d.jlist + li.offset + (size_t)step0 * 32;
+    it.rsite = (size_t)r * d.Smax;
+    it.comp_stride = (size_t)d.R * d.Smax;
+    if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, parity, lane);
+    else nb2_item<true, STATS>(d, it, parity, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,6 +879,9 @@ __global__ void nb_special_pairs_kernel(NbDev d, int parity, const int2 *__restr
 // ------------------------------------------------------------------------------------------------
 constexpr int MERGE2_THREADS = 256;
 
+// One thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
+// read-modify-write of the caller's force buffer is a scatter.  The thread of a displaced atom also folds in (and
+// zeroes) the S2 accumulator of its ghost site; ghost and padding slots have no thread work.
 __global__ void __launch_bounds__(MERGE2_THREADS)
 nb_merge_kernel(NbDev d, int parity, long long *__restrict__ force, const long long *__restrict__ f1_ext,
                 const long long *__restrict__ f2_ext, const double *__restrict__ energy_ext, int include_energy) {
@@ -729,14 +909,14 @@ nb_merge_kernel(NbDev d, int parity, long long *__restrict__ force, const long l
         }
     }
     __syncthreads();
-    const int i = blockIdx.x * MERGE2_THREADS + threadIdx.x;
-    if (i >= d.N) return;
+    const int s = blockIdx.x * MERGE2_THREADS + threadIdx.x;
+    if (s >= CL * d.nclusters[r]) return;
+    const size_t rsite = (size_t)r * d.Smax;
+    const int i = d.slot_out[rsite + s];  // caller's slot of this site's atom, -1 for ghosts and padding
+    if (i < 0) return;
     const double sp = s_sp, sp1 = 1.0 - s_sp;
-    const int a = d.atom_of_slot[i];
-    const int s = d.site_slot[(size_t)r * d.U + a];
-    const int gm = d.ghost_of_atom[a];
-    const int gs = gm >= 0 ? d.site_slot[(size_t)r * d.U + d.N + gm] : -1;
-    const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
+    const int gs = d.slot_ghost[rsite + s];
+    const size_t cs = (size_t)d.R * d.Smax;
     long long *bufC = (long long *)d.buf + rsite, *buf1 = bufC + 3 * cs, *buf2 = bufC + 6 * cs;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -843,6 +1023,7 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     d.U = N + d.M;
     d.cutoff2 = (float)(nb->desc.cutoff * nb->desc.cutoff);
     d.rlist = (float)(nb->desc.cutoff + nb->desc.skin);
+    d.rlist_outer = (float)(nb->desc.cutoff + std::max(nb->desc.skin, nb->desc.skin_outer));
     d.alpha = (float)nb->desc.ewald_alpha;
     d.two_alpha_over_sqrtpi = (float)(2.0 * nb->desc.ewald_alpha / sqrt(M_PI));
     d.displ = h->d_displ;
@@ -867,7 +1048,7 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     // list capacities from the expected partner count of an 8-atom cube (half list for env, full for ligand/ghost)
     {
         const double rho = (double)N / (Lx * Ly * Lz);
-        const double a = edge, rl = d.rlist;
+        const double a = edge, rl = d.rlist_outer;
         const double vol = a * a * a + 6 * a * a * rl + 3 * M_PI * a * rl * rl + 4.0 / 3.0 * M_PI * rl * rl * rl;
         const double full = vol * rho;
         if (d.capC == 0) d.capC = 32 * (int)ceil(0.5 * full * 1.6 / 32.0 + 2);
@@ -914,6 +1095,8 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     if ((rc = dev_alloc(nb, &d.slot_site, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.site_slot, RU))) return rc;
     if ((rc = dev_alloc(nb, &d.slot_src, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.slot_out, RS))) return rc;
+    if ((rc = dev_alloc(nb, &d.slot_ghost, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.slot_qp, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.xs, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.par, RS))) return rc;
@@ -923,7 +1106,23 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     const size_t per_replica = (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)d.CLmax * d.capC;
     nb->jlist_entries = per_replica * R;
     if ((rc = dev_alloc(nb, &d.jlist, nb->jlist_entries))) return rc;
+    if ((rc = dev_alloc(nb, &d.jlist_outer, nb->jlist_entries))) return rc;
+    if ((rc = dev_alloc(nb, &d.outer_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
     if ((rc = dev_alloc(nb, &d.list_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
+    {
+        const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
+        nb->max_items = R * (d.CenvMax * chunksC + d.CXmax * chunksX + d.CLmax * chunksC);
+        const int nl = R * (d.Cmax + d.CLmax);
+        if ((rc = dev_alloc(nb, &d.items, (size_t)nb->max_items))) return rc;
+        if ((rc = dev_alloc(nb, &nb->item_counts, (size_t)nl))) return rc;
+        if ((rc = dev_alloc(nb, &nb->item_offsets, (size_t)nl))) return rc;
+        nb->scan_tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, nb->scan_tmp_bytes, nb->item_counts, nb->item_offsets, nl, stream);
+        char *stmp;
+        if ((rc = dev_alloc(nb, &stmp, nb->scan_tmp_bytes))) return rc;
+        nb->scan_tmp = stmp;
+        nb->n_items = 0;
+    }
     if ((rc = dev_alloc(nb, &d.flags, 8))) return rc;
     if ((rc = dev_alloc(nb, &d.buf, 9 * RS))) return rc;
     if ((rc = dev_alloc(nb, &d.eacc, (size_t)2 * R * EACC_SLOTS))) return rc;
@@ -963,11 +1162,40 @@ static int upload_box_if_dirty(atm_handle *h, cudaStream_t stream) {
     return ATM_OK;
 }
 
+// pack must have run on the current coordinates; optionally refresh the cluster boxes/centres first
+static int launch_prune(atm_handle *h, cudaStream_t stream, bool refresh_boxes) {
+    NbState *nb = h->nb;
+    NbDev &d = nb->d;
+    const int nlists = d.Cmax + d.CLmax;
+    if (refresh_boxes) nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * 2, stream));
+    nl_prune_kernel<<<dim3((nlists + 3) / 4, d.R), 128, 0, stream>>>(d);
+    const int nl = d.R * nlists;
+    nl_item_count_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(d, nb->item_counts);
+    size_t sbytes = nb->scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(nb->scan_tmp, sbytes, nb->item_counts, nb->item_offsets, nl, stream);
+    nl_item_fill_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(d, nb->item_counts, nb->item_offsets);
+    ATM_CUDA_CHECK(cudaGetLastError());
+    return ATM_OK;
+}
+
 }  // namespace atm
 
 using namespace atm;
 
 extern "C" {
+
+int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && posq, ATM_ERR_INVALID, "atm_nb_prune: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->list_valid, ATM_ERR_STATE, "atm_nb_prune: no outer list (call atm_nb_rebuild)");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    NbDev &d = h->nb->d;
+    int rc;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)posq);
+    return launch_prune(h, stream, /*refresh_boxes=*/true);
+}
 
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -976,8 +1204,8 @@ int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
                 "atm_nb_setup: the fused direct-space path computes in fp32 with fixed-point accumulation "
                 "(single/mixed); double precision is Tier 1 only");
     ATM_REQUIRE(desc->charge && desc->sigma && desc->epsilon, ATM_ERR_INVALID, "atm_nb_setup: null parameter array");
-    ATM_REQUIRE(desc->cutoff > 0 && desc->skin >= 0 && desc->ewald_alpha >= 0, ATM_ERR_INVALID,
-                "atm_nb_setup: cutoff must be > 0, skin and ewald_alpha >= 0");
+    ATM_REQUIRE(desc->cutoff > 0 && desc->skin >= 0 && desc->skin_outer >= 0 && desc->ewald_alpha >= 0, ATM_ERR_INVALID,
+                "atm_nb_setup: cutoff must be > 0, skins and ewald_alpha >= 0");
     ATM_REQUIRE(desc->num_exclusions >= 0 && desc->num_exceptions >= 0, ATM_ERR_INVALID, "atm_nb_setup: negative count");
     ATM_REQUIRE(h->N > 0, ATM_ERR_INVALID, "atm_nb_setup: empty system");
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
@@ -1071,21 +1299,25 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
     for (int attempt = 0; attempt < 4; attempt++) {
         NbDev &d = nb->d;
         for (int r = 0; r < h->R; r++)
-            ATM_REQUIRE(2.0 * d.rlist < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
+            ATM_REQUIRE(2.0 * d.rlist_outer < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
                         "atm_nb_rebuild: box edge smaller than 2*(cutoff+skin)");
         const int RU = d.R * d.U;
         ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
         ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
         ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
         nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
         nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
         size_t tmp_bytes = nb->sort_tmp_bytes;
         cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
         nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
+        if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
         nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq);
         nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
         const int nlists = d.Cmax + d.CLmax;
-        nl_build_kernel<<<dim3((nlists + 3) / 4, d.R), 128, 0, stream>>>(d);
+        nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
+        if ((rc = launch_prune(h, stream, /*refresh_boxes=*/false))) return rc;
         ATM_CUDA_CHECK(cudaGetLastError());
         int flags[8];
         ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream));
@@ -1107,6 +1339,10 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         memcpy(&entries, &flags[2], 8);
         nb->stats[0] = d.U; nb->stats[1] = ncl0; nb->stats[2] = (int64_t)(entries / d.R); nb->stats[3] = d.capC; nb->stats[4] = d.capX;
         nb->stats[5] = d.M; nb->stats[6] = d.G; nb->stats[7] = d.ncol;
+        nb->n_items = flags[5];  // upper bound from the outer list; the inner count stays on the device
+        unsigned long long inner_entries = 0;
+        memcpy(&inner_entries, &flags[6], 8);
+        nb->stats[2] = (int64_t)(inner_entries / d.R);
         nb->list_valid = true;
         return ATM_OK;
     }
@@ -1131,15 +1367,17 @@ int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
     }
     const int parity = nb->parity;
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
-    const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
-    const int items = d.CenvMax * chunksC + d.CXmax * chunksX + d.CLmax * chunksC;
     const int warps_per_block = NB_THREADS / 32;
-    nb2_kernel<<<dim3((items + warps_per_block - 1) / warps_per_block, d.R), NB_THREADS, 0, stream>>>(d, parity);
+    const int nblocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
+    if (nblocks > 0) {
+        if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, parity, nb->n_items, io->include_energy);
+        else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, parity, nb->n_items, io->include_energy);
+    }
     const int nsp = nb->n_excl + nb->n_exc;
     if (nsp > 0)
         nb_special_pairs_kernel<<<dim3((nsp + 127) / 128, d.R), 128, 0, stream>>>(d, parity, nb->d_excl_pairs, nb->n_excl, nb->d_exc_pairs,
                                                                                  nb->d_exc_par, nb->n_exc);
-    nb_merge_kernel<<<dim3((d.N + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
+    nb_merge_kernel<<<dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
         d, parity, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext,
         io->energy_ext, io->include_energy);
     ATM_CUDA_CHECK(cudaGetLastError());

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG, "libatm_b200.so")
+# ATM_B200_LIB lets a developer A/B an experimental build of the SAME CUDA library; it is not a fallback path
+LIB_PATH = os.environ.get("ATM_B200_LIB") or os.path.join(_PKG, "libatm_b200.so")
 
 ATM_OK = 0
 PREC_SINGLE, PREC_MIXED, PREC_DOUBLE = 0, 1, 2
@@ -20,7 +21,7 @@ PARAM_NAMES = ("lambda1", "lambda2", "alpha", "u0", "w0", "umax", "ubcore", "aco
 SYMBOLS = (
     "atm_last_error", "atm_version", "atm_create", "atm_destroy", "atm_set_displacements", "atm_set_parameters",
     "atm_get_parameters", "atm_copy_state", "atm_wrap_positions", "atm_hybrid_force", "atm_softcore_softplus",
-    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_set_box", "atm_nb_rebuild", "atm_step",
+    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
 )
 
@@ -39,14 +40,14 @@ class NonbondedDesc(C.Structure):
     _fields_ = [("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
                 ("num_exclusions", C.c_int32), ("exclusions", C.c_void_p),
                 ("num_exceptions", C.c_int32), ("exception_pairs", C.c_void_p), ("exception_params", C.c_void_p),
-                ("cutoff", C.c_double), ("ewald_alpha", C.c_double), ("skin", C.c_double)]
+                ("cutoff", C.c_double), ("ewald_alpha", C.c_double), ("skin", C.c_double), ("skin_outer", C.c_double)]
 
 
 class StepIO(C.Structure):
     _fields_ = [("posq", C.c_void_p), ("posq_corr", C.c_void_p), ("force", C.c_void_p),
                 ("force_state1_ext", C.c_void_p), ("force_state2_ext", C.c_void_p), ("energy_ext", C.c_void_p),
                 ("posq1", C.c_void_p), ("posq1_corr", C.c_void_p), ("posq2", C.c_void_p), ("posq2_corr", C.c_void_p),
-                ("include_energy", C.c_int32)]
+                ("include_energy", C.c_int32), ("collect_stats", C.c_int32)]
 
 
 _lib = None
@@ -78,6 +79,7 @@ def lib():
     L.atm_nb_setup.argtypes = [vp, C.POINTER(NonbondedDesc), vp]
     L.atm_set_box.argtypes = [vp, i32, vp]
     L.atm_nb_rebuild.argtypes = [vp, vp, vp]
+    L.atm_nb_prune.argtypes = [vp, vp, vp]
     L.atm_step.argtypes = [vp, C.POINTER(StepIO), vp]
     L.atm_energies_device.argtypes = [vp, C.POINTER(vp)]
     L.atm_get_energies.argtypes = [vp, vp, vp]

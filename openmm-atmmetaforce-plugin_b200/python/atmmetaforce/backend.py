@@ -101,7 +101,7 @@ class ATMBackend:
         return u.value
 
     # -- Tier 2 -------------------------------------------------------------------------------------
-    def nb_setup(self, charge, sigma, epsilon, cutoff, ewald_alpha, skin=0.1, exclusions=None, exception_pairs=None,
+    def nb_setup(self, charge, sigma, epsilon, cutoff, ewald_alpha, skin=0.1, skin_outer=0.0, exclusions=None, exception_pairs=None,
                  exception_params=None, stream=None):
         q, s, e = _np(charge, np.float64), _np(sigma, np.float64), _np(epsilon, np.float64)
         assert q.size == self.N and s.size == self.N and e.size == self.N
@@ -110,7 +110,7 @@ class ATMBackend:
         xq = _np(exception_params if exception_params is not None else np.zeros((0, 3)), np.float64).reshape(-1, 3)
         assert xp.shape[0] == xq.shape[0]
         d = _capi.NonbondedDesc(q.ctypes.data, s.ctypes.data, e.ctypes.data, ex.shape[0], ex.ctypes.data, xp.shape[0],
-                                xp.ctypes.data, xq.ctypes.data, float(cutoff), float(ewald_alpha), float(skin))
+                                xp.ctypes.data, xq.ctypes.data, float(cutoff), float(ewald_alpha), float(skin), float(skin_outer))
         check(_capi.lib().atm_nb_setup(self._h, C.byref(d), _stream_ptr(stream)))
 
     def set_box(self, box, replica=-1):
@@ -123,13 +123,16 @@ class ATMBackend:
     def rebuild(self, posq, stream=None):
         check(_capi.lib().atm_nb_rebuild(self._h, _dptr(posq), _stream_ptr(stream)))
 
+    def prune(self, posq, stream=None):
+        check(_capi.lib().atm_nb_prune(self._h, _dptr(posq), _stream_ptr(stream)))
+
     def step(self, posq, force, posq_corr=None, f1_ext=None, f2_ext=None, energy_ext=None, posq1=None, posq1_corr=None,
-             posq2=None, posq2_corr=None, include_energy=True, stream=None):
+             posq2=None, posq2_corr=None, include_energy=True, collect_stats=False, stream=None):
         def v(t):
             p = _dptr(t)
             return p.value if p is not None else None
         io = _capi.StepIO(v(posq), v(posq_corr), v(force), v(f1_ext), v(f2_ext), v(energy_ext), v(posq1), v(posq1_corr),
-                          v(posq2), v(posq2_corr), 1 if include_energy else 0)
+                          v(posq2), v(posq2_corr), 1 if include_energy else 0, 1 if collect_stats else 0)
         check(_capi.lib().atm_step(self._h, C.byref(io), _stream_ptr(stream)))
 
     def energies_device_ptr(self):

@@ -146,3 +146,51 @@ def test_small_box_is_rejected():
     with pytest.raises(atm.ATMError):
         be, posq, _ = make_backend(atm, s, 1.2, 2.0, [0.5, 0.5, 0, 0, 0, 800, 400, 0.0625, 1.0])
         be.rebuild(posq)
+
+
+def test_dual_list_prune_after_motion(abfe):
+    """Outer list with a wide skin, atoms then move by < skin/2 and only the cheap prune runs: results must match an
+    oracle evaluation at the NEW coordinates (validates list reuse, the per-step image shift and the prune)."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from helpers import oracle_system, make_backend, force_from_fixed, rel_rms
+    s = dict(abfe)
+    alpha = O.ewald_alpha(1.0)
+    params = abfe["params"]
+    n = s["pos"].shape[0]
+    import atmmetaforce.backend as B
+    be = atm.ATMBackend(n, precision="mixed")
+    be.set_displacements(s["displ"])
+    be.set_box(s["box"])
+    be.set_parameters(params)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], 1.0, alpha, skin=0.05, skin_outer=0.3, exclusions=s["excl"],
+                exception_pairs=s["exc14"], exception_params=s["exc14_par"])
+    P = be.P
+    posq = np.zeros((1, P, 4), np.float32)
+    posq[0, :n, :3] = s["pos"]
+    posq[0, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    be.rebuild(d_posq)
+    rng = np.random.default_rng(5)
+    S = oracle_system(O, s, 1.0, alpha)
+    moved = posq.copy()
+    for it in range(3):
+        # total drift since the rebuild stays below skin_outer/2 = 0.15; since the last prune below skin/2 = 0.025
+        moved[0, :n, :3] += rng.uniform(-0.012, 0.012, (n, 3)).astype(np.float32)
+        d_moved = torch.from_numpy(moved).cuda()
+        be.prune(d_moved)
+        force = torch.zeros((1, 3 * P), dtype=torch.int64, device="cuda")
+        be.step(d_moved, force)
+        en = be.get_energies()[0]
+        pos32 = moved[0, :n, :3].astype(np.float64)
+        pos2_32 = (moved[0, :n, :3] + s["displ"].astype(np.float32)).astype(np.float64)
+        e1, _, f1 = S.nb_direct(pos32)
+        e2, _, f2 = S.nb_direct(pos2_32)
+        sc = O.scalars(params, e1, e2)
+        f_ref = O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], params[8])
+        f_gpu = force_from_fixed(force.cpu().numpy()[0], n, P)
+        assert abs(en[E_U1] - e1) <= 1e-6 * abs(e1)
+        assert abs(en[E_U] - (e2 - e1)) <= 5e-3
+        assert rel_rms(f_gpu, f_ref) <= 1e-5
+    be.close()

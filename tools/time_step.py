@@ -13,6 +13,8 @@ ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--skin", type=float, default=0.1)
 ap.add_argument("--natoms", type=int, default=25000)
+ap.add_argument("--skin-outer", type=float, default=0.3)
+ap.add_argument("--no-energy", action="store_true")
 args = ap.parse_args()
 
 s = synthetic.config3() if args.system == "config3" else (synthetic.config4() if args.system == "config4" else synthetic.water_box(args.natoms))
@@ -25,7 +27,7 @@ be.set_box(s["box"])
 sched = synthetic.atm_schedule_22()
 for r in range(R):
     be.set_parameters(sched[r % 22], replica=r)
-be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin, exclusions=s["excl"])
+be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin, skin_outer=args.skin_outer, exclusions=s["excl"])
 posq = np.zeros((R, P, 4), np.float32)
 rng = np.random.default_rng(0)
 for r in range(R):
@@ -39,20 +41,28 @@ ev[0].record()
 for _ in range(5):
     be.rebuild(posq)
 ev[1].record()
+be.step(posq, force, collect_stats=True)
+en_stats = be.get_energies()
 for _ in range(5):
-    be.step(posq, force)
+    be.step(posq, force, include_energy=not args.no_energy)
 torch.cuda.synchronize()
 ev[2].record()
 for _ in range(args.steps):
-    be.step(posq, force)
+    be.step(posq, force, include_energy=not args.no_energy)
 ev[3].record()
+evp = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+evp[0].record()
+for _ in range(10):
+    be.prune(posq)
+evp[1].record()
 torch.cuda.synchronize()
+ms_prune = evp[0].elapsed_time(evp[1]) / 10
 en = be.get_energies()
 st = be.nb_stats()
 ms_step = ev[2].elapsed_time(ev[3]) / args.steps
 ms_rebuild = ev[0].elapsed_time(ev[1]) / 5
-pairs = en[:, 7].sum()
+pairs = en_stats[:, 7].sum()
 print(f"system={args.system} N={n} R={R} skin={args.skin} stats={st}")
-print(f"first rebuild {t_first*1e3:.1f} ms; rebuild {ms_rebuild:.3f} ms; step {ms_step*1e3:.1f} us; pairs in cutoff/step {pairs:.3e}; "
+print(f"first rebuild {t_first*1e3:.1f} ms; rebuild {ms_rebuild:.3f} ms; prune {ms_prune*1e3:.1f} us; step {ms_step*1e3:.1f} us; pairs in cutoff/step {pairs:.3e}; "
       f"listed pair slots {st['list_entries']*8*R:.3e}; fill {pairs/(st['list_entries']*8*R):.3f}; "
       f"Gpairs/s {pairs/ms_step/1e6:.2f}; u[0]={en[0,2]:.3f} U1[0]={en[0,0]:.2f}")
