@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- ATM Meta-Force hot path: aggregate replica-ns/day on N B200 GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference [--steps K] [--warmup W]      (the CPU arm: the oracle port on the host cores)
+
+Workload (BASELINE.json configs[2]): synthetic ~23k-atom solvated blob + 40-atom ligand (TIP3P-like water, Ewald real
+space, 0.9 nm cutoff), 22-state ABFE softplus lambda schedule = 22 replicas, block-cyclically partitioned over the
+ranks (no data-path collective; an NCCL all-gather of the per-replica (U1,U2) every --exchange-every steps feeds the
+Hamiltonian replica-exchange sweep).  One "step" = one pass of the hot path (copy-state/pack -> two-state direct-space
+nonbonded -> device scalar stage -> merge) for every replica resident on the rank, plus the pair-list maintenance on
+its declared cadence (prune every --prune-every steps, full rebuild every --rebuild-every steps).
+
+metric = aggregate replica-ns/day = 22 replicas * dt / (max-over-ranks time per step); dt = 1 fs as in the reference's
+example scripts (example/abfe/abfe.py:94).  OpenMM's PME reciprocal space, bonded terms and integrator are NOT part of
+the measured path (they stay in OpenMM, which is not installable here) -- see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "openmm-atmmetaforce-plugin_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+DT_FS = 1.0
+NUM_REPLICAS = 22
+FP32_PEAK_TFLOPS = None  # derived from the device at run time: SMs * 128 lanes * 2 flop * max SM clock
+FLOP_PER_PAIR = 60.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "rbfe", "abfe"])
+    ap.add_argument("--replicas", type=int, default=NUM_REPLICAS)
+    ap.add_argument("--prune-every", type=int, default=10)
+    ap.add_argument("--rebuild-every", type=int, default=40)
+    ap.add_argument("--exchange-every", type=int, default=100)
+    ap.add_argument("--skin", type=float, default=0.1)
+    ap.add_argument("--skin-outer", type=float, default=0.3)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    return ap.parse_args()
+
+
+def load_workload(name):
+    from atmmetaforce import synthetic
+    if name == "config3":
+        s = synthetic.config3()
+        label = "synthetic 23k-atom solvated blob + 40-atom ligand, 22-state ABFE softplus schedule (BASELINE configs[2])"
+    elif name == "config4":
+        s = synthetic.config4()
+        label = "synthetic 100k-atom box, two 40-atom ligands (RBFE), 22 replicas (BASELINE configs[3])"
+    else:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden",
+                                      "temoa_g1_abfe.npz" if name == "abfe" else "temoa_g1_g4_rbfe.npz")))
+        g["cutoff"] = 1.0
+        g["ewald_alpha"] = synthetic.ewald_alpha(1.0)
+        s = g
+        label = ("TEMOA-G1 ABFE fixture (BASELINE configs[0])" if name == "abfe"
+                 else "TEMOA-G1/G4 RBFE fixture, two displacement groups (BASELINE configs[1])")
+    return s, synthetic.atm_schedule_22(), label
+
+
+def replica_positions(s, replica):
+    """Replica k = base coordinates + seeded 0.002 nm noise (the same for any number of ranks)."""
+    rng = np.random.default_rng(1000 + replica)
+    pos = s["pos"].copy()
+    if replica > 0:
+        pos += rng.normal(0.0, 0.002, pos.shape)
+    return pos
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(s, sched, steps):
+    """Times the CPU restatement of the same hot path (oracle port, OpenMP) on one replica; returns
+    (replica-ns/day, seconds per step, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], s["cutoff"], s["ewald_alpha"], s["excl"],
+                 s["exc14"], s["exc14_par"])
+    pos = replica_positions(s, 0)
+    S.step(sched[0], pos, s["displ"])  # warm-up (page-in, OpenMP pool)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        S.step(sched[k % len(sched)], pos, s["displ"])
+    dt = (time.perf_counter() - t0) / steps
+    return DT_FS * 1e-6 * 86400.0 / dt, dt, O.num_threads()
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU path cannot be built here (every translation unit needs OpenMM,
+    which is absent from the image), so this times the oracle port -- a C/OpenMP restatement of the same path -- with
+    all host threads, replicas evaluated one after another."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s, sched, label = load_workload(args.workload)
+    steps = max(1, min(args.steps, args.cpu_steps))
+    rate, sec, threads = cpu_oracle_rate(s, sched, steps)
+    line = {
+        "impl": "reference", "metric": "aggregate replica-ns/day (ATM hot path)", "value": rate, "unit": "replica-ns/day",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3 * args.replicas,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "replicas": args.replicas, "atoms": int(s["pos"].shape[0]), "dt_fs": DT_FS,
+                   "cutoff_nm": s["cutoff"]},
+        "cpu_baseline": {"value": rate, "unit": "replica-ns/day", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of 1 replica (two full direct-space evaluations + merge per step), "
+                                   f"replicas run sequentially so the aggregate rate equals the per-replica rate"},
+        "e2e": {"value": rate, "unit": "replica-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/_ref (the reference compiled in place) is not buildable: OpenMM is absent; kind=port",
+    }
+    print(json.dumps(line))
+
+
+class _DevView:
+    """CUDA-array-interface view of library-owned device memory (for torch.as_tensor)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic, _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    s, sched, label = load_workload(args.workload)
+    n = s["pos"].shape[0]
+    total_replicas = args.replicas
+    mine = synthetic.partition_replicas(total_replicas, world)[rank]
+    R = len(mine)
+    max_per_rank = max(len(x) for x in synthetic.partition_replicas(total_replicas, world))
+    replica_state = np.arange(total_replicas, dtype=np.int32) % len(sched)
+
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=max(R, 1), device=local_rank)
+    P = be.P
+    be.set_displacements(s["displ"])
+    be.set_box(s["box"])
+    for k, g in enumerate(mine):
+        be.set_parameters(sched[replica_state[g]], replica=k)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin,
+                skin_outer=args.skin_outer, exclusions=s["excl"], exception_pairs=s["exc14"],
+                exception_params=s["exc14_par"])
+    posq_h = torch.zeros((max(R, 1), P, 4), dtype=torch.float32).pin_memory()
+    corr_h = torch.zeros((max(R, 1), P, 4), dtype=torch.float32).pin_memory()
+    for k, g in enumerate(mine):
+        p64 = replica_positions(s, g)
+        p32 = p64.astype(np.float32)
+        posq_h[k, :n, :3] = torch.from_numpy(p32)
+        posq_h[k, :n, 3] = torch.from_numpy(s["charge"].astype(np.float32))
+        corr_h[k, :n, :3] = torch.from_numpy((p64 - p32).astype(np.float32))
+    posq = posq_h.to(dev)
+    corr = corr_h.to(dev)
+    force = torch.zeros((max(R, 1), 3 * P), dtype=torch.int64, device=dev)
+    force_h = torch.zeros((max(R, 1), 3 * P), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.Stream(device=dev)
+    use_graph = not args.no_graph
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    beta = 1.0 / (0.0083144626 * 300.0)
+
+    gather_in = torch.zeros((max_per_rank, 2), dtype=torch.float64, device=dev)
+    gather_out = torch.zeros((world * max_per_rank, 2), dtype=torch.float64, device=dev)
+    owner_slot = {}
+    for r_, lst in enumerate(synthetic.partition_replicas(total_replicas, world)):
+        for k, g in enumerate(lst):
+            owner_slot[g] = r_ * max_per_rank + k
+
+    def exchange(cycle):
+        """all-gather (U1,U2) of every replica, identical Metropolis sweep on every rank, swap lambda states."""
+        en = torch.as_tensor(_DevView(be.energies_device_ptr(), (max(R, 1), _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
+        gather_in.zero_()
+        gather_in[:R] = en[:R, 0:2]
+        if world > 1:
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            allu = gather_out.cpu().numpy()
+        else:
+            allu = gather_in.cpu().numpy()
+        u12 = np.stack([allu[owner_slot[g]] for g in range(total_replicas)])
+        new_state, _acc = atm.hrex_sweep(sched, u12, replica_state, beta, 2022, cycle)
+        for k, g in enumerate(mine):
+            if new_state[g] != replica_state[g]:
+                be.set_parameters(sched[new_state[g]], replica=k)
+        replica_state[:] = new_state
+
+    step_no = [0]
+
+    def one_step(timed_events=None):
+        with torch.cuda.stream(stream):
+            if flush is not None:
+                flush.zero_()
+            if timed_events is not None:
+                timed_events[0].record(stream)
+            k = step_no[0]
+            if k % args.rebuild_every == 0:
+                be.rebuild(posq, stream=stream)
+            elif k % args.prune_every == 0:
+                be.prune(posq, stream=stream)
+            be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream)
+            if (k + 1) % args.exchange_every == 0:
+                exchange((k + 1) // args.exchange_every)
+            if timed_events is not None:
+                timed_events[1].record(stream)
+            step_no[0] += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (>= 3 steps), then one statistics step (pair counts; not timed)
+    W = max(3, args.warmup)
+    if R > 0:
+        for _ in range(W):
+            one_step()
+        with torch.cuda.stream(stream):
+            be.step(posq, force, posq_corr=corr, include_energy=True, collect_stats=True, stream=stream)
+        stats_en = be.get_energies(stream=stream)
+    else:
+        stats_en = np.zeros((1, _capi.NUM_ENERGY_SLOTS))
+    nb_stats = be.nb_stats() if R > 0 else {}
+
+    # ---- timed region: exactly K steps, per-step CUDA events on the launching stream (the L2 flush between steps
+    #      stays outside the event pairs), barrier + synchronize on both sides, max over ranks
+    K = args.steps
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = be.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    if R > 0:
+        for k in range(K):
+            one_step(events[k])
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = be.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in events) if R > 0 else 0.0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = total_replicas * DT_FS * 1e-6 * 86400.0 / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (nb2): CUDA events around the launch, 20 more steps right after the timed region
+    nb2_ms = None
+    if R > 0:
+        be.profile_enable(True)
+        with torch.cuda.stream(stream):
+            for _ in range(20):
+                if flush is not None:
+                    flush.zero_()
+                be.step(posq, force, posq_corr=corr, include_energy=True, graph=False, stream=stream)
+        tot, cnt = be.profile_read()
+        be.profile_enable(False)
+        nb2_ms = tot / max(cnt, 1)
+
+    # ---- end to end through the public call with HOST buffers: H2D coordinates, step, D2H forces + energies
+    e2e_ms = None
+    h2d = d2h = 0
+    if R > 0:
+        KE = min(K, 50)
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
+        for k in range(KE + 3):
+            with torch.cuda.stream(stream):
+                if flush is not None:
+                    flush.zero_()
+                if k >= 3:
+                    ee[k - 3][0].record(stream)
+                posq.copy_(posq_h, non_blocking=True)
+                corr.copy_(corr_h, non_blocking=True)
+                force.zero_()
+                if k % args.prune_every == 0:
+                    be.prune(posq, stream=stream)
+                be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream)
+                force_h.copy_(force, non_blocking=True)
+                en_h = be.get_energies(stream=stream)  # D2H + synchronise: the step's result is on the host
+                if k >= 3:
+                    ee[k - 3][1].record(stream)
+        torch.cuda.synchronize()
+        e2e_ms = sum(a.elapsed_time(b) for a, b in ee) / KE
+        h2d = posq_h.numel() * 4 + corr_h.numel() * 4
+        d2h = force_h.numel() * 8 + en_h.size * 8
+    t = torch.tensor([e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = total_replicas * DT_FS * 1e-6 * 86400.0 / (e2e_ms * 1e-3) if e2e_ms > 0 else None
+
+    if rank == 0:
+        prop = torch.cuda.get_device_properties(dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp32_peak = prop.multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
+        pc, p1, p2 = stats_en[:R, 8].sum(), stats_en[:R, 9].sum(), stats_en[:R, 10].sum()
+        pairs_two_state = 2.0 * pc + p1 + p2          # what two separate inner-context evaluations would compute
+        pairs_computed = pc + p1 + p2
+        roofline = None
+        if nb2_ms:
+            ach = pairs_two_state * FLOP_PER_PAIR / (nb2_ms * 1e-3) / 1e12
+            roofline = {"kernel": "nb2_kernel (two-state direct space)", "bound": "fp32", "achieved": ach,
+                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                        "peak_source": "derived: SMs*128 lanes*2 flop*max SM clock (no measured fp32 peak in MEASURED_PEAKS.json)",
+                        "flop_per_pair": FLOP_PER_PAIR, "pairs_two_state_equivalent": pairs_two_state,
+                        "pairs_computed": pairs_computed, "nb2_ms": nb2_ms,
+                        "computed_tflops": pairs_computed * FLOP_PER_PAIR / (nb2_ms * 1e-3) / 1e12,
+                        "nb2_timed_over": "20 non-graph steps right after the timed region, CUDA events around the launch"}
+        cpu_baseline = None
+        if world == 1:
+            rate, sec, threads = cpu_oracle_rate(s, sched, args.cpu_steps)
+            cpu_baseline = {"value": rate, "unit": "replica-ns/day", "cores": threads, "kind": "port",
+                            "sample": f"{args.cpu_steps} steps of 1 replica on the host cores ({sec:.3f} s/step); replicas "
+                                      f"run sequentially on the CPU so aggregate == per-replica rate"}
+        line = {
+            "metric": "aggregate replica-ns/day (ATM hot path)", "value": value, "unit": "replica-ns/day",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 pair math, int64 fixed-point accumulation, f64 scalar stage",
+            "data": "synthetic",
+            "config": {"workload": label, "replicas": total_replicas, "replicas_per_rank": max_per_rank, "atoms": int(n),
+                       "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
+                       "prune_every": args.prune_every, "rebuild_every": args.rebuild_every,
+                       "exchange_every": args.exchange_every, "cuda_graph": use_graph,
+                       "l2": "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)",
+                       "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
+            "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
+            "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

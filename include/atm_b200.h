@@ -62,8 +62,11 @@ enum atm_energy_slot {
     ATM_E_EBIAS = 4,   /* W(u_sc) */
     ATM_E_ENERGY = 5,  /* e0 + W : what calcForcesAndEnergy returns */
     ATM_E_SP = 6,      /* weight of F2 in the merged force */
-    ATM_E_NPAIRS = 7,  /* pairs inside the cutoff evaluated by the last nb2 launch (diagnostic) */
-    ATM_NUM_ENERGY_SLOTS = 8
+    ATM_E_NPAIRS = 7,  /* pairs inside the cutoff evaluated by the last nb2 launch (only with collect_stats) */
+    ATM_E_NPAIRS_C = 8,   /* ... of which shared by both states */
+    ATM_E_NPAIRS_S1 = 9,  /* ... state-1 only */
+    ATM_E_NPAIRS_S2 = 10, /* ... state-2 only */
+    ATM_NUM_ENERGY_SLOTS = 12
 };
 
 typedef struct {
@@ -187,6 +190,17 @@ typedef struct {
  * stage -> merge.  No host synchronisation; safe to capture into a CUDA graph.
  * ref: ATMMetaForceImpl::calcForcesAndEnergy (openmmapi/src/ATMMetaForceImpl.cpp:90-128). */
 int atm_step(atm_handle *h, const atm_step_io *io, void *stream);
+
+/* atm_step replayed from a cached CUDA graph (re-captured when buffers / flags / the pair list change).
+ * `stream` must be a non-default stream. */
+int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream);
+
+/* Measurement hooks.  With profiling on, atm_step brackets the nb2 launch with CUDA events on the launching
+ * stream; atm_profile_read synchronises those events and returns their summed time and count since the last read.
+ * atm_launch_count: kernels of this library launched through the handle so far. */
+int atm_profile_enable(atm_handle *h, int32_t on);
+int atm_profile_read(atm_handle *h, double *nb2_ms_total, int32_t *nb2_launches);
+int atm_launch_count(atm_handle *h, uint64_t *count);
 
 /* Device pointer to the [R][ATM_NUM_ENERGY_SLOTS] energy records (valid after atm_step completes). */
 int atm_energies_device(atm_handle *h, const double **dev_ptr);

@@ -71,6 +71,7 @@ int atm_create(const atm_config *cfg, atm_handle **out) {
     h->d_displ = nullptr;
     h->d_params = nullptr;
     h->have_displ = false;
+    h->launches = 0;
     h->nb = nullptr;
     cudaDeviceProp prop;
     ATM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
@@ -164,12 +165,14 @@ int atm_copy_state(atm_handle *h, const void *posq, const void *posq_corr, void 
     ATM_REQUIRE(!(h->cfg.precision == ATM_PREC_DOUBLE && posq_corr != nullptr), ATM_ERR_INVALID,
                 "atm_copy_state: double precision has no posqCorrection buffers");
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    if (h->N > 0) h->launches++;
     return launch_copy_state(h, posq, posq_corr, posq1, posq1_corr, posq2, posq2_corr, (cudaStream_t)stream);
 }
 
 int atm_wrap_positions(atm_handle *h, const void *posq_in, void *posq_out, const double box[9], void *stream) {
     ATM_REQUIRE(h && posq_in && posq_out && box, ATM_ERR_INVALID, "atm_wrap_positions: null argument");
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    h->launches++;
     return launch_wrap(h, posq_in, posq_out, box, (cudaStream_t)stream);
 }
 
@@ -178,6 +181,7 @@ int atm_hybrid_force(atm_handle *h, int64_t *force, const int64_t *f1, const int
     if (h->N == 0) return ATM_OK;
     ATM_REQUIRE(force && f1 && f2, ATM_ERR_INVALID, "atm_hybrid_force: null force buffer");
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    h->launches++;
     return launch_hybrid_force(h, force, f1, f2, sp, (cudaStream_t)stream);
 }
 

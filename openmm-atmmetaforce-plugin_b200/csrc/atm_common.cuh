@@ -93,6 +93,7 @@ struct atm_handle {
     double *d_params;
     bool params_dirty;
     std::vector<double> pert_energy;   // cached u_sc per replica (Tier-1 execute)
+    uint64_t launches;                 // kernels of this library launched through this handle
     atm::NbState *nb;
 };
 

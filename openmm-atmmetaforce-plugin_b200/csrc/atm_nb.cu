@@ -34,7 +34,7 @@ constexpr int NB_THREADS = 128;    // force kernel block size (4 warps, one work
 constexpr int NB_MIN_BLOCKS = 4;   // 16 warps / SM at <= 128 registers
 constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
-constexpr int EACC_SLOTS = 4;                  // Uc, U(S1), U(S2), pairs in cutoff
+constexpr int EACC_SLOTS = 6;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2)
 
 struct NbDev {  // everything the kernels need, passed by value
     int N, P, R, M, G, U;
@@ -91,13 +91,20 @@ struct NbState {
     int2 *d_excl_pairs = nullptr, *d_exc_pairs = nullptr;
     float4 *d_exc_par = nullptr;
     int n_excl = 0, n_exc = 0;
-    int parity = 0;
     int sort_bits = 64;
     size_t jlist_entries = 0;
     int *item_counts = nullptr, *item_offsets = nullptr;
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     int n_items = 0, max_items = 0;
+    uint64_t generation = 0;  // bumped by every rebuild (grid sizes and list pointers may change)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    atm_step_io graph_io{};
+    uint64_t graph_generation = 0;
+    int graph_nodes = 0;
     int64_t stats[8] = {0};
 };
 
@@ -625,8 +632,8 @@ struct PairConst {
 template <bool ENERGY>
 __device__ __forceinline__ float pair_interaction(float r2, float qq, float sig, float eps4, const PairConst &pc, float &energy) {
     float rinv = mufu_rsqrt(r2);
-#ifndef ATM_NO_NEWTON
-    rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);  // one Newton step: MUFU.RSQ alone is ~2^-22.5
+#ifdef ATM_RSQRT_NEWTON  // A/B switch: measured force/energy parity is identical without the Newton step
+    rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);
 #endif
     const float rinv2 = rinv * rinv;
     const float r = r2 * rinv;
@@ -656,7 +663,7 @@ struct ItemCtx {
 };
 
 template <bool ENERGY, bool STATS>
-__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int parity, int lane) {
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane) {
     const float4 L = d.box[it.r], iL = d.invbox[it.r];
     const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
     PairConst pc;
@@ -774,15 +781,15 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
             if (STATS) npairs += __shfl_xor_sync(0xffffffffu, npairs, off);
         }
         if (lane == 0) {
-            unsigned long long *ea = d.eacc + ((size_t)parity * d.R + it.r) * EACC_SLOTS;
+            unsigned long long *ea = d.eacc + (size_t)it.r * EACC_SLOTS;
             if (ENERGY) atomicAdd(ea + it.target, (unsigned long long)__double2ll_rn(e_acc * ENERGY_SCALE));
-            if (STATS) atomicAdd(ea + 3, (unsigned long long)npairs);
+            if (STATS) atomicAdd(ea + 3 + it.target, (unsigned long long)npairs);
         }
     }
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) nb2_kernel(NbDev d, int parity, int n_items, int energy_common) {
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) nb2_kernel(NbDev d, int n_items, int energy_common) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
     if (warp >= d.flags[4]) return;  // the pruned list's item count lives on the device (n_items is the outer bound)
@@ -800,8 +807,8 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) nb2_kernel(NbDev d,
     it.list = d.jlist + li.offset + (size_t)step0 * 32;
     it.rsite = (size_t)r * d.Smax;
     it.comp_stride = (size_t)d.R * d.Smax;
-    if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, parity, lane);
-    else nb2_item<true, STATS>(d, it, parity, lane);
+    if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane);
+    else nb2_item<true, STATS>(d, it, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -815,7 +822,7 @@ __device__ __forceinline__ void add_pair_force(const NbDev &d, int r, int target
     red_add_fixed(buf + sj, -fx); red_add_fixed(buf + cs + sj, -fy); red_add_fixed(buf + 2 * cs + sj, -fz);
 }
 
-__global__ void nb_special_pairs_kernel(NbDev d, int parity, const int2 *__restrict__ excl, int n_excl,
+__global__ void nb_special_pairs_kernel(NbDev d, const int2 *__restrict__ excl, int n_excl,
                                         const int2 *__restrict__ exc, const float4 *__restrict__ exc_par, int n_exc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
@@ -866,7 +873,7 @@ __global__ void nb_special_pairs_kernel(NbDev d, int parity, const int2 *__restr
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0 && v != 0.0) {
-            unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
+            unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;
             atomicAdd(ea + k, (unsigned long long)__double2ll_rn(v * ENERGY_SCALE));
         }
     }
@@ -879,56 +886,67 @@ __global__ void nb_special_pairs_kernel(NbDev d, int parity, const int2 *__restr
 // ------------------------------------------------------------------------------------------------
 constexpr int MERGE2_THREADS = 256;
 
-// One thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
+// Scalar stage, one thread per replica: u = U(S2) - U(S1), soft-core, softplus, sp -- all in double on the device
+// (the reference does this on the host after two blocking energy downloads, CommonATMMetaForceKernels.cpp:164-199).
+__global__ void nb_scalar_kernel(NbDev d, const double *__restrict__ energy_ext, int include_energy) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;
+    const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
+                 u2 = (double)(long long)ea[2] / ENERGY_SCALE;
+    double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
+    if (energy_ext) {
+        U1 += energy_ext[2 * r];
+        U2 += energy_ext[2 * r + 1];
+        du += energy_ext[2 * r + 1] - energy_ext[2 * r];
+    }
+    const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
+    double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
+    e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
+    e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp;
+    e[ATM_E_NPAIRS] = (double)(ea[3] + ea[4] + ea[5]);
+    e[ATM_E_NPAIRS_C] = (double)ea[3]; e[ATM_E_NPAIRS_S1] = (double)ea[4]; e[ATM_E_NPAIRS_S2] = (double)ea[5];
+    // this thread is the only reader: hand the accumulators back zeroed for the next step (stream order protects them)
+#pragma unroll
+    for (int k = 0; k < EACC_SLOTS; k++) ea[k] = 0ull;
+}
+
+// Merge, one thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
 // read-modify-write of the caller's force buffer is a scatter.  The thread of a displaced atom also folds in (and
 // zeroes) the S2 accumulator of its ghost site; ghost and padding slots have no thread work.
+// F[slot] += C + llrint(sp * S2 + (1 - sp) * S1), blend in double (kernels/atmmetaforce.cc:8-16 semantics).
 __global__ void __launch_bounds__(MERGE2_THREADS)
-nb_merge_kernel(NbDev d, int parity, long long *__restrict__ force, const long long *__restrict__ f1_ext,
-                const long long *__restrict__ f2_ext, const double *__restrict__ energy_ext, int include_energy) {
+nb_merge_kernel(NbDev d, long long *__restrict__ force, const long long *__restrict__ f1_ext,
+                const long long *__restrict__ f2_ext) {
     const int r = blockIdx.y;
-    __shared__ double s_sp;
-    if (threadIdx.x == 0) {
-        const unsigned long long *ea = d.eacc + ((size_t)parity * d.R + r) * EACC_SLOTS;
-        const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
-                     u2 = (double)(long long)ea[2] / ENERGY_SCALE;
-        double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
-        if (energy_ext) {
-            U1 += energy_ext[2 * r];
-            U2 += energy_ext[2 * r + 1];
-            du += energy_ext[2 * r + 1] - energy_ext[2 * r];
-        }
-        const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
-        s_sp = s.sp;
-        if (blockIdx.x == 0) {
-            double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
-            e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
-            e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp; e[ATM_E_NPAIRS] = (double)ea[3];
-            // zero the accumulators the NEXT step will use (nobody reads them during this launch)
-            unsigned long long *eo = d.eacc + ((size_t)(parity ^ 1) * d.R + r) * EACC_SLOTS;
-            eo[0] = eo[1] = eo[2] = eo[3] = 0ull;
-        }
-    }
-    __syncthreads();
     const int s = blockIdx.x * MERGE2_THREADS + threadIdx.x;
     if (s >= CL * d.nclusters[r]) return;
     const size_t rsite = (size_t)r * d.Smax;
     const int i = d.slot_out[rsite + s];  // caller's slot of this site's atom, -1 for ghosts and padding
     if (i < 0) return;
-    const double sp = s_sp, sp1 = 1.0 - s_sp;
     const int gs = d.slot_ghost[rsite + s];
+    const double sp = d.energies[(size_t)r * ATM_NUM_ENERGY_SLOTS + ATM_E_SP], sp1 = 1.0 - sp;
     const size_t cs = (size_t)d.R * d.Smax;
     long long *bufC = (long long *)d.buf + rsite, *buf1 = bufC + 3 * cs, *buf2 = bufC + 6 * cs;
+    long long fc[3], fa[3], fb[3], fg[3], fo_old[3];
+    size_t fo[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {  // every load first
+        fc[c] = bufC[c * cs + s];
+        fa[c] = buf1[c * cs + s];
+        fb[c] = buf2[c * cs + s];
+        fg[c] = gs >= 0 ? buf2[c * cs + gs] : 0;
+        fo[c] = (size_t)r * 3 * d.P + (size_t)c * d.P + i;
+        fo_old[c] = force[fo[c]];
+        if (f1_ext) fa[c] += f1_ext[fo[c]];
+        if (f2_ext) fb[c] += f2_ext[fo[c]];
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const long long fc = bufC[c * cs + s];
-        long long fa = buf1[c * cs + s], fb = buf2[c * cs + s];
         bufC[c * cs + s] = 0; buf1[c * cs + s] = 0; buf2[c * cs + s] = 0;
-        if (gs >= 0) { fb += buf2[c * cs + gs]; buf2[c * cs + gs] = 0; }
-        const size_t fo = (size_t)r * 3 * d.P + (size_t)c * d.P + i;
-        if (f1_ext) fa += f1_ext[fo];
-        if (f2_ext) fb += f2_ext[fo];
-        const double v = __dadd_rn(__dmul_rn(sp, (double)fb), __dmul_rn(sp1, (double)fa));
-        force[fo] += fc + __double2ll_rn(v);
+        if (gs >= 0) buf2[c * cs + gs] = 0;
+        const double v = __dadd_rn(__dmul_rn(sp, (double)(fb[c] + fg[c])), __dmul_rn(sp1, (double)fa[c]));
+        force[fo[c]] = fo_old[c] + fc[c] + __double2ll_rn(v);
     }
 }
 
@@ -958,6 +976,8 @@ static int dev_upload(NbState *nb, T **ptr, const std::vector<T> &v, cudaStream_
 
 void nb_destroy(atm_handle *h) {
     if (!h->nb) return;
+    if (h->nb->graph_exec) cudaGraphExecDestroy(h->nb->graph_exec);
+    for (auto &ev : h->nb->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (void *p : h->nb->owned) cudaFree(p);
     delete h->nb;
     h->nb = nullptr;
@@ -1014,6 +1034,7 @@ static void free_owned(NbState *nb) {
 static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     NbState *nb = h->nb;
     ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    nb->generation++;
     free_owned(nb);
     int rc = derive_groups(h);
     if (rc) return rc;
@@ -1125,13 +1146,12 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     }
     if ((rc = dev_alloc(nb, &d.flags, 8))) return rc;
     if ((rc = dev_alloc(nb, &d.buf, 9 * RS))) return rc;
-    if ((rc = dev_alloc(nb, &d.eacc, (size_t)2 * R * EACC_SLOTS))) return rc;
+    if ((rc = dev_alloc(nb, &d.eacc, (size_t)R * EACC_SLOTS))) return rc;
     if ((rc = dev_alloc(nb, &d.energies, (size_t)R * ATM_NUM_ENERGY_SLOTS))) return rc;
     ATM_CUDA_CHECK(cudaMemsetAsync(d.buf, 0, 9 * RS * sizeof(unsigned long long), stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.eacc, 0, (size_t)2 * R * EACC_SLOTS * sizeof(unsigned long long), stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.eacc, 0, (size_t)R * EACC_SLOTS * sizeof(unsigned long long), stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.energies, 0, (size_t)R * ATM_NUM_ENERGY_SLOTS * sizeof(double), stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.list_nsteps, 0, (size_t)R * (d.Cmax + d.CLmax) * sizeof(int), stream));
-    nb->parity = 0;
 
     // radix sort scratch
     int key_bits = 16;
@@ -1175,6 +1195,7 @@ static int launch_prune(atm_handle *h, cudaStream_t stream, bool refresh_boxes) 
     size_t sbytes = nb->scan_tmp_bytes;
     cub::DeviceScan::ExclusiveSum(nb->scan_tmp, sbytes, nb->item_counts, nb->item_offsets, nl, stream);
     nl_item_fill_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(d, nb->item_counts, nb->item_offsets);
+    h->launches += (refresh_boxes ? 1 : 0) + 3;  // own kernels only (the CUB scan is library code)
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
 }
@@ -1194,6 +1215,7 @@ int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
     int rc;
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)posq);
+    h->launches++;
     return launch_prune(h, stream, /*refresh_boxes=*/true);
 }
 
@@ -1317,6 +1339,7 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
         const int nlists = d.Cmax + d.CLmax;
         nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
+        h->launches += 6 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox, build
         if ((rc = launch_prune(h, stream, /*refresh_boxes=*/false))) return rc;
         ATM_CUDA_CHECK(cudaGetLastError());
         int flags[8];
@@ -1344,44 +1367,142 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         memcpy(&inner_entries, &flags[6], 8);
         nb->stats[2] = (int64_t)(inner_entries / d.R);
         nb->list_valid = true;
+        nb->generation++;
         return ATM_OK;
     }
     set_error("atm_nb_rebuild: neighbour list capacity could not be satisfied after 4 attempts");
     return ATM_ERR_NOMEM;
 }
 
-int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    ATM_REQUIRE(h && io, ATM_ERR_INVALID, "atm_step: null argument");
-    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->list_valid, ATM_ERR_STATE, "atm_step: no valid neighbour structure (call atm_nb_rebuild)");
-    ATM_REQUIRE(io->posq && io->force, ATM_ERR_INVALID, "atm_step: posq and force are required");
-    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+// the launches of one step (no validation, no uploads): shared by atm_step and the graph capture
+static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream, bool profile) {
     NbState *nb = h->nb;
     NbDev &d = nb->d;
     int rc;
-    if ((rc = upload_params_if_dirty(h, stream))) return rc;
-    if ((rc = upload_box_if_dirty(h, stream))) return rc;
     if (io->posq1 || io->posq2) {
-        ATM_REQUIRE(h->R == 1, ATM_ERR_UNSUPPORTED, "atm_step: inner-context coordinate outputs need num_replicas == 1");
-        if ((rc = atm_copy_state(h, io->posq, io->posq_corr, io->posq1, io->posq1_corr, io->posq2, io->posq2_corr, stream_))) return rc;
+        if ((rc = launch_copy_state(h, io->posq, io->posq_corr, io->posq1, io->posq1_corr, io->posq2, io->posq2_corr, stream))) return rc;
+        h->launches++;
     }
-    const int parity = nb->parity;
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
     const int warps_per_block = NB_THREADS / 32;
     const int nblocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
     if (nblocks > 0) {
-        if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, parity, nb->n_items, io->include_energy);
-        else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, parity, nb->n_items, io->include_energy);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (profile) {
+            if (nb->prof_used == nb->prof_events.size()) {
+                cudaEvent_t a, b;
+                ATM_CUDA_CHECK(cudaEventCreate(&a));
+                ATM_CUDA_CHECK(cudaEventCreate(&b));
+                nb->prof_events.push_back(std::make_pair(a, b));
+            }
+            e0 = nb->prof_events[nb->prof_used].first;
+            e1 = nb->prof_events[nb->prof_used].second;
+            nb->prof_used++;
+            ATM_CUDA_CHECK(cudaEventRecord(e0, stream));
+        }
+        if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, nb->n_items, io->include_energy);
+        else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, nb->n_items, io->include_energy);
+        if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
+        h->launches++;
     }
     const int nsp = nb->n_excl + nb->n_exc;
-    if (nsp > 0)
-        nb_special_pairs_kernel<<<dim3((nsp + 127) / 128, d.R), 128, 0, stream>>>(d, parity, nb->d_excl_pairs, nb->n_excl, nb->d_exc_pairs,
+    if (nsp > 0) {
+        nb_special_pairs_kernel<<<dim3((nsp + 127) / 128, d.R), 128, 0, stream>>>(d, nb->d_excl_pairs, nb->n_excl, nb->d_exc_pairs,
                                                                                  nb->d_exc_par, nb->n_exc);
+        h->launches++;
+    }
+    nb_scalar_kernel<<<(d.R + 31) / 32, 32, 0, stream>>>(d, io->energy_ext, io->include_energy);
     nb_merge_kernel<<<dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
-        d, parity, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext,
-        io->energy_ext, io->include_energy);
+        d, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext);
+    h->launches += 3;
     ATM_CUDA_CHECK(cudaGetLastError());
-    nb->parity ^= 1;
+    return ATM_OK;
+}
+
+static int validate_step(atm_handle *h, const atm_step_io *io, const char *who) {
+    ATM_REQUIRE(h && io, ATM_ERR_INVALID, "%s: null argument", who);
+    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->list_valid, ATM_ERR_STATE, "%s: no valid neighbour structure (call atm_nb_rebuild)", who);
+    ATM_REQUIRE(io->posq && io->force, ATM_ERR_INVALID, "%s: posq and force are required", who);
+    if (io->posq1 || io->posq2) {
+        ATM_REQUIRE(h->R == 1, ATM_ERR_UNSUPPORTED, "%s: inner-context coordinate outputs need num_replicas == 1", who);
+        ATM_REQUIRE(io->posq1 && io->posq2, ATM_ERR_INVALID, "%s: posq1 and posq2 must be given together", who);
+        ATM_REQUIRE(!(h->cfg.precision == ATM_PREC_MIXED && !(io->posq_corr && io->posq1_corr && io->posq2_corr)), ATM_ERR_INVALID,
+                    "%s: mixed precision inner-context outputs need the three posqCorrection buffers", who);
+    }
+    return ATM_OK;
+}
+
+int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = validate_step(h, io, "atm_step"))) return rc;
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    if ((rc = upload_params_if_dirty(h, stream))) return rc;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    return launch_step(h, io, stream, h->nb->profiling);
+}
+
+// Same step, replayed from a cached CUDA graph (one driver call per step instead of 5-6 launches).  The graph is
+// re-captured when the buffers, the flags or the pair-list generation change.  `stream` must be a real (non-legacy)
+// stream because it is put into capture mode.
+int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = validate_step(h, io, "atm_step_graph"))) return rc;
+    ATM_REQUIRE(stream != nullptr, ATM_ERR_INVALID, "atm_step_graph: needs a non-default stream (it is captured)");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    NbState *nb = h->nb;
+    if ((rc = upload_params_if_dirty(h, stream))) return rc;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    const bool same = nb->graph_exec && memcmp(&nb->graph_io, io, sizeof(*io)) == 0 && nb->graph_generation == nb->generation;
+    if (!same) {
+        if (nb->graph_exec) { cudaGraphExecDestroy(nb->graph_exec); nb->graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const uint64_t launches_before = h->launches;
+        ATM_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        rc = launch_step(h, io, stream, false);
+        cudaError_t err = cudaStreamEndCapture(stream, &graph);
+        h->launches = launches_before;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        ATM_REQUIRE(err == cudaSuccess && graph, ATM_ERR_CUDA, "atm_step_graph: capture failed: %s", cudaGetErrorString(err));
+        err = cudaGraphInstantiate(&nb->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        ATM_REQUIRE(err == cudaSuccess, ATM_ERR_CUDA, "atm_step_graph: instantiate failed: %s", cudaGetErrorString(err));
+        nb->graph_io = *io;
+        nb->graph_generation = nb->generation;
+        nb->graph_nodes = 3 + (io->posq1 ? 1 : 0) + (nb->n_items > 0 ? 1 : 0) + (nb->n_excl + nb->n_exc > 0 ? 1 : 0);
+    }
+    ATM_CUDA_CHECK(cudaGraphLaunch(nb->graph_exec, stream));
+    h->launches += nb->graph_nodes;
+    return ATM_OK;
+}
+
+int atm_profile_enable(atm_handle *h, int32_t on) {
+    ATM_REQUIRE(h && h->nb, ATM_ERR_STATE, "atm_profile_enable: Tier 2 not set up");
+    h->nb->profiling = on != 0;
+    return ATM_OK;
+}
+
+// Sum of the device time of the nb2 launches recorded since the last read (CUDA events on the launching stream).
+int atm_profile_read(atm_handle *h, double *nb2_ms_total, int32_t *nb2_launches) {
+    ATM_REQUIRE(h && h->nb && nb2_ms_total && nb2_launches, ATM_ERR_INVALID, "atm_profile_read: null argument");
+    NbState *nb = h->nb;
+    double total = 0.0;
+    for (size_t k = 0; k < nb->prof_used; k++) {
+        ATM_CUDA_CHECK(cudaEventSynchronize(nb->prof_events[k].second));
+        float ms = 0.f;
+        ATM_CUDA_CHECK(cudaEventElapsedTime(&ms, nb->prof_events[k].first, nb->prof_events[k].second));
+        total += ms;
+    }
+    *nb2_ms_total = total;
+    *nb2_launches = (int32_t)nb->prof_used;
+    nb->prof_used = 0;
+    return ATM_OK;
+}
+
+int atm_launch_count(atm_handle *h, uint64_t *count) {
+    ATM_REQUIRE(h && count, ATM_ERR_INVALID, "atm_launch_count: null argument");
+    *count = h->launches;
     return ATM_OK;
 }
 

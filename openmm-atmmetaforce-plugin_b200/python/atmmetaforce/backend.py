@@ -127,13 +127,28 @@ class ATMBackend:
         check(_capi.lib().atm_nb_prune(self._h, _dptr(posq), _stream_ptr(stream)))
 
     def step(self, posq, force, posq_corr=None, f1_ext=None, f2_ext=None, energy_ext=None, posq1=None, posq1_corr=None,
-             posq2=None, posq2_corr=None, include_energy=True, collect_stats=False, stream=None):
+             posq2=None, posq2_corr=None, include_energy=True, collect_stats=False, graph=False, stream=None):
         def v(t):
             p = _dptr(t)
             return p.value if p is not None else None
         io = _capi.StepIO(v(posq), v(posq_corr), v(force), v(f1_ext), v(f2_ext), v(energy_ext), v(posq1), v(posq1_corr),
                           v(posq2), v(posq2_corr), 1 if include_energy else 0, 1 if collect_stats else 0)
-        check(_capi.lib().atm_step(self._h, C.byref(io), _stream_ptr(stream)))
+        fn = _capi.lib().atm_step_graph if graph else _capi.lib().atm_step
+        check(fn(self._h, C.byref(io), _stream_ptr(stream)))
+
+    def profile_enable(self, on=True):
+        check(_capi.lib().atm_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """(total nb2 milliseconds, number of nb2 launches) since the last read; synchronises the recorded events."""
+        ms, n = C.c_double(), C.c_int32()
+        check(_capi.lib().atm_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(_capi.lib().atm_launch_count(self._h, C.byref(n)))
+        return n.value
 
     def energies_device_ptr(self):
         p = C.c_void_p()
