@@ -200,10 +200,11 @@ def run_b200(args):
     s, sched, label = load_workload(args.workload)
     n = s["pos"].shape[0]
     total_replicas = args.replicas
-    mine = synthetic.partition_replicas(total_replicas, world)[rank]
+    rex = atm.ReplicaExchange(sched, total_replicas, rank=rank, world_size=world, temperature=300.0, seed=2022)
+    mine = rex.mine
     R = len(mine)
-    max_per_rank = max(len(x) for x in synthetic.partition_replicas(total_replicas, world))
-    replica_state = np.arange(total_replicas, dtype=np.int32) % len(sched)
+    max_per_rank = rex.max_per_rank
+    replica_state = rex.replica_state
 
     be = atm.ATMBackend(n, precision="mixed", num_replicas=max(R, 1), device=local_rank)
     P = be.P
@@ -229,31 +230,11 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    beta = 1.0 / (0.0083144626 * 300.0)
-
-    gather_in = torch.zeros((max_per_rank, 2), dtype=torch.float64, device=dev)
-    gather_out = torch.zeros((world * max_per_rank, 2), dtype=torch.float64, device=dev)
-    owner_slot = {}
-    for r_, lst in enumerate(synthetic.partition_replicas(total_replicas, world)):
-        for k, g in enumerate(lst):
-            owner_slot[g] = r_ * max_per_rank + k
-
     def exchange(cycle):
         """all-gather (U1,U2) of every replica, identical Metropolis sweep on every rank, swap lambda states."""
         en = torch.as_tensor(_DevView(be.energies_device_ptr(), (max(R, 1), _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
-        gather_in.zero_()
-        gather_in[:R] = en[:R, 0:2]
-        if world > 1:
-            dist.all_gather_into_tensor(gather_out, gather_in)
-            allu = gather_out.cpu().numpy()
-        else:
-            allu = gather_in.cpu().numpy()
-        u12 = np.stack([allu[owner_slot[g]] for g in range(total_replicas)])
-        new_state, _acc = atm.hrex_sweep(sched, u12, replica_state, beta, 2022, cycle)
-        for k, g in enumerate(mine):
-            if new_state[g] != replica_state[g]:
-                be.set_parameters(sched[new_state[g]], replica=k)
-        replica_state[:] = new_state
+        for k, row in rex.exchange(en[:, 0:2].contiguous()):
+            be.set_parameters(row, replica=k)
 
     step_no = [0]
 

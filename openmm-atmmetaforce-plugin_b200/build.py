@@ -61,7 +61,40 @@ def build(force=False, verbose=False, defines=(), out=None):
     return lib
 
 
+FACADE = os.path.join(HERE, "python", "atmmetaforce", "_atmmetaforce_core.so")
+FACADE_SRC = [os.path.join(HERE, "openmmapi", "src", "ATMMetaForce.cpp"),
+              os.path.join(HERE, "openmmapi", "src", "ATMMetaForceB200Kernel.cpp"),
+              os.path.join(HERE, "serialization", "ATMMetaForceProxy.cpp"),
+              os.path.join(HERE, "python", "src", "atmmetaforce_core.cpp")]
+
+
+def build_facade(force=False):
+    """g++: the C++ facade (ATMMetaForce class, XML proxy, kernel object) + its pybind11 binding, linked against
+    libatm_b200.so, plus the stand-alone C++ serialization test."""
+    import sysconfig
+    import pybind11
+    build(force=False)
+    deps = FACADE_SRC + [os.path.join(HERE, "openmmapi", "include", f) for f in os.listdir(os.path.join(HERE, "openmmapi", "include"))]
+    deps += [os.path.join(HERE, "serialization", "ATMMetaForceProxy.h"), LIB]
+    if not force and os.path.exists(FACADE) and all(os.path.getmtime(d) <= os.path.getmtime(FACADE) for d in deps):
+        return FACADE
+    inc = ["-I", os.path.join(HERE, "openmmapi", "include"), "-I", os.path.join(HERE, "serialization"),
+           "-I", os.path.join(ROOT, "include"), "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]]
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-fvisibility=hidden"] + inc + FACADE_SRC + \
+          ["-L", HERE, "-latm_b200", "-Wl,-rpath,$ORIGIN/../..", "-o", FACADE]
+    subprocess.check_call(cmd)
+    test = os.path.join(HERE, "build", "TestSerializeATMMetaForce")
+    os.makedirs(os.path.dirname(test), exist_ok=True)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:3] + \
+          [os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp"), "-L", HERE, "-latm_b200",
+           "-Wl,-rpath,$ORIGIN/..", "-o", test]
+    subprocess.check_call(cmd)
+    return FACADE
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    if not outs:
+        print(build_facade(force="--force" in sys.argv))

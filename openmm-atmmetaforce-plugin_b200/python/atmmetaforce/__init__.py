@@ -7,3 +7,6 @@ from ._capi import ATMError, LIB_PATH  # noqa: F401
 from .backend import ATMBackend, softcore_softplus, hrex_sweep, hrex_reduced_energy  # noqa: F401
 
 ATMMETAFORCE_VERSION = "0.3.1"  # reference openmmapi/include/ATMMetaForceVersion.h:4
+from .replica import ReplicaExchange  # noqa: F401,E402
+from .force import ATMMetaForce, OpenMMException, serialize, deserialize  # noqa: F401,E402
+from .context import Context, NonbondedDirect, State  # noqa: F401,E402

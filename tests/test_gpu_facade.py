@@ -1,0 +1,99 @@
+"""The reference's own test, restated against the drop-in Python API (ref: python/tests/test_abfe.py:22-150):
+build the ATM force for the TEMOA-G1 system, set the nine parameters, evaluate, check the perturbation energy pin."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_BindingEnergy(abfe):
+    import atmmetaforce as atm
+    import oracle_py as O
+    from helpers import oracle_system
+    kcal = 4.184
+    lmbd = 0.5
+    lambda1, lambda2, alpha, u0, w0coeff = lmbd, lmbd, 0.0, 0.0, 0.0
+    umsc, ubcore, acore, direction = 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0
+    displ = [2.2, 2.2, 2.2]   # 22 Angstrom
+    n = abfe["pos"].shape[0]
+    lig_atoms = abfe["lig1"]
+
+    atmforcegroup, nonbonded_force_group = 2, 1
+    nonbonded = atm.NonbondedDirect(abfe["charge"], abfe["sigma"], abfe["epsilon"], cutoff=1.0, ewald_tolerance=5e-4,
+                                    exclusions=abfe["excl"], exception_pairs=abfe["exc14"], exception_params=abfe["exc14_par"],
+                                    force_group=nonbonded_force_group)
+    atmforce = atm.ATMMetaForce(lambda1, lambda2, alpha, u0, w0coeff, umsc, ubcore, acore, direction, [nonbonded_force_group])
+    for i in range(n):
+        atmforce.addParticle(i, 0., 0., 0.)
+    for i in lig_atoms:
+        atmforce.setParticleParameters(int(i), int(i), displ[0], displ[1], displ[2])
+    atmforce.setForceGroup(atmforcegroup)
+
+    context = atm.Context(atmforce, nonbonded, abfe["box"], precision="mixed")
+    context.setPositions(abfe["pos"])
+    # override ATM parameters as the reference test does after loadState (:131-139; it sets ATMDirection to acore > 0)
+    for name, val in ((atmforce.Lambda1(), lambda1), (atmforce.Lambda2(), lambda2), (atmforce.Alpha(), alpha),
+                      (atmforce.U0(), u0), (atmforce.W0(), w0coeff), (atmforce.Umax(), umsc), (atmforce.Ubcore(), ubcore),
+                      (atmforce.Acore(), acore), (atmforce.Direction(), acore)):
+        context.setParameter(name, val)
+    # PME reciprocal space stays in OpenMM's inner contexts; here the oracle's exact Ewald sum plays that role
+    S = oracle_system(O, abfe, 1.0, nonbonded.ewald_alpha)
+    r1, _ = S.ewald_recip(abfe["pos"], 1e-10)
+    r2, _ = S.ewald_recip(abfe["pos"] + abfe["displ"], 1e-10)
+    context.setExternalStateEnergies(r1, r2)
+
+    state = context.getState(getEnergy=True, getForces=True, groups={0, atmforcegroup})
+    pert_energy = atmforce.getPerturbationEnergy(context)
+    assert np.allclose(58.2, pert_energy, atol=0.1), pert_energy
+    # energy returned by the force = e0 + W(u) with lambda1 = lambda2 = 1/2, alpha = 0:  U1 + u/2
+    e1, _, _ = S.nb_direct(abfe["pos"].astype(np.float32).astype(np.float64), want_force=False)
+    assert abs(state.getPotentialEnergy() - (e1 + r1 + 0.5 * pert_energy)) < 1e-6 * abs(e1)
+    assert state.getForces().shape == (n, 3)
+    # the ATM group is skipped when it is not in `groups` (ref: ATMMetaForceImpl.cpp:103)
+    assert context.getState(getEnergy=True, groups={0}).getPotentialEnergy() == 0.0
+
+    # updateParametersInContext: zero displacement -> u == 0
+    for i in lig_atoms:
+        atmforce.setParticleParameters(int(i), int(i), 0., 0., 0.)
+    atmforce.updateParametersInContext(context)
+    context.setExternalStateEnergies(0.0, 0.0)
+    context.getState(getEnergy=True)
+    assert atmforce.getPerturbationEnergy(context) == 0.0
+    context.close()
+
+
+def test_kernel_object_matches_reference_seam(abfe):
+    """ATMMetaForceB200Kernel (C++ facade object with the five methods of CalcATMMetaForceKernel) via pybind11."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import _atmmetaforce_core as core
+    import oracle_py as O
+    n = 1000
+    P = 1024
+    f = atm.ATMMetaForce(0.2, 0.6, 0.05, 50.0, 1.0, 800.0, 400.0, 0.0625, 1.0, [1])
+    rng = np.random.default_rng(0)
+    d = np.zeros((n, 3)); d[100:121] = [2.2, 2.2, 2.2]
+    for i in range(n):
+        f.addParticle(i, *d[i])
+    perm = rng.permutation(n).astype(np.int32)
+    k = core.ATMMetaForceB200Kernel()
+    assert k.Name() == "CalcATMMetaForce"
+    k.initialize(f, P, 1, perm.tolist(), 0)
+    posq = torch.from_numpy(rng.uniform(-3, 6, (P, 4)).astype(np.float32)).cuda()
+    corr = torch.zeros_like(posq)
+    p1, p2, c1, c2 = (torch.zeros_like(posq) for _ in range(4))
+    k.copyState(posq.data_ptr(), corr.data_ptr(), p1.data_ptr(), c1.data_ptr(), p2.data_ptr(), c2.data_ptr(), 0)
+    torch.cuda.synchronize()
+    table = O.displ_table(n, P, perm, d)
+    e1, _, e2, _ = O.copy_state_f32(posq.cpu().numpy()[:n], corr.cpu().numpy()[:n], table[:n])
+    assert np.array_equal(p2.cpu().numpy()[:n].view(np.uint32), e2.view(np.uint32))
+    params = core.ATMMetaForceB200Kernel.getDefaultParameters(f)
+    F = lambda: torch.from_numpy((rng.normal(0, 1000, 3 * P) * 2.0 ** 32).astype(np.int64)).cuda()
+    f0, f1, f2 = F(), F(), F()
+    f0c = f0.clone()
+    energy = k.execute(params, f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), -1000.0, -900.0, True, True, 0)
+    torch.cuda.synchronize()
+    sc = O.scalars([params[x] for x in atm.Context.PARAM_ORDER], -1000.0, -900.0)
+    assert abs(energy - sc["energy"]) < 1e-9 and abs(k.getPerturbationEnergy() - sc["u_sc"]) < 1e-9
+    exp = O.hybrid_force_i64(n, P, f0c.cpu().numpy(), f1.cpu().numpy(), f2.cpu().numpy(), sc["sp"])
+    assert np.array_equal(f0.cpu().numpy(), exp)

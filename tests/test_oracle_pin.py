@@ -1,0 +1,215 @@
+"""CPU tests of the oracle (the checker) itself: it is pinned against the reference's only golden vector on this
+path and against analytic properties.  No GPU needed."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import oracle_system
+
+
+def test_abfe_perturbation_energy_pin(abfe):
+    """Reference pin: u = 58.2 +- 0.1 kJ/mol at lambda 0.5 (reference python/tests/test_abfe.py:148,150).
+    U2-U1 = direct-space difference + exact Ewald reciprocal difference (everything else cancels for a rigid shift)."""
+    alpha = O.ewald_alpha(1.0)
+    assert abs(alpha - 2.62826) < 1e-4   # OpenMM's rule for tolerance 5e-4, cutoff 1 nm
+    S = oracle_system(O, abfe, 1.0, alpha)
+    pos, pos2 = abfe["pos"], abfe["pos"] + abfe["displ"]
+    e1, c1, _ = S.nb_direct(pos, want_force=False)
+    e2, c2, _ = S.nb_direct(pos2, want_force=False)
+    r1, _ = S.ewald_recip(pos, 1e-10)
+    r2, _ = S.ewald_recip(pos2, 1e-10)
+    u = (e2 - e1) + (r2 - r1)
+    sc = O.scalars(abfe["params"], e1 + r1, e2 + r2)
+    assert abs(sc["u_sc"] - u) < 1e-9           # below ubcore: the soft core is the identity
+    assert abs(u - float(abfe["pin_u"])) <= 0.1, u
+    # components recorded at survey time: LJ -4.1811, Coulomb real +76.0584, reciprocal -13.6472
+    assert abs((c2[0] - c1[0]) - (-4.1811)) < 2e-4
+    assert abs((c2[1] - c1[1]) - 76.0584) < 2e-4
+    assert abs((r2 - r1) - (-13.6472)) < 2e-4
+    # exclusion corrections and 1-4 exceptions are intramolecular: they cancel exactly for a rigid translation
+    assert abs(c2[2] - c1[2]) < 1e-6 and abs(c2[3] - c1[3]) < 1e-6
+
+
+def test_rbfe_self_consistency(rbfe):
+    """No reference pin exists for the RBFE system (parity unpinned); value recorded at survey time: 2.1072."""
+    alpha = O.ewald_alpha(1.0)
+    S = oracle_system(O, rbfe, 1.0, alpha)
+    e1, _, _ = S.nb_direct(rbfe["pos"], want_force=False)
+    e2, _, _ = S.nb_direct(rbfe["pos"] + rbfe["displ"], want_force=False)
+    assert abs((e2 - e1) - 5.9243) < 2e-3       # direct space only (LJ +8.0678, Coulomb -2.1435)
+
+
+def test_direct_space_forces_are_gradients():
+    """Finite-difference check of the oracle's direct-space forces (incl. exclusion correction and exceptions)."""
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(3000, n_lig=12, seed=3)
+    n = s["pos"].shape[0]
+    # give it a few exceptions too
+    exc = np.array([[0, 5], [2, 9]], np.int32)
+    par = np.array([[0.1, 0.25, 0.3], [-0.05, 0.3, 0.2]])
+    excl = np.concatenate([s["excl"], exc])
+    S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], 0.9, s["ewald_alpha"], excl, exc, par)
+    e0, _, f = S.nb_direct(s["pos"])
+    rng = np.random.default_rng(0)
+    h = 1e-5
+    for a in list(rng.integers(0, n, 6)) + [0, 5, 2, 9]:
+        for c in range(3):
+            p = s["pos"].copy(); p[a, c] += h
+            ep, _, _ = S.nb_direct(p, want_force=False)
+            p[a, c] -= 2 * h
+            em, _, _ = S.nb_direct(p, want_force=False)
+            fd = -(ep - em) / (2 * h)
+            assert abs(fd - f[a, c]) <= 1e-4 * max(1.0, abs(f[a, c])), (a, c, fd, f[a, c])
+    assert np.abs(f.sum(0)).max() < 1e-6 * np.abs(f).max() * n ** 0.5   # Newton's third law
+
+
+def test_reciprocal_forces_are_gradients():
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(600, n_lig=0, seed=4)
+    S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], 0.8, 3.0, s["excl"])
+    e0, f = S.ewald_recip(s["pos"], 1e-10, want_force=True)
+    h = 1e-5
+    for a in (0, 7, 100):
+        for c in range(3):
+            p = s["pos"].copy(); p[a, c] += h
+            ep, _ = S.ewald_recip(p, 1e-10)
+            p[a, c] -= 2 * h
+            em, _ = S.ewald_recip(p, 1e-10)
+            assert abs(-(ep - em) / (2 * h) - f[a, c]) <= 1e-5 * max(1.0, abs(f[a, c]))
+
+
+def test_cell_list_matches_all_pairs():
+    """The oracle's cell-list path (>= 3 cells per edge) against its own all-pairs fallback (small box)."""
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(3000, n_lig=10, seed=5)
+    S_cells = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], 0.9, s["ewald_alpha"], s["excl"])
+    S_brute = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], 0.9, s["ewald_alpha"], s["excl"])
+    # a cutoff > L/3 forces the all-pairs path; compare at the same physical cutoff by evaluating both with 0.9
+    # through a system whose box has < 3 cells only along one axis
+    assert (s["box"] / 0.9 >= 3).all()
+    e_cells, c_cells, f_cells = S_cells.nb_direct(s["pos"])
+    pos = s["pos"]
+    L = s["box"]
+    n = pos.shape[0]
+    # plain numpy O(N^2) restatement for a random subset of atoms
+    rng = np.random.default_rng(1)
+    ex = {(int(a), int(b)) for a, b in s["excl"]} | {(int(b), int(a)) for a, b in s["excl"]}
+    from scipy.special import erfc
+    for i in rng.integers(0, n, 5):
+        d = pos[i] - pos
+        d -= L * np.round(d / L)
+        r2 = (d ** 2).sum(1)
+        mask = (r2 < 0.81) & (np.arange(n) != i)
+        mask &= np.array([(int(i), j) not in ex for j in range(n)])
+        r = np.sqrt(r2[mask])
+        sig = 0.5 * (s["sigma"][i] + s["sigma"][mask]); eps = np.sqrt(s["epsilon"][i] * s["epsilon"][mask])
+        s6 = (sig / r) ** 6
+        qq = 138.935456 * s["charge"][i] * s["charge"][mask]
+        ar = s["ewald_alpha"] * r
+        fr = (24 * eps * s6 * (2 * s6 - 1) + qq / r * (erfc(ar) + 2 / np.sqrt(np.pi) * ar * np.exp(-ar * ar))) / r ** 2
+        f_i = (fr[:, None] * d[mask]).sum(0)
+        # add the exclusion-correction force on atom i
+        for j in [b for (a, b) in ex if a == i]:
+            dd = pos[i] - pos[j]; dd -= L * np.round(dd / L)
+            rr = np.linalg.norm(dd); q2 = 138.935456 * s["charge"][i] * s["charge"][j]; a_r = s["ewald_alpha"] * rr
+            from scipy.special import erf
+            f_i += -q2 / rr * (erf(a_r) - 2 / np.sqrt(np.pi) * a_r * np.exp(-a_r * a_r)) / rr ** 2 * dd
+        assert np.allclose(f_i, f_cells[i], rtol=1e-9, atol=1e-7)
+
+
+# ------------------------------------------------------------------ scalar stage properties
+
+def test_softcore_identity_below_ubcore():
+    for u in (-1e6, -3.0, 0.0, 99.9, 100.0):
+        v, fp = O.softcore(u, 200.0, 0.0625, 100.0)
+        assert v == u and fp == 1.0
+
+
+def test_softcore_is_bounded_and_smooth():
+    umax, a, ub = 836.8, 0.0625, 418.4
+    v, fp = O.softcore(1e9, umax, a, ub)
+    assert ub < v < umax and 0 <= fp < 1e-6
+    # continuity of value and slope at the knee
+    v1, fp1 = O.softcore(ub + 1e-9, umax, a, ub)
+    assert abs(v1 - ub) < 1e-8 and abs(fp1 - 1.0) < 1e-8
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(u=st.floats(-500, 5000), lam1=st.floats(0, 1), lam2=st.floats(0, 1), alpha=st.floats(0.001, 0.5),
+       u0=st.floats(-100, 600), direction=st.sampled_from([1.0, -1.0]))
+def test_scalar_stage_derivatives(u, lam1, lam2, alpha, u0, direction):
+    """fp = d u_sc/du, bfp = dW/d u_sc (finite differences), sp = dW/du for direction +1 and 1 - dW/du for -1."""
+    p = [lam1, lam2, alpha, u0, 1.5, 800.0, 400.0, 0.0625, direction]
+    U1 = -1234.5
+    U2 = U1 + direction * u
+    s = O.scalars(p, U1, U2)
+    h = 1e-4
+    sp_ = O.scalars(p, U1, U2 + direction * h)
+    sm_ = O.scalars(p, U1, U2 - direction * h)
+    dusc = (sp_["u_sc"] - sm_["u_sc"]) / (2 * h)
+    assert abs(dusc - s["fp"]) <= 1e-5 * max(1.0, abs(s["fp"])) or abs(u - 400.0) < 2 * h
+    dW = (sp_["ebias"] - sm_["ebias"]) / (2 * h)
+    assert abs(dW - s["bfp"] * s["fp"]) <= 1e-5 or abs(u - 400.0) < 2 * h
+    want = s["bfp"] * s["fp"] if direction > 0 else 1.0 - s["bfp"] * s["fp"]
+    assert abs(s["sp"] - want) < 1e-15
+    e0 = U1 if direction > 0 else U2
+    assert abs(s["energy"] - (e0 + s["ebias"])) < 1e-9
+
+
+def test_alpha_zero_branch():
+    """alpha = 0: no logarithmic term, ebias = lambda2 u_sc + w0, bfp = (lambda1+lambda2)/2 (reference quirk)."""
+    p = [0.3, 0.7, 0.0, 10.0, 2.0, 800.0, 400.0, 0.0625, 1.0]
+    s = O.scalars(p, -100.0, -50.0)
+    assert abs(s["ebias"] - (0.7 * 50.0 + 2.0)) < 1e-12
+    assert abs(s["bfp"] - 0.5) < 1e-12
+
+
+# ------------------------------------------------------------------ copy-state / merge definitions
+
+def test_copy_state_modes_agree_where_exact():
+    rng = np.random.default_rng(2)
+    n = 50
+    pos = rng.uniform(-3, 6, (n, 3))
+    d = np.zeros((n, 3)); d[10:20] = [2.2, -2.2, 0.5]
+    p1, p2 = O.copy_state_ref(pos, d)
+    assert np.array_equal(p1, pos) and np.array_equal(p2, pos + d)
+    table = O.displ_table(n, 64, None, d)
+    assert table.shape == (64, 4) and np.all(table[n:] == 0) and np.all(table[:, 3] == 0)
+    assert np.array_equal(table[10:20, :3], np.tile(np.float32([2.2, -2.2, 0.5]), (10, 1)))
+    posq = np.zeros((n, 4)); posq[:, :3] = pos; posq[:, 3] = rng.uniform(-1, 1, n)
+    q1, q2 = O.copy_state_f64(posq, table[:n])
+    assert np.array_equal(q2[:, :3], pos + table[:n, :3].astype(np.float64)) and np.array_equal(q2[:, 3], posq[:, 3])
+    f1, _, f2, _ = O.copy_state_f32(posq.astype(np.float32), None, table[:n])
+    assert np.array_equal(f2[:, :3], posq[:, :3].astype(np.float32) + table[:n, :3])
+
+
+def test_displacement_table_permutation():
+    n = 10
+    d = np.arange(30, dtype=np.float64).reshape(10, 3)
+    perm = np.array([3, 1, 4, 0, 9, 2, 6, 5, 8, 7], np.int32)
+    t = O.displ_table(n, 32, perm, d)
+    assert np.array_equal(t[:n, :3], d[perm].astype(np.float32))
+
+
+def test_merge_direction_symmetry():
+    rng = np.random.default_rng(0)
+    f0, f1, f2 = rng.normal(size=(3, 20, 3))
+    a = O.merge_ref(f0, f1, f2, 0.3, 1.0)
+    b = O.merge_ref(f0, f1, f2, 0.3, -1.0)
+    assert np.allclose(a, f0 + 0.3 * f2 + 0.7 * f1) and np.allclose(b, f0 + 0.3 * f1 + 0.7 * f2)
+
+
+def test_hybrid_force_fixed_point_matches_double_merge():
+    rng = np.random.default_rng(1)
+    n, P = 37, 64
+    F = 2.0 ** 32
+    f1 = rng.normal(0, 1000, (n, 3)); f2 = rng.normal(0, 1000, (n, 3)); f0 = rng.normal(0, 10, (n, 3))
+
+    def fx(f):
+        b = np.zeros(3 * P, np.int64); b.reshape(3, P)[:, :n] = np.rint(f.T * F).astype(np.int64); return b
+    out = O.hybrid_force_i64(n, P, fx(f0), fx(f1), fx(f2), 0.37)
+    got = out.reshape(3, P)[:, :n].T / F
+    assert np.allclose(got, f0 + 0.37 * f2 + 0.63 * f1, atol=1e-8)
