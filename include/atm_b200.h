@@ -163,8 +163,11 @@ int atm_set_box(atm_handle *h, int32_t replica, const double box[9]);
 /* (Re)builds the cluster pair lists of every replica for both coordinate states from posq ([R][P] float4, slot
  * order): spatial sort, clusters, the OUTER list (radius cutoff+skin_outer, with exclusion masks) and the pruned INNER
  * list (radius cutoff+skin).  Must be called before the first atm_step, whenever any atom has moved by more than
- * skin_outer/2 since the last rebuild, and after atm_set_displacements / reordering.  SYNCHRONISES `stream` once (it
- * reads back the capacity check). */
+ * skin_outer/2 since the last rebuild, and after atm_set_displacements / reordering.
+ * The first build after a (re)allocation SYNCHRONISES `stream` (it verifies and, if needed, grows the list
+ * capacities).  Later builds on a non-default stream are fully asynchronous (one cached CUDA graph); their capacity
+ * flags are copied to pinned host memory and inspected by the next API call that finds them complete -- a list that
+ * outgrew its capacity then surfaces as ATM_ERR_STATE from that call (and is cured by calling atm_nb_rebuild again). */
 int atm_nb_rebuild(atm_handle *h, const void *posq, void *stream);
 
 /* Re-prunes the INNER list from the outer one at the current coordinates (cheap, asynchronous, capturable).

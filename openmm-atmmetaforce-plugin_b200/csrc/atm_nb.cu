@@ -31,7 +31,10 @@ namespace atm {
 constexpr int CL = 8;            // sites per cluster
 constexpr int ITEM_STEPS = 16;     // 32-entry list steps per work item
 constexpr int NB_THREADS = 128;    // force kernel block size (4 warps, one work item each)
-constexpr int NB_MIN_BLOCKS = 4;   // 16 warps / SM at <= 128 registers
+#ifndef ATM_NB_MIN_BLOCKS
+#define ATM_NB_MIN_BLOCKS 5
+#endif
+constexpr int NB_MIN_BLOCKS = ATM_NB_MIN_BLOCKS;   // 5 -> 20 warps / SM at <= 102 registers (cluster atoms live in shared memory)
 constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int EACC_SLOTS = 6;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2)
@@ -97,7 +100,15 @@ struct NbState {
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     int n_items = 0, max_items = 0;
-    uint64_t generation = 0;  // bumped by every rebuild (grid sizes and list pointers may change)
+    uint64_t generation = 0;        // bumped by every rebuild
+    uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
+    bool verified = false, needs_realloc = false, flags_pending = false;
+    int *h_flags = nullptr;         // pinned
+    cudaEvent_t flags_event = nullptr;
+    cudaGraphExec_t rebuild_graph = nullptr, prune_graph = nullptr;
+    const void *rebuild_graph_posq = nullptr, *prune_graph_posq = nullptr;
+    uint64_t rebuild_graph_generation = 0, prune_graph_generation = 0;
+    int rebuild_graph_launches = 0, prune_graph_launches = 0;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
@@ -663,79 +674,8 @@ struct ItemCtx {
 };
 
 template <bool ENERGY, bool STATS>
-__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane) {
-    const float4 L = d.box[it.r], iL = d.invbox[it.r];
-    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
-    PairConst pc;
-    pc.cutoff2 = d.cutoff2;
-    pc.p_alpha = ERFC_P * d.alpha;
-    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
-    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
-
-    // software pipeline: list entries two steps ahead, partner coordinates one step ahead
-    unsigned int e_cur = __ldg(it.list + lane);
-    unsigned int e_nxt = it.nst > 1 ? __ldg(it.list + 32 + lane) : 0xffu;
-    float4 xj = __ldg(d.xs + it.rsite + (e_cur >> 8));
-    float2 pj = __ldg(d.par + it.rsite + (e_cur >> 8));
-
-    // the 8 cluster atoms, broadcast-loaded into every lane's registers, shifted next to the cluster centre
-    float4 xi[CL];
-    float2 pi[CL];
-    float fix[CL], fiy[CL], fiz[CL];
-#pragma unroll
-    for (int k = 0; k < CL; k++) {
-        xi[k] = __ldg(d.xs + it.rsite + (size_t)it.A * CL + k);
-        pi[k] = __ldg(d.par + it.rsite + (size_t)it.A * CL + k);
-        xi[k].x -= L.x * fast_rint((xi[k].x - cA.x) * iL.x);
-        xi[k].y -= L.y * fast_rint((xi[k].y - cA.y) * iL.y);
-        xi[k].z -= L.z * fast_rint((xi[k].z - cA.z) * iL.z);
-        fix[k] = fiy[k] = fiz[k] = 0.f;
-    }
-    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
-    double e_acc = 0.0;
-    int npairs = 0;
-
-    for (int st = 0; st < it.nst; st++) {
-        const unsigned int e = e_cur;
-        const float4 xjc = xj;
-        const float2 pjc = pj;
-        // prefetch
-        e_cur = e_nxt;
-        if (st + 1 < it.nst) {
-            xj = __ldg(d.xs + it.rsite + (e_cur >> 8));
-            pj = __ldg(d.par + it.rsite + (e_cur >> 8));
-        }
-        e_nxt = (st + 2 < it.nst) ? __ldg(it.list + (st + 2) * 32 + lane) : 0xffu;
-
-        const int j = e >> 8;
-        const unsigned int m = e & 0xffu;
-        const float xjx = xjc.x - L.x * fast_rint((xjc.x - cA.x) * iL.x);
-        const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
-        const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
-        float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < CL; k++) {
-            const float dx = xi[k].x - xjx, dy = xi[k].y - xjy, dz = xi[k].z - xjz;
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
-            float en = 0.f;
-            const float fsc = pair_interaction<ENERGY>(r2, xi[k].w * xjc.w, pi[k].x + pjc.x, pi[k].y * pjc.y, pc, en);
-            const float fs = in ? fsc : 0.f;
-            if (ENERGY) e_step += in ? en : 0.f;
-            if (STATS) npairs += in ? 1 : 0;
-            any |= in;
-            fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
-            fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
-        }
-        if (ENERGY) e_acc += (double)e_step;
-        if (any) {
-            red_add_fixed(buf + j, fjx);
-            red_add_fixed(buf + it.comp_stride + j, fjy);
-            red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
-        }
-    }
-
+__device__ __forceinline__ void nb2_item_epilogue(const NbDev &d, const ItemCtx &it, int lane, unsigned long long *buf,
+                                                  float (&fix)[CL], float (&fiy)[CL], float (&fiz)[CL], double e_acc, int npairs) {
     // transpose-reduce the 24 i-force accumulators: after three halving exchanges lane (l&7) owns atom l&7
     {
         const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
@@ -788,27 +728,129 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     }
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) nb2_kernel(NbDev d, int n_items, int energy_common) {
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
-    if (warp >= d.flags[4]) return;  // the pruned list's item count lives on the device (n_items is the outer bound)
-    const int2 item = __ldg(d.items + warp);
-    const int r = item.x >> 24, l = item.x & 0xffffff;
-    const int nlists = d.Cmax + d.CLmax;
-    const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
-    const int step0 = item.y * ITEM_STEPS;
-    const ListInfo li = decode_list(d, r, l);
-    ItemCtx it;
-    it.r = r;
-    it.A = li.cluster;
-    it.target = li.target;
-    it.nst = min(ITEM_STEPS, nsteps_total - step0);
-    it.list = d.jlist + li.offset + (size_t)step0 * 32;
-    it.rsite = (size_t)r * d.Smax;
-    it.comp_stride = (size_t)d.R * d.Smax;
-    if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane);
-    else nb2_item<true, STATS>(d, it, lane);
+// Partner data is staged through a per-lane shared-memory ring with cp.async (prefetch distance 3 steps); the cluster
+// atoms are broadcast from shared memory instead of living in 48 registers, which buys a fifth resident block per SM.
+constexpr int NB_WARPS = NB_THREADS / 32;
+constexpr int RING = 4;      // ring slots per lane
+constexpr int PF_DIST = 3;   // coordinate steps in flight
+constexpr int E_AHEAD = 3;   // list entries run this many steps ahead of the coordinate prefetch
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct __align__(16) Nb2Smem {
+    float4 xi[NB_WARPS][CL];
+    float2 pi[NB_WARPS][CL];
+    float4 xj[NB_WARPS][RING][32];
+    float2 pj[NB_WARPS][RING][32];
+    unsigned int e[NB_WARPS][RING][32];
+};
+
+template <bool ENERGY, bool STATS>
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm) {
+    const float4 L = d.box[it.r], iL = d.invbox[it.r];
+    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
+    PairConst pc;
+    pc.cutoff2 = d.cutoff2;
+    pc.p_alpha = ERFC_P * d.alpha;
+    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
+    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+
+    // list entries of the first PF_DIST + E_AHEAD steps (all loads in flight together); entries run E_AHEAD steps
+    // ahead of the coordinate prefetch because they stream from DRAM while the coordinates hit L2
+    unsigned int e_pre[PF_DIST + E_AHEAD];
+#pragma unroll
+    for (int q = 0; q < PF_DIST + E_AHEAD; q++) e_pre[q] = q < it.nst ? __ldg(it.list + q * 32 + lane) : 0xffu;
+    // cluster atoms -> shared memory (lanes 0..7), shifted next to the cluster centre
+    if (lane < CL) {
+        float4 x = __ldg(d.xs + it.rsite + (size_t)it.A * CL + lane);
+        x.x -= L.x * fast_rint((x.x - cA.x) * iL.x);
+        x.y -= L.y * fast_rint((x.y - cA.y) * iL.y);
+        x.z -= L.z * fast_rint((x.z - cA.z) * iL.z);
+        sm.xi[w][lane] = x;
+        sm.pi[w][lane] = __ldg(d.par + it.rsite + (size_t)it.A * CL + lane);
+    }
+#pragma unroll
+    for (int q = 0; q < PF_DIST; q++) {
+        if (q < it.nst) {
+            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (e_pre[q] >> 8));
+            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (e_pre[q] >> 8));
+            sm.e[w][q][lane] = e_pre[q];
+        }
+        cp_async_commit();
+    }
+    unsigned int e_ring[E_AHEAD];  // e_ring[q] = entry of step st + PF_DIST + q at the top of iteration st
+#pragma unroll
+    for (int q = 0; q < E_AHEAD; q++) e_ring[q] = e_pre[PF_DIST + q];
+    __syncwarp();
+
+    float fix[CL], fiy[CL], fiz[CL];
+#pragma unroll
+    for (int k = 0; k < CL; k++) fix[k] = fiy[k] = fiz[k] = 0.f;
+    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
+    double e_acc = 0.0;
+    int npairs = 0;
+
+    for (int st = 0; st < it.nst; st++) {
+        cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
+        const int slot = st & (RING - 1);
+        const float4 xjc = sm.xj[w][slot][lane];
+        const float2 pjc = sm.pj[w][slot][lane];
+        const unsigned int e = sm.e[w][slot][lane];
+        // keep PF_DIST steps in flight
+        {
+            const int sp = st + PF_DIST;
+            const unsigned int e_next = e_ring[0];
+            if (sp < it.nst) {
+                const int ps = sp & (RING - 1);
+                cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
+                cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
+                sm.e[w][ps][lane] = e_next;
+            }
+            cp_async_commit();
+#pragma unroll
+            for (int q = 0; q + 1 < E_AHEAD; q++) e_ring[q] = e_ring[q + 1];
+            e_ring[E_AHEAD - 1] = (sp + E_AHEAD < it.nst) ? __ldg(it.list + (sp + E_AHEAD) * 32 + lane) : 0xffu;
+        }
+        const int j = e >> 8;
+        const unsigned int m = e & 0xffu;
+        const float xjx = xjc.x - L.x * fast_rint((xjc.x - cA.x) * iL.x);
+        const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
+        const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < CL; k++) {
+            const float4 xi = sm.xi[w][k];
+            const float2 pi = sm.pi[w][k];
+            const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
+            float en = 0.f;
+            const float fsc = pair_interaction<ENERGY>(r2, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
+            const float fs = in ? fsc : 0.f;
+            if (ENERGY) e_step += in ? en : 0.f;
+            if (STATS) npairs += in ? 1 : 0;
+            any |= in;
+            fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
+            fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
+        }
+        if (ENERGY) e_acc += (double)e_step;
+        if (any) {
+            red_add_fixed(buf + j, fjx);
+            red_add_fixed(buf + it.comp_stride + j, fjy);
+            red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
+        }
+    }
+    cp_async_wait<0>();
+    nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, fix, fiy, fiz, e_acc, npairs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -822,10 +864,8 @@ __device__ __forceinline__ void add_pair_force(const NbDev &d, int r, int target
     red_add_fixed(buf + sj, -fx); red_add_fixed(buf + cs + sj, -fy); red_add_fixed(buf + 2 * cs + sj, -fz);
 }
 
-__global__ void nb_special_pairs_kernel(NbDev d, const int2 *__restrict__ excl, int n_excl,
-                                        const int2 *__restrict__ exc, const float4 *__restrict__ exc_par, int n_exc) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+__device__ __forceinline__ void special_pairs_body(const NbDev &d, int t, int r, const int2 *__restrict__ excl, int n_excl,
+                                                   const int2 *__restrict__ exc, const float4 *__restrict__ exc_par, int n_exc) {
     double e_tgt[3] = {0.0, 0.0, 0.0};
     if (t < n_excl + n_exc) {
         const bool is_exc = t >= n_excl;
@@ -888,10 +928,8 @@ constexpr int MERGE2_THREADS = 256;
 
 // Scalar stage, one thread per replica: u = U(S2) - U(S1), soft-core, softplus, sp -- all in double on the device
 // (the reference does this on the host after two blocking energy downloads, CommonATMMetaForceKernels.cpp:164-199).
-__global__ void nb_scalar_kernel(NbDev d, const double *__restrict__ energy_ext, int include_energy) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= d.R) return;
-    unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;
+__device__ void scalar_stage_replica(const NbDev &d, int r, const double *__restrict__ energy_ext, int include_energy) {
+    volatile unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;  // written by atomics of other blocks: read through L2
     const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
                  u2 = (double)(long long)ea[2] / ENERGY_SCALE;
     double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
@@ -909,6 +947,58 @@ __global__ void nb_scalar_kernel(NbDev d, const double *__restrict__ energy_ext,
     // this thread is the only reader: hand the accumulators back zeroed for the next step (stream order protects them)
 #pragma unroll
     for (int k = 0; k < EACC_SLOTS; k++) ea[k] = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The per-step compute launch: work items of the pair lists (one warp each), then blocks of excluded / exception
+// pairs.
+// ------------------------------------------------------------------------------------------------
+struct SpecialArgs {
+    const int2 *excl;
+    const int2 *exc;
+    const float4 *exc_par;
+    int n_excl, n_exc;
+    int blocks_per_replica;  // ceil((n_excl + n_exc) / NB_THREADS)
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS)
+nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < n_item_blocks) {
+        const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
+        if (warp < d.flags[4]) {  // the pruned list's item count lives on the device (the grid is an upper bound)
+            const int2 item = __ldg(d.items + warp);
+            const int r = item.x >> 24, l = item.x & 0xffffff;
+            const int nlists = d.Cmax + d.CLmax;
+            const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
+            const int step0 = item.y * ITEM_STEPS;
+            const ListInfo li = decode_list(d, r, l);
+            ItemCtx it;
+            it.r = r;
+            it.A = li.cluster;
+            it.target = li.target;
+            it.nst = min(ITEM_STEPS, nsteps_total - step0);
+            it.list = d.jlist + li.offset + (size_t)step0 * 32;
+            it.rsite = (size_t)r * d.Smax;
+            it.comp_stride = (size_t)d.R * d.Smax;
+            __shared__ Nb2Smem sm;
+            const int w = threadIdx.x >> 5;
+            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm);
+            else nb2_item<true, STATS>(d, it, lane, w, sm);
+        }
+    } else {
+        const int sb = blockIdx.x - n_item_blocks;
+        const int r = sb / sp.blocks_per_replica, chunk = sb - r * sp.blocks_per_replica;
+        special_pairs_body(d, chunk * NB_THREADS + threadIdx.x, r, sp.excl, sp.n_excl, sp.exc, sp.exc_par, sp.n_exc);
+    }
+}
+
+// Scalar stage, one thread per replica (a separate 1-block launch: a "last block done" fusion into nb2 costs one
+// same-address atomic per warp and measurably slows the force kernel).
+__global__ void nb_scalar_kernel(NbDev d, const double *__restrict__ energy_ext, int include_energy) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < d.R) scalar_stage_replica(d, r, energy_ext, include_energy);
 }
 
 // Merge, one thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
@@ -977,6 +1067,10 @@ static int dev_upload(NbState *nb, T **ptr, const std::vector<T> &v, cudaStream_
 void nb_destroy(atm_handle *h) {
     if (!h->nb) return;
     if (h->nb->graph_exec) cudaGraphExecDestroy(h->nb->graph_exec);
+    if (h->nb->rebuild_graph) cudaGraphExecDestroy(h->nb->rebuild_graph);
+    if (h->nb->prune_graph) cudaGraphExecDestroy(h->nb->prune_graph);
+    if (h->nb->h_flags) cudaFreeHost(h->nb->h_flags);
+    if (h->nb->flags_event) cudaEventDestroy(h->nb->flags_event);
     for (auto &ev : h->nb->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (void *p : h->nb->owned) cudaFree(p);
     delete h->nb;
@@ -1035,6 +1129,11 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     NbState *nb = h->nb;
     ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
     nb->generation++;
+    nb->alloc_generation++;
+    nb->verified = false;
+    nb->flags_pending = false;
+    if (!nb->h_flags) ATM_CUDA_CHECK(cudaMallocHost(&nb->h_flags, sizeof(int) * 8));
+    if (!nb->flags_event) ATM_CUDA_CHECK(cudaEventCreateWithFlags(&nb->flags_event, cudaEventDisableTiming));
     free_owned(nb);
     int rc = derive_groups(h);
     if (rc) return rc;
@@ -1144,7 +1243,8 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
         nb->scan_tmp = stmp;
         nb->n_items = 0;
     }
-    if ((rc = dev_alloc(nb, &d.flags, 8))) return rc;
+    if ((rc = dev_alloc(nb, &d.flags, 16))) return rc;
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 16, stream));
     if ((rc = dev_alloc(nb, &d.buf, 9 * RS))) return rc;
     if ((rc = dev_alloc(nb, &d.eacc, (size_t)R * EACC_SLOTS))) return rc;
     if ((rc = dev_alloc(nb, &d.energies, (size_t)R * ATM_NUM_ENERGY_SLOTS))) return rc;
@@ -1206,17 +1306,51 @@ using namespace atm;
 
 extern "C" {
 
-int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    ATM_REQUIRE(h && posq, ATM_ERR_INVALID, "atm_nb_prune: null argument");
-    ATM_REQUIRE(h->nb && h->nb->ready && h->nb->list_valid, ATM_ERR_STATE, "atm_nb_prune: no outer list (call atm_nb_rebuild)");
-    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+static int check_pending_rebuild(atm_handle *h, bool wait);
+
+static int launch_prune_all(atm_handle *h, const void *posq, cudaStream_t stream) {
     NbDev &d = h->nb->d;
-    int rc;
-    if ((rc = upload_box_if_dirty(h, stream))) return rc;
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)posq);
     h->launches++;
     return launch_prune(h, stream, /*refresh_boxes=*/true);
+}
+
+int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && posq, ATM_ERR_INVALID, "atm_nb_prune: null argument");
+    ATM_REQUIRE(h->nb && h->nb->ready, ATM_ERR_STATE, "atm_nb_prune: Tier 2 not set up");
+    int rc;
+    if ((rc = check_pending_rebuild(h, false))) return rc;
+    ATM_REQUIRE(h->nb->list_valid, ATM_ERR_STATE, "atm_nb_prune: no outer list (call atm_nb_rebuild)");
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    NbState *nb = h->nb;
+    if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    if (stream == nullptr) return launch_prune_all(h, posq, stream);
+    if (!nb->prune_graph || nb->prune_graph_posq != posq || nb->prune_graph_generation != nb->alloc_generation) {
+        if (nb->prune_graph) { cudaGraphExecDestroy(nb->prune_graph); nb->prune_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = h->launches;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = launch_prune_all(h, posq, stream);
+            cudaError_t err = cudaStreamEndCapture(stream, &graph);
+            nb->prune_graph_launches = (int)(h->launches - before);
+            h->launches = before;
+            if (rc == ATM_OK && err == cudaSuccess && graph && cudaGraphInstantiate(&nb->prune_graph, graph, 0) == cudaSuccess) {
+                nb->prune_graph_posq = posq;
+                nb->prune_graph_generation = nb->alloc_generation;
+            } else {
+                nb->prune_graph = nullptr;
+                cudaGetLastError();
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+    }
+    if (nb->prune_graph) {
+        ATM_CUDA_CHECK(cudaGraphLaunch(nb->prune_graph, stream));
+        h->launches += nb->prune_graph_launches;
+        return ATM_OK;
+    }
+    return launch_prune_all(h, posq, stream);
 }
 
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
@@ -1309,6 +1443,77 @@ int atm_set_box(atm_handle *h, int32_t replica, const double box[9]) {
     return ATM_OK;
 }
 
+// every launch of a rebuild, asynchronous
+static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream) {
+    NbState *nb = h->nb;
+    NbDev &d = nb->d;
+    int rc;
+    const int RU = d.R * d.U;
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
+    nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
+    nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
+    size_t tmp_bytes = nb->sort_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
+    nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
+    if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq);
+    nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
+    const int nlists = d.Cmax + d.CLmax;
+    nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
+    h->launches += 6 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox, build
+    if ((rc = launch_prune(h, stream, /*refresh_boxes=*/false))) return rc;
+    ATM_CUDA_CHECK(cudaGetLastError());
+    return ATM_OK;
+}
+
+// Looks at the capacity / geometry flags of a finished rebuild.  Returns ATM_OK, or an error after marking the lists
+// invalid.  `grow` tells the caller that the capacities were raised and the structure must be reallocated.
+static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
+    NbState *nb = h->nb;
+    NbDev &d = nb->d;
+    *grow = false;
+    if (flags[0] & 2) {
+        nb->list_valid = false;
+        set_error("atm_nb_rebuild: a cluster's extent + list radius exceeds half the box; box too small for this build");
+        return ATM_ERR_UNSUPPORTED;
+    }
+    if (flags[0] & 1) {
+        const int need = flags[1];
+        d.capC = std::max(d.capC, 32 * ((int)(need * 1.25) / 32 + 1));
+        d.capX = std::max(d.capX, 32 * ((int)(need * 1.25) / 32 + 1));
+        *grow = true;
+    }
+    unsigned long long inner_entries = 0;
+    memcpy(&inner_entries, &flags[6], 8);
+    nb->stats[2] = (int64_t)(inner_entries / d.R);
+    return ATM_OK;
+}
+
+// Deferred verification of an asynchronous rebuild (never blocks unless `wait`).
+static int check_pending_rebuild(atm_handle *h, bool wait) {
+    NbState *nb = h->nb;
+    if (!nb || !nb->flags_pending) return ATM_OK;
+    cudaError_t q = wait ? cudaEventSynchronize(nb->flags_event) : cudaEventQuery(nb->flags_event);
+    if (q == cudaErrorNotReady) return ATM_OK;
+    ATM_REQUIRE(q == cudaSuccess, ATM_ERR_CUDA, "pair-list verification failed: %s", cudaGetErrorString(q));
+    nb->flags_pending = false;
+    bool grow = false;
+    int rc = inspect_rebuild_flags(h, nb->h_flags, &grow);
+    if (rc) return rc;
+    if (grow) {
+        nb->list_valid = false;
+        nb->needs_realloc = true;
+        set_error("a pair list outgrew its capacity during the last asynchronous atm_nb_rebuild; steps since then dropped "
+                  "interactions -- call atm_nb_rebuild again (capacities were raised)");
+        return ATM_ERR_STATE;
+    }
+    return ATM_OK;
+}
+
 int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && posq_, ATM_ERR_INVALID, "atm_nb_rebuild: null argument");
@@ -1317,56 +1522,72 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
     NbState *nb = h->nb;
     const float4 *posq = (const float4 *)posq_;
     int rc;
+    if ((rc = check_pending_rebuild(h, false)) && rc != ATM_ERR_STATE) return rc;  // a capacity error is cured right here
+    if (nb->needs_realloc) {
+        if ((rc = nb_allocate(h, stream))) return rc;
+        nb->needs_realloc = false;
+        nb->verified = false;
+    }
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
+    for (int r = 0; r < h->R; r++)
+        ATM_REQUIRE(2.0 * nb->d.rlist_outer < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
+                    "atm_nb_rebuild: box edge smaller than 2*(cutoff+skin)");
+    if (nb->verified && stream != nullptr) {
+        // steady state: fully asynchronous (a cached CUDA graph when the coordinate buffer is unchanged); the capacity
+        // flags travel to pinned host memory and are inspected by the next API call that finds them ready
+        if (!nb->rebuild_graph || nb->rebuild_graph_posq != posq_ || nb->rebuild_graph_generation != nb->alloc_generation) {
+            if (nb->rebuild_graph) { cudaGraphExecDestroy(nb->rebuild_graph); nb->rebuild_graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const uint64_t before = h->launches;
+            if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = launch_rebuild(h, posq, stream);
+                cudaError_t err = cudaStreamEndCapture(stream, &graph);
+                nb->rebuild_graph_launches = (int)(h->launches - before);
+                h->launches = before;
+                if (rc == ATM_OK && err == cudaSuccess && graph && cudaGraphInstantiate(&nb->rebuild_graph, graph, 0) == cudaSuccess) {
+                    nb->rebuild_graph_posq = posq_;
+                    nb->rebuild_graph_generation = nb->alloc_generation;
+                } else {
+                    nb->rebuild_graph = nullptr;
+                    cudaGetLastError();
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+        }
+        if (nb->rebuild_graph) {
+            ATM_CUDA_CHECK(cudaGraphLaunch(nb->rebuild_graph, stream));
+            h->launches += nb->rebuild_graph_launches;
+        } else if ((rc = launch_rebuild(h, posq, stream))) {
+            return rc;
+        }
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaEventRecord(nb->flags_event, stream));
+        nb->flags_pending = true;
+        nb->list_valid = true;
+        nb->generation++;
+        return ATM_OK;
+    }
+    // first build after (re)allocation: synchronous, verified, grows the capacities until everything fits
     for (int attempt = 0; attempt < 4; attempt++) {
         NbDev &d = nb->d;
-        for (int r = 0; r < h->R; r++)
-            ATM_REQUIRE(2.0 * d.rlist_outer < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
-                        "atm_nb_rebuild: box edge smaller than 2*(cutoff+skin)");
-        const int RU = d.R * d.U;
-        ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
-        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-        ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
-        nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
-        nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
-        size_t tmp_bytes = nb->sort_tmp_bytes;
-        cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
-        nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
-        if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
-        nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq);
-        nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
-        const int nlists = d.Cmax + d.CLmax;
-        nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
-        h->launches += 6 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox, build
-        if ((rc = launch_prune(h, stream, /*refresh_boxes=*/false))) return rc;
-        ATM_CUDA_CHECK(cudaGetLastError());
+        if ((rc = launch_rebuild(h, posq, stream))) return rc;
         int flags[8];
         ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream));
         ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
-        ATM_REQUIRE(!(flags[0] & 2), ATM_ERR_UNSUPPORTED,
-                    "atm_nb_rebuild: a cluster's extent + list radius exceeds half the box; box too small for this build");
-        if (flags[0] & 1) {
-            // a list overflowed its capacity: grow and retry
-            const int need = flags[1];
-            d.capC = std::max(d.capC, 32 * ((int)(need * 1.25) / 32 + 1));
-            d.capX = std::max(d.capX, 32 * ((int)(need * 1.25) / 32 + 1));
+        bool grow = false;
+        if ((rc = inspect_rebuild_flags(h, flags, &grow))) return rc;
+        if (grow) {
             if ((rc = nb_allocate(h, stream))) return rc;
             if ((rc = upload_box_if_dirty(h, stream))) return rc;
             continue;
         }
         int ncl0 = 0;
         ATM_CUDA_CHECK(cudaMemcpy(&ncl0, d.nclusters, sizeof(int), cudaMemcpyDeviceToHost));
-        unsigned long long entries = 0;
-        memcpy(&entries, &flags[2], 8);
-        nb->stats[0] = d.U; nb->stats[1] = ncl0; nb->stats[2] = (int64_t)(entries / d.R); nb->stats[3] = d.capC; nb->stats[4] = d.capX;
+        nb->stats[0] = d.U; nb->stats[1] = ncl0; nb->stats[3] = d.capC; nb->stats[4] = d.capX;
         nb->stats[5] = d.M; nb->stats[6] = d.G; nb->stats[7] = d.ncol;
-        nb->n_items = flags[5];  // upper bound from the outer list; the inner count stays on the device
-        unsigned long long inner_entries = 0;
-        memcpy(&inner_entries, &flags[6], 8);
-        nb->stats[2] = (int64_t)(inner_entries / d.R);
+        nb->n_items = nb->max_items;  // launch bound; the live item count stays on the device (flags[4])
         nb->list_valid = true;
+        nb->verified = true;
         nb->generation++;
         return ATM_OK;
     }
@@ -1385,8 +1606,13 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
     }
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
     const int warps_per_block = NB_THREADS / 32;
-    const int nblocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
-    if (nblocks > 0) {
+    const int item_blocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
+    SpecialArgs spa;
+    spa.excl = nb->d_excl_pairs; spa.exc = nb->d_exc_pairs; spa.exc_par = nb->d_exc_par;
+    spa.n_excl = nb->n_excl; spa.n_exc = nb->n_exc;
+    spa.blocks_per_replica = (nb->n_excl + nb->n_exc + NB_THREADS - 1) / NB_THREADS;
+    const int nblocks = item_blocks + spa.blocks_per_replica * d.R;
+    {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (profile) {
             if (nb->prof_used == nb->prof_events.size()) {
@@ -1400,21 +1626,18 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
             nb->prof_used++;
             ATM_CUDA_CHECK(cudaEventRecord(e0, stream));
         }
-        if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, nb->n_items, io->include_energy);
-        else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, nb->n_items, io->include_energy);
+        if (nblocks > 0) {
+            if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, item_blocks, io->include_energy, spa);
+            else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, item_blocks, io->include_energy, spa);
+            h->launches++;
+        }
         if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
-        h->launches++;
-    }
-    const int nsp = nb->n_excl + nb->n_exc;
-    if (nsp > 0) {
-        nb_special_pairs_kernel<<<dim3((nsp + 127) / 128, d.R), 128, 0, stream>>>(d, nb->d_excl_pairs, nb->n_excl, nb->d_exc_pairs,
-                                                                                 nb->d_exc_par, nb->n_exc);
-        h->launches++;
     }
     nb_scalar_kernel<<<(d.R + 31) / 32, 32, 0, stream>>>(d, io->energy_ext, io->include_energy);
+    h->launches++;
     nb_merge_kernel<<<dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
         d, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext);
-    h->launches += 3;
+    h->launches += 2;  // pack, merge
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
 }
@@ -1435,6 +1658,7 @@ static int validate_step(atm_handle *h, const atm_step_io *io, const char *who) 
 int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc;
+    if (h && h->nb && (rc = check_pending_rebuild(h, false))) return rc;
     if ((rc = validate_step(h, io, "atm_step"))) return rc;
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
     if ((rc = upload_params_if_dirty(h, stream))) return rc;
@@ -1448,13 +1672,14 @@ int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
 int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc;
+    if (h && h->nb && (rc = check_pending_rebuild(h, false))) return rc;
     if ((rc = validate_step(h, io, "atm_step_graph"))) return rc;
     ATM_REQUIRE(stream != nullptr, ATM_ERR_INVALID, "atm_step_graph: needs a non-default stream (it is captured)");
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
     NbState *nb = h->nb;
     if ((rc = upload_params_if_dirty(h, stream))) return rc;
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
-    const bool same = nb->graph_exec && memcmp(&nb->graph_io, io, sizeof(*io)) == 0 && nb->graph_generation == nb->generation;
+    const bool same = nb->graph_exec && memcmp(&nb->graph_io, io, sizeof(*io)) == 0 && nb->graph_generation == nb->alloc_generation;
     if (!same) {
         if (nb->graph_exec) { cudaGraphExecDestroy(nb->graph_exec); nb->graph_exec = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -1469,8 +1694,8 @@ int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
         cudaGraphDestroy(graph);
         ATM_REQUIRE(err == cudaSuccess, ATM_ERR_CUDA, "atm_step_graph: instantiate failed: %s", cudaGetErrorString(err));
         nb->graph_io = *io;
-        nb->graph_generation = nb->generation;
-        nb->graph_nodes = 3 + (io->posq1 ? 1 : 0) + (nb->n_items > 0 ? 1 : 0) + (nb->n_excl + nb->n_exc > 0 ? 1 : 0);
+        nb->graph_generation = nb->alloc_generation;
+        nb->graph_nodes = 4 + (io->posq1 ? 1 : 0);  // pack, nb2 (+special pairs), scalar stage, merge
     }
     ATM_CUDA_CHECK(cudaGraphLaunch(nb->graph_exec, stream));
     h->launches += nb->graph_nodes;
@@ -1520,6 +1745,10 @@ int atm_get_energies(atm_handle *h, double *out, void *stream_) {
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
     ATM_CUDA_CHECK(cudaMemcpyAsync(out, h->nb->d.energies, sizeof(double) * (size_t)h->R * ATM_NUM_ENERGY_SLOTS, cudaMemcpyDeviceToHost, stream));
     ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    {
+        int rc = check_pending_rebuild(h, false);
+        if (rc) return rc;
+    }
     for (int r = 0; r < h->R; r++) h->pert_energy[r] = out[(size_t)r * ATM_NUM_ENERGY_SLOTS + ATM_E_USC];
     return ATM_OK;
 }
