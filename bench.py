@@ -267,6 +267,11 @@ def run_b200(args):
     if R > 0:
         for _ in range(W):
             one_step()
+    # one untimed exchange cycle: the first NCCL collective builds the communicator (tens of ms), which is set-up
+    # cost, not steady-state step time
+    with torch.cuda.stream(stream):
+        exchange(0)
+    if R > 0:
         with torch.cuda.stream(stream):
             be.step(posq, force, posq_corr=corr, include_energy=True, collect_stats=True, stream=stream)
         stats_en = be.get_energies(stream=stream)

@@ -17,7 +17,6 @@
 // shuffles and no shared-memory traffic; f_j goes out with three 64-bit fixed-point RED.ADDs per lane per
 // 8 pairs, f_i is reduced by a 27-shuffle transpose-reduction once per work item.
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -37,6 +36,8 @@ constexpr int NB_THREADS = 128;    // force kernel block size (4 warps, one work
 constexpr int NB_MIN_BLOCKS = ATM_NB_MIN_BLOCKS;   // 5 -> 20 warps / SM at <= 102 registers (cluster atoms live in shared memory)
 constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
+constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
+constexpr int NUM_FLAGS = 40;
 constexpr int EACC_SLOTS = 6;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2)
 
 struct NbDev {  // everything the kernels need, passed by value
@@ -44,6 +45,7 @@ struct NbDev {  // everything the kernels need, passed by value
     int nx, ny, ncol, nbins;
     int Smax, Cmax, CLmax, CXmax, CenvMax;
     int capC, capX;
+    int max_items;  // capacity of one item bucket
     float cutoff2, rlist, rlist_outer, alpha, two_alpha_over_sqrtpi;
     // static, by atom
     const float *qp_atom;
@@ -64,7 +66,7 @@ struct NbDev {  // everything the kernels need, passed by value
     int *cmeta;
     unsigned int *jlist, *jlist_outer;
     int *list_nsteps, *outer_nsteps;
-    int2 *items;
+    int4 *items;  // work items: {list offset in entries, cluster | target << 28, replica | steps << 8, first entry step}
     int *flags;
     // accumulators
     unsigned long long *buf;
@@ -96,9 +98,6 @@ struct NbState {
     int n_excl = 0, n_exc = 0;
     int sort_bits = 64;
     size_t jlist_entries = 0;
-    int *item_counts = nullptr, *item_offsets = nullptr;
-    void *scan_tmp = nullptr;
-    size_t scan_tmp_bytes = 0;
     int n_items = 0, max_items = 0;
     uint64_t generation = 0;        // bumped by every rebuild
     uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
@@ -135,7 +134,10 @@ __device__ __forceinline__ int pair_target(int ca, int cb, int G) {
     return TGT_S1;
 }
 
-__device__ __forceinline__ float wrap_delta(float d, float L, float invL) { return d - L * rintf(d * invL); }
+__device__ __forceinline__ float wrap_delta(float d, float L, float invL) {
+    // round-to-nearest through the 1.5*2^23 trick (|d/L| < 2^22): avoids the quarter-rate FRND instruction
+    return d - L * __fadd_rn(__fadd_rn(d * invL, 12582912.0f), -12582912.0f);
+}
 
 __device__ __forceinline__ void red_add_fixed(unsigned long long *addr, float f) {
     long long v = __float2ll_rn(f * 4294967296.0f);
@@ -559,13 +561,20 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
     const unsigned int *in = d.jlist_outer + li.offset;
     unsigned int *out = d.jlist + li.offset;
     int count = 0;
-    unsigned int e = __ldg(in + lane);
+    // software pipeline: entries three steps ahead (they stream from DRAM), coordinates one step ahead
+    unsigned int e0 = __ldg(in + lane);
+    unsigned int e1 = nst_outer > 1 ? __ldg(in + 32 + lane) : 0xffu;
+    unsigned int e2 = nst_outer > 2 ? __ldg(in + 64 + lane) : 0xffu;
+    float4 pnext = __ldg(d.xs + rsite + (e0 >> 8));
     for (int st = 0; st < nst_outer; st++) {
-        const unsigned int ec = e;
-        if (st + 1 < nst_outer) e = __ldg(in + (st + 1) * 32 + lane);
+        const unsigned int ec = e0;
+        const float4 p = pnext;
+        e0 = e1;
+        e1 = e2;
+        e2 = (st + 3 < nst_outer) ? __ldg(in + (st + 3) * 32 + lane) : 0xffu;
+        if (st + 1 < nst_outer) pnext = __ldg(d.xs + rsite + (e0 >> 8));
         bool keep = false;
         if ((ec & 0xffu) != 0xffu) {
-            const float4 p = __ldg(d.xs + rsite + (ec >> 8));
             const float px = cA.x + wrap_delta(p.x - cA.x, L.x, iL.x), py = cA.y + wrap_delta(p.y - cA.y, L.y, iL.y),
                         pz = cA.z + wrap_delta(p.z - cA.z, L.z, iL.z);
             float d2min = 1e30f;
@@ -582,32 +591,27 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
     }
     const int nsteps = (count + 31) >> 5;
     for (int p = count + lane; p < nsteps * 32; p += 32) out[p] = 0xffu;
+    // work items of this list: (<= ITEM_STEPS)-step chunks, slots reserved with one atomic (their order only affects
+    // scheduling: every accumulation downstream is fixed point, hence order independent)
+    // Buckets by chunk length: the force kernel hands out the longest chunks first (longest-processing-time order keeps
+    // the tail of the launch short when only a few replicas share the GPU).
+    const int nfull = nsteps / ITEM_STEPS, rem = nsteps - nfull * ITEM_STEPS;
+    int base_full = 0, base_rem = 0;
     if (lane == 0) {
         *nsteps_out = nsteps;
         atomicAdd((unsigned long long *)&d.flags[6], (unsigned long long)count);
+        if (nfull > 0) base_full = atomicAdd(&d.flags[ITEM_BUCKET0 + ITEM_STEPS], nfull);
+        if (rem > 0) base_rem = atomicAdd(&d.flags[ITEM_BUCKET0 + rem], 1);
+        if (nfull + (rem > 0) > 0) atomicAdd(&d.flags[4], nfull + (rem > 0 ? 1 : 0));
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Rebuild step 6: compact work items (replica, list, chunk of ITEM_STEPS steps), longest lists first.
-// ------------------------------------------------------------------------------------------------
-__global__ void nl_item_count_kernel(NbDev d, int *__restrict__ counts) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nlists = d.Cmax + d.CLmax;
-    if (t >= d.R * nlists) return;
-    // reversed list order inside a replica: ligand/ghost lists (the long ones) get the lowest item indices
-    const int r = t / nlists, l = nlists - 1 - (t - r * nlists);
-    counts[t] = (d.list_nsteps[(size_t)r * nlists + l] + ITEM_STEPS - 1) / ITEM_STEPS;
-}
-
-__global__ void nl_item_fill_kernel(NbDev d, const int *__restrict__ counts, const int *__restrict__ offsets) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nlists = d.Cmax + d.CLmax;
-    if (t >= d.R * nlists) return;
-    const int r = t / nlists, l = nlists - 1 - (t - r * nlists);
-    const int n = counts[t], o = offsets[t];
-    for (int c = 0; c < n; c++) d.items[o + c] = make_int2(l | (r << 24), c);
-    if (t == d.R * nlists - 1) d.flags[4] = o + n;
+    base_full = __shfl_sync(0xffffffffu, base_full, 0);
+    base_rem = __shfl_sync(0xffffffffu, base_rem, 0);
+    for (int c = lane; c < nfull; c += 32)
+        d.items[(size_t)ITEM_STEPS * d.max_items + base_full + c] =
+            make_int4((int)(li.offset + (size_t)c * ITEM_STEPS * 32), A | (li.target << 28), r | (ITEM_STEPS << 8), c * ITEM_STEPS);
+    if (lane == 0 && rem > 0)
+        d.items[(size_t)rem * d.max_items + base_rem] =
+            make_int4((int)(li.offset + (size_t)nfull * ITEM_STEPS * 32), A | (li.target << 28), r | (rem << 8), nfull * ITEM_STEPS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -968,19 +972,20 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     if ((int)blockIdx.x < n_item_blocks) {
         const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
         if (warp < d.flags[4]) {  // the pruned list's item count lives on the device (the grid is an upper bound)
-            const int2 item = __ldg(d.items + warp);
-            const int r = item.x >> 24, l = item.x & 0xffffff;
-            const int nlists = d.Cmax + d.CLmax;
-            const int nsteps_total = d.list_nsteps[(size_t)r * nlists + l];
-            const int step0 = item.y * ITEM_STEPS;
-            const ListInfo li = decode_list(d, r, l);
+            int wi = warp, b = ITEM_STEPS;
+            for (; b > 1; --b) {  // longest chunks first
+                const int c = d.flags[ITEM_BUCKET0 + b];
+                if (wi < c) break;
+                wi -= c;
+            }
+            const int4 item = __ldg(d.items + (size_t)b * d.max_items + wi);
             ItemCtx it;
-            it.r = r;
-            it.A = li.cluster;
-            it.target = li.target;
-            it.nst = min(ITEM_STEPS, nsteps_total - step0);
-            it.list = d.jlist + li.offset + (size_t)step0 * 32;
-            it.rsite = (size_t)r * d.Smax;
+            it.r = item.z & 0xff;
+            it.A = item.y & 0x0fffffff;
+            it.target = (item.y >> 28) & 3;
+            it.nst = item.z >> 8;
+            it.list = d.jlist + (unsigned int)item.x;
+            it.rsite = (size_t)it.r * d.Smax;
             it.comp_stride = (size_t)d.R * d.Smax;
             __shared__ Nb2Smem sm;
             const int w = threadIdx.x >> 5;
@@ -1232,19 +1237,12 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     {
         const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
         nb->max_items = R * (d.CenvMax * chunksC + d.CXmax * chunksX + d.CLmax * chunksC);
-        const int nl = R * (d.Cmax + d.CLmax);
-        if ((rc = dev_alloc(nb, &d.items, (size_t)nb->max_items))) return rc;
-        if ((rc = dev_alloc(nb, &nb->item_counts, (size_t)nl))) return rc;
-        if ((rc = dev_alloc(nb, &nb->item_offsets, (size_t)nl))) return rc;
-        nb->scan_tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, nb->scan_tmp_bytes, nb->item_counts, nb->item_offsets, nl, stream);
-        char *stmp;
-        if ((rc = dev_alloc(nb, &stmp, nb->scan_tmp_bytes))) return rc;
-        nb->scan_tmp = stmp;
+        d.max_items = nb->max_items;
+        if ((rc = dev_alloc(nb, &d.items, (size_t)nb->max_items * (ITEM_STEPS + 1)))) return rc;
         nb->n_items = 0;
     }
-    if ((rc = dev_alloc(nb, &d.flags, 16))) return rc;
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 16, stream));
+    if ((rc = dev_alloc(nb, &d.flags, NUM_FLAGS))) return rc;
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * NUM_FLAGS, stream));
     if ((rc = dev_alloc(nb, &d.buf, 9 * RS))) return rc;
     if ((rc = dev_alloc(nb, &d.eacc, (size_t)R * EACC_SLOTS))) return rc;
     if ((rc = dev_alloc(nb, &d.energies, (size_t)R * ATM_NUM_ENERGY_SLOTS))) return rc;
@@ -1288,14 +1286,11 @@ static int launch_prune(atm_handle *h, cudaStream_t stream, bool refresh_boxes) 
     NbDev &d = nb->d;
     const int nlists = d.Cmax + d.CLmax;
     if (refresh_boxes) nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * 2, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 4, 0, sizeof(int), stream));      // live item count
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + ITEM_BUCKET0, 0, sizeof(int) * (ITEM_STEPS + 1), stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * 2, stream));  // pruned-entry counter
     nl_prune_kernel<<<dim3((nlists + 3) / 4, d.R), 128, 0, stream>>>(d);
-    const int nl = d.R * nlists;
-    nl_item_count_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(d, nb->item_counts);
-    size_t sbytes = nb->scan_tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(nb->scan_tmp, sbytes, nb->item_counts, nb->item_offsets, nl, stream);
-    nl_item_fill_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(d, nb->item_counts, nb->item_offsets);
-    h->launches += (refresh_boxes ? 1 : 0) + 3;  // own kernels only (the CUB scan is library code)
+    h->launches += (refresh_boxes ? 1 : 0) + 1;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
 }
