@@ -361,10 +361,17 @@ def run_b200(args):
         pairs_two_state = 2.0 * pc + p1 + p2          # what two separate inner-context evaluations would compute
         pairs_computed = pc + p1 + p2
         roofline = None
+        traffic = None
+        try:  # DRAM bytes of one nb2 launch from the committed ncu --set full capture (same workload / replica count only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_nb2_traffic.json")))
+            if tj["workload"] == args.workload and tj["replicas"] == R and world == 1:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         if nb2_ms:
             ach = pairs_two_state * FLOP_PER_PAIR / (nb2_ms * 1e-3) / 1e12
             roofline = {"kernel": "nb2_kernel (two-state direct space)", "bound": "fp32", "achieved": ach,
-                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": traffic,
                         "peak_source": "derived: SMs*128 lanes*2 flop*max SM clock (no measured fp32 peak in MEASURED_PEAKS.json)",
                         "flop_per_pair": FLOP_PER_PAIR, "pairs_two_state_equivalent": pairs_two_state,
                         "pairs_computed": pairs_computed, "nb2_ms": nb2_ms,

@@ -28,7 +28,10 @@
 namespace atm {
 
 constexpr int CL = 8;            // sites per cluster
-constexpr int ITEM_STEPS = 16;     // 32-entry list steps per work item
+#ifndef ATM_ITEM_STEPS
+#define ATM_ITEM_STEPS 16
+#endif
+constexpr int ITEM_STEPS = ATM_ITEM_STEPS;     // 32-entry list steps per work item
 constexpr int NB_THREADS = 128;    // force kernel block size (4 warps, one work item each)
 #ifndef ATM_NB_MIN_BLOCKS
 #define ATM_NB_MIN_BLOCKS 5
