@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--skip-two-separate", action="store_true")
     return ap.parse_args()
 
 
@@ -316,6 +317,49 @@ def run_b200(args):
         be.profile_enable(False)
         nb2_ms = tot / max(cnt, 1)
 
+    # ---- north_star comparison: the fused two-state launch against TWO separate single-state evaluations (what two
+    #      inner contexts do), measured with this library's own kernel on zero-displacement handles at x and at x+d
+    two_sep = None
+    if R > 0 and world == 1 and not args.skip_two_separate:
+        zero = np.zeros_like(s["displ"])
+        d32 = torch.from_numpy(s["displ"].astype(np.float32)).to(dev)
+        posq2 = posq.clone()
+        posq2[:, :n, :3] += d32  # the CopyState float add
+        singles = []
+        for pq in (posq, posq2):
+            b1 = atm.ATMBackend(n, precision="mixed", num_replicas=R, device=local_rank)
+            b1.set_displacements(zero)
+            b1.set_box(s["box"])
+            b1.set_parameters(sched[0])
+            b1.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin,
+                        skin_outer=args.skin_outer, exclusions=s["excl"], exception_pairs=s["exc14"],
+                        exception_params=s["exc14_par"])
+            with torch.cuda.stream(stream):
+                b1.rebuild(pq, stream=stream)
+            singles.append((b1, pq))
+        f_tmp = torch.zeros_like(force)
+
+        def timed_loop(fn, iters=20):
+            evs = []
+            with torch.cuda.stream(stream):
+                for it in range(iters + 3):
+                    if flush is not None:
+                        flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream); fn(); b.record(stream)
+                    if it >= 3:
+                        evs.append((a, b))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
+        t_two = timed_loop(lambda: [b1.step(pq, f_tmp, include_energy=True, graph=use_graph, stream=stream) for b1, pq in singles])
+        t_fused = timed_loop(lambda: be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream))
+        two_sep = {"two_single_state_steps_ms": t_two, "fused_two_state_step_ms": t_fused, "speedup": t_two / t_fused,
+                   "note": "same kernels, same pair-list settings; the two single-state handles evaluate x and x+d separately"}
+        for b1, _ in singles:
+            b1.close()
+        del singles, posq2, f_tmp
+
     # ---- end to end through the public call with HOST buffers: H2D coordinates, step, D2H forces + energies
     e2e_ms = None
     h2d = d2h = 0
@@ -397,7 +441,7 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,
         }
         print(json.dumps(line))
     if world > 1:

@@ -9,11 +9,11 @@
 // in ONE launch:  F1 = C + S1, F2 = C + S2, U2 - U1 = U(S2) - U(S1) (formed from the few thousand
 // state-specific pairs only, so it does not suffer the cancellation of two 1e5 kJ/mol totals).
 //
-// Layout: "sites" = N atoms + M ghosts (displaced atoms at x+d).  Sites are binned (xy columns for the
-// environment, one bin per displacement group for ligand atoms and for their ghosts), z-sorted inside a
-// bin and cut into clusters of 8.  Every cluster owns a list of individual partner sites inside
-// cutoff+skin of its bounding box.  The force kernel gives one warp a (cluster, list chunk): each LANE
-// holds one partner site j, the 8 cluster atoms are broadcast from registers, so the inner loop has no
+// Layout: "sites" = N atoms + M ghosts (displaced atoms at x+d).  Sites are binned by (class, xy column) -- class =
+// environment, displaced atoms of group g, ghosts of group g -- z-sorted inside a bin and cut into clusters of 8
+// (so clusters are class-pure and compact whatever the size of a displaced group).  Every cluster owns a list of
+// individual partner sites inside cutoff+skin of its atoms.  The force kernel gives one warp a (cluster, list
+// chunk): each LANE holds one partner site j, the 8 cluster atoms are broadcast from shared memory, so the inner loop has no
 // shuffles and no shared-memory traffic; f_j goes out with three 64-bit fixed-point RED.ADDs per lane per
 // 8 pairs, f_i is reduced by a 27-shuffle transpose-reduction once per work item.
 #include <cub/device/device_radix_sort.cuh>
@@ -166,15 +166,13 @@ __global__ void nl_keys_kernel(NbDev d, const float4 *__restrict__ posq) {
     }
     const float4 L = d.box[r], iL = d.invbox[r];
     float wx = p.x - L.x * floorf(p.x * iL.x), wy = p.y - L.y * floorf(p.y * iL.y), wz = p.z - L.z * floorf(p.z * iL.z);
+    // bins are class-major: class 0 = environment, 1..G = displaced atoms of group g, G+1..2G = their ghosts; inside a
+    // class one bin per xy column, so a displaced group of any size is cut into compact clusters like the environment
     const int g = d.group_of_atom[a];
-    int bin;
-    if (g == 0) {
-        int ix = min(max((int)(wx * iL.x * d.nx), 0), d.nx - 1);
-        int iy = min(max((int)(wy * iL.y * d.ny), 0), d.ny - 1);
-        bin = ix * d.ny + iy;
-    } else {
-        bin = d.ncol + (ghost ? d.G : 0) + g - 1;
-    }
+    const int cls = g == 0 ? 0 : (ghost ? d.G + g : g);
+    const int ix = min(max((int)(wx * iL.x * d.nx), 0), d.nx - 1);
+    const int iy = min(max((int)(wy * iL.y * d.ny), 0), d.ny - 1);
+    const int bin = cls * d.ncol + ix * d.ny + iy;
     const int zq = min(max((int)(wz * iL.z * 65536.0f), 0), 65535);
     d.keys[t] = ((unsigned long long)(r * d.nbins + bin) << 16) | (unsigned long long)zq;
     d.vals[t] = u;
@@ -325,7 +323,7 @@ struct ListInfo {
 __device__ __forceinline__ ListInfo decode_list(const NbDev &d, int r, int l) {
     ListInfo li;
     const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
-    const int nenv = bcs[d.ncol], firstG = bcs[d.ncol + d.G], ncl = d.nclusters[r];
+    const int nenv = bcs[d.ncol], firstG = bcs[d.ncol * (d.G + 1)], ncl = d.nclusters[r];
     const size_t per_replica = (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)d.CLmax * d.capC;
     const size_t rbase = (size_t)r * per_replica;
     li.valid = false;
@@ -408,6 +406,13 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
     __syncwarp();
     const int T = s_tn[w];
     const bool tbl_ok = T <= TBL_CAP;
+    // 64-bit Bloom filter over the clusters that hold an exclusion partner: almost every candidate site skips the table
+    unsigned long long bloom = 0ull;
+    if (tbl_ok) {
+        for (int t = lane; t < T; t += 32) bloom |= 1ull << ((s_tbl[w][t].x >> 3) & 63);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) bloom |= __shfl_xor_sync(0xffffffffu, bloom, off);
+    }
 
     // candidate cluster ranges: env columns near A (only when env clusters can be partners), then all ligand/ghost clusters
     const float cwx = cA.x - L.x * floorf(cA.x * iL.x), cwy = cA.y - L.y * floorf(cA.y * iL.y);
@@ -478,9 +483,11 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
                             unsigned int m = (~validA) & 0xff;
                             if (B2 == A) m |= (0xffu << k) & 0xff;  // within a cluster: pairs (i<j) once
                             if (tbl_ok) {
-                                for (int t = 0; t < T; t++) {
-                                    const int2 te = s_tbl[w][t];
-                                    if (te.x == j) m |= te.y;
+                                if ((bloom >> (B2 & 63)) & 1ull) {
+                                    for (int t = 0; t < T; t++) {
+                                        const int2 te = s_tbl[w][t];
+                                        if (te.x == j) m |= te.y;
+                                    }
                                 }
                             } else {  // rare: a cluster with more exclusion partners than the table holds
                                 const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
@@ -1164,11 +1171,12 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     d.nx = std::max(1, (int)floor(Lx / edge + 0.5));
     d.ny = std::max(1, (int)floor(Ly / edge + 0.5));
     d.ncol = d.nx * d.ny;
-    d.nbins = d.ncol + 2 * d.G;
+    d.nbins = d.ncol * (2 * d.G + 1);
     std::vector<int> group_count(d.G + 1, 0);
     for (int a = 0; a < N; a++) group_count[nb->h_group_of_atom[a]]++;
     d.CLmax = 0;
-    for (int g = 1; g <= d.G; g++) d.CLmax += (group_count[g] + CL - 1) / CL;
+    // a class adds at most one partially filled cluster per non-empty column bin
+    for (int g = 1; g <= d.G; g++) d.CLmax += group_count[g] / CL + std::min(group_count[g], d.ncol);
     d.CXmax = 2 * d.CLmax;
     d.CenvMax = (N - d.M + CL - 1) / CL + d.ncol;
     d.Cmax = d.CenvMax + d.CXmax;

@@ -194,3 +194,118 @@ def test_dual_list_prune_after_motion(abfe):
         assert abs(en[E_U] - (e2 - e1)) <= 5e-3
         assert rel_rms(f_gpu, f_ref) <= 1e-5
     be.close()
+
+
+def test_batched_replicas_match_oracle_individually():
+    """R = 3 replicas with different coordinates and different lambda states in ONE handle: each must match its own
+    oracle evaluation (the batching is invisible)."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic
+    from helpers import oracle_system, force_from_fixed, rel_rms
+    s = synthetic.water_box(9000, n_lig=30, seed=21)
+    n = s["pos"].shape[0]
+    sched = synthetic.atm_schedule_22()
+    states = [3, 9, 15]     # includes a direction = -1 state
+    R = 3
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=R)
+    P = be.P
+    be.set_displacements(s["displ"])
+    be.set_box(s["box"])
+    for r in range(R):
+        be.set_parameters(sched[states[r]], replica=r)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.08, skin_outer=0.2, exclusions=s["excl"])
+    rng = np.random.default_rng(8)
+    posq = np.zeros((R, P, 4), np.float32)
+    for r in range(R):
+        posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.01, (n, 3))
+        posq[r, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+    be.rebuild(d_posq)
+    be.step(d_posq, force)
+    en = be.get_energies()
+    S = oracle_system(O, s, s["cutoff"], s["ewald_alpha"])
+    d32 = s["displ"].astype(np.float32)
+    for r in range(R):
+        p1 = posq[r, :n, :3].astype(np.float64)
+        p2 = (posq[r, :n, :3] + d32).astype(np.float64)
+        e1, _, f1 = S.nb_direct(p1)
+        e2, _, f2 = S.nb_direct(p2)
+        prm = sched[states[r]]
+        sc = O.scalars(prm, e1, e2)
+        f_ref = O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], prm[8])
+        f_gpu = force_from_fixed(force.cpu().numpy()[r], n, P)
+        assert abs(en[r, E_U1] - e1) <= 1e-6 * abs(e1)
+        assert abs(en[r, E_USC] - sc["u_sc"]) <= 5e-3
+        assert abs(en[r, E_SP] - sc["sp"]) <= 1e-4
+        assert rel_rms(f_gpu, f_ref) <= 1e-5
+    be.close()
+
+
+def test_config4_100k_rbfe():
+    """BASELINE configs[3]: ~100k atoms, two 40-atom ligands displaced +d / -d (two displacement groups)."""
+    from atmmetaforce import synthetic
+    s = synthetic.config4()
+    assert s["pos"].shape[0] > 90000
+    params = synthetic.atm_schedule_22()[5]
+    res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
+    err = _check(res, tol_u=2e-2)
+    assert res["stats"]["groups"] == 2 and res["stats"]["displaced_atoms"] == 80
+    print("config4 u = %.4f, force rel rms = %.2e, stats %s" % (res["en"][E_U], err, res["stats"]))
+
+
+def test_single_atom_ligand_and_graph_replay():
+    """One displaced atom (a monatomic ion); the CUDA-graph replay of the step must equal the plain launches bit for bit."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(7000, n_lig=0, seed=2)
+    n = s["pos"].shape[0]
+    s["displ"][0] = [1.7, -1.1, 0.9]          # displace the oxygen of the first water only (its exclusions split states)
+    params = [0.3, 0.6, 0.02, 20.0, 0.0, 800.0, 400.0, 0.0625, 1.0]
+    res = _run(s, s["cutoff"], s["ewald_alpha"], params)
+    _check(res, tol_u=2e-2)
+    assert res["stats"]["displaced_atoms"] == 1
+    from helpers import make_backend
+    be, posq, _ = make_backend(atm, s, s["cutoff"], s["ewald_alpha"], params)
+    be.rebuild(posq)
+    f_plain = torch.zeros((1, 3 * be.P), dtype=torch.int64, device="cuda")
+    f_graph = torch.zeros_like(f_plain)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        be.step(posq, f_plain, stream=st)
+        for _ in range(3):
+            f_graph.zero_()
+            be.step(posq, f_graph, graph=True, stream=st)
+    st.synchronize()
+    assert torch.equal(f_plain, f_graph)
+    be.close()
+
+
+def test_large_displaced_group():
+    """A displaced group that spans the box (every third water of a slab, ~1500 atoms): ligand classes are binned into
+    xy columns like the environment, so no cluster outgrows the half-box limit."""
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(12000, n_lig=0, seed=9)
+    n = s["pos"].shape[0]
+    pos = s["pos"]
+    sel = np.where((pos[:, 2] < 0.35 * s["box"][2]))[0]
+    sel = sel[(sel // 3) % 2 == 0]                     # whole molecules (O,H,H share index // 3)
+    # the water generator is a jittered cubic lattice: shift by (k + 1/2) lattice spacings so that displaced molecules
+    # land in interstitial positions instead of on top of other molecules (overlaps would overflow any fixed-point force)
+    nl = int(round((n / 3) ** (1.0 / 3.0)))
+    a = s["box"][0] / nl
+    s["displ"][sel] = [0.5 * a, 0.5 * a, (int(0.45 * nl) + 0.5) * a]
+    assert 1000 < sel.size < 4000
+    params = [0.4, 0.4, 0.0, 0.0, 0.0, 1e7, 5e6, 0.0625, 1.0]   # the overlap energy is huge: keep the soft core out
+    res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.05)
+    from helpers import rel_rms
+    en = res["en"]
+    print("large group: U1 %.2f/%.2f U2 %.2f/%.2f frms %.2e stats %s" % (en[E_U1], res["e1"], en[E_U2], res["e2"],
+          rel_rms(res["f_gpu"], res["f_ref"]), res["stats"]))
+    assert abs(en[E_U1] - res["e1"]) <= 1e-6 * abs(res["e1"])
+    assert abs(en[E_U2] - res["e2"]) <= 1e-6 * abs(res["e2"])
+    assert rel_rms(res["f_gpu"], res["f_ref"]) <= 1e-5
+    assert res["stats"]["displaced_atoms"] == sel.size
