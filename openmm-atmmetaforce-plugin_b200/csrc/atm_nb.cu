@@ -1459,6 +1459,7 @@ static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.par, 0, sizeof(float2) * (size_t)d.R * d.Smax, stream));  // padding slots are read (masked)
     ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
     nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
     nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
