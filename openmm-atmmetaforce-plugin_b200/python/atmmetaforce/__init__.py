@@ -10,3 +10,5 @@ ATMMETAFORCE_VERSION = "0.3.1"  # reference openmmapi/include/ATMMetaForceVersio
 from .replica import ReplicaExchange  # noqa: F401,E402
 from .force import ATMMetaForce, OpenMMException, serialize, deserialize  # noqa: F401,E402
 from .context import Context, NonbondedDirect, State  # noqa: F401,E402
+from . import io  # noqa: F401,E402
+from .utils import ATMMetaForceUtils  # noqa: F401,E402
