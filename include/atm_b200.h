@@ -66,7 +66,10 @@ enum atm_energy_slot {
     ATM_E_NPAIRS_C = 8,   /* ... of which shared by both states */
     ATM_E_NPAIRS_S1 = 9,  /* ... state-1 only */
     ATM_E_NPAIRS_S2 = 10, /* ... state-2 only */
-    ATM_NUM_ENERGY_SLOTS = 12
+    ATM_E_UREC1 = 11,     /* PME reciprocal energy of state 1 (0 when atm_pme_setup was not called) */
+    ATM_E_UREC2 = 12,     /* ... of state 2 */
+    ATM_E_USELF = 13,     /* Ewald self energy (included in U1 and U2 when PME is on) */
+    ATM_NUM_ENERGY_SLOTS = 16
 };
 
 typedef struct {
@@ -155,6 +158,13 @@ typedef struct {
 } atm_nonbonded_desc;
 
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
+
+/* Optional: evaluate the PME reciprocal space of BOTH states inside atm_step as well (smooth PME,
+ * B-splines of `order` (OpenMM: 5), mesh nx*ny*nz, double precision, cuFFT for the transforms; the environment charge
+ * is spread once for the two states).  U1/U2 then contain direct + reciprocal + self energy, i.e. the complete
+ * NonbondedForce of both inner contexts except the long-range dispersion correction.  nx = ny = nz = 0 switches it off.
+ * Call after atm_nb_setup.  SYNCHRONISES the device. */
+int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t order);
 
 /* Box vectors (row-major a,b,c in nm) of one replica (-1 = all).  Rectangular boxes only in this build.
  * ref: the box mirror in copyState (CommonATMMetaForceKernels.cpp:214-219). */

@@ -17,6 +17,7 @@
 // shuffles and no shared-memory traffic; f_j goes out with three 64-bit fixed-point RED.ADDs per lane per
 // 8 pairs, f_i is reduced by a 27-shuffle transpose-reduction once per work item.
 #include <cub/device/device_radix_sort.cuh>
+#include <cufft.h>
 
 #include <algorithm>
 #include <cmath>
@@ -41,7 +42,8 @@ constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
 constexpr int NUM_FLAGS = 40;
-constexpr int EACC_SLOTS = 6;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2)
+constexpr int EACC_SLOTS = 8;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2), Urec(1), Urec(2)
+constexpr double PME_SCALE = 1099511627776.0;  // 2^40 fixed point of the charge-grid accumulation
 
 struct NbDev {  // everything the kernels need, passed by value
     int N, P, R, M, G, U;
@@ -76,6 +78,13 @@ struct NbDev {  // everything the kernels need, passed by value
     unsigned long long *eacc;
     double *energies;
     const double *params;
+    // smooth PME reciprocal space (optional, atm_pme_setup)
+    int pme_on, pme_order, gx, gy, gz;
+    unsigned long long *pme_acc;   // [R][3][ng] fixed point: environment, displaced atoms, ghosts
+    double *pme_grid;              // [R][2][ng] real charge grids of the two states (overwritten by the potentials)
+    double2 *pme_spec;             // [R][2][gx][gy][gz/2+1]
+    const double *pme_mod;         // |b(m)|^2 moduli: gx + gy + gz doubles
+    double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms
 };
 
 struct NbState {
@@ -102,6 +111,10 @@ struct NbState {
     int sort_bits = 64;
     size_t jlist_entries = 0;
     int n_items = 0, max_items = 0;
+    // PME (optional)
+    std::vector<void *> pme_owned;
+    cufftHandle pme_plan_fwd = 0, pme_plan_bwd = 0;
+    bool pme_plans = false;
     uint64_t generation = 0;        // bumped by every rebuild
     uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
     bool verified = false, needs_realloc = false, flags_pending = false;
@@ -947,13 +960,24 @@ __device__ void scalar_stage_replica(const NbDev &d, int r, const double *__rest
     const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
                  u2 = (double)(long long)ea[2] / ENERGY_SCALE;
     double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
+    double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
+    if (d.pme_on) {
+        // reciprocal energies of the two states (accumulated in double, so their difference is as good as the sum)
+        const double r1 = (double)(long long)ea[6] / ENERGY_SCALE, r2 = (double)(long long)ea[7] / ENERGY_SCALE;
+        const double self = -d.pme_self_sum * (double)d.alpha * 0.5641895835477563;  // -alpha/sqrt(pi) sum q^2
+        U1 += r1 + self;
+        U2 += r2 + self;
+        du += r2 - r1;
+        e[ATM_E_UREC1] = r1; e[ATM_E_UREC2] = r2; e[ATM_E_USELF] = self;
+    } else {
+        e[ATM_E_UREC1] = 0.0; e[ATM_E_UREC2] = 0.0; e[ATM_E_USELF] = 0.0;
+    }
     if (energy_ext) {
         U1 += energy_ext[2 * r];
         U2 += energy_ext[2 * r + 1];
         du += energy_ext[2 * r + 1] - energy_ext[2 * r];
     }
     const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
-    double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
     e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
     e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp;
     e[ATM_E_NPAIRS] = (double)(ea[3] + ea[4] + ea[5]);
@@ -1056,6 +1080,176 @@ nb_merge_kernel(NbDev d, long long *__restrict__ force, const long long *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-state smooth PME reciprocal space.  Works on the cluster-order sites in double:
+// the environment is spread ONCE; the displaced atoms (state 1) and their ghosts (state 2) are spread into two small
+// extra accumulators; Q1 = env + lig, Q2 = env + ghost.  Two batched FFT pairs give the two potentials; environment
+// sites gather from both (their reciprocal force differs between the states because the ligand's field moved).
+// Charges carry sqrt(k_e), so the influence function needs no Coulomb constant.  Grid accumulation is 2^40 fixed
+// point (deterministic), everything after it double precision: U2 - U1 keeps its digits.
+// ------------------------------------------------------------------------------------------------
+constexpr int PME_MAX_ORDER = 8;
+
+// cardinal B-spline weights theta[k] and derivatives dtheta[k], k = 0..order-1, for fractional offset w (Essmann 1995)
+__device__ __forceinline__ void pme_bspline(double w, int order, double *theta, double *dtheta) {
+    for (int k = 0; k < order; k++) theta[k] = 0.0;
+    theta[1] = w;
+    theta[0] = 1.0 - w;
+    for (int k = 3; k < order; k++) {
+        const double div = 1.0 / (k - 1.0);
+        theta[k - 1] = div * w * theta[k - 2];
+        for (int j = 1; j <= k - 2; j++) theta[k - j - 1] = div * ((w + j) * theta[k - j - 2] + (k - j - w) * theta[k - j - 1]);
+        theta[0] = div * (1.0 - w) * theta[0];
+    }
+    dtheta[0] = -theta[0];
+    for (int k = 1; k < order; k++) dtheta[k] = theta[k - 1] - theta[k];
+    const double div = 1.0 / (order - 1.0);
+    theta[order - 1] = div * w * theta[order - 2];
+    for (int j = 1; j <= order - 2; j++)
+        theta[order - j - 1] = div * ((w + j) * theta[order - j - 2] + (order - j - w) * theta[order - j - 1]);
+    theta[0] = div * (1.0 - w) * theta[0];
+}
+
+struct PmeSite {
+    int k0[3];
+    double th[3][PME_MAX_ORDER], dth[3][PME_MAX_ORDER];
+};
+
+__device__ __forceinline__ void pme_site_setup(const NbDev &d, const float4 &x, const float4 &L, PmeSite &ps) {
+    const int n[3] = {d.gx, d.gy, d.gz};
+    const double xr[3] = {(double)x.x / (double)L.x, (double)x.y / (double)L.y, (double)x.z / (double)L.z};
+    for (int c = 0; c < 3; c++) {
+        double u = (xr[c] - floor(xr[c])) * n[c];
+        int fl = (int)floor(u);
+        if (fl >= n[c]) fl = n[c] - 1;
+        pme_bspline(u - fl, d.pme_order, ps.th[c], ps.dth[c]);
+        ps.k0[c] = fl - d.pme_order + 1;
+    }
+}
+
+// one thread per site slot: order^3 fixed-point atomics into the accumulator of its class kind
+__global__ void __launch_bounds__(128) pme_spread_kernel(NbDev d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (s >= CL * d.nclusters[r]) return;
+    const size_t rs = (size_t)r * d.Smax + s;
+    if (d.slot_site[rs] < 0) return;
+    const int cls = d.cmeta[(size_t)r * d.Cmax + (s >> 3)] & 0xffff;
+    const int kind = class_kind(cls, d.G);
+    const float4 x = d.xs[rs];
+    PmeSite ps;
+    pme_site_setup(d, x, d.box[r], ps);
+    const size_t ng = (size_t)d.gx * d.gy * d.gz;
+    unsigned long long *acc = d.pme_acc + ((size_t)r * 3 + kind) * ng;
+    const double q = (double)x.w * PME_SCALE;
+    for (int a = 0; a < d.pme_order; a++) {
+        int ia = ps.k0[0] + a; ia += ia < 0 ? d.gx : 0; ia -= ia >= d.gx ? d.gx : 0;
+        for (int b = 0; b < d.pme_order; b++) {
+            int ib = ps.k0[1] + b; ib += ib < 0 ? d.gy : 0; ib -= ib >= d.gy ? d.gy : 0;
+            const double qab = q * ps.th[0][a] * ps.th[1][b];
+            unsigned long long *row = acc + ((size_t)ia * d.gy + ib) * d.gz;
+            for (int c = 0; c < d.pme_order; c++) {
+                int ic = ps.k0[2] + c; ic += ic < 0 ? d.gz : 0; ic -= ic >= d.gz ? d.gz : 0;
+                atomicAdd(row + ic, (unsigned long long)__double2ll_rn(qab * ps.th[2][c]));
+            }
+        }
+    }
+}
+
+// Q1 = env + displaced, Q2 = env + ghosts as doubles; the three accumulators are handed back zeroed
+__global__ void pme_finalize_kernel(NbDev d) {
+    const size_t ng = (size_t)d.gx * d.gy * d.gz;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= ng) return;
+    unsigned long long *acc = d.pme_acc + (size_t)r * 3 * ng;
+    const long long e = (long long)acc[i], l = (long long)acc[ng + i], g = (long long)acc[2 * ng + i];
+    acc[i] = 0ull; acc[ng + i] = 0ull; acc[2 * ng + i] = 0ull;
+    double *grid = d.pme_grid + (size_t)r * 2 * ng;
+    grid[i] = (double)(e + l) * (1.0 / PME_SCALE);
+    grid[ng + i] = (double)(e + g) * (1.0 / PME_SCALE);
+}
+
+// multiply the spectra by exp(-pi^2 m^2/alpha^2) / (pi V m^2 B(m)); accumulate the two reciprocal energies
+__global__ void __launch_bounds__(256) pme_convolve_kernel(NbDev d) {
+    const int nzh = d.gz / 2 + 1;
+    const size_t nspec = (size_t)d.gx * d.gy * nzh;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y, state = blockIdx.z;
+    double en = 0.0;
+    if (i < nspec) {
+        const int c = (int)(i % nzh), b = (int)((i / nzh) % d.gy), a = (int)(i / ((size_t)nzh * d.gy));
+        double2 *spec = d.pme_spec + ((size_t)r * 2 + state) * nspec;
+        if (a == 0 && b == 0 && c == 0) {
+            spec[i] = make_double2(0.0, 0.0);
+        } else {
+            const float4 L = d.box[r];
+            const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y,
+                         mc = (double)c / (double)L.z;
+            const double m2 = ma * ma + mb * mb + mc * mc;
+            const double V = (double)L.x * (double)L.y * (double)L.z;
+            const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
+            const double eterm = exp(-fac * m2) / (3.141592653589793 * V * m2 * d.pme_mod[a] * d.pme_mod[d.gx + b] * d.pme_mod[d.gx + d.gy + c]);
+            double2 v = spec[i];
+            const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
+            en = 0.5 * w * eterm * (v.x * v.x + v.y * v.y);
+            v.x *= eterm; v.y *= eterm;
+            spec[i] = v;
+        }
+    }
+    // block reduction, one fixed-point atomic per block
+    __shared__ double red[256 / 32];
+    for (int off = 16; off > 0; off >>= 1) en += __shfl_xor_sync(0xffffffffu, en, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = en;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 256 / 32; k++) t += red[k];
+        atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 6 + state, (unsigned long long)__double2ll_rn(t * ENERGY_SCALE));
+    }
+}
+
+// one thread per site: F = -q (n/L) sum dtheta theta theta phi, into the state-specific accumulators
+__global__ void __launch_bounds__(128) pme_gather_kernel(NbDev d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (s >= CL * d.nclusters[r]) return;
+    const size_t rs = (size_t)r * d.Smax + s;
+    if (d.slot_site[rs] < 0) return;
+    const int cls = d.cmeta[(size_t)r * d.Cmax + (s >> 3)] & 0xffff;
+    const int kind = class_kind(cls, d.G);
+    const float4 x = d.xs[rs];
+    const float4 L = d.box[r];
+    PmeSite ps;
+    pme_site_setup(d, x, L, ps);
+    const size_t ng = (size_t)d.gx * d.gy * d.gz;
+    const double *phi1 = d.pme_grid + (size_t)r * 2 * ng, *phi2 = phi1 + ng;
+    double f1[3] = {0, 0, 0}, f2[3] = {0, 0, 0};
+    const bool want1 = kind != 2, want2 = kind != 1;
+    for (int a = 0; a < d.pme_order; a++) {
+        int ia = ps.k0[0] + a; ia += ia < 0 ? d.gx : 0; ia -= ia >= d.gx ? d.gx : 0;
+        for (int b = 0; b < d.pme_order; b++) {
+            int ib = ps.k0[1] + b; ib += ib < 0 ? d.gy : 0; ib -= ib >= d.gy ? d.gy : 0;
+            const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
+            const double tx = ps.dth[0][a] * ps.th[1][b], ty = ps.th[0][a] * ps.dth[1][b], tz = ps.th[0][a] * ps.th[1][b];
+            for (int c = 0; c < d.pme_order; c++) {
+                int ic = ps.k0[2] + c; ic += ic < 0 ? d.gz : 0; ic -= ic >= d.gz ? d.gz : 0;
+                const double wx = tx * ps.th[2][c], wy = ty * ps.th[2][c], wz = tz * ps.dth[2][c];
+                if (want1) { const double p = phi1[row + ic]; f1[0] += wx * p; f1[1] += wy * p; f1[2] += wz * p; }
+                if (want2) { const double p = phi2[row + ic]; f2[0] += wx * p; f2[1] += wy * p; f2[2] += wz * p; }
+            }
+        }
+    }
+    const double q = (double)x.w;
+    const double sc[3] = {-q * d.gx / (double)L.x, -q * d.gy / (double)L.y, -q * d.gz / (double)L.z};
+    const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
+    unsigned long long *buf1 = d.buf + 3 * cs + rsite, *buf2 = d.buf + 6 * cs + rsite;
+    for (int c = 0; c < 3; c++) {
+        if (want1) atomicAdd(buf1 + c * cs + s, (unsigned long long)__double2ll_rn(sc[c] * f1[c] * FORCE_SCALE));
+        if (want2) atomicAdd(buf2 + c * cs + s, (unsigned long long)__double2ll_rn(sc[c] * f2[c] * FORCE_SCALE));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -1084,6 +1278,8 @@ void nb_destroy(atm_handle *h) {
     if (h->nb->graph_exec) cudaGraphExecDestroy(h->nb->graph_exec);
     if (h->nb->rebuild_graph) cudaGraphExecDestroy(h->nb->rebuild_graph);
     if (h->nb->prune_graph) cudaGraphExecDestroy(h->nb->prune_graph);
+    for (void *p : h->nb->pme_owned) cudaFree(p);
+    if (h->nb->pme_plans) { cufftDestroy(h->nb->pme_plan_fwd); cufftDestroy(h->nb->pme_plan_bwd); }
     if (h->nb->h_flags) cudaFreeHost(h->nb->h_flags);
     if (h->nb->flags_event) cudaEventDestroy(h->nb->flags_event);
     for (auto &ev : h->nb->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1640,6 +1836,20 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         }
         if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
     }
+    if (d.pme_on) {
+        const size_t ng = (size_t)d.gx * d.gy * d.gz, nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
+        pme_spread_kernel<<<dim3((d.Smax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        pme_finalize_kernel<<<dim3((unsigned)((ng + 255) / 256), d.R), 256, 0, stream>>>(d);
+        ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
+        ATM_REQUIRE(cufftExecD2Z(nb->pme_plan_fwd, d.pme_grid, (cufftDoubleComplex *)d.pme_spec) == CUFFT_SUCCESS, ATM_ERR_CUDA,
+                    "cufftExecD2Z failed");
+        pme_convolve_kernel<<<dim3((unsigned)((nspec + 255) / 256), d.R, 2), 256, 0, stream>>>(d);
+        ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
+        ATM_REQUIRE(cufftExecZ2D(nb->pme_plan_bwd, (cufftDoubleComplex *)d.pme_spec, d.pme_grid) == CUFFT_SUCCESS, ATM_ERR_CUDA,
+                    "cufftExecZ2D failed");
+        pme_gather_kernel<<<dim3((d.Smax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        h->launches += 4;  // own kernels (the FFTs are cuFFT library code)
+    }
     nb_scalar_kernel<<<(d.R + 31) / 32, 32, 0, stream>>>(d, io->energy_ext, io->include_energy);
     h->launches++;
     nb_merge_kernel<<<dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
@@ -1702,7 +1912,7 @@ int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
         ATM_REQUIRE(err == cudaSuccess, ATM_ERR_CUDA, "atm_step_graph: instantiate failed: %s", cudaGetErrorString(err));
         nb->graph_io = *io;
         nb->graph_generation = nb->alloc_generation;
-        nb->graph_nodes = 4 + (io->posq1 ? 1 : 0);  // pack, nb2 (+special pairs), scalar stage, merge
+        nb->graph_nodes = 4 + (io->posq1 ? 1 : 0) + (nb->d.pme_on ? 4 : 0);  // pack, nb2 (+special pairs), [PME x4], scalar stage, merge
     }
     ATM_CUDA_CHECK(cudaGraphLaunch(nb->graph_exec, stream));
     h->launches += nb->graph_nodes;
@@ -1757,6 +1967,88 @@ int atm_get_energies(atm_handle *h, double *out, void *stream_) {
         if (rc) return rc;
     }
     for (int r = 0; r < h->R; r++) h->pert_energy[r] = out[(size_t)r * ATM_NUM_ENERGY_SLOTS + ATM_E_USC];
+    return ATM_OK;
+}
+
+// B-spline moduli |b(m)|^2 of one dimension (host, double)
+static void pme_moduli(int n, int order, std::vector<double> &mod) {
+    std::vector<double> th(order, 0.0);
+    // spline values at the integers: the recursion at w = 0
+    th[1] = 0.0; th[0] = 1.0;
+    for (int k = 3; k <= order; k++) {
+        const double div = 1.0 / (k - 1.0), w = 0.0;
+        th[k - 1] = div * w * th[k - 2];
+        for (int j = 1; j <= k - 2; j++) th[k - j - 1] = div * ((w + j) * th[k - j - 2] + (k - j - w) * th[k - j - 1]);
+        th[0] = div * (1.0 - w) * th[0];
+    }
+    mod.assign(n, 0.0);
+    for (int m = 0; m < n; m++) {
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < order; k++) {
+            const double arg = 2.0 * M_PI * m * k / n;
+            sr += th[k] * cos(arg);
+            si += th[k] * sin(arg);
+        }
+        mod[m] = sr * sr + si * si;
+    }
+    for (int m = 0; m < n; m++)
+        if (mod[m] < 1e-7) mod[m] = 0.5 * (mod[(m + n - 1) % n] + mod[(m + 1) % n]);
+}
+
+int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t order) {
+    ATM_REQUIRE(h && h->nb && h->nb->ready, ATM_ERR_STATE, "atm_pme_setup: call atm_nb_setup first");
+    NbState *nb = h->nb;
+    NbDev &d = nb->d;
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    ATM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (void *p : nb->pme_owned) cudaFree(p);
+    nb->pme_owned.clear();
+    if (nb->pme_plans) { cufftDestroy(nb->pme_plan_fwd); cufftDestroy(nb->pme_plan_bwd); nb->pme_plans = false; }
+    d.pme_on = 0;
+    nb->alloc_generation++;  // cached graphs are stale
+    if (nx == 0 && ny == 0 && nz == 0) return ATM_OK;  // switched off
+    ATM_REQUIRE(order >= 4 && order <= PME_MAX_ORDER, ATM_ERR_INVALID, "atm_pme_setup: spline order must be 4..%d", PME_MAX_ORDER);
+    ATM_REQUIRE(nx >= order && ny >= order && nz >= order, ATM_ERR_INVALID, "atm_pme_setup: grid smaller than the spline order");
+    ATM_REQUIRE(nb->desc.ewald_alpha > 0, ATM_ERR_INVALID, "atm_pme_setup: needs ewald_alpha > 0");
+    const size_t ng = (size_t)nx * ny * nz, nspec = (size_t)nx * ny * (nz / 2 + 1);
+    const int R = h->R;
+    auto alloc = [&](void **ptr, size_t bytes) -> int {
+        if (cudaMalloc(ptr, bytes) != cudaSuccess) { set_error("atm_pme_setup: cudaMalloc of %zu bytes failed", bytes); return ATM_ERR_NOMEM; }
+        nb->pme_owned.push_back(*ptr);
+        return ATM_OK;
+    };
+    int rc;
+    void *p;
+    if ((rc = alloc(&p, sizeof(unsigned long long) * 3 * ng * R))) return rc;
+    d.pme_acc = (unsigned long long *)p;
+    ATM_CUDA_CHECK(cudaMemset(d.pme_acc, 0, sizeof(unsigned long long) * 3 * ng * R));
+    if ((rc = alloc(&p, sizeof(double) * 2 * ng * R))) return rc;
+    d.pme_grid = (double *)p;
+    if ((rc = alloc(&p, sizeof(double2) * 2 * nspec * R))) return rc;
+    d.pme_spec = (double2 *)p;
+    std::vector<double> mods, m1;
+    for (int n : {nx, ny, nz}) {
+        pme_moduli(n, order, m1);
+        mods.insert(mods.end(), m1.begin(), m1.end());
+    }
+    if ((rc = alloc(&p, sizeof(double) * mods.size()))) return rc;
+    ATM_CUDA_CHECK(cudaMemcpy(p, mods.data(), sizeof(double) * mods.size(), cudaMemcpyHostToDevice));
+    d.pme_mod = (const double *)p;
+    int dims[3] = {nx, ny, nz};
+    ATM_REQUIRE(cufftPlanMany(&nb->pme_plan_fwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, 2 * R) == CUFFT_SUCCESS, ATM_ERR_CUDA,
+                "atm_pme_setup: cufftPlanMany(D2Z) failed");
+    if (cufftPlanMany(&nb->pme_plan_bwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, 2 * R) != CUFFT_SUCCESS) {
+        cufftDestroy(nb->pme_plan_fwd);
+        set_error("atm_pme_setup: cufftPlanMany(Z2D) failed");
+        return ATM_ERR_CUDA;
+    }
+    nb->pme_plans = true;
+    double self = 0.0;
+    for (float q : nb->h_qp) self += (double)q * (double)q;
+    d.pme_self_sum = self;
+    d.gx = nx; d.gy = ny; d.gz = nz;
+    d.pme_order = order;
+    d.pme_on = 1;
     return ATM_OK;
 }
 

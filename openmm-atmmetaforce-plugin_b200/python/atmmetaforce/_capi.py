@@ -13,15 +13,16 @@ LIB_PATH = os.environ.get("ATM_B200_LIB") or os.path.join(_PKG, "libatm_b200.so"
 ATM_OK = 0
 PREC_SINGLE, PREC_MIXED, PREC_DOUBLE = 0, 1, 2
 NUM_PARAMS = 9
-NUM_ENERGY_SLOTS = 12
-E_U1, E_U2, E_U, E_USC, E_EBIAS, E_ENERGY, E_SP, E_NPAIRS, E_NPAIRS_C, E_NPAIRS_S1, E_NPAIRS_S2 = range(11)
+NUM_ENERGY_SLOTS = 16
+(E_U1, E_U2, E_U, E_USC, E_EBIAS, E_ENERGY, E_SP, E_NPAIRS, E_NPAIRS_C, E_NPAIRS_S1, E_NPAIRS_S2, E_UREC1, E_UREC2,
+ E_USELF) = range(14)
 PARAM_NAMES = ("lambda1", "lambda2", "alpha", "u0", "w0", "umax", "ubcore", "acore", "direction")
 
 # every symbol include/atm_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "atm_last_error", "atm_version", "atm_create", "atm_destroy", "atm_set_displacements", "atm_set_parameters",
     "atm_get_parameters", "atm_copy_state", "atm_wrap_positions", "atm_hybrid_force", "atm_softcore_softplus",
-    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
+    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
 )
 
@@ -78,6 +79,7 @@ def lib():
     L.atm_get_perturbation_energy.argtypes = [vp, i32, C.POINTER(dbl)]
     L.atm_nb_setup.argtypes = [vp, C.POINTER(NonbondedDesc), vp]
     L.atm_set_box.argtypes = [vp, i32, vp]
+    L.atm_pme_setup.argtypes = [vp, i32, i32, i32, i32]
     L.atm_nb_rebuild.argtypes = [vp, vp, vp]
     L.atm_nb_prune.argtypes = [vp, vp, vp]
     L.atm_step.argtypes = [vp, C.POINTER(StepIO), vp]

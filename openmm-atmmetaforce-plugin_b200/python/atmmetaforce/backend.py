@@ -113,6 +113,10 @@ class ATMBackend:
                                 xp.ctypes.data, xq.ctypes.data, float(cutoff), float(ewald_alpha), float(skin), float(skin_outer))
         check(_capi.lib().atm_nb_setup(self._h, C.byref(d), _stream_ptr(stream)))
 
+    def pme_setup(self, grid, order=5):
+        """Switch on the two-state PME reciprocal space (grid = (nx, ny, nz); (0,0,0) switches it off)."""
+        check(_capi.lib().atm_pme_setup(self._h, int(grid[0]), int(grid[1]), int(grid[2]), int(order)))
+
     def set_box(self, box, replica=-1):
         b = np.asarray(box, np.float64)
         if b.size == 3:

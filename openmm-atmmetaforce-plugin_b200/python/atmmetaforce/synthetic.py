@@ -20,6 +20,20 @@ def ewald_alpha(cutoff, tol=5e-4):
     return float(np.sqrt(-np.log(2.0 * tol)) / cutoff)
 
 
+def pme_grid(box, alpha, tol=5e-4):
+    """OpenMM's rule for the PME mesh: ceil(2 alpha L / (3 tol^(1/5))) rounded up to a 2/3/5/7-smooth size."""
+    def legal(n):
+        while True:
+            m = n
+            for p in (2, 3, 5, 7):
+                while m % p == 0:
+                    m //= p
+            if m == 1:
+                return n
+            n += 1
+    return [legal(max(6, int(np.ceil(2.0 * alpha * float(L) / (3.0 * tol ** 0.2))))) for L in box]
+
+
 def _lattice_in_sphere(center, radius, n, rng, jitter=0.02):
     """n jittered simple-cubic lattice points inside a sphere (spacing chosen to fit exactly n)."""
     spacing = (4.0 / 3.0 * np.pi * radius ** 3 / n) ** (1.0 / 3.0)

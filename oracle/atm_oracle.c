@@ -393,6 +393,186 @@ double atm_oracle_ewald_recip(const atm_oracle_system *s, const double *pos, dou
     return energy;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Smooth PME reciprocal space (double precision, naive separable DFT -- this is a checker, not a fast code)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* cardinal B-spline weights M_p(w + p-1-k), k = 0..p-1, and their derivatives, by the Essmann recursion */
+static void bspline(double w, int order, double *theta, double *dtheta) {
+    double a[16];
+    for (int k = 0; k < order; k++) a[k] = 0.0;
+    a[1] = w;
+    a[0] = 1.0 - w;
+    for (int k = 3; k < order; k++) {
+        double div = 1.0 / (k - 1.0);
+        a[k - 1] = div * w * a[k - 2];
+        for (int j = 1; j <= k - 2; j++) a[k - j - 1] = div * ((w + j) * a[k - j - 2] + (k - j - w) * a[k - j - 1]);
+        a[0] = div * (1.0 - w) * a[0];
+    }
+    /* derivative from the order-1 spline */
+    dtheta[0] = -a[0];
+    for (int k = 1; k < order; k++) dtheta[k] = a[k - 1] - a[k];
+    /* last recursion step */
+    {
+        double div = 1.0 / (order - 1.0);
+        a[order - 1] = div * w * a[order - 2];
+        for (int j = 1; j <= order - 2; j++)
+            a[order - j - 1] = div * ((w + j) * a[order - j - 2] + (order - j - w) * a[order - j - 1]);
+        a[0] = div * (1.0 - w) * a[0];
+    }
+    for (int k = 0; k < order; k++) theta[k] = a[k];
+}
+
+/* in-place separable DFT of a complex grid g[n0][n1][n2] (re, im interleaved); sign = -1 forward, +1 backward (unscaled) */
+static void dft3(double *g, const int n[3], int sign) {
+    for (int axis = 0; axis < 3; axis++) {
+        const int len = n[axis];
+        double *cs = (double *)malloc(sizeof(double) * 2 * (size_t)len);
+        for (int k = 0; k < len; k++) {
+            cs[2 * k] = cos(2.0 * M_PI * k / len);
+            cs[2 * k + 1] = sign * sin(2.0 * M_PI * k / len);
+        }
+        const size_t stride = axis == 0 ? (size_t)n[1] * n[2] : (axis == 1 ? (size_t)n[2] : 1);
+        const size_t nlines = (size_t)n[0] * n[1] * n[2] / len;
+#pragma omp parallel
+        {
+            double *line = (double *)malloc(sizeof(double) * 4 * (size_t)len);
+#pragma omp for
+            for (long li = 0; li < (long)nlines; li++) {
+                size_t base;
+                if (axis == 0) base = (size_t)li;
+                else if (axis == 1) base = ((size_t)li / n[2]) * (size_t)n[1] * n[2] + (size_t)li % n[2];
+                else base = (size_t)li * n[2];
+                for (int k = 0; k < len; k++) {
+                    line[2 * k] = g[2 * (base + k * stride)];
+                    line[2 * k + 1] = g[2 * (base + k * stride) + 1];
+                }
+                double *out = line + 2 * len;
+                for (int m = 0; m < len; m++) {
+                    double re = 0.0, im = 0.0;
+                    for (int k = 0; k < len; k++) {
+                        const int t = (int)(((long)m * k) % len);
+                        re += line[2 * k] * cs[2 * t] - line[2 * k + 1] * cs[2 * t + 1];
+                        im += line[2 * k] * cs[2 * t + 1] + line[2 * k + 1] * cs[2 * t];
+                    }
+                    out[2 * m] = re;
+                    out[2 * m + 1] = im;
+                }
+                for (int k = 0; k < len; k++) {
+                    g[2 * (base + k * stride)] = out[2 * k];
+                    g[2 * (base + k * stride) + 1] = out[2 * k + 1];
+                }
+            }
+            free(line);
+        }
+        free(cs);
+    }
+}
+
+/* |b(m)|^2 of the Euler exponential spline for one dimension */
+static void bspline_moduli(int n, int order, double *mod) {
+    double theta[16], dtheta[16];
+    bspline(0.0, order, theta, dtheta);  /* theta[k] = M_p(p-1-k) ... values at the integers */
+    for (int m = 0; m < n; m++) {
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < order; k++) {
+            const double arg = 2.0 * M_PI * m * k / n;
+            sr += theta[k] * cos(arg);
+            si += theta[k] * sin(arg);
+        }
+        mod[m] = sr * sr + si * si;
+    }
+    for (int m = 0; m < n; m++)
+        if (mod[m] < 1e-7) mod[m] = 0.5 * (mod[(m + n - 1) % n] + mod[(m + 1) % n]);
+}
+
+double atm_oracle_pme_recip(const atm_oracle_system *s, const double *pos, const int n[3], int order, double *force) {
+    const int N = s->n;
+    const double *L = s->box;
+    const double V = L[0] * L[1] * L[2];
+    const size_t ng = (size_t)n[0] * n[1] * n[2];
+    double *g = (double *)calloc(2 * ng, sizeof(double));
+    double *th = (double *)malloc(sizeof(double) * 3 * 16 * (size_t)N), *dth = (double *)malloc(sizeof(double) * 3 * 16 * (size_t)N);
+    int *k0 = (int *)malloc(sizeof(int) * 3 * (size_t)N);
+    /* spread */
+    for (int i = 0; i < N; i++) {
+        for (int d = 0; d < 3; d++) {
+            double u = pos[3 * i + d] / L[d];
+            u = (u - floor(u)) * n[d];
+            int fl = (int)floor(u);
+            if (fl >= n[d]) fl = n[d] - 1;
+            bspline(u - fl, order, th + (3 * (size_t)i + d) * 16, dth + (3 * (size_t)i + d) * 16);
+            k0[3 * i + d] = fl - order + 1;
+        }
+        const double q = s->charge[i];
+        for (int a = 0; a < order; a++) {
+            const int ia = ((k0[3 * i] + a) % n[0] + n[0]) % n[0];
+            for (int b = 0; b < order; b++) {
+                const int ib = ((k0[3 * i + 1] + b) % n[1] + n[1]) % n[1];
+                const double qab = q * th[(3 * (size_t)i) * 16 + a] * th[(3 * (size_t)i + 1) * 16 + b];
+                for (int c = 0; c < order; c++) {
+                    const int ic = ((k0[3 * i + 2] + c) % n[2] + n[2]) % n[2];
+                    g[2 * (((size_t)ia * n[1] + ib) * n[2] + ic)] += qab * th[(3 * (size_t)i + 2) * 16 + c];
+                }
+            }
+        }
+    }
+    dft3(g, n, -1);
+    /* convolution with exp(-pi^2 m^2 / alpha^2) / (pi V m^2 B(m)) and the energy */
+    double *mod[3];
+    for (int d = 0; d < 3; d++) {
+        mod[d] = (double *)malloc(sizeof(double) * (size_t)n[d]);
+        bspline_moduli(n[d], order, mod[d]);
+    }
+    const double fac = M_PI * M_PI / (s->ewald_alpha * s->ewald_alpha);
+    double energy = 0.0;
+    for (int a = 0; a < n[0]; a++) {
+        const double ma = (a <= n[0] / 2 ? a : a - n[0]) / L[0];
+        for (int b = 0; b < n[1]; b++) {
+            const double mb = (b <= n[1] / 2 ? b : b - n[1]) / L[1];
+            for (int c = 0; c < n[2]; c++) {
+                const size_t idx = ((size_t)a * n[1] + b) * n[2] + c;
+                if (a == 0 && b == 0 && c == 0) { g[2 * idx] = g[2 * idx + 1] = 0.0; continue; }
+                const double mc = (c <= n[2] / 2 ? c : c - n[2]) / L[2];
+                const double m2 = ma * ma + mb * mb + mc * mc;
+                const double eterm = ATM_ORACLE_ONE_4PI_EPS0 * exp(-fac * m2) / (M_PI * V * m2 * mod[0][a] * mod[1][b] * mod[2][c]);
+                energy += 0.5 * eterm * (g[2 * idx] * g[2 * idx] + g[2 * idx + 1] * g[2 * idx + 1]);
+                g[2 * idx] *= eterm;
+                g[2 * idx + 1] *= eterm;
+            }
+        }
+    }
+    if (force) {
+        dft3(g, n, +1); /* potential on the grid (real part) */
+        for (int i = 0; i < N; i++) {
+            const double q = s->charge[i];
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            for (int a = 0; a < order; a++) {
+                const int ia = ((k0[3 * i] + a) % n[0] + n[0]) % n[0];
+                const double ta = th[(3 * (size_t)i) * 16 + a], da = dth[(3 * (size_t)i) * 16 + a];
+                for (int b = 0; b < order; b++) {
+                    const int ib = ((k0[3 * i + 1] + b) % n[1] + n[1]) % n[1];
+                    const double tb = th[(3 * (size_t)i + 1) * 16 + b], db = dth[(3 * (size_t)i + 1) * 16 + b];
+                    for (int c = 0; c < order; c++) {
+                        const int ic = ((k0[3 * i + 2] + c) % n[2] + n[2]) % n[2];
+                        const double tc = th[(3 * (size_t)i + 2) * 16 + c], dc = dth[(3 * (size_t)i + 2) * 16 + c];
+                        const double phi = g[2 * (((size_t)ia * n[1] + ib) * n[2] + ic)];
+                        f0 += da * tb * tc * phi;
+                        f1 += ta * db * tc * phi;
+                        f2 += ta * tb * dc * phi;
+                    }
+                }
+            }
+            force[3 * i] -= q * f0 * n[0] / L[0];
+            force[3 * i + 1] -= q * f1 * n[1] / L[1];
+            force[3 * i + 2] -= q * f2 * n[2] / L[2];
+        }
+    }
+    for (int d = 0; d < 3; d++) free(mod[d]);
+    free(g); free(th); free(dth); free(k0);
+    return energy;
+}
+
 /* ATMMetaForceImpl.cpp:110-122 on the CPU: copyState, inner evaluation 1, inner evaluation 2, execute. */
 void atm_oracle_step(const atm_oracle_system *s, const double p[9], const double *pos, const double *displ,
                      double du_ext, double *force_out, double energies[5]) {

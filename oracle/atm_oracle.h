@@ -82,6 +82,11 @@ double atm_oracle_nb_direct(const atm_oracle_system *sys, const double *pos, dou
  * force accumulated when non-NULL. */
 double atm_oracle_ewald_recip(const atm_oracle_system *sys, const double *pos, double tol, double *force);
 
+/* Smooth particle-mesh Ewald reciprocal energy (Essmann et al. 1995; the algorithm OpenMM's NonbondedForce uses for
+ * PME): B-splines of the given order (4..8), grid (n[0], n[1], n[2]), plain separable DFTs in double.  Self energy NOT
+ * included.  force accumulated when non-NULL.  With a fine grid it converges to atm_oracle_ewald_recip. */
+double atm_oracle_pme_recip(const atm_oracle_system *sys, const double *pos, const int n[3], int order, double *force);
+
 /* Whole reference step on the CPU: copy-state (ref), two full direct-space evaluations, scalar stage, merge.
  * pos, displ: 3n doubles; force_out (3n) is accumulated into; energies[5] = {U1, U2, u_sc, energy, sp_common}.
  * du_ext is added to U2 (e.g. the reciprocal-space difference computed elsewhere). */

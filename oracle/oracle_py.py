@@ -40,6 +40,8 @@ def lib():
         _lib.atm_oracle_nb_direct.restype = C.c_double
         _lib.atm_oracle_ewald_recip.restype = C.c_double
         _lib.atm_oracle_ewald_recip.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        _lib.atm_oracle_pme_recip.restype = C.c_double
+        _lib.atm_oracle_pme_recip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.atm_oracle_num_threads.restype = C.c_int
         _lib.atm_oracle_merge_ref.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         _lib.atm_oracle_hybrid_force_i64.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
@@ -90,6 +92,13 @@ class System:
         e = lib().atm_oracle_ewald_recip(C.byref(self.c), _p(pos), tol, _p(f))
         return e, f
 
+    def pme_recip(self, pos, grid, order=5, want_force=False):
+        pos = np.ascontiguousarray(pos, np.float64)
+        g = np.ascontiguousarray(grid, np.int32)
+        f = np.zeros_like(pos) if want_force else None
+        e = lib().atm_oracle_pme_recip(C.byref(self.c), _p(pos), _p(g), int(order), _p(f))
+        return e, f
+
     def step(self, params, pos, displ, du_ext=0.0, want_force=True):
         pos = np.ascontiguousarray(pos, np.float64)
         displ = np.ascontiguousarray(displ, np.float64)
@@ -98,6 +107,20 @@ class System:
         en = np.zeros(5)
         lib().atm_oracle_step(C.byref(self.c), _p(params), _p(pos), _p(displ), du_ext, _p(f), _p(en))
         return dict(U1=en[0], U2=en[1], u_sc=en[2], energy=en[3], sp=en[4]), f
+
+
+def pme_grid(box, alpha, tol=5e-4):
+    """OpenMM's rule for the PME mesh: ceil(2 alpha L / (3 tol^(1/5))) rounded up to a 2/3/5/7-smooth size."""
+    def legal(n):
+        while True:
+            m = n
+            for p in (2, 3, 5, 7):
+                while m % p == 0:
+                    m //= p
+            if m == 1:
+                return n
+            n += 1
+    return [legal(max(6, int(np.ceil(2.0 * alpha * float(L) / (3.0 * tol ** 0.2))))) for L in box]
 
 
 def softcore(u, umax, a, ub):

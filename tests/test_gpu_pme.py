@@ -1,0 +1,90 @@
+"""GPU parity of the two-state PME reciprocal space against the oracle's double-precision
+smooth-PME restatement (same mesh, same spline order), and the reference pin with EVERYTHING evaluated on the GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+E_U1, E_U2, E_U, E_USC, E_EBIAS, E_ENERGY, E_SP = range(7)
+E_UREC1, E_UREC2, E_USELF = 11, 12, 13
+
+
+def _run_pme(s, cutoff, alpha, params, grid, order=5):
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from helpers import oracle_system, make_backend, force_from_fixed
+    n = s["pos"].shape[0]
+    be, posq, _ = make_backend(atm, s, cutoff, alpha, params, skin=0.1)
+    be.pme_setup(grid, order)
+    be.rebuild(posq)
+    force = torch.zeros((1, 3 * be.P), dtype=torch.int64, device="cuda")
+    be.step(posq, force)
+    en = be.get_energies()[0]
+    f_gpu = force_from_fixed(force.cpu().numpy()[0], n, be.P)
+    force2 = torch.zeros_like(force)
+    be.step(posq, force2)
+    torch.cuda.synchronize()
+    assert torch.equal(force, force2)          # fixed-point spreading: bit-reproducible
+    be.close()
+    S = oracle_system(O, s, cutoff, alpha)
+    pos1 = s["pos"].astype(np.float32).astype(np.float64)
+    pos2 = (s["pos"].astype(np.float32) + s["displ"].astype(np.float32)).astype(np.float64)
+    e1, _, f1 = S.nb_direct(pos1)
+    e2, _, f2 = S.nb_direct(pos2)
+    r1, g1 = S.pme_recip(pos1, grid, order, want_force=True)
+    r2, g2 = S.pme_recip(pos2, grid, order, want_force=True)
+    self_e = -138.935456 * alpha / np.sqrt(np.pi) * float((s["charge"] ** 2).sum())
+    U1, U2 = e1 + r1 + self_e, e2 + r2 + self_e
+    sc = O.scalars(params, U1, U2)
+    f_ref = O.merge_ref(np.zeros_like(f1), f1 + g1, f2 + g2, sc["sp_ref"], params[8])
+    return dict(en=en, f_gpu=f_gpu, f_ref=f_ref, U1=U1, U2=U2, r1=r1, r2=r2, self_e=self_e, sc=sc)
+
+
+def test_abfe_pin_fully_on_gpu(abfe):
+    """Direct space + PME reciprocal of both states on the GPU: u = 58.2 +- 0.1 (ref: python/tests/test_abfe.py:148-150)
+    with OpenMM's mesh rule for tolerance 5e-4 (35 x 40 x 35 here)."""
+    import oracle_py as O
+    from helpers import rel_rms
+    alpha = O.ewald_alpha(1.0)
+    grid = O.pme_grid(abfe["box"], alpha)
+    r = _run_pme(abfe, 1.0, alpha, abfe["params"], grid)
+    en = r["en"]
+    print("abfe+PME: u_sc %.4f  Urec1 %.4f (oracle %.4f)  dUrec %.5f (oracle %.5f)  U1 %.3f (oracle %.3f)  frms %.2e" % (
+        en[E_USC], en[E_UREC1], r["r1"], en[E_UREC2] - en[E_UREC1], r["r2"] - r["r1"], en[E_U1], r["U1"], rel_rms(r["f_gpu"], r["f_ref"])))
+    assert abs(en[E_USC] - 58.2) <= 0.1
+    assert abs(en[E_UREC1] - r["r1"]) <= 1e-6 * abs(r["r1"]) + 1e-4
+    assert abs((en[E_UREC2] - en[E_UREC1]) - (r["r2"] - r["r1"])) <= 1e-4
+    assert abs(en[E_USELF] - r["self_e"]) <= 1e-6 * abs(r["self_e"])
+    assert abs(en[E_U1] - r["U1"]) <= 1e-6 * abs(r["U1"])
+    assert abs(en[E_USC] - r["sc"]["u_sc"]) <= 5e-3
+    assert rel_rms(r["f_gpu"], r["f_ref"]) <= 1e-5
+
+
+def test_rbfe_pme(rbfe):
+    import oracle_py as O
+    from helpers import rel_rms
+    alpha = O.ewald_alpha(1.0)
+    grid = O.pme_grid(rbfe["box"], alpha)
+    r = _run_pme(rbfe, 1.0, alpha, rbfe["params"], grid)
+    en = r["en"]
+    assert abs(en[E_U1] - r["U1"]) <= 1e-6 * abs(r["U1"]) and abs(en[E_U2] - r["U2"]) <= 1e-6 * abs(r["U2"])
+    assert abs(en[E_U] - (r["U2"] - r["U1"])) <= 5e-3
+    assert abs(en[E_U] - 2.107) <= 0.05        # survey-time value with the exact Ewald sum (unpinned by the reference)
+    assert rel_rms(r["f_gpu"], r["f_ref"]) <= 1e-5
+
+
+def test_pme_order_and_odd_grid():
+    """Spline order 4 and an odd, non-cubic mesh."""
+    from atmmetaforce import synthetic
+    from helpers import rel_rms
+    s = synthetic.water_box(6000, n_lig=15, seed=6)
+    params = synthetic.atm_schedule_22()[14]     # direction -1
+    r = _run_pme(s, s["cutoff"], s["ewald_alpha"], params, [27, 30, 25], order=4)
+    en = r["en"]
+    # direct space, reciprocal space and the self energy nearly cancel in this system: the 1e-6 bar is relative to the
+    # largest component (the self energy), not to their small sum
+    assert abs(en[E_U1] - r["U1"]) <= 1e-6 * (abs(r["U1"]) + abs(r["self_e"]))
+    assert abs(en[E_UREC1] - r["r1"]) <= 1e-6 * abs(r["r1"]) + 1e-4
+    assert abs((en[E_UREC2] - en[E_UREC1]) - (r["r2"] - r["r1"])) <= 1e-4
+    assert rel_rms(r["f_gpu"], r["f_ref"]) <= 1e-5

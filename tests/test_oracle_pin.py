@@ -213,3 +213,32 @@ def test_hybrid_force_fixed_point_matches_double_merge():
     out = O.hybrid_force_i64(n, P, fx(f0), fx(f1), fx(f2), 0.37)
     got = out.reshape(3, P)[:, :n].T / F
     assert np.allclose(got, f0 + 0.37 * f2 + 0.63 * f1, atol=1e-8)
+
+
+def test_pme_restatement_converges_to_exact_ewald(abfe):
+    """The oracle's smooth PME (the algorithm OpenMM uses) against its exact Ewald sum: mesh rule of tolerance 5e-4 is
+    within 3e-4 relative, and the state difference on the reference fixture within 5e-3 kJ/mol."""
+    alpha = O.ewald_alpha(1.0)
+    S = oracle_system(O, abfe, 1.0, alpha)
+    grid = O.pme_grid(abfe["box"], alpha)
+    assert grid == [35, 40, 35]
+    pos, pos2 = abfe["pos"], abfe["pos"] + abfe["displ"]
+    p1, _ = S.pme_recip(pos, grid, 5)
+    p2, _ = S.pme_recip(pos2, grid, 5)
+    r1, _ = S.ewald_recip(pos, 1e-10)
+    r2, _ = S.ewald_recip(pos2, 1e-10)
+    assert abs(p1 - r1) <= 3e-4 * abs(r1)
+    assert abs((p2 - p1) - (r2 - r1)) <= 5e-3
+    # forces are the gradient of the PME energy
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(900, n_lig=0, seed=1)
+    S2 = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], 0.7, 3.2, s["excl"])
+    e0, f = S2.pme_recip(s["pos"], [20, 20, 20], 5, want_force=True)
+    h = 1e-5
+    for a in (0, 11, 500):
+        for c in range(3):
+            p = s["pos"].copy(); p[a, c] += h
+            ep, _ = S2.pme_recip(p, [20, 20, 20], 5)
+            p[a, c] -= 2 * h
+            em, _ = S2.pme_recip(p, [20, 20, 20], 5)
+            assert abs(-(ep - em) / (2 * h) - f[a, c]) <= 2e-5 * max(1.0, abs(f[a, c]))
