@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--skip-two-separate", action="store_true")
+    ap.add_argument("--pme", action="store_true", help="also evaluate the two-state PME reciprocal space inside the step "
+                    "(SURVEY 8f row 1; NOT part of the headline workload, which is the direct-space path)")
     return ap.parse_args()
 
 
@@ -216,6 +218,10 @@ def run_b200(args):
     be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin,
                 skin_outer=args.skin_outer, exclusions=s["excl"], exception_pairs=s["exc14"],
                 exception_params=s["exc14_par"])
+    pme_grid = None
+    if args.pme:
+        pme_grid = synthetic.pme_grid(s["box"], s["ewald_alpha"])
+        be.pme_setup(pme_grid)
     posq_h = torch.zeros((max(R, 1), P, 4), dtype=torch.float32).pin_memory()
     corr_h = torch.zeros((max(R, 1), P, 4), dtype=torch.float32).pin_memory()
     for k, g in enumerate(mine):
@@ -334,6 +340,8 @@ def run_b200(args):
             b1.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin,
                         skin_outer=args.skin_outer, exclusions=s["excl"], exception_pairs=s["exc14"],
                         exception_params=s["exc14_par"])
+            if pme_grid is not None:
+                b1.pme_setup(pme_grid)
             with torch.cuda.stream(stream):
                 b1.rebuild(pq, stream=stream)
             singles.append((b1, pq))
@@ -435,7 +443,7 @@ def run_b200(args):
             "config": {"workload": label, "replicas": total_replicas, "replicas_per_rank": max_per_rank, "atoms": int(n),
                        "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
                        "prune_every": args.prune_every, "rebuild_every": args.rebuild_every,
-                       "exchange_every": args.exchange_every, "cuda_graph": use_graph,
+                       "exchange_every": args.exchange_every, "cuda_graph": use_graph, "pme_grid": pme_grid,
                        "l2": "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)",
                        "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,

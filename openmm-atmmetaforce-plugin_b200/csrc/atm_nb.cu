@@ -80,7 +80,7 @@ struct NbDev {  // everything the kernels need, passed by value
     const double *params;
     // smooth PME reciprocal space (optional, atm_pme_setup)
     int pme_on, pme_order, gx, gy, gz;
-    unsigned long long *pme_acc;   // [R][3][ng] fixed point: environment, displaced atoms, ghosts
+    unsigned long long *pme_acc;   // [R][2][ng] fixed point: Q1 (environment + displaced atoms), Q2 - Q1 (ghosts - displaced)
     double *pme_grid;              // [R][2][ng] real charge grids of the two states (overwritten by the potentials)
     double2 *pme_spec;             // [R][2][gx][gy][gz/2+1]
     const double *pme_mod;         // |b(m)|^2 moduli: gx + gy + gz doubles
@@ -1089,44 +1089,62 @@ nb_merge_kernel(NbDev d, long long *__restrict__ force, const long long *__restr
 // ------------------------------------------------------------------------------------------------
 constexpr int PME_MAX_ORDER = 8;
 
-// cardinal B-spline weights theta[k] and derivatives dtheta[k], k = 0..order-1, for fractional offset w (Essmann 1995)
-__device__ __forceinline__ void pme_bspline(double w, int order, double *theta, double *dtheta) {
-    for (int k = 0; k < order; k++) theta[k] = 0.0;
+// cardinal B-spline weights theta[k] and derivatives dtheta[k], k = 0..ORDER-1, for fractional offset w (Essmann 1995);
+// ORDER is a compile-time constant so that everything stays in registers
+template <int ORDER>
+__device__ __forceinline__ void pme_bspline(double w, double (&theta)[ORDER], double (&dtheta)[ORDER]) {
+#pragma unroll
+    for (int k = 0; k < ORDER; k++) theta[k] = 0.0;
     theta[1] = w;
     theta[0] = 1.0 - w;
-    for (int k = 3; k < order; k++) {
+#pragma unroll
+    for (int k = 3; k < ORDER; k++) {
         const double div = 1.0 / (k - 1.0);
         theta[k - 1] = div * w * theta[k - 2];
+#pragma unroll
         for (int j = 1; j <= k - 2; j++) theta[k - j - 1] = div * ((w + j) * theta[k - j - 2] + (k - j - w) * theta[k - j - 1]);
         theta[0] = div * (1.0 - w) * theta[0];
     }
     dtheta[0] = -theta[0];
-    for (int k = 1; k < order; k++) dtheta[k] = theta[k - 1] - theta[k];
-    const double div = 1.0 / (order - 1.0);
-    theta[order - 1] = div * w * theta[order - 2];
-    for (int j = 1; j <= order - 2; j++)
-        theta[order - j - 1] = div * ((w + j) * theta[order - j - 2] + (order - j - w) * theta[order - j - 1]);
+#pragma unroll
+    for (int k = 1; k < ORDER; k++) dtheta[k] = theta[k - 1] - theta[k];
+    const double div = 1.0 / (ORDER - 1.0);
+    theta[ORDER - 1] = div * w * theta[ORDER - 2];
+#pragma unroll
+    for (int j = 1; j <= ORDER - 2; j++)
+        theta[ORDER - j - 1] = div * ((w + j) * theta[ORDER - j - 2] + (ORDER - j - w) * theta[ORDER - j - 1]);
     theta[0] = div * (1.0 - w) * theta[0];
 }
 
+template <int ORDER>
 struct PmeSite {
     int k0[3];
-    double th[3][PME_MAX_ORDER], dth[3][PME_MAX_ORDER];
+    double th[3][ORDER], dth[3][ORDER];
 };
 
-__device__ __forceinline__ void pme_site_setup(const NbDev &d, const float4 &x, const float4 &L, PmeSite &ps) {
+template <int ORDER>
+__device__ __forceinline__ void pme_site_setup(const NbDev &d, const float4 &x, const float4 &L, PmeSite<ORDER> &ps) {
     const int n[3] = {d.gx, d.gy, d.gz};
     const double xr[3] = {(double)x.x / (double)L.x, (double)x.y / (double)L.y, (double)x.z / (double)L.z};
+#pragma unroll
     for (int c = 0; c < 3; c++) {
         double u = (xr[c] - floor(xr[c])) * n[c];
         int fl = (int)floor(u);
         if (fl >= n[c]) fl = n[c] - 1;
-        pme_bspline(u - fl, d.pme_order, ps.th[c], ps.dth[c]);
-        ps.k0[c] = fl - d.pme_order + 1;
+        pme_bspline<ORDER>(u - fl, ps.th[c], ps.dth[c]);
+        ps.k0[c] = fl - ORDER + 1;
     }
 }
 
-// one thread per site slot: order^3 fixed-point atomics into the accumulator of its class kind
+__device__ __forceinline__ int pme_wrap(int i, int n) {
+    i += i < 0 ? n : 0;
+    return i - (i >= n ? n : 0);
+}
+
+// One thread per site slot: ORDER^3 fixed-point atomics.  Two accumulators per replica:
+//   acc[0] = Q1 = environment + displaced atoms,  acc[1] = Q2 - Q1 = ghosts - displaced atoms
+// so the environment (almost every site) is spread exactly once.
+template <int ORDER>
 __global__ void __launch_bounds__(128) pme_spread_kernel(NbDev d) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
@@ -1136,37 +1154,44 @@ __global__ void __launch_bounds__(128) pme_spread_kernel(NbDev d) {
     const int cls = d.cmeta[(size_t)r * d.Cmax + (s >> 3)] & 0xffff;
     const int kind = class_kind(cls, d.G);
     const float4 x = d.xs[rs];
-    PmeSite ps;
-    pme_site_setup(d, x, d.box[r], ps);
+    PmeSite<ORDER> ps;
+    pme_site_setup<ORDER>(d, x, d.box[r], ps);
     const size_t ng = (size_t)d.gx * d.gy * d.gz;
-    unsigned long long *acc = d.pme_acc + ((size_t)r * 3 + kind) * ng;
+    unsigned long long *acc1 = d.pme_acc + (size_t)r * 2 * ng, *accd = acc1 + ng;
     const double q = (double)x.w * PME_SCALE;
-    for (int a = 0; a < d.pme_order; a++) {
-        int ia = ps.k0[0] + a; ia += ia < 0 ? d.gx : 0; ia -= ia >= d.gx ? d.gx : 0;
-        for (int b = 0; b < d.pme_order; b++) {
-            int ib = ps.k0[1] + b; ib += ib < 0 ? d.gy : 0; ib -= ib >= d.gy ? d.gy : 0;
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+        const int ia = pme_wrap(ps.k0[0] + a, d.gx);
+#pragma unroll
+        for (int b = 0; b < ORDER; b++) {
+            const int ib = pme_wrap(ps.k0[1] + b, d.gy);
             const double qab = q * ps.th[0][a] * ps.th[1][b];
-            unsigned long long *row = acc + ((size_t)ia * d.gy + ib) * d.gz;
-            for (int c = 0; c < d.pme_order; c++) {
-                int ic = ps.k0[2] + c; ic += ic < 0 ? d.gz : 0; ic -= ic >= d.gz ? d.gz : 0;
-                atomicAdd(row + ic, (unsigned long long)__double2ll_rn(qab * ps.th[2][c]));
+            const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
+#pragma unroll
+            for (int c = 0; c < ORDER; c++) {
+                const int ic = pme_wrap(ps.k0[2] + c, d.gz);
+                const long long v = __double2ll_rn(qab * ps.th[2][c]);
+                if (kind != 2) atomicAdd(acc1 + row + ic, (unsigned long long)v);        // environment, displaced atoms -> Q1
+                if (kind == 1) atomicAdd(accd + row + ic, (unsigned long long)(-v));     // displaced atoms leave in state 2
+                if (kind == 2) atomicAdd(accd + row + ic, (unsigned long long)v);        // ghosts arrive in state 2
             }
         }
     }
 }
 
-// Q1 = env + displaced, Q2 = env + ghosts as doubles; the three accumulators are handed back zeroed
+// Q1, Q2 = Q1 + (Q2 - Q1) as doubles; the accumulators are handed back zeroed
 __global__ void pme_finalize_kernel(NbDev d) {
     const size_t ng = (size_t)d.gx * d.gy * d.gz;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (i >= ng) return;
-    unsigned long long *acc = d.pme_acc + (size_t)r * 3 * ng;
-    const long long e = (long long)acc[i], l = (long long)acc[ng + i], g = (long long)acc[2 * ng + i];
-    acc[i] = 0ull; acc[ng + i] = 0ull; acc[2 * ng + i] = 0ull;
+    unsigned long long *acc = d.pme_acc + (size_t)r * 2 * ng;
+    const long long q1 = (long long)acc[i], dq = (long long)acc[ng + i];
+    acc[i] = 0ull;
+    if (dq != 0) acc[ng + i] = 0ull;
     double *grid = d.pme_grid + (size_t)r * 2 * ng;
-    grid[i] = (double)(e + l) * (1.0 / PME_SCALE);
-    grid[ng + i] = (double)(e + g) * (1.0 / PME_SCALE);
+    grid[i] = (double)q1 * (1.0 / PME_SCALE);
+    grid[ng + i] = (double)(q1 + dq) * (1.0 / PME_SCALE);
 }
 
 // multiply the spectra by exp(-pi^2 m^2/alpha^2) / (pi V m^2 B(m)); accumulate the two reciprocal energies
@@ -1209,7 +1234,8 @@ __global__ void __launch_bounds__(256) pme_convolve_kernel(NbDev d) {
 }
 
 // one thread per site: F = -q (n/L) sum dtheta theta theta phi, into the state-specific accumulators
-__global__ void __launch_bounds__(128) pme_gather_kernel(NbDev d) {
+template <int ORDER>
+__global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (s >= CL * d.nclusters[r]) return;
@@ -1219,33 +1245,64 @@ __global__ void __launch_bounds__(128) pme_gather_kernel(NbDev d) {
     const int kind = class_kind(cls, d.G);
     const float4 x = d.xs[rs];
     const float4 L = d.box[r];
-    PmeSite ps;
-    pme_site_setup(d, x, L, ps);
+    PmeSite<ORDER> ps;
+    pme_site_setup<ORDER>(d, x, L, ps);
     const size_t ng = (size_t)d.gx * d.gy * d.gz;
     const double *phi1 = d.pme_grid + (size_t)r * 2 * ng, *phi2 = phi1 + ng;
-    double f1[3] = {0, 0, 0}, f2[3] = {0, 0, 0};
+    double f1x = 0, f1y = 0, f1z = 0, f2x = 0, f2y = 0, f2z = 0;
     const bool want1 = kind != 2, want2 = kind != 1;
-    for (int a = 0; a < d.pme_order; a++) {
-        int ia = ps.k0[0] + a; ia += ia < 0 ? d.gx : 0; ia -= ia >= d.gx ? d.gx : 0;
-        for (int b = 0; b < d.pme_order; b++) {
-            int ib = ps.k0[1] + b; ib += ib < 0 ? d.gy : 0; ib -= ib >= d.gy ? d.gy : 0;
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+        const int ia = pme_wrap(ps.k0[0] + a, d.gx);
+#pragma unroll
+        for (int b = 0; b < ORDER; b++) {
+            const int ib = pme_wrap(ps.k0[1] + b, d.gy);
             const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
             const double tx = ps.dth[0][a] * ps.th[1][b], ty = ps.th[0][a] * ps.dth[1][b], tz = ps.th[0][a] * ps.th[1][b];
-            for (int c = 0; c < d.pme_order; c++) {
-                int ic = ps.k0[2] + c; ic += ic < 0 ? d.gz : 0; ic -= ic >= d.gz ? d.gz : 0;
+#pragma unroll
+            for (int c = 0; c < ORDER; c++) {
+                const int ic = pme_wrap(ps.k0[2] + c, d.gz);
                 const double wx = tx * ps.th[2][c], wy = ty * ps.th[2][c], wz = tz * ps.dth[2][c];
-                if (want1) { const double p = phi1[row + ic]; f1[0] += wx * p; f1[1] += wy * p; f1[2] += wz * p; }
-                if (want2) { const double p = phi2[row + ic]; f2[0] += wx * p; f2[1] += wy * p; f2[2] += wz * p; }
+                if (want1) { const double p = __ldg(phi1 + row + ic); f1x += wx * p; f1y += wy * p; f1z += wz * p; }
+                if (want2) { const double p = __ldg(phi2 + row + ic); f2x += wx * p; f2y += wy * p; f2z += wz * p; }
             }
         }
     }
     const double q = (double)x.w;
-    const double sc[3] = {-q * d.gx / (double)L.x, -q * d.gy / (double)L.y, -q * d.gz / (double)L.z};
+    const double sx = -q * d.gx / (double)L.x, sy = -q * d.gy / (double)L.y, sz = -q * d.gz / (double)L.z;
     const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
     unsigned long long *buf1 = d.buf + 3 * cs + rsite, *buf2 = d.buf + 6 * cs + rsite;
-    for (int c = 0; c < 3; c++) {
-        if (want1) atomicAdd(buf1 + c * cs + s, (unsigned long long)__double2ll_rn(sc[c] * f1[c] * FORCE_SCALE));
-        if (want2) atomicAdd(buf2 + c * cs + s, (unsigned long long)__double2ll_rn(sc[c] * f2[c] * FORCE_SCALE));
+    if (want1) {
+        atomicAdd(buf1 + s, (unsigned long long)__double2ll_rn(sx * f1x * FORCE_SCALE));
+        atomicAdd(buf1 + cs + s, (unsigned long long)__double2ll_rn(sy * f1y * FORCE_SCALE));
+        atomicAdd(buf1 + 2 * cs + s, (unsigned long long)__double2ll_rn(sz * f1z * FORCE_SCALE));
+    }
+    if (want2) {
+        atomicAdd(buf2 + s, (unsigned long long)__double2ll_rn(sx * f2x * FORCE_SCALE));
+        atomicAdd(buf2 + cs + s, (unsigned long long)__double2ll_rn(sy * f2y * FORCE_SCALE));
+        atomicAdd(buf2 + 2 * cs + s, (unsigned long long)__double2ll_rn(sz * f2z * FORCE_SCALE));
+    }
+}
+
+static void launch_pme_spread(const NbDev &d, cudaStream_t stream) {
+    const dim3 grid((d.Smax + 127) / 128, d.R);
+    switch (d.pme_order) {
+        case 4: pme_spread_kernel<4><<<grid, 128, 0, stream>>>(d); break;
+        case 5: pme_spread_kernel<5><<<grid, 128, 0, stream>>>(d); break;
+        case 6: pme_spread_kernel<6><<<grid, 128, 0, stream>>>(d); break;
+        case 7: pme_spread_kernel<7><<<grid, 128, 0, stream>>>(d); break;
+        default: pme_spread_kernel<8><<<grid, 128, 0, stream>>>(d); break;
+    }
+}
+
+static void launch_pme_gather(const NbDev &d, cudaStream_t stream) {
+    const dim3 grid((d.Smax + 127) / 128, d.R);
+    switch (d.pme_order) {
+        case 4: pme_gather_kernel<4><<<grid, 128, 0, stream>>>(d); break;
+        case 5: pme_gather_kernel<5><<<grid, 128, 0, stream>>>(d); break;
+        case 6: pme_gather_kernel<6><<<grid, 128, 0, stream>>>(d); break;
+        case 7: pme_gather_kernel<7><<<grid, 128, 0, stream>>>(d); break;
+        default: pme_gather_kernel<8><<<grid, 128, 0, stream>>>(d); break;
     }
 }
 
@@ -1838,7 +1895,7 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
     }
     if (d.pme_on) {
         const size_t ng = (size_t)d.gx * d.gy * d.gz, nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
-        pme_spread_kernel<<<dim3((d.Smax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        launch_pme_spread(d, stream);
         pme_finalize_kernel<<<dim3((unsigned)((ng + 255) / 256), d.R), 256, 0, stream>>>(d);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecD2Z(nb->pme_plan_fwd, d.pme_grid, (cufftDoubleComplex *)d.pme_spec) == CUFFT_SUCCESS, ATM_ERR_CUDA,
@@ -1847,7 +1904,7 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecZ2D(nb->pme_plan_bwd, (cufftDoubleComplex *)d.pme_spec, d.pme_grid) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecZ2D failed");
-        pme_gather_kernel<<<dim3((d.Smax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        launch_pme_gather(d, stream);
         h->launches += 4;  // own kernels (the FFTs are cuFFT library code)
     }
     nb_scalar_kernel<<<(d.R + 31) / 32, 32, 0, stream>>>(d, io->energy_ext, io->include_energy);
@@ -2019,9 +2076,9 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
     };
     int rc;
     void *p;
-    if ((rc = alloc(&p, sizeof(unsigned long long) * 3 * ng * R))) return rc;
+    if ((rc = alloc(&p, sizeof(unsigned long long) * 2 * ng * R))) return rc;
     d.pme_acc = (unsigned long long *)p;
-    ATM_CUDA_CHECK(cudaMemset(d.pme_acc, 0, sizeof(unsigned long long) * 3 * ng * R));
+    ATM_CUDA_CHECK(cudaMemset(d.pme_acc, 0, sizeof(unsigned long long) * 2 * ng * R));
     if ((rc = alloc(&p, sizeof(double) * 2 * ng * R))) return rc;
     d.pme_grid = (double *)p;
     if ((rc = alloc(&p, sizeof(double2) * 2 * nspec * R))) return rc;

@@ -15,6 +15,7 @@ ap.add_argument("--skin", type=float, default=0.1)
 ap.add_argument("--natoms", type=int, default=25000)
 ap.add_argument("--skin-outer", type=float, default=0.3)
 ap.add_argument("--no-energy", action="store_true")
+ap.add_argument("--pme", action="store_true")
 args = ap.parse_args()
 
 s = synthetic.config3() if args.system == "config3" else (synthetic.config4() if args.system == "config4" else synthetic.water_box(args.natoms))
@@ -28,6 +29,10 @@ sched = synthetic.atm_schedule_22()
 for r in range(R):
     be.set_parameters(sched[r % 22], replica=r)
 be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin, skin_outer=args.skin_outer, exclusions=s["excl"])
+if args.pme:
+    grid = synthetic.pme_grid(s["box"], s["ewald_alpha"])
+    be.pme_setup(grid)
+    print("pme grid", grid)
 posq = np.zeros((R, P, 4), np.float32)
 rng = np.random.default_rng(0)
 for r in range(R):
