@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--skip-two-separate", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=6)
     ap.add_argument("--pme", action="store_true", help="also evaluate the two-state PME reciprocal space inside the step "
                     "(SURVEY 8f row 1; NOT part of the headline workload, which is the direct-space path)")
     return ap.parse_args()
@@ -368,32 +369,73 @@ def run_b200(args):
             b1.close()
         del singles, posq2, f_tmp
 
-    # ---- end to end through the public call with HOST buffers: H2D coordinates, step, D2H forces + energies
+    # ---- end to end through the public call with HOST buffers: every step copies that step's coordinates H2D from
+    #      pinned memory, runs the step, and reads forces + energies back D2H.  The replicas of the rank are split into
+    #      --e2e-chunks handles on their own streams so that the copies of one chunk overlap the compute of another
+    #      (everything still happens inside the timed step; PCIe is full duplex).
     e2e_ms = None
     h2d = d2h = 0
+    e2e_chunks = 0
     if R > 0:
+        e2e_chunks = max(1, min(args.e2e_chunks, R))
+        bounds = [round(i * R / e2e_chunks) for i in range(e2e_chunks + 1)]
+        chunks = []
+        for c in range(e2e_chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if e2e_chunks == 1:
+                bc = be
+            else:
+                bc = atm.ATMBackend(n, precision="mixed", num_replicas=hi - lo, device=local_rank)
+                bc.set_displacements(s["displ"])
+                bc.set_box(s["box"])
+                for k in range(lo, hi):
+                    bc.set_parameters(sched[replica_state[mine[k]]], replica=k - lo)
+                bc.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=args.skin,
+                            skin_outer=args.skin_outer, exclusions=s["excl"], exception_pairs=s["exc14"],
+                            exception_params=s["exc14_par"])
+                if pme_grid is not None:
+                    bc.pme_setup(pme_grid)
+            st_c = torch.cuda.Stream(device=dev)
+            en_c = torch.zeros((hi - lo, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory()
+            with torch.cuda.stream(st_c):
+                bc.rebuild(posq[lo:hi], stream=st_c)
+            chunks.append((bc, lo, hi, st_c, en_c))
+        torch.cuda.synchronize()
         KE = min(K, 50)
         ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
+        done = [torch.cuda.Event() for _ in range(e2e_chunks)]
         for k in range(KE + 3):
             with torch.cuda.stream(stream):
                 if flush is not None:
                     flush.zero_()
-                if k >= 3:
-                    ee[k - 3][0].record(stream)
-                posq.copy_(posq_h, non_blocking=True)
-                corr.copy_(corr_h, non_blocking=True)
-                force.zero_()
-                if k % args.prune_every == 0:
-                    be.prune(posq, stream=stream)
-                be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream)
-                force_h.copy_(force, non_blocking=True)
-                en_h = be.get_energies(stream=stream)  # D2H + synchronise: the step's result is on the host
+                start = ee[k - 3][0] if k >= 3 else torch.cuda.Event()
+                start.record(stream)
+            for ci, (bc, lo, hi, st_c, en_c) in enumerate(chunks):
+                with torch.cuda.stream(st_c):
+                    st_c.wait_event(start)
+                    posq[lo:hi].copy_(posq_h[lo:hi], non_blocking=True)
+                    corr[lo:hi].copy_(corr_h[lo:hi], non_blocking=True)
+                    force[lo:hi].zero_()
+                    if k % args.prune_every == 0:
+                        bc.prune(posq[lo:hi], stream=st_c)
+                    bc.step(posq[lo:hi], force[lo:hi], posq_corr=corr[lo:hi], include_energy=True, graph=use_graph, stream=st_c)
+                    force_h[lo:hi].copy_(force[lo:hi], non_blocking=True)
+                    en_dev = torch.as_tensor(_DevView(bc.energies_device_ptr(), (hi - lo, _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
+                    en_c.copy_(en_dev, non_blocking=True)
+                    done[ci].record(st_c)
+            with torch.cuda.stream(stream):
+                for ev in done:
+                    stream.wait_event(ev)
                 if k >= 3:
                     ee[k - 3][1].record(stream)
+            stream.synchronize()  # the step's result (forces, energies) is on the host before the next step starts
         torch.cuda.synchronize()
         e2e_ms = sum(a.elapsed_time(b) for a, b in ee) / KE
         h2d = posq_h.numel() * 4 + corr_h.numel() * 4
-        d2h = force_h.numel() * 8 + en_h.size * 8
+        d2h = force_h.numel() * 8 + R * _capi.NUM_ENERGY_SLOTS * 8
+        for bc, *_ in chunks:
+            if bc is not be:
+                bc.close()
     t = torch.tensor([e2e_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -448,7 +490,7 @@ def run_b200(args):
                        "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "chunks": e2e_chunks},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,
         }
         print(json.dumps(line))
