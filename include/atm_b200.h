@@ -162,9 +162,16 @@ int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
 /* Optional: evaluate the PME reciprocal space of BOTH states inside atm_step as well (smooth PME,
  * B-splines of `order` (OpenMM: 5), mesh nx*ny*nz, double precision, cuFFT for the transforms; the environment charge
  * is spread once for the two states).  U1/U2 then contain direct + reciprocal + self energy, i.e. the complete
- * NonbondedForce of both inner contexts except the long-range dispersion correction.  nx = ny = nz = 0 switches it off.
+ * NonbondedForce of both inner contexts (the long-range dispersion correction: atm_nb_set_dispersion_correction).  nx = ny = nz = 0 switches it off.
  * Call after atm_nb_setup.  SYNCHRONISES the device. */
 int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t order);
+
+/* NonbondedForce::setUseDispersionCorrection (OpenMM default: on; ref: the inner contexts evaluate the cloned
+ * NonbondedForce as is, openmmapi/src/ATMMetaForceImpl.cpp:51-65).  When on, the isotropic long-range Lennard-Jones
+ * tail energy  8 pi N^2/V (<eps sig^12>/(9 rc^9) - <eps sig^6>/(3 rc^3))  is added to U1 and U2 by the scalar stage
+ * (identical in both states, so u, W and the forces are unaffected; off by default here).  With PME on, the
+ * neutralising-background term -pi Q^2/(2 V alpha^2) of a charged cell is always included.  Call after atm_nb_setup. */
+int atm_nb_set_dispersion_correction(atm_handle *h, int32_t on);
 
 /* Box vectors (row-major a,b,c in nm) of one replica (-1 = all).  Rectangular boxes only in this build.
  * ref: the box mirror in copyState (CommonATMMetaForceKernels.cpp:214-219). */

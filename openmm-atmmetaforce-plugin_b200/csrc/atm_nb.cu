@@ -85,6 +85,8 @@ struct NbDev {  // everything the kernels need, passed by value
     double2 *pme_spec;             // [R][2][gx][gy][gz/2+1]
     const double *pme_mod;         // |b(m)|^2 moduli: gx + gy + gz doubles
     double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms
+    double pme_qtot2;              // (sum of q sqrt(ke))^2: neutralising-background term -pi Q^2 / (2 V alpha^2)
+    double disp_coeff;             // long-range dispersion correction = disp_coeff / V (0 = off)
 };
 
 struct NbState {
@@ -98,6 +100,8 @@ struct NbState {
     std::vector<int> h_group_of_atom, h_ghost_atom, h_ghost_of_atom;
     std::vector<double> h_box;  // [R][3]
     bool box_set = false, box_dirty = true;
+    double disp_coeff_full = 0.0;  // 8 pi N^2 (<eps sig^12>/(9 rc^9) - <eps sig^6>/(3 rc^3)), applied when switched on
+    bool disp_on = false;
     NbDev d{};
     // owned device memory (freed in nb_destroy)
     std::vector<void *> owned;
@@ -965,12 +969,21 @@ __device__ void scalar_stage_replica(const NbDev &d, int r, const double *__rest
         // reciprocal energies of the two states (accumulated in double, so their difference is as good as the sum)
         const double r1 = (double)(long long)ea[6] / ENERGY_SCALE, r2 = (double)(long long)ea[7] / ENERGY_SCALE;
         const double self = -d.pme_self_sum * (double)d.alpha * 0.5641895835477563;  // -alpha/sqrt(pi) sum q^2
-        U1 += r1 + self;
-        U2 += r2 + self;
+        const float4 Lb = d.box[r];
+        const double bg = -3.141592653589793 * d.pme_qtot2 /
+                          (2.0 * (double)Lb.x * (double)Lb.y * (double)Lb.z * (double)d.alpha * (double)d.alpha);
+        U1 += r1 + self + bg;
+        U2 += r2 + self + bg;
         du += r2 - r1;
         e[ATM_E_UREC1] = r1; e[ATM_E_UREC2] = r2; e[ATM_E_USELF] = self;
     } else {
         e[ATM_E_UREC1] = 0.0; e[ATM_E_UREC2] = 0.0; e[ATM_E_USELF] = 0.0;
+    }
+    if (d.disp_coeff != 0.0) {  // same constant in both states: u is unaffected
+        const float4 Lb = d.box[r];
+        const double ed = d.disp_coeff / ((double)Lb.x * (double)Lb.y * (double)Lb.z);
+        U1 += ed;
+        U2 += ed;
     }
     if (energy_ext) {
         U1 += energy_ext[2 * r];
@@ -1667,6 +1680,30 @@ int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
         nb->h_exc_par[k] = make_float4((float)(ONE_4PI_EPS0 * desc->exception_params[3 * k]), (float)desc->exception_params[3 * k + 1],
                                        (float)(4.0 * desc->exception_params[3 * k + 2]), 0.f);
     }
+    // long-range dispersion correction coefficient (OpenMM theory guide, "Lennard-Jones interaction": the mean of
+    // eps sig^6 and eps sig^12 over all atom pairs, same-atom pairs included, times 8 pi N^2 / V); atoms are grouped
+    // into (sigma, epsilon) classes so the double sum is over classes
+    {
+        std::map<std::pair<double, double>, long long> classes;
+        for (int a = 0; a < N; a++) classes[std::make_pair(desc->sigma[a], desc->epsilon[a])]++;
+        std::vector<std::pair<std::pair<double, double>, long long>> cl(classes.begin(), classes.end());
+        double s12 = 0.0, s6 = 0.0;
+        for (size_t a = 0; a < cl.size(); a++) {
+            const double sa = cl[a].first.first, ea = cl[a].first.second, na = (double)cl[a].second;
+            const double sa6 = pow(sa, 6.0);
+            s12 += 0.5 * na * (na + 1.0) * ea * sa6 * sa6;
+            s6 += 0.5 * na * (na + 1.0) * ea * sa6;
+            for (size_t b = a + 1; b < cl.size(); b++) {
+                const double sg = 0.5 * (sa + cl[b].first.first), ep = sqrt(ea * cl[b].first.second), nn = na * (double)cl[b].second;
+                const double sg6 = pow(sg, 6.0);
+                s12 += nn * ep * sg6 * sg6;
+                s6 += nn * ep * sg6;
+            }
+        }
+        const double npairs = 0.5 * (double)N * ((double)N + 1.0), rc3 = desc->cutoff * desc->cutoff * desc->cutoff;
+        nb->disp_coeff_full = 8.0 * (double)N * (double)N * M_PI * (s12 / npairs / (9.0 * rc3 * rc3 * rc3) - s6 / npairs / (3.0 * rc3));
+        nb->d.disp_coeff = nb->disp_on ? nb->disp_coeff_full : 0.0;
+    }
     // the desc pointers are not kept
     nb->desc.charge = nb->desc.sigma = nb->desc.epsilon = nullptr;
     nb->desc.exclusions = nb->desc.exception_pairs = nullptr;
@@ -2100,12 +2137,22 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         return ATM_ERR_CUDA;
     }
     nb->pme_plans = true;
-    double self = 0.0;
-    for (float q : nb->h_qp) self += (double)q * (double)q;
+    double self = 0.0, qtot = 0.0;
+    for (float q : nb->h_qp) { self += (double)q * (double)q; qtot += (double)q; }
     d.pme_self_sum = self;
+    d.pme_qtot2 = qtot * qtot;
     d.gx = nx; d.gy = ny; d.gz = nz;
     d.pme_order = order;
     d.pme_on = 1;
+    return ATM_OK;
+}
+
+int atm_nb_set_dispersion_correction(atm_handle *h, int32_t on) {
+    ATM_REQUIRE(h && h->nb && h->nb->ready, ATM_ERR_STATE, "atm_nb_set_dispersion_correction: call atm_nb_setup first");
+    NbState *nb = h->nb;
+    nb->disp_on = on != 0;
+    nb->d.disp_coeff = nb->disp_on ? nb->disp_coeff_full : 0.0;
+    nb->alloc_generation++;  // kernel arguments of the cached step graph are stale
     return ATM_OK;
 }
 

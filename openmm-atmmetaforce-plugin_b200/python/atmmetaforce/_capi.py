@@ -22,7 +22,7 @@ PARAM_NAMES = ("lambda1", "lambda2", "alpha", "u0", "w0", "umax", "ubcore", "aco
 SYMBOLS = (
     "atm_last_error", "atm_version", "atm_create", "atm_destroy", "atm_set_displacements", "atm_set_parameters",
     "atm_get_parameters", "atm_copy_state", "atm_wrap_positions", "atm_hybrid_force", "atm_softcore_softplus",
-    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
+    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
 )
 
@@ -80,6 +80,7 @@ def lib():
     L.atm_nb_setup.argtypes = [vp, C.POINTER(NonbondedDesc), vp]
     L.atm_set_box.argtypes = [vp, i32, vp]
     L.atm_pme_setup.argtypes = [vp, i32, i32, i32, i32]
+    L.atm_nb_set_dispersion_correction.argtypes = [vp, i32]
     L.atm_nb_rebuild.argtypes = [vp, vp, vp]
     L.atm_nb_prune.argtypes = [vp, vp, vp]
     L.atm_step.argtypes = [vp, C.POINTER(StepIO), vp]

@@ -117,6 +117,10 @@ class ATMBackend:
         """Switch on the two-state PME reciprocal space (grid = (nx, ny, nz); (0,0,0) switches it off)."""
         check(_capi.lib().atm_pme_setup(self._h, int(grid[0]), int(grid[1]), int(grid[2]), int(order)))
 
+    def set_dispersion_correction(self, on=True):
+        """NonbondedForce.setUseDispersionCorrection: add the long-range LJ tail energy (a constant / V) to U1 and U2."""
+        check(_capi.lib().atm_nb_set_dispersion_correction(self._h, 1 if on else 0))
+
     def set_box(self, box, replica=-1):
         b = np.asarray(box, np.float64)
         if b.size == 3:

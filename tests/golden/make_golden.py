@@ -22,6 +22,20 @@ what the direct-space ATM hot path consumes:
     pin_u    f8  kJ/mol        the reference's pinned perturbation energy (test_abfe.py:148) or NaN
     params   (9,)  f8          lambda1 lambda2 alpha u0 w0 umax ubcore acore direction
 
+and, for the second pin of the reference's test (potential energy of force groups {0, ATM}, test_abfe.py:147), the
+rest of the Amber energy function as prmtop.createSystem(PME, 1 nm, constraints=HBonds) defines it
+(test_abfe.py:41-43) plus the two restraints the test adds (test_abfe.py:60-83):
+
+    pin_pe   f8  kJ/mol        -116071.0 (abfe) or NaN
+    mass     (N,)  f8  amu     prmtop MASS (centroid weights of the CM-CM restraint)
+    bonds    (B,2) i4, bond_par  (B,2) f8   k (kJ/mol/nm^2, E = k (r-r0)^2), r0 (nm); bonds WITHOUT hydrogen only
+                                            (bonds to hydrogen are constraints, rigid water has no bond term)
+    angles   (A,3) i4, angle_par (A,2) f8   k (kJ/mol/rad^2, E = k (t-t0)^2), t0 (rad)
+    dihedrals (D,4) i4, dihedral_par (D,3) f8   k (kJ/mol), periodicity, phase (rad); E = k (1 + cos(n phi - phase))
+    restr_ref (N,3) f8 nm      inpcrd coordinates (centres of the flat-bottom position restraints)
+    posres_atoms i4            receptor carbons with index < 40 (test_abfe.py:76-83); fc 25 kcal/mol/A^2, tol 0.5 A
+    cm_lig, cm_rcpt i4         atoms of the CM-CM flat-bottom restraint (kf 25 kcal/mol/A^2, tol 5 A, offset 0)
+
 The GPU box has no /root/reference, so the tests only ever read the .npz files.
 Nothing from the reference's *source code* is copied; these are data fixtures.
 """
@@ -87,7 +101,40 @@ def read_state_xml(path):
     return np.array(pos), np.diag(box).copy()
 
 
-def build(prmtop_path, xml_path, lig_resids, signs, params, pin_u):
+def read_inpcrd(path, natom):
+    with open(path) as fh:
+        lines = fh.readlines()
+    assert int(lines[1].split()[0]) == natom
+    vals = []
+    for ln in lines[2:]:
+        ln = ln.rstrip("\n")
+        vals += [float(ln[k:k + 12]) for k in range(0, len(ln), 12) if ln[k:k + 12].strip()]
+    return np.array(vals[:3 * natom]).reshape(natom, 3) * 0.1
+
+
+def bonded_terms(top, natom):
+    """The bonded part of the Amber energy function in OpenMM units (kJ/mol, nm, rad)."""
+    kcal = 4.184
+    out = {}
+    bk, br = floats(top["BOND_FORCE_CONSTANT"]), floats(top["BOND_EQUIL_VALUE"])
+    b = ints(top["BONDS_WITHOUT_HYDROGEN"]).reshape(-1, 3)
+    out["bonds"] = (b[:, :2] // 3).astype(np.int32)
+    out["bond_par"] = np.stack([bk[b[:, 2] - 1] * kcal * 100.0, br[b[:, 2] - 1] * 0.1], axis=1)
+    ak, a0 = floats(top["ANGLE_FORCE_CONSTANT"]), floats(top["ANGLE_EQUIL_VALUE"])
+    a = np.concatenate([ints(top[n]).reshape(-1, 4) for n in ("ANGLES_INC_HYDROGEN", "ANGLES_WITHOUT_HYDROGEN")])
+    out["angles"] = (a[:, :3] // 3).astype(np.int32)
+    out["angle_par"] = np.stack([ak[a[:, 3] - 1] * kcal, a0[a[:, 3] - 1]], axis=1)
+    dk, dn, dp = (floats(top["DIHEDRAL_FORCE_CONSTANT"]), floats(top["DIHEDRAL_PERIODICITY"]),
+                  floats(top["DIHEDRAL_PHASE"]))
+    d = np.concatenate([ints(top[n]).reshape(-1, 5) for n in ("DIHEDRALS_INC_HYDROGEN", "DIHEDRALS_WITHOUT_HYDROGEN")])
+    out["dihedrals"] = (np.abs(d[:, :4]) // 3).astype(np.int32)
+    out["dihedral_par"] = np.stack([dk[d[:, 4] - 1] * kcal, dn[d[:, 4] - 1], dp[d[:, 4] - 1]], axis=1)
+    out["mass"] = floats(top["MASS"])
+    assert out["mass"].size == natom
+    return out
+
+
+def build(prmtop_path, xml_path, lig_resids, signs, params, pin_u, inpcrd_path=None, pin_pe=float("nan")):
     top = read_prmtop(prmtop_path)
     ptr = ints(top["POINTERS"])
     natom, ntypes = int(ptr[0]), int(ptr[1])
@@ -165,6 +212,15 @@ def build(prmtop_path, xml_path, lig_resids, signs, params, pin_u):
                exc14=e14, exc14_par=p14, displ=displ,
                lig1=ligs[0], lig2=(ligs[1] if len(ligs) > 1 else np.zeros(0, np.int32)),
                pin_u=np.float64(pin_u), params=np.array(params, dtype=np.float64))
+    out.update(bonded_terms(top, natom))
+    out["pin_pe"] = np.float64(pin_pe)
+    if inpcrd_path is not None:
+        names = [x.strip() for x in top["ATOM_NAME"]]
+        rcpt = np.arange(rptr[0] - 1, rptr[1] - 1, dtype=np.int32)   # residue 1 (test_abfe.py:33,49-52)
+        out["restr_ref"] = read_inpcrd(inpcrd_path, natom)
+        out["posres_atoms"] = np.array([i for i in rcpt if names[i].startswith("C") and i < 40], dtype=np.int32)
+        out["cm_lig"] = ligs[0]
+        out["cm_rcpt"] = rcpt
     return out
 
 
@@ -174,7 +230,8 @@ def main():
     kcal = 4.184
     # test_abfe.py:22-31 (lambda .5/.5, alpha 0, u0 0, w0 0, umax 200 kcal, ubcore 100 kcal, acore 1/16, dir +1)
     abfe = build(f"{REF}/python/tests/temoa-g1.prmtop", f"{REF}/python/tests/temoa-g1-equil.xml",
-                 [2], [+1.0], [0.5, 0.5, 0.0, 0.0, 0.0, 200 * kcal, 100 * kcal, 0.0625, 1.0], 58.2)
+                 [2], [+1.0], [0.5, 0.5, 0.0, 0.0, 0.0, 200 * kcal, 100 * kcal, 0.0625, 1.0], 58.2,
+                 inpcrd_path=f"{REF}/python/tests/temoa-g1.inpcrd", pin_pe=-116071.0)
     np.savez_compressed(os.path.join(OUT, "temoa_g1_abfe.npz"), **abfe)
     # rbfe.py:18-26 (umax 100 kcal, ubcore 50 kcal); no reference pin exists for this system
     rbfe = build(f"{REF}/example/rbfe/temoa-g1-g4.prmtop", f"{REF}/example/rbfe/temoa-g1-g4-equil.xml",

@@ -61,6 +61,39 @@ def test_abfe_pin_fully_on_gpu(abfe):
     assert rel_rms(r["f_gpu"], r["f_ref"]) <= 1e-5
 
 
+def test_abfe_potential_energy_pin_on_gpu(abfe):
+    """Reference pin no. 2 (python/tests/test_abfe.py:147,149): PE of force groups {0, ATM} = -116071.0 +- 0.1 kJ/mol.
+    The ATM force's energy e0 + W (the complete NonbondedForce of state 1 incl. dispersion correction, plus lambda2 u)
+    comes from the GPU; the group-0 terms (bonds, angles, torsions, restraints; not on the ATM path) from the numpy
+    oracle.  Also checks that the dispersion switch changes U1 and U2 by the same constant and nothing else."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    import oracle_bonded as B
+    from helpers import make_backend
+    alpha = O.ewald_alpha(1.0)
+    grid = O.pme_grid(abfe["box"], alpha)
+    be, posq, _ = make_backend(atm, abfe, 1.0, alpha, abfe["params"], skin=0.1)
+    be.pme_setup(grid, 5)
+    be.rebuild(posq)
+    force0 = torch.zeros((1, 3 * be.P), dtype=torch.int64, device="cuda")
+    be.step(posq, force0)
+    en0 = be.get_energies()[0].copy()
+    be.set_dispersion_correction(True)
+    force = torch.zeros_like(force0)
+    be.step(posq, force, graph=True, stream=torch.cuda.Stream())
+    torch.cuda.synchronize()
+    en = be.get_energies()[0].copy()
+    be.close()
+    disp = B.dispersion_correction(abfe["sigma"], abfe["epsilon"], 1.0, float(abfe["box"].prod()))
+    assert abs((en[E_U1] - en0[E_U1]) - disp) <= 2e-3 and abs((en[E_U2] - en0[E_U2]) - disp) <= 2e-3
+    assert en[E_USC] == en0[E_USC] and en[E_SP] == en0[E_SP] and torch.equal(force, force0)
+    g0, _ = B.group0_energy(abfe)
+    pe = g0 + en[E_ENERGY]
+    print("abfe PE on the GPU: %.4f (pin %.1f), dispersion %.4f" % (pe, float(abfe["pin_pe"]), disp))
+    assert abs(pe - float(abfe["pin_pe"])) <= 0.1
+
+
 def test_rbfe_pme(rbfe):
     import oracle_py as O
     from helpers import rel_rms

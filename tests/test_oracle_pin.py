@@ -30,6 +30,39 @@ def test_abfe_perturbation_energy_pin(abfe):
     assert abs(c2[2] - c1[2]) < 1e-6 and abs(c2[3] - c1[3]) < 1e-6
 
 
+def test_abfe_potential_energy_pin(abfe):
+    """Reference pin no. 2: potential energy of force groups {0, ATM} = -116071.0 +- 0.1 kJ/mol
+    (reference python/tests/test_abfe.py:138-149).  PE = bonds + angles + torsions + restraints (group 0) + U1 + W(u),
+    U1 = the complete NonbondedForce of state 1: direct space + exceptions + smooth-PME reciprocal (OpenMM's mesh rule,
+    order 5) + self + neutralising background + long-range dispersion correction; W = lambda2 * u at alpha = 0.
+    This pins the oracle's ABSOLUTE nonbonded energy (1e-6 relative), not just the difference u."""
+    import oracle_bonded as B
+    alpha = O.ewald_alpha(1.0)
+    S = oracle_system(O, abfe, 1.0, alpha)
+    pos, pos2 = abfe["pos"], abfe["pos"] + abfe["displ"]
+    box, q = abfe["box"], abfe["charge"]
+    grid = O.pme_grid(box, alpha)
+    assert grid == [35, 40, 35]
+    e1, _, _ = S.nb_direct(pos, want_force=False)
+    e2, _, _ = S.nb_direct(pos2, want_force=False)
+    r1, _ = S.pme_recip(pos, grid, 5)
+    r2, _ = S.pme_recip(pos2, grid, 5)
+    V = float(box.prod())
+    const = (-138.935456 * alpha / np.sqrt(np.pi) * (q ** 2).sum()             # Ewald self energy
+             - np.pi * 138.935456 * q.sum() ** 2 / (2.0 * V * alpha ** 2)       # neutralising background
+             + B.dispersion_correction(abfe["sigma"], abfe["epsilon"], 1.0, V))
+    U1, U2 = e1 + r1 + const, e2 + r2 + const
+    sc = O.scalars(abfe["params"], U1, U2)
+    g0, parts = B.group0_energy(abfe)
+    assert parts["cmcm"] == 0.0 and parts["posres"] == 0.0      # both flat bottoms are inactive in this snapshot
+    assert abs(g0 - 1465.5653) < 1e-3, parts                    # 253.7223 + 485.0019 + 726.8411
+    pe = g0 + sc["energy"]
+    assert abs(sc["u_sc"] - float(abfe["pin_u"])) <= 0.1
+    assert abs(pe - float(abfe["pin_pe"])) <= 0.1, pe           # measured: -116071.0345
+    # the dispersion convention is discriminated by the pin: without the i = j pairs the total misses by 0.19
+    assert abs(B.dispersion_correction(abfe["sigma"], abfe["epsilon"], 1.0, V) - (-512.3157)) < 1e-3
+
+
 def test_rbfe_self_consistency(rbfe):
     """No reference pin exists for the RBFE system (parity unpinned); value recorded at survey time: 2.1072."""
     alpha = O.ewald_alpha(1.0)
