@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -159,6 +160,13 @@ __device__ __forceinline__ float wrap_delta(float d, float L, float invL) {
     return d - L * __fadd_rn(__fadd_rn(d * invL, 12582912.0f), -12582912.0f);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor drains; it must not touch the predecessor's output before pdl_wait() returns (which
+// waits for the predecessor grid to complete and its writes to be visible).  pdl_trigger() in the predecessor lets the
+// dependent grid be scheduled as soon as every predecessor block has started.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void red_add_fixed(unsigned long long *addr, float f) {
     long long v = __float2ll_rn(f * 4294967296.0f);
     atomicAdd(addr, (unsigned long long)v);
@@ -271,8 +279,11 @@ __global__ void nl_link_ghosts_kernel(NbDev d) {
 // Every step: gather current coordinates into cluster order; ghosts get posq + displ (the same float add as
 // CopyState, so a ghost sits exactly at the reference's posq2).
 __global__ void nb_pack_kernel(NbDev d, const float4 *__restrict__ posq) {
+    pdl_trigger();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
+    // first kernel of a step: the energy / pair-count accumulators of the previous step have been consumed by its merge
+    if (blockIdx.x == 0 && threadIdx.x < EACC_SLOTS) d.eacc[(size_t)r * EACC_SLOTS + threadIdx.x] = 0ull;
     if (t >= CL * d.nclusters[r]) return;
     const size_t rs = (size_t)r * d.Smax + t;
     const int src = d.slot_src[rs];
@@ -959,12 +970,14 @@ constexpr int MERGE2_THREADS = 256;
 
 // Scalar stage, one thread per replica: u = U(S2) - U(S1), soft-core, softplus, sp -- all in double on the device
 // (the reference does this on the host after two blocking energy downloads, CommonATMMetaForceKernels.cpp:164-199).
-__device__ void scalar_stage_replica(const NbDev &d, int r, const double *__restrict__ energy_ext, int include_energy) {
+__device__ double scalar_stage_replica(const NbDev &d, int r, const double *__restrict__ energy_ext, int include_energy,
+                                       bool write_record) {
     volatile unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;  // written by atomics of other blocks: read through L2
     const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
                  u2 = (double)(long long)ea[2] / ENERGY_SCALE;
     double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
     double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
+    double rec1 = 0.0, rec2 = 0.0, eself = 0.0;
     if (d.pme_on) {
         // reciprocal energies of the two states (accumulated in double, so their difference is as good as the sum)
         const double r1 = (double)(long long)ea[6] / ENERGY_SCALE, r2 = (double)(long long)ea[7] / ENERGY_SCALE;
@@ -975,9 +988,7 @@ __device__ void scalar_stage_replica(const NbDev &d, int r, const double *__rest
         U1 += r1 + self + bg;
         U2 += r2 + self + bg;
         du += r2 - r1;
-        e[ATM_E_UREC1] = r1; e[ATM_E_UREC2] = r2; e[ATM_E_USELF] = self;
-    } else {
-        e[ATM_E_UREC1] = 0.0; e[ATM_E_UREC2] = 0.0; e[ATM_E_USELF] = 0.0;
+        rec1 = r1; rec2 = r2; eself = self;
     }
     if (d.disp_coeff != 0.0) {  // same constant in both states: u is unaffected
         const float4 Lb = d.box[r];
@@ -991,13 +1002,14 @@ __device__ void scalar_stage_replica(const NbDev &d, int r, const double *__rest
         du += energy_ext[2 * r + 1] - energy_ext[2 * r];
     }
     const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
-    e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
-    e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp;
-    e[ATM_E_NPAIRS] = (double)(ea[3] + ea[4] + ea[5]);
-    e[ATM_E_NPAIRS_C] = (double)ea[3]; e[ATM_E_NPAIRS_S1] = (double)ea[4]; e[ATM_E_NPAIRS_S2] = (double)ea[5];
-    // this thread is the only reader: hand the accumulators back zeroed for the next step (stream order protects them)
-#pragma unroll
-    for (int k = 0; k < EACC_SLOTS; k++) ea[k] = 0ull;
+    if (write_record) {
+        e[ATM_E_UREC1] = rec1; e[ATM_E_UREC2] = rec2; e[ATM_E_USELF] = eself;
+        e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
+        e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp;
+        e[ATM_E_NPAIRS] = (double)(ea[3] + ea[4] + ea[5]);
+        e[ATM_E_NPAIRS_C] = (double)ea[3]; e[ATM_E_NPAIRS_S1] = (double)ea[4]; e[ATM_E_NPAIRS_S2] = (double)ea[5];
+    }
+    return s.sp;  // the accumulators are zeroed by the next step's pack kernel
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1015,6 +1027,8 @@ struct SpecialArgs {
 template <bool STATS>
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS)
 nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
+    pdl_trigger();  // the merge may be scheduled once every block of this grid has started (it waits for completion)
+    pdl_wait();     // cluster-order coordinates come from the pack kernel
     const int lane = threadIdx.x & 31;
     if ((int)blockIdx.x < n_item_blocks) {
         const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
@@ -1046,28 +1060,29 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     }
 }
 
-// Scalar stage, one thread per replica (a separate 1-block launch: a "last block done" fusion into nb2 costs one
-// same-address atomic per warp and measurably slows the force kernel).
-__global__ void nb_scalar_kernel(NbDev d, const double *__restrict__ energy_ext, int include_energy) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < d.R) scalar_stage_replica(d, r, energy_ext, include_energy);
-}
-
 // Merge, one thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
 // read-modify-write of the caller's force buffer is a scatter.  The thread of a displaced atom also folds in (and
 // zeroes) the S2 accumulator of its ghost site; ghost and padding slots have no thread work.
 // F[slot] += C + llrint(sp * S2 + (1 - sp) * S1), blend in double (kernels/atmmetaforce.cc:8-16 semantics).
+// The scalar stage is fused in: thread 0 of every block forms u, the soft core, the softplus bias and sp = dW/du of the
+// block's replica in double (the reference does this on the host after two blocking energy downloads,
+// CommonATMMetaForceKernels.cpp:164-199); every block gets the same bits, block 0 of a replica writes the energy record.
 __global__ void __launch_bounds__(MERGE2_THREADS)
 nb_merge_kernel(NbDev d, long long *__restrict__ force, const long long *__restrict__ f1_ext,
-                const long long *__restrict__ f2_ext) {
+                const long long *__restrict__ f2_ext, const double *__restrict__ energy_ext, int include_energy) {
+    __shared__ double s_sp;
     const int r = blockIdx.y;
     const int s = blockIdx.x * MERGE2_THREADS + threadIdx.x;
-    if (s >= CL * d.nclusters[r]) return;
     const size_t rsite = (size_t)r * d.Smax;
-    const int i = d.slot_out[rsite + s];  // caller's slot of this site's atom, -1 for ghosts and padding
+    // everything that does not depend on the force kernel first
+    const bool live = s < CL * d.nclusters[r];
+    const int i = live ? d.slot_out[rsite + s] : -1;  // caller's slot of this site's atom, -1 for ghosts and padding
+    const int gs = i >= 0 ? d.slot_ghost[rsite + s] : -1;
+    pdl_wait();
+    if (threadIdx.x == 0) s_sp = scalar_stage_replica(d, r, energy_ext, include_energy, blockIdx.x == 0);
+    __syncthreads();
     if (i < 0) return;
-    const int gs = d.slot_ghost[rsite + s];
-    const double sp = d.energies[(size_t)r * ATM_NUM_ENERGY_SLOTS + ATM_E_SP], sp1 = 1.0 - sp;
+    const double sp = s_sp, sp1 = 1.0 - sp;
     const size_t cs = (size_t)d.R * d.Smax;
     long long *bufC = (long long *)d.buf + rsite, *buf1 = bufC + 3 * cs, *buf2 = bufC + 6 * cs;
     long long fc[3], fa[3], fb[3], fg[3], fo_old[3];
@@ -1295,6 +1310,31 @@ __global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
         atomicAdd(buf2 + cs + s, (unsigned long long)__double2ll_rn(sy * f2y * FORCE_SCALE));
         atomicAdd(buf2 + 2 * cs + s, (unsigned long long)__double2ll_rn(sz * f2z * FORCE_SCALE));
     }
+}
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its predecessor
+// in the stream drains (see pdl_wait / pdl_trigger).  ATM_B200_PDL=0 in the environment switches the overlap off (A/B).
+static bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("ATM_B200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 static void launch_pme_spread(const NbDev &d, cudaStream_t stream) {
@@ -1924,8 +1964,9 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
             ATM_CUDA_CHECK(cudaEventRecord(e0, stream));
         }
         if (nblocks > 0) {
-            if (io->collect_stats) nb2_kernel<true><<<nblocks, NB_THREADS, 0, stream>>>(d, item_blocks, io->include_energy, spa);
-            else nb2_kernel<false><<<nblocks, NB_THREADS, 0, stream>>>(d, item_blocks, io->include_energy, spa);
+            // dependent launch on the pack kernel (not when profiling: the event pair must bracket nb2 alone)
+            ATM_CUDA_CHECK(launch_dependent(io->collect_stats ? nb2_kernel<true> : nb2_kernel<false>, dim3(nblocks), dim3(NB_THREADS), stream,
+                                            !profile, d, item_blocks, (int)io->include_energy, spa));
             h->launches++;
         }
         if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
@@ -1944,10 +1985,10 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         launch_pme_gather(d, stream);
         h->launches += 4;  // own kernels (the FFTs are cuFFT library code)
     }
-    nb_scalar_kernel<<<(d.R + 31) / 32, 32, 0, stream>>>(d, io->energy_ext, io->include_energy);
-    h->launches++;
-    nb_merge_kernel<<<dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), MERGE2_THREADS, 0, stream>>>(
-        d, (long long *)io->force, (const long long *)io->force_state1_ext, (const long long *)io->force_state2_ext);
+    // scalar stage + merge; a dependent launch only directly behind nb2 (its pdl_wait needs nb2 as the predecessor)
+    ATM_CUDA_CHECK(launch_dependent(nb_merge_kernel, dim3((d.Smax + MERGE2_THREADS - 1) / MERGE2_THREADS, d.R), dim3(MERGE2_THREADS), stream,
+                                    !profile && !d.pme_on && nblocks > 0, d, (long long *)io->force, (const long long *)io->force_state1_ext,
+                                    (const long long *)io->force_state2_ext, io->energy_ext, (int)io->include_energy));
     h->launches += 2;  // pack, merge
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
@@ -2006,7 +2047,7 @@ int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
         ATM_REQUIRE(err == cudaSuccess, ATM_ERR_CUDA, "atm_step_graph: instantiate failed: %s", cudaGetErrorString(err));
         nb->graph_io = *io;
         nb->graph_generation = nb->alloc_generation;
-        nb->graph_nodes = 4 + (io->posq1 ? 1 : 0) + (nb->d.pme_on ? 4 : 0);  // pack, nb2 (+special pairs), [PME x4], scalar stage, merge
+        nb->graph_nodes = 3 + (io->posq1 ? 1 : 0) + (nb->d.pme_on ? 4 : 0);  // pack, nb2 (+special pairs), [PME x4], scalar stage + merge
     }
     ATM_CUDA_CHECK(cudaGraphLaunch(nb->graph_exec, stream));
     h->launches += nb->graph_nodes;
