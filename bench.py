@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--exchange-every", type=int, default=100)
     ap.add_argument("--skin", type=float, default=0.1)
     ap.add_argument("--skin-outer", type=float, default=0.3)
+    ap.add_argument("--host-exchange", action="store_true", help="run the replica-exchange sweep on the host (D2H copy + "
+                    "synchronisation per cycle) instead of the on-device cycle")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
@@ -238,8 +240,16 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    device_exchange = not args.host_exchange and total_replicas >= world
+    if device_exchange:
+        with torch.cuda.stream(stream):
+            rex.attach_device(be, stream=stream)
+
     def exchange(cycle):
         """all-gather (U1,U2) of every replica, identical Metropolis sweep on every rank, swap lambda states."""
+        if device_exchange:   # pack kernel -> NCCL all-gather -> sweep kernel, no host synchronisation
+            rex.exchange_device(stream=stream)
+            return
         en = torch.as_tensor(_DevView(be.energies_device_ptr(), (max(R, 1), _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
         for k, row in rex.exchange(en[:, 0:2].contiguous()):
             be.set_parameters(row, replica=k)
@@ -303,6 +313,8 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
+    if device_exchange:
+        rex.sync_from_device(stream=stream)   # bookkeeping only (raises on a non-finite energy), outside the timed region
     launches = be.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in events) if R > 0 else 0.0
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -485,7 +497,7 @@ def run_b200(args):
             "config": {"workload": label, "replicas": total_replicas, "replicas_per_rank": max_per_rank, "atoms": int(n),
                        "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
                        "prune_every": args.prune_every, "rebuild_every": args.rebuild_every,
-                       "exchange_every": args.exchange_every, "cuda_graph": use_graph, "pme_grid": pme_grid,
+                       "exchange_every": args.exchange_every, "exchange": "device" if device_exchange else "host", "cuda_graph": use_graph, "pme_grid": pme_grid,
                        "l2": "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)",
                        "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,

@@ -243,6 +243,24 @@ int atm_nb_stats(atm_handle *h, int64_t out[8]);
 int atm_hrex_sweep(int32_t num_states, const double *state_params, int32_t num_replicas, const double *u12,
                    int32_t *replica_state, double beta, uint64_t seed, uint64_t cycle, int32_t *num_accepted);
 
+/* The same exchange cycle WITHOUT a host round trip (no synchronisation, capturable): the replica -> state table lives
+ * on the device (replicated on every rank), the sweep runs in one small kernel behind the all-gather, and the parameter
+ * rows of the local replicas are rewritten in place.  Bit-identical decisions to atm_hrex_sweep.
+ *   setup    : state_params [num_states][9]; replica_state [num_replicas] initial table; local_replicas [R] global id
+ *              of each local replica (-1 = unused slot); gather_slot [num_replicas] row of replica g in the gathered
+ *              array ([gathered_rows][2] doubles).  SYNCHRONISES `stream` (host arrays are copied).
+ *   pack     : send[k] = {U1, U2} of local replica k (rows >= R are zero) -- the all-gather input.
+ *   exchange : gathered = the all-gathered rows (device); cycle keys the RNG together with the seed.
+ *   state    : copies the table and {accepted swaps, cycles, error flag (a non-finite energy skipped a cycle)} to the
+ *              host; SYNCHRONISES `stream`.  atm_get_parameters / atm_set_parameters refresh the host mirror of the
+ *              parameter rows from the device first. */
+int atm_hrex_device_setup(atm_handle *h, int32_t num_states, const double *state_params, int32_t num_replicas,
+                          const int32_t *replica_state, const int32_t *local_replicas, const int32_t *gather_slot,
+                          int32_t gathered_rows, double beta, uint64_t seed, void *stream);
+int atm_hrex_device_pack(atm_handle *h, double *send, int32_t rows, void *stream);
+int atm_hrex_device_exchange(atm_handle *h, const double *gathered, uint64_t cycle, void *stream);
+int atm_hrex_device_state(atm_handle *h, int32_t *replica_state, int64_t counters[3], void *stream);
+
 /* Reduced energy beta*E_s(x) of coordinates with energies (U1,U2) under state parameters p (host). */
 double atm_hrex_reduced_energy(const double p[ATM_NUM_PARAMS], double U1, double U2, double beta);
 

@@ -29,6 +29,17 @@ int upload_params_if_dirty(atm_handle *h, cudaStream_t stream) {
     return ATM_OK;
 }
 
+// The on-device replica exchange rewrites parameter rows behind the host mirror's back; host reads / edits pull them
+// back first (synchronises the device: rare, bookkeeping only).
+int refresh_params_from_device(atm_handle *h) {
+    if (!h->params_device_newer) return ATM_OK;
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    ATM_CUDA_CHECK(cudaDeviceSynchronize());
+    ATM_CUDA_CHECK(cudaMemcpy(h->params.data(), h->d_params, sizeof(double) * h->params.size(), cudaMemcpyDeviceToHost));
+    h->params_device_newer = false;
+    return ATM_OK;
+}
+
 }  // namespace atm
 
 using namespace atm;
@@ -70,6 +81,8 @@ int atm_create(const atm_config *cfg, atm_handle **out) {
     h->device = dev;
     h->d_displ = nullptr;
     h->d_params = nullptr;
+    h->params_device_newer = false;
+    h->hrex = nullptr;
     h->have_displ = false;
     h->launches = 0;
     h->nb = nullptr;
@@ -98,6 +111,7 @@ int atm_destroy(atm_handle *h) {
     if (h == nullptr) return ATM_OK;
     cudaSetDevice(h->device);
     nb_destroy(h);
+    hrex_destroy(h);
     if (h->d_displ) cudaFree(h->d_displ);
     if (h->d_params) cudaFree(h->d_params);
     delete h;
@@ -139,6 +153,8 @@ int atm_set_displacements(atm_handle *h, const int32_t *atom_index, const double
 int atm_set_parameters(atm_handle *h, int32_t replica, const double p[ATM_NUM_PARAMS]) {
     ATM_REQUIRE(h != nullptr && p != nullptr, ATM_ERR_INVALID, "atm_set_parameters: null argument");
     ATM_REQUIRE(replica >= -1 && replica < h->R, ATM_ERR_INVALID, "atm_set_parameters: replica %d out of range", replica);
+    int rc0 = refresh_params_from_device(h);
+    if (rc0) return rc0;
     for (int r = 0; r < h->R; r++)
         if (replica < 0 || replica == r) std::copy(p, p + ATM_NUM_PARAMS, h->params.begin() + (size_t)r * ATM_NUM_PARAMS);
     h->params_dirty = true;
@@ -148,6 +164,8 @@ int atm_set_parameters(atm_handle *h, int32_t replica, const double p[ATM_NUM_PA
 int atm_get_parameters(atm_handle *h, int32_t replica, double p[ATM_NUM_PARAMS]) {
     ATM_REQUIRE(h != nullptr && p != nullptr, ATM_ERR_INVALID, "atm_get_parameters: null argument");
     ATM_REQUIRE(replica >= 0 && replica < h->R, ATM_ERR_INVALID, "atm_get_parameters: replica %d out of range", replica);
+    int rc0 = refresh_params_from_device(h);
+    if (rc0) return rc0;
     std::copy(h->params.begin() + (size_t)replica * ATM_NUM_PARAMS,
               h->params.begin() + (size_t)(replica + 1) * ATM_NUM_PARAMS, p);
     return ATM_OK;

@@ -92,6 +92,8 @@ struct atm_handle {
     std::vector<double> params;
     double *d_params;
     bool params_dirty;
+    bool params_device_newer;          // the device rows were rewritten by the on-device exchange: refresh the host mirror first
+    void *hrex;                        // atm::HrexState (atm_hrex.cu) or NULL
     std::vector<double> pert_energy;   // cached u_sc per replica (Tier-1 execute)
     uint64_t launches;                 // kernels of this library launched through this handle
     atm::NbState *nb;
@@ -102,6 +104,8 @@ namespace atm {
 void nb_destroy(atm_handle *h);
 int nb_on_displacements_changed(atm_handle *h, cudaStream_t stream);
 int upload_params_if_dirty(atm_handle *h, cudaStream_t stream);
+int refresh_params_from_device(atm_handle *h);
+void hrex_destroy(atm_handle *h);
 
 // Tier-1 launchers implemented in atm_copy_merge.cu
 int launch_copy_state(atm_handle *h, const void *posq, const void *corr, void *posq1, void *corr1, void *posq2,

@@ -24,6 +24,7 @@ SYMBOLS = (
     "atm_get_parameters", "atm_copy_state", "atm_wrap_positions", "atm_hybrid_force", "atm_softcore_softplus",
     "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
+    "atm_hrex_device_setup", "atm_hrex_device_pack", "atm_hrex_device_exchange", "atm_hrex_device_state",
 )
 
 
@@ -93,6 +94,10 @@ def lib():
     L.atm_nb_stats.argtypes = [vp, vp]
     L.atm_hrex_sweep.argtypes = [i32, vp, i32, vp, vp, dbl, C.c_uint64, C.c_uint64, C.POINTER(i32)]
     L.atm_hrex_reduced_energy.argtypes = [vp, dbl, dbl, dbl]
+    L.atm_hrex_device_setup.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, dbl, C.c_uint64, vp]
+    L.atm_hrex_device_pack.argtypes = [vp, vp, i32, vp]
+    L.atm_hrex_device_exchange.argtypes = [vp, vp, C.c_uint64, vp]
+    L.atm_hrex_device_state.argtypes = [vp, vp, vp, vp]
     L.atm_hrex_reduced_energy.restype = dbl
     for name in SYMBOLS:
         fn = getattr(L, name)

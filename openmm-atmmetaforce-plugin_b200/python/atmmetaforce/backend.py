@@ -144,6 +144,38 @@ class ATMBackend:
         fn = _capi.lib().atm_step_graph if graph else _capi.lib().atm_step
         check(fn(self._h, C.byref(io), _stream_ptr(stream)))
 
+    # ---- on-device Hamiltonian replica exchange (no host round trip; include/atm_b200.h atm_hrex_device_*)
+    def hrex_setup(self, schedule, replica_state, local_replicas, gather_slot, gathered_rows, beta, seed, stream=None):
+        sp = _np(schedule, np.float64).reshape(-1, _capi.NUM_PARAMS)
+        rs = _np(replica_state, np.int32)
+        loc = np.full(self.R, -1, np.int32)
+        loc[:len(local_replicas)] = np.asarray(local_replicas, np.int32)
+        gs = _np(gather_slot, np.int32)
+        check(_capi.lib().atm_hrex_device_setup(self._h, sp.shape[0], sp.ctypes.data_as(C.c_void_p), rs.size,
+                                                rs.ctypes.data_as(C.c_void_p), loc.ctypes.data_as(C.c_void_p),
+                                                gs.ctypes.data_as(C.c_void_p), int(gathered_rows), float(beta), int(seed),
+                                                _stream_ptr(stream)))
+
+    def hrex_pack(self, send, stream=None):
+        """send: [rows][2] float64 CUDA tensor <- (U1, U2) of the local replicas (rows >= R zero-filled)."""
+        check(_capi.lib().atm_hrex_device_pack(self._h, _dptr(send), int(send.shape[0]), _stream_ptr(stream)))
+
+    def hrex_exchange(self, gathered, cycle, stream=None):
+        check(_capi.lib().atm_hrex_device_exchange(self._h, _dptr(gathered), int(cycle), _stream_ptr(stream)))
+
+    def hrex_state(self, num_replicas, stream=None):
+        """Synchronises.  Returns (replica_state[num_replicas], accepted swaps, cycles, error flag)."""
+        rs = np.zeros(int(num_replicas), np.int32)
+        cnt = np.zeros(3, np.int64)
+        check(_capi.lib().atm_hrex_device_state(self._h, rs.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p),
+                                                _stream_ptr(stream)))
+        return rs, int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+    def get_parameters(self, replica=0):
+        p = np.zeros(_capi.NUM_PARAMS)
+        check(_capi.lib().atm_get_parameters(self._h, int(replica), p.ctypes.data_as(C.c_void_p)))
+        return p
+
     def profile_enable(self, on=True):
         check(_capi.lib().atm_profile_enable(self._h, 1 if on else 0))
 

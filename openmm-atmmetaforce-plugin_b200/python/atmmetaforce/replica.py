@@ -68,6 +68,39 @@ class ReplicaExchange:
         self.attempted_cycles += 1
         return changed
 
+    # ---- the same cycle without a host round trip (GPU back-end only)
+    def attach_device(self, backend, stream=None):
+        """Move the exchange bookkeeping onto the device of `backend` (an ATMBackend holding this rank's replicas in the
+        order of self.mine).  After this, exchange_device() runs a whole cycle asynchronously on the stream:
+        pack kernel -> all-gather (NCCL) -> sweep kernel that rewrites the local parameter rows in place."""
+        import torch
+        self._be = backend
+        rows = self.world * self.max_per_rank
+        gather_slot = np.array([self._slot[g] for g in range(self.num_replicas)], np.int32)
+        backend.hrex_setup(self.schedule, self.replica_state, self.mine, gather_slot, rows, self.beta, self.seed, stream=stream)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._send = torch.zeros((self.max_per_rank, 2), dtype=torch.float64, device=dev)
+        self._recv = torch.zeros((rows, 2), dtype=torch.float64, device=dev) if self.world > 1 else self._send
+
+    def exchange_device(self, stream=None):
+        """One cycle, fully asynchronous (no .cpu(), no synchronisation).  Bookkeeping: sync_from_device()."""
+        self._be.hrex_pack(self._send, stream=stream)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        self.cycle += 1
+        self._be.hrex_exchange(self._recv, self.cycle, stream=stream)
+        self.attempted_cycles += 1
+
+    def sync_from_device(self, stream=None):
+        """Pull the state permutation and the acceptance count back (synchronises the stream)."""
+        rs, acc, cycles, err = self._be.hrex_state(self.num_replicas, stream=stream)
+        if err:
+            raise FloatingPointError("non-finite replica energy in an exchange step (that cycle was skipped)")
+        self.replica_state[:] = rs
+        self.accepted = acc
+        return rs
+
     def state_dict(self):
         """Checkpoint of the exchange bookkeeping (state permutation, RNG counter)."""
         return {"replica_state": self.replica_state.tolist(), "cycle": self.cycle, "seed": self.seed,
