@@ -425,12 +425,11 @@ def run_b200(args):
             for ci, (bc, lo, hi, st_c, en_c) in enumerate(chunks):
                 with torch.cuda.stream(st_c):
                     st_c.wait_event(start)
-                    posq[lo:hi].copy_(posq_h[lo:hi], non_blocking=True)
-                    corr[lo:hi].copy_(corr_h[lo:hi], non_blocking=True)
+                    posq[lo:hi].copy_(posq_h[lo:hi], non_blocking=True)   # posqCorrection is not an input of this path
                     force[lo:hi].zero_()
                     if k % args.prune_every == 0:
                         bc.prune(posq[lo:hi], stream=st_c)
-                    bc.step(posq[lo:hi], force[lo:hi], posq_corr=corr[lo:hi], include_energy=True, graph=use_graph, stream=st_c)
+                    bc.step(posq[lo:hi], force[lo:hi], include_energy=True, graph=use_graph, stream=st_c)
                     force_h[lo:hi].copy_(force[lo:hi], non_blocking=True)
                     en_dev = torch.as_tensor(_DevView(bc.energies_device_ptr(), (hi - lo, _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
                     en_c.copy_(en_dev, non_blocking=True)
@@ -443,7 +442,7 @@ def run_b200(args):
             stream.synchronize()  # the step's result (forces, energies) is on the host before the next step starts
         torch.cuda.synchronize()
         e2e_ms = sum(a.elapsed_time(b) for a, b in ee) / KE
-        h2d = posq_h.numel() * 4 + corr_h.numel() * 4
+        h2d = posq_h.numel() * 4
         d2h = force_h.numel() * 8 + R * _capi.NUM_ENERGY_SLOTS * 8
         for bc, *_ in chunks:
             if bc is not be:

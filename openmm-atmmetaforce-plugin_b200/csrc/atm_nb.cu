@@ -115,7 +115,7 @@ struct NbState {
     int n_excl = 0, n_exc = 0;
     int sort_bits = 64;
     size_t jlist_entries = 0;
-    int n_items = 0, max_items = 0;
+    int n_items = 0, max_items = 0, items_seen = 0;
     // PME (optional)
     std::vector<void *> pme_owned;
     cufftHandle pme_plan_fwd = 0, pme_plan_bwd = 0;
@@ -587,14 +587,17 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
     const int validA = (d.cmeta[rcA] >> 16) & 0xff;
     const float4 L = d.box[r], iL = d.invbox[r];
     const float rl2 = d.rlist * d.rlist;
-    float xa[CL], ya[CL], za[CL];
+    // cluster atoms relative to the cluster centre as (-2a, |a|^2): |p - a|^2 = |p|^2 + (-2a).p + |a|^2 costs three
+    // FFMAs and a min per atom; all coordinates are within ~1.5 nm of the centre, so the expansion loses nothing that
+    // matters for a skin test
+    float xa[CL], ya[CL], za[CL], a2[CL];
 #pragma unroll
     for (int k = 0; k < CL; k++) {
         const float4 p = __ldg(d.xs + rsite + (size_t)A * CL + k);
         const bool ok = (validA >> k) & 1;
-        xa[k] = ok ? cA.x + wrap_delta(p.x - cA.x, L.x, iL.x) : 1e18f;
-        ya[k] = ok ? cA.y + wrap_delta(p.y - cA.y, L.y, iL.y) : 1e18f;
-        za[k] = ok ? cA.z + wrap_delta(p.z - cA.z, L.z, iL.z) : 1e18f;
+        const float ax = wrap_delta(p.x - cA.x, L.x, iL.x), ay = wrap_delta(p.y - cA.y, L.y, iL.y), az = wrap_delta(p.z - cA.z, L.z, iL.z);
+        xa[k] = -2.f * ax; ya[k] = -2.f * ay; za[k] = -2.f * az;
+        a2[k] = ok ? fmaf(az, az, fmaf(ay, ay, ax * ax)) : 1e30f;
     }
     const unsigned int *in = d.jlist_outer + li.offset;
     unsigned int *out = d.jlist + li.offset;
@@ -613,15 +616,12 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
         if (st + 1 < nst_outer) pnext = __ldg(d.xs + rsite + (e0 >> 8));
         bool keep = false;
         if ((ec & 0xffu) != 0xffu) {
-            const float px = cA.x + wrap_delta(p.x - cA.x, L.x, iL.x), py = cA.y + wrap_delta(p.y - cA.y, L.y, iL.y),
-                        pz = cA.z + wrap_delta(p.z - cA.z, L.z, iL.z);
+            const float px = wrap_delta(p.x - cA.x, L.x, iL.x), py = wrap_delta(p.y - cA.y, L.y, iL.y),
+                        pz = wrap_delta(p.z - cA.z, L.z, iL.z);
             float d2min = 1e30f;
 #pragma unroll
-            for (int k = 0; k < CL; k++) {
-                const float ex = px - xa[k], ey = py - ya[k], ez = pz - za[k];
-                d2min = fminf(d2min, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-            }
-            keep = d2min <= rl2;
+            for (int k = 0; k < CL; k++) d2min = fminf(d2min, fmaf(px, xa[k], fmaf(py, ya[k], fmaf(pz, za[k], a2[k]))));
+            keep = d2min + fmaf(pz, pz, fmaf(py, py, px * px)) <= rl2;
         }
         const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
         if (keep) out[count + __popc(kmask & ((1u << lane) - 1))] = ec;
@@ -1031,8 +1031,11 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     pdl_wait();     // cluster-order coordinates come from the pack kernel
     const int lane = threadIdx.x & 31;
     if ((int)blockIdx.x < n_item_blocks) {
-        const int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
-        if (warp < d.flags[4]) {  // the pruned list's item count lives on the device (the grid is an upper bound)
+        // The pruned list's item count lives on the device; the grid is sized from the count the last verified build
+        // saw plus a margin, and this grid-stride loop picks up whatever a later prune added beyond it.
+        const int n_items = d.flags[4], stride = n_item_blocks * (NB_THREADS / 32);
+        for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride) {
+            __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
             int wi = warp, b = ITEM_STEPS;
             for (; b > 1; --b) {  // longest chunks first
                 const int c = d.flags[ITEM_BUCKET0 + b];
@@ -1314,6 +1317,14 @@ __global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its predecessor
 // in the stream drains (see pdl_wait / pdl_trigger).  ATM_B200_PDL=0 in the environment switches the overlap off (A/B).
+static bool tight_grid_enabled() {  // ATM_B200_TIGHT_GRID=0: size the force kernel's grid from the list capacity (A/B)
+    static const bool on = [] {
+        const char *e = getenv("ATM_B200_TIGHT_GRID");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static bool pdl_enabled() {
     static const bool on = [] {
         const char *e = getenv("ATM_B200_PDL");
@@ -1827,6 +1838,7 @@ static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
     unsigned long long inner_entries = 0;
     memcpy(&inner_entries, &flags[6], 8);
     nb->stats[2] = (int64_t)(inner_entries / d.R);
+    nb->items_seen = flags[4];
     return ATM_OK;
 }
 
@@ -1922,7 +1934,9 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         ATM_CUDA_CHECK(cudaMemcpy(&ncl0, d.nclusters, sizeof(int), cudaMemcpyDeviceToHost));
         nb->stats[0] = d.U; nb->stats[1] = ncl0; nb->stats[3] = d.capC; nb->stats[4] = d.capX;
         nb->stats[5] = d.M; nb->stats[6] = d.G; nb->stats[7] = d.ncol;
-        nb->n_items = nb->max_items;  // launch bound; the live item count stays on the device (flags[4])
+        // launch bound of the force kernel: the item count of this verified build + 12.5 % (the kernel's grid-stride
+        // loop covers any excess); the capacity bound max_items would start ~3x as many blocks, most of them empty
+        nb->n_items = tight_grid_enabled() ? std::min(nb->max_items, nb->items_seen + nb->items_seen / 8 + 64) : nb->max_items;
         nb->list_valid = true;
         nb->verified = true;
         nb->generation++;
@@ -1943,7 +1957,11 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
     }
     nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
     const int warps_per_block = NB_THREADS / 32;
-    const int item_blocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
+    int item_blocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
+    {   // ATM_B200_NB2_WAVES=k: cap the grid at k resident waves and let the grid-stride loop do the rest (experiment)
+        static const int waves = [] { const char *e = getenv("ATM_B200_NB2_WAVES"); return e ? atoi(e) : 0; }();
+        if (waves > 0) item_blocks = std::min(item_blocks, h->num_sms * NB_MIN_BLOCKS * waves);
+    }
     SpecialArgs spa;
     spa.excl = nb->d_excl_pairs; spa.exc = nb->d_exc_pairs; spa.exc_par = nb->d_exc_par;
     spa.n_excl = nb->n_excl; spa.n_exc = nb->n_exc;
