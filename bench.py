@@ -51,8 +51,9 @@ def parse_args():
                     "synchronisation per cycle) instead of the on-device cycle")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=200, help="upper bound of the CPU-baseline sample (also capped at ~15 s)")
     ap.add_argument("--skip-two-separate", action="store_true")
+    ap.add_argument("--skip-tier1", action="store_true", help="skip the 8M-atom HBM roofline probe of copy-state / hybrid-force")
     ap.add_argument("--e2e-chunks", type=int, default=6)
     ap.add_argument("--pme", action="store_true", help="also evaluate the two-state PME reciprocal space inside the step "
                     "(SURVEY 8f row 1; NOT part of the headline workload, which is the direct-space path)")
@@ -139,9 +140,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(s, sched, steps):
+def cpu_oracle_rate(s, sched, steps, budget_s=15.0):
     """Times the CPU restatement of the same hot path (oracle port, OpenMP) on one replica; returns
-    (replica-ns/day, seconds per step, threads)."""
+    (replica-ns/day, seconds per step, threads, steps done)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], s["cutoff"], s["ewald_alpha"], s["excl"],
@@ -149,10 +150,51 @@ def cpu_oracle_rate(s, sched, steps):
     pos = replica_positions(s, 0)
     S.step(sched[0], pos, s["displ"])  # warm-up (page-in, OpenMP pool)
     t0 = time.perf_counter()
+    done = 0
     for k in range(steps):
         S.step(sched[k % len(sched)], pos, s["displ"])
-    dt = (time.perf_counter() - t0) / steps
-    return DT_FS * 1e-6 * 86400.0 / dt, dt, O.num_threads()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:   # bounded sample: stop after ~budget_s seconds of CPU work
+            break
+    dt = (time.perf_counter() - t0) / done
+    return DT_FS * 1e-6 * 86400.0 / dt, dt, O.num_threads(), done
+
+
+def tier1_hbm_probe(torch, atm, dev, flush, atoms=8_000_000):
+    """HBM roofline of the two Tier-1 kernels (north_star: copy + merge >= 70 % of peak), measured live on a working
+    set far beyond L2: CopyState in mixed precision (112 B/atom) and HybridForce (96 B/atom), median of 10 launches,
+    CUDA events on the launching stream, L2 flushed between launches.  Peak = MEASURED_PEAKS.json hbm_gbs."""
+    try:
+        peak, src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        peak, src = 6650.0, "fallback"
+    n = atoms
+    P = 32 * ((n + 31) // 32)
+    d = np.zeros((n, 3)); d[:50] = [2.2, 2.2, 2.2]
+    be = atm.ATMBackend(n, padded_num_particles=P, precision="mixed", device=dev.index)
+    be.set_displacements(d)
+    posq = torch.rand((P, 4), device=dev)
+    c = torch.zeros_like(posq)
+    p1, p2, c1, c2 = (torch.empty_like(posq) for _ in range(4))
+    f0 = torch.zeros(3 * P, dtype=torch.int64, device=dev)
+    f1 = torch.randint(-2**40, 2**40, (3 * P,), dtype=torch.int64, device=dev)
+    f2 = torch.randint(-2**40, 2**40, (3 * P,), dtype=torch.int64, device=dev)
+    out = {"atoms": n, "peak_GBps": peak, "peak_source": src, "l2": "flushed between launches"}
+    for name, bpa, fn in (("copy_state_mixed", 112, lambda: be.copy_state(posq, p1, p2, c, c1, c2)),
+                          ("hybrid_force", 96, lambda: be.hybrid_force(f0, f1, f2, 0.37))):
+        ts = []
+        for it in range(13):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        out[name] = {"bytes": bpa * n, "ms": ms, "GBps": bpa * n / (ms * 1e-3) / 1e9, "frac": bpa * n / (ms * 1e-3) / 1e9 / peak}
+    be.close()
+    return out
 
 
 def run_reference(args):
@@ -164,7 +206,7 @@ def run_reference(args):
         return
     s, sched, label = load_workload(args.workload)
     steps = max(1, min(args.steps, args.cpu_steps))
-    rate, sec, threads = cpu_oracle_rate(s, sched, steps)
+    rate, sec, threads, steps = cpu_oracle_rate(s, sched, steps)
     line = {
         "impl": "reference", "metric": "aggregate replica-ns/day (ATM hot path)", "value": rate, "unit": "replica-ns/day",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3 * args.replicas,
@@ -381,6 +423,13 @@ def run_b200(args):
             b1.close()
         del singles, posq2, f_tmp
 
+    # ---- Tier-1 kernels (copy-state, hybrid-force) against the HBM roofline, on a working set beyond L2
+    tier1 = None
+    if rank == 0 and world == 1 and not args.skip_tier1:
+        with torch.cuda.stream(torch.cuda.default_stream(dev)):
+            tier1 = tier1_hbm_probe(torch, atm, dev, flush)
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public call with HOST buffers: every step copies that step's coordinates H2D from
     #      pinned memory, runs the step, and reads forces + energies back D2H.  The replicas of the rank are split into
     #      --e2e-chunks handles on their own streams so that the copies of one chunk overlap the compute of another
@@ -484,9 +533,9 @@ def run_b200(args):
                         "nb2_timed_over": "20 non-graph steps right after the timed region, CUDA events around the launch"}
         cpu_baseline = None
         if world == 1:
-            rate, sec, threads = cpu_oracle_rate(s, sched, args.cpu_steps)
+            rate, sec, threads, cpu_done = cpu_oracle_rate(s, sched, args.cpu_steps)
             cpu_baseline = {"value": rate, "unit": "replica-ns/day", "cores": threads, "kind": "port",
-                            "sample": f"{args.cpu_steps} steps of 1 replica on the host cores ({sec:.3f} s/step); replicas "
+                            "sample": f"{cpu_done} steps of 1 replica on the host cores ({sec:.3f} s/step, {cpu_done * sec:.1f} s of CPU work); replicas "
                                       f"run sequentially on the CPU so aggregate == per-replica rate"}
         line = {
             "metric": "aggregate replica-ns/day (ATM hot path)", "value": value, "unit": "replica-ns/day",
@@ -503,6 +552,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "chunks": e2e_chunks},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,
+            "tier1_hbm_roofline": tier1,
         }
         print(json.dumps(line))
     if world > 1:
