@@ -309,3 +309,61 @@ def test_large_displaced_group():
     assert abs(en[E_U2] - res["e2"]) <= 1e-6 * abs(res["e2"])
     assert rel_rms(res["f_gpu"], res["f_ref"]) <= 1e-5
     assert res["stats"]["displaced_atoms"] == sel.size
+
+
+def test_unwrapped_coordinates_and_per_replica_boxes():
+    """OpenMM keeps molecules whole and re-wraps them by their centres, so atoms sit up to about one box length outside
+    the primary cell: whole molecules translated by -1/0/+1 box vectors must give the oracle's minimum-image result.
+    (Farther out the fp32 coordinates themselves lose the digits the 1e-5 force bar needs -- at +-3 box lengths the
+    measured deviation is 1.2e-5 -- which is why OpenMM re-wraps.)  Replica 1 also lives in its own (2 % larger) box, as under a
+    barostat (the box mirror of copyState, CommonATMMetaForceKernels.cpp:214-219, is per context)."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic
+    from helpers import force_from_fixed, rel_rms
+    s = synthetic.water_box(9000, n_lig=30, seed=33)
+    n = s["pos"].shape[0]
+    sched = synthetic.atm_schedule_22()
+    rng = np.random.default_rng(5)
+    # molecule id per atom: the ligand (displaced atoms) is one molecule, every water (3 consecutive atoms) another
+    lig = np.nonzero(np.abs(s["displ"]).sum(1) > 0)[0]
+    mol = np.full(n, -1)
+    mol[lig] = 0
+    rest = np.nonzero(mol < 0)[0]
+    mol[rest] = 1 + np.arange(rest.size) // 3
+    shifts = rng.integers(-1, 2, (mol.max() + 1, 3)).astype(np.float64)
+    scale = [1.0, 1.02]
+    R = 2
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=R)
+    P = be.P
+    be.set_displacements(s["displ"])
+    for r in range(R):
+        be.set_box(s["box"] * scale[r], replica=r)
+        be.set_parameters(sched[4 + 11 * r], replica=r)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.1, exclusions=s["excl"])
+    posq = np.zeros((R, P, 4), np.float32)
+    for r in range(R):
+        box = s["box"] * scale[r]
+        posq[r, :n, :3] = s["pos"] * scale[r] + shifts[mol] * box
+        posq[r, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+    be.rebuild(d_posq)
+    be.step(d_posq, force)
+    en = be.get_energies()
+    d32 = s["displ"].astype(np.float32)
+    for r in range(R):
+        S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"] * scale[r], s["cutoff"], s["ewald_alpha"], s["excl"])
+        p1 = posq[r, :n, :3].astype(np.float64)
+        p2 = (posq[r, :n, :3] + d32).astype(np.float64)
+        e1, _, f1 = S.nb_direct(p1)
+        e2, _, f2 = S.nb_direct(p2)
+        prm = sched[4 + 11 * r]
+        sc = O.scalars(prm, e1, e2)
+        f_ref = O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], prm[8])
+        f_gpu = force_from_fixed(force.cpu().numpy()[r], n, P)
+        assert abs(en[r, E_U1] - e1) <= 1e-6 * abs(e1), (r, en[r, E_U1], e1)
+        assert abs(en[r, E_USC] - sc["u_sc"]) <= 5e-3, (r, en[r, E_USC], sc["u_sc"])
+        assert rel_rms(f_gpu, f_ref) <= 1e-5, r
+    be.close()
