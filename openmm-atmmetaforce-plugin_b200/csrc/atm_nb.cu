@@ -773,9 +773,44 @@ __device__ __forceinline__ void nb2_item_epilogue(const NbDev &d, const ItemCtx 
 // Partner data is staged through a per-lane shared-memory ring with cp.async (prefetch distance 3 steps); the cluster
 // atoms are broadcast from shared memory instead of living in 48 registers, which buys a fifth resident block per SM.
 constexpr int NB_WARPS = NB_THREADS / 32;
-constexpr int RING = 4;      // ring slots per lane
-constexpr int PF_DIST = 3;   // coordinate steps in flight
-constexpr int E_AHEAD = 3;   // list entries run this many steps ahead of the coordinate prefetch
+#ifndef ATM_PF_DIST
+#define ATM_PF_DIST 3
+#endif
+#ifndef ATM_RING
+#define ATM_RING 4
+#endif
+constexpr int RING = ATM_RING;        // ring slots per lane (power of two, > PF_DIST)
+constexpr int PF_DIST = ATM_PF_DIST;  // coordinate steps in flight
+
+// The list entries of a work item (<= ITEM_STEPS x 128 B, contiguous, streaming from DRAM) are brought into shared
+// memory by ONE bulk asynchronous copy (the TMA unit: cp.async.bulk, SASS UBLKCP) that signals an mbarrier, instead of
+// a rolling register prefetch of one LDG per step.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_arm(unsigned long long *bar, void *smem, const void *gmem, unsigned int bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -787,16 +822,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct __align__(16) Nb2Smem {
-    float4 xi[NB_WARPS][CL];
-    float2 pi[NB_WARPS][CL];
+struct __align__(128) Nb2Smem {
+    unsigned int el[NB_WARPS][ITEM_STEPS][32];  // the item's list entries (bulk copy destination)
     float4 xj[NB_WARPS][RING][32];
     float2 pj[NB_WARPS][RING][32];
-    unsigned int e[NB_WARPS][RING][32];
+    float4 xi[NB_WARPS][CL];
+    float2 pi[NB_WARPS][CL];
+    unsigned long long bar[NB_WARPS];           // one mbarrier per warp
 };
 
 template <bool ENERGY, bool STATS>
-__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm) {
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
     const float4 L = d.box[it.r], iL = d.invbox[it.r];
     const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
     PairConst pc;
@@ -805,11 +841,8 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
     pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
 
-    // list entries of the first PF_DIST + E_AHEAD steps (all loads in flight together); entries run E_AHEAD steps
-    // ahead of the coordinate prefetch because they stream from DRAM while the coordinates hit L2
-    unsigned int e_pre[PF_DIST + E_AHEAD];
-#pragma unroll
-    for (int q = 0; q < PF_DIST + E_AHEAD; q++) e_pre[q] = q < it.nst ? __ldg(it.list + q * 32 + lane) : 0xffu;
+    // the whole entry list of the item: one bulk copy, in flight while the cluster atoms are staged
+    if (lane == 0) bulk_load_arm(&sm.bar[w], &sm.el[w][0][0], it.list, (unsigned)it.nst * 128u);
     // cluster atoms -> shared memory (lanes 0..7), shifted next to the cluster centre
     if (lane < CL) {
         float4 x = __ldg(d.xs + it.rsite + (size_t)it.A * CL + lane);
@@ -819,18 +852,16 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         sm.xi[w][lane] = x;
         sm.pi[w][lane] = __ldg(d.par + it.rsite + (size_t)it.A * CL + lane);
     }
+    mbar_wait(&sm.bar[w], parity);
 #pragma unroll
     for (int q = 0; q < PF_DIST; q++) {
         if (q < it.nst) {
-            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (e_pre[q] >> 8));
-            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (e_pre[q] >> 8));
-            sm.e[w][q][lane] = e_pre[q];
+            const unsigned int eq = sm.el[w][q][lane];
+            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (eq >> 8));
+            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (eq >> 8));
         }
         cp_async_commit();
     }
-    unsigned int e_ring[E_AHEAD];  // e_ring[q] = entry of step st + PF_DIST + q at the top of iteration st
-#pragma unroll
-    for (int q = 0; q < E_AHEAD; q++) e_ring[q] = e_pre[PF_DIST + q];
     __syncwarp();
 
     float fix[CL], fiy[CL], fiz[CL];
@@ -845,21 +876,17 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         const int slot = st & (RING - 1);
         const float4 xjc = sm.xj[w][slot][lane];
         const float2 pjc = sm.pj[w][slot][lane];
-        const unsigned int e = sm.e[w][slot][lane];
+        const unsigned int e = sm.el[w][st][lane];
         // keep PF_DIST steps in flight
         {
             const int sp = st + PF_DIST;
-            const unsigned int e_next = e_ring[0];
             if (sp < it.nst) {
+                const unsigned int e_next = sm.el[w][sp][lane];
                 const int ps = sp & (RING - 1);
                 cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
                 cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
-                sm.e[w][ps][lane] = e_next;
             }
             cp_async_commit();
-#pragma unroll
-            for (int q = 0; q + 1 < E_AHEAD; q++) e_ring[q] = e_ring[q + 1];
-            e_ring[E_AHEAD - 1] = (sp + E_AHEAD < it.nst) ? __ldg(it.list + (sp + E_AHEAD) * 32 + lane) : 0xffu;
         }
         const int j = e >> 8;
         const unsigned int m = e & 0xffu;
@@ -1033,8 +1060,13 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     if ((int)blockIdx.x < n_item_blocks) {
         // The pruned list's item count lives on the device; the grid is sized from the count the last verified build
         // saw plus a margin, and this grid-stride loop picks up whatever a later prune added beyond it.
+        __shared__ Nb2Smem sm;
+        const int w = threadIdx.x >> 5;
+        if (lane == 0) mbar_init(&sm.bar[w], 1);
+        __syncwarp();
+        unsigned int parity = 0;  // phase of this warp's mbarrier: flips with every completed bulk copy
         const int n_items = d.flags[4], stride = n_item_blocks * (NB_THREADS / 32);
-        for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride) {
+        for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
             __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
             int wi = warp, b = ITEM_STEPS;
             for (; b > 1; --b) {  // longest chunks first
@@ -1051,10 +1083,8 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
             it.list = d.jlist + (unsigned int)item.x;
             it.rsite = (size_t)it.r * d.Smax;
             it.comp_stride = (size_t)d.R * d.Smax;
-            __shared__ Nb2Smem sm;
-            const int w = threadIdx.x >> 5;
-            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm);
-            else nb2_item<true, STATS>(d, it, lane, w, sm);
+            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm, parity);
+            else nb2_item<true, STATS>(d, it, lane, w, sm, parity);
         }
     } else {
         const int sb = blockIdx.x - n_item_blocks;
