@@ -32,7 +32,8 @@ def timed(fn, iters=20):
     return float(np.median(ts)), float(np.min(ts))
 
 
-for n in [25_000, 100_000, 500_000, 1_000_000, 4_000_000, 8_000_000, 16_000_000]:
+SIZES = [int(x) for x in sys.argv[1:]] or [25_000, 100_000, 500_000, 1_000_000, 4_000_000, 8_000_000, 16_000_000]
+for n in SIZES:
     P = 32 * ((n + 31) // 32)
     d = np.zeros((n, 3)); d[:50] = [2.2, 2.2, 2.2]
     for mode, bpa in (("mixed", 112), ("single", 64)):
