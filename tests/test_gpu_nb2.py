@@ -367,3 +367,69 @@ def test_unwrapped_coordinates_and_per_replica_boxes():
         assert abs(en[r, E_USC] - sc["u_sc"]) <= 5e-3, (r, en[r, E_USC], sc["u_sc"])
         assert rel_rms(f_gpu, f_ref) <= 1e-5, r
     be.close()
+
+
+def test_three_groups_interleaved_indices_and_equal_displacements():
+    """Ragged / irregular topology: three displaced groups of whole waters picked with non-contiguous atom indices
+    (every 5th / 7th molecule of two separate slabs), two of them with the SAME displacement vector (pairs between
+    them move together, i.e. belong to both states) and one with the opposite one; N is neither a multiple of 8 nor of
+    32.  Also evaluates the partially overlapping exclusion structure of the synthetic chain ligand."""
+    from atmmetaforce import synthetic
+    from helpers import rel_rms
+    s = synthetic.water_box(9000, n_lig=13, seed=17)
+    n = s["pos"].shape[0]
+    assert n % 8 != 0
+    pos, box = s["pos"], s["box"]
+    nl = int(round((n / 3) ** (1.0 / 3.0)))
+    a = box[0] / nl
+    lig = np.nonzero(np.abs(s["displ"]).sum(1) > 0)[0]
+    first_water = lig.max() + 1
+    mol = (np.arange(n) - first_water) // 3
+    is_water = np.arange(n) >= first_water
+    d_up = np.array([0.5 * a, 0.5 * a, (int(0.4 * nl) + 0.5) * a])
+    g1 = is_water & (pos[:, 2] < 0.2 * box[2]) & (mol % 5 == 0)
+    g2 = is_water & (pos[:, 2] > 0.25 * box[2]) & (pos[:, 2] < 0.4 * box[2]) & (mol % 7 == 0)
+    # whole molecules only: take the decision of the oxygen (first atom of each triple)
+    for g in (g1, g2):
+        ox = g[first_water::3].copy()
+        g[first_water:] = np.repeat(ox, 3)[: n - first_water]
+    s["displ"][g1] = d_up           # same vector as ...
+    s["displ"][g2] = d_up           # ... this group: one displacement class
+    s["displ"][lig] = -s["displ"][lig]   # the ligand goes the other way
+    assert g1.sum() > 20 and g2.sum() > 20
+    params = [0.3, 0.6, 0.02, 50.0, 1.5, 1e7, 5e6, 0.0625, -1.0]     # alpha > 0, direction -1, w0 != 0
+    res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.07)
+    en = res["en"]
+    print("three groups: U1 %.3f/%.3f u %.4f/%.4f frms %.2e stats %s" % (en[E_U1], res["e1"], en[E_USC], res["sc"]["u_sc"],
+          rel_rms(res["f_gpu"], res["f_ref"]), res["stats"]))
+    assert res["stats"]["groups"] == 2          # equal displacement vectors form ONE class
+    assert abs(en[E_U1] - res["e1"]) <= 1e-6 * abs(res["e1"])
+    assert abs(en[E_U2] - res["e2"]) <= 1e-6 * abs(res["e2"])
+    # hundreds of displaced atoms: |u| ~ 1e5 kJ/mol, so the energy bar is the relative one (1e-6)
+    assert abs(en[E_USC] - res["sc"]["u_sc"]) <= max(2e-2, 1e-6 * abs(res["sc"]["u_sc"]))
+    assert abs(en[E_SP] - res["sc"]["sp"]) <= 1e-4
+    assert rel_rms(res["f_gpu"], res["f_ref"]) <= 1e-5
+
+
+def test_tiny_system_in_a_large_box():
+    """37 atoms (a 13-atom ligand and 8 waters) in a 4.4 nm box: almost every cluster slot and list step is padding."""
+    from atmmetaforce import synthetic
+    from helpers import rel_rms
+    s = synthetic.water_box(9000, n_lig=13, seed=17)
+    keep = np.arange(37)
+    idx = {int(a): k for k, a in enumerate(keep)}
+    t = dict(s)
+    for key in ("pos", "charge", "sigma", "epsilon", "displ"):
+        t[key] = s[key][keep].copy()
+    t["excl"] = np.array([[idx[a], idx[b]] for a, b in s["excl"] if a in idx and b in idx], np.int32).reshape(-1, 2)
+    t["exc14"] = np.zeros((0, 2), np.int32)
+    t["exc14_par"] = np.zeros((0, 3))
+    # spread the waters so that some pairs are inside and some outside the cutoff
+    t["pos"][13:] += np.random.default_rng(2).normal(0, 0.15, (24, 3))
+    params = [0.5, 0.5, 0, 0, 0, 800, 400, 0.0625, 1.0]
+    res = _run(t, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
+    en = res["en"]
+    assert abs(en[E_U1] - res["e1"]) <= 1e-6 * abs(res["e1"]) + 1e-4
+    assert abs(en[E_U2] - res["e2"]) <= 1e-6 * abs(res["e2"]) + 1e-4
+    assert abs(en[E_USC] - res["sc"]["u_sc"]) <= 5e-3
+    assert rel_rms(res["f_gpu"], res["f_ref"]) <= 1e-5
