@@ -1,0 +1,49 @@
+"""Small two-replica case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): rebuild, prune, two plain
+steps with statistics, one CUDA-graph step (programmatic dependent launches inside), PME on for the last step, the
+on-device replica exchange, energies read back.
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_case.py
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "openmm-atmmetaforce-plugin_b200", "python"))
+import numpy as np
+import torch
+import atmmetaforce as atm
+from atmmetaforce import synthetic
+
+s = synthetic.water_box(6000, n_lig=15, seed=6)
+n = s["pos"].shape[0]
+R = 2
+sched = synthetic.atm_schedule_22()
+be = atm.ATMBackend(n, precision="mixed", num_replicas=R)
+be.set_displacements(s["displ"])
+be.set_box(s["box"])
+for r in range(R):
+    be.set_parameters(sched[5 + 11 * r], replica=r)
+be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.1, skin_outer=0.2, exclusions=s["excl"])
+posq = np.zeros((R, be.P, 4), np.float32)
+rng = np.random.default_rng(0)
+for r in range(R):
+    posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.003, (n, 3)) * r
+    posq[r, :n, 3] = s["charge"]
+posq = torch.from_numpy(posq).cuda()
+force = torch.zeros((R, 3 * be.P), dtype=torch.int64, device="cuda")
+stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    be.rebuild(posq, stream=stream)
+    be.step(posq, force, collect_stats=True, stream=stream)
+    be.prune(posq, stream=stream)
+    be.step(posq, force, stream=stream)
+    be.step(posq, force, graph=True, stream=stream)
+    rex = atm.ReplicaExchange(sched, R, temperature=300.0, seed=1)
+    rex.attach_device(be, stream=stream)
+    rex.exchange_device(stream=stream)
+en = be.get_energies(stream=stream)
+rex.sync_from_device(stream=stream)
+be.pme_setup(synthetic.pme_grid(s["box"], s["ewald_alpha"]))
+with torch.cuda.stream(stream):
+    be.step(posq, force, stream=stream)
+en2 = be.get_energies(stream=stream)
+print("u:", en[:, 3], "u with PME:", en2[:, 3], "states:", rex.replica_state)
+be.close()
