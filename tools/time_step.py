@@ -16,6 +16,7 @@ ap.add_argument("--natoms", type=int, default=25000)
 ap.add_argument("--skin-outer", type=float, default=0.3)
 ap.add_argument("--no-energy", action="store_true")
 ap.add_argument("--pme", action="store_true")
+ap.add_argument("--flush", action="store_true", help="also time the graph step with a 256 MiB L2 flush before every step")
 args = ap.parse_args()
 
 s = synthetic.config3() if args.system == "config3" else (synthetic.config4() if args.system == "config4" else synthetic.water_box(args.natoms))
@@ -64,6 +65,19 @@ torch.cuda.synchronize()
 ms_prune = evp[0].elapsed_time(evp[1]) / 10
 en = be.get_energies()
 st = be.nb_stats()
+if args.flush:
+    fl = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    evs = []
+    with torch.cuda.stream(stream):
+        for it in range(args.steps + 5):
+            fl.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); be.step(posq, force, include_energy=not args.no_energy, graph=True, stream=stream); b.record(stream)
+            if it >= 5:
+                evs.append((a, b))
+    torch.cuda.synchronize()
+    print(f"cold (L2 flushed) graph step: {1e3 * sum(a.elapsed_time(b) for a, b in evs) / len(evs):.1f} us")
 ms_step = ev[2].elapsed_time(ev[3]) / args.steps
 ms_rebuild = ev[0].elapsed_time(ev[1]) / 5
 pairs = en_stats[:, 7].sum()
