@@ -215,6 +215,8 @@ int atm_execute(atm_handle *h, int32_t replica, double U1, double U2, int64_t *f
                 const int64_t *f2, int32_t include_energy, double *energy, void *stream) {
     ATM_REQUIRE(h != nullptr, ATM_ERR_INVALID, "atm_execute: null handle");
     ATM_REQUIRE(replica >= 0 && replica < h->R, ATM_ERR_INVALID, "atm_execute: replica %d out of range", replica);
+    int rc0 = refresh_params_from_device(h);  // the on-device exchange may have rewritten the rows
+    if (rc0) return rc0;
     Scalars s = scalar_stage(h->params.data() + (size_t)replica * ATM_NUM_PARAMS, U1, U2, U2 - U1);
     h->pert_energy[replica] = s.usc;
     if (energy) *energy = include_energy ? s.energy : 0.0;

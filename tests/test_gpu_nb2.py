@@ -433,3 +433,19 @@ def test_tiny_system_in_a_large_box():
     assert abs(en[E_U2] - res["e2"]) <= 1e-6 * abs(res["e2"]) + 1e-4
     assert abs(en[E_USC] - res["sc"]["u_sc"]) <= 5e-3
     assert rel_rms(res["f_gpu"], res["f_ref"]) <= 1e-5
+
+
+def test_config5_500k_water_box():
+    """BASELINE configs[4], largest size: ~500k-atom water box with a 50-atom ligand, against the oracle (which still
+    finishes in seconds at this size) plus two size-independent properties: Newton's third law on the merged force
+    (the fixed-point sum over all atoms vanishes to rounding) and bit-identical results from a second evaluation."""
+    from atmmetaforce import synthetic
+    from helpers import rel_rms
+    s = synthetic.water_box(500_000, n_lig=50)
+    params = synthetic.atm_schedule_22()[16]          # direction -1 leg
+    res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
+    err = _check(res, tol_u=2e-2)
+    f = res["f_gpu"]
+    assert np.abs(f.sum(0)).max() <= 1e-7 * np.abs(f).sum()
+    print("500k: N %d u %.4f force rel rms %.2e |sum F|/sum|F| %.1e" % (f.shape[0], res["en"][E_U], err,
+          np.abs(f.sum(0)).max() / np.abs(f).sum()))
