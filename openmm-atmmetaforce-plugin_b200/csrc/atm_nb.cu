@@ -1215,6 +1215,9 @@ __device__ __forceinline__ int pme_wrap(int i, int n) {
 // One thread per site slot: ORDER^3 fixed-point atomics.  Two accumulators per replica:
 //   acc[0] = Q1 = environment + displaced atoms,  acc[1] = Q2 - Q1 = ghosts - displaced atoms
 // so the environment (almost every site) is spread exactly once.
+// (A cooperative variant -- B-spline weights staged in shared memory, the block walking the (site, grid point) items
+// with z fastest so that a warp-wide RED touches ~13 sectors instead of 32 -- was measured and is SLOWER, 295 vs 257 us
+// at 22 replicas: the limit is the L2 atomic-operation rate (64 M 64-bit REDs per launch), not the sector count.)
 template <int ORDER>
 __global__ void __launch_bounds__(128) pme_spread_kernel(NbDev d) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1253,16 +1256,28 @@ __global__ void __launch_bounds__(128) pme_spread_kernel(NbDev d) {
 // Q1, Q2 = Q1 + (Q2 - Q1) as doubles; the accumulators are handed back zeroed
 __global__ void pme_finalize_kernel(NbDev d) {
     const size_t ng = (size_t)d.gx * d.gy * d.gz;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);  // two cells per thread: 128-bit accesses
     const int r = blockIdx.y;
     if (i >= ng) return;
     unsigned long long *acc = d.pme_acc + (size_t)r * 2 * ng;
-    const long long q1 = (long long)acc[i], dq = (long long)acc[ng + i];
-    acc[i] = 0ull;
-    if (dq != 0) acc[ng + i] = 0ull;
     double *grid = d.pme_grid + (size_t)r * 2 * ng;
-    grid[i] = (double)q1 * (1.0 / PME_SCALE);
-    grid[ng + i] = (double)(q1 + dq) * (1.0 / PME_SCALE);
+    if (i + 1 < ng && (ng & 1) == 0) {
+        const ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(acc + i), ad = *reinterpret_cast<const ulonglong2 *>(acc + ng + i);
+        *reinterpret_cast<ulonglong2 *>(acc + i) = make_ulonglong2(0ull, 0ull);
+        if (ad.x != 0ull || ad.y != 0ull) *reinterpret_cast<ulonglong2 *>(acc + ng + i) = make_ulonglong2(0ull, 0ull);
+        const long long q1x = (long long)a1.x, q1y = (long long)a1.y;
+        *reinterpret_cast<double2 *>(grid + i) = make_double2((double)q1x * (1.0 / PME_SCALE), (double)q1y * (1.0 / PME_SCALE));
+        *reinterpret_cast<double2 *>(grid + ng + i) = make_double2((double)(q1x + (long long)ad.x) * (1.0 / PME_SCALE),
+                                                                   (double)(q1y + (long long)ad.y) * (1.0 / PME_SCALE));
+    } else {
+        for (size_t k = i; k < ng && k < i + 2; k++) {
+            const long long q1 = (long long)acc[k], dq = (long long)acc[ng + k];
+            acc[k] = 0ull;
+            if (dq != 0) acc[ng + k] = 0ull;
+            grid[k] = (double)q1 * (1.0 / PME_SCALE);
+            grid[ng + k] = (double)(q1 + dq) * (1.0 / PME_SCALE);
+        }
+    }
 }
 
 // multiply the spectra by exp(-pi^2 m^2/alpha^2) / (pi V m^2 B(m)); accumulate the two reciprocal energies
@@ -2032,7 +2047,7 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
     if (d.pme_on) {
         const size_t ng = (size_t)d.gx * d.gy * d.gz, nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
         launch_pme_spread(d, stream);
-        pme_finalize_kernel<<<dim3((unsigned)((ng + 255) / 256), d.R), 256, 0, stream>>>(d);
+        pme_finalize_kernel<<<dim3((unsigned)((ng / 2 + 256) / 256), d.R), 256, 0, stream>>>(d);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecD2Z(nb->pme_plan_fwd, d.pme_grid, (cufftDoubleComplex *)d.pme_spec) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecD2Z failed");
