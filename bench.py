@@ -471,39 +471,32 @@ def run_b200(args):
                             exception_params=s["exc14_par"])
                 if pme_grid is not None:
                     bc.pme_setup(pme_grid)
-            st_c = torch.cuda.Stream(device=dev)
-            en_c = torch.zeros((hi - lo, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory()
-            with torch.cuda.stream(st_c):
-                bc.rebuild(posq[lo:hi], stream=st_c)
-            chunks.append((bc, lo, hi, st_c, en_c))
-        torch.cuda.synchronize()
-        KE = min(K, 50)
+            chunks.append((bc, lo, hi))
+        # the public host-buffer call (atm_host_pipeline_step, include/atm_b200.h): pinned coordinates in, pinned forces
+        # and energy records out, the chunks' copies and kernels overlapped on streams of their own, one cached CUDA
+        # graph launch per step; pair-list maintenance on the same cadence as the device-resident loop
+        pipe = atm.HostPipeline([c[0] for c in chunks])
+        en_h = torch.zeros((R, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory()
+        pq_c = [posq_h[lo:hi] for _, lo, hi in chunks]
+        f_c = [force_h[lo:hi] for _, lo, hi in chunks]
+        en_c = [en_h[lo:hi] for _, lo, hi in chunks]
+        KE = min(K, 200)
+        WE = 5
         ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
-        done = [torch.cuda.Event() for _ in range(e2e_chunks)]
-        for k in range(KE + 3):
+        with torch.cuda.stream(stream):
+            pipe.step(pq_c, f_c, en_c, maintenance=pipe.REBUILD, stream=stream)   # first build: synchronous, verified
+        for k in range(KE + WE):
             with torch.cuda.stream(stream):
                 if flush is not None:
                     flush.zero_()
-                start = ee[k - 3][0] if k >= 3 else torch.cuda.Event()
-                start.record(stream)
-            for ci, (bc, lo, hi, st_c, en_c) in enumerate(chunks):
-                with torch.cuda.stream(st_c):
-                    st_c.wait_event(start)
-                    posq[lo:hi].copy_(posq_h[lo:hi], non_blocking=True)   # posqCorrection is not an input of this path
-                    force[lo:hi].zero_()
-                    if k % args.prune_every == 0:
-                        bc.prune(posq[lo:hi], stream=st_c)
-                    bc.step(posq[lo:hi], force[lo:hi], include_energy=True, graph=use_graph, stream=st_c)
-                    force_h[lo:hi].copy_(force[lo:hi], non_blocking=True)
-                    en_dev = torch.as_tensor(_DevView(bc.energies_device_ptr(), (hi - lo, _capi.NUM_ENERGY_SLOTS), "<f8"), device=dev)
-                    en_c.copy_(en_dev, non_blocking=True)
-                    done[ci].record(st_c)
-            with torch.cuda.stream(stream):
-                for ev in done:
-                    stream.wait_event(ev)
-                if k >= 3:
-                    ee[k - 3][1].record(stream)
+                if k >= WE:
+                    ee[k - WE][0].record(stream)
+                maint = pipe.REBUILD if k % args.rebuild_every == 0 else (pipe.PRUNE if k % args.prune_every == 0 else pipe.NONE)
+                pipe.step(pq_c, f_c, en_c, maintenance=maint, stream=stream)
+                if k >= WE:
+                    ee[k - WE][1].record(stream)
             stream.synchronize()  # the step's result (forces, energies) is on the host before the next step starts
+        pipe.close()
         torch.cuda.synchronize()
         e2e_ms = sum(a.elapsed_time(b) for a, b in ee) / KE
         h2d = posq_h.numel() * 4
@@ -575,7 +568,9 @@ def run_b200(args):
                        "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "chunks": e2e_chunks},
+                    "ms_per_step": e2e_ms, "chunks": e2e_chunks,
+                    "call": "atm_host_pipeline_step (pinned host coordinates in, pinned host forces + energy records out, "
+                            "one cached CUDA graph per step; pair-list maintenance on the bench cadence)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,
             "tier1_hbm_roofline": tier1,
         }

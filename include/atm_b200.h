@@ -231,6 +231,33 @@ int atm_get_energies(atm_handle *h, double *out, void *stream);
  * env list capacity, ligand/ghost list capacity, displaced atoms M, displacement groups G, xy columns}. */
 int atm_nb_stats(atm_handle *h, int64_t out[8]);
 
+/* ------------------------------------------------------------------ the step with HOST buffers on both sides */
+
+/* The reference's callers move coordinates in and forces / energies out through host memory every time they touch a
+ * Context (context.setPositions(...), context.getState(getEnergy=True, getForces=True); ref: python/tests/test_abfe.py:115-146,
+ * example/abfe/abfe.py:140-160).  atm_host_pipeline_step is that round trip for the Tier-2 path as ONE call:
+ *   per handle: H2D coordinates -> [rebuild | prune] -> atm_step -> D2H forces and energy records,
+ * every handle on a stream of its own, forked from and joined back into `stream`, the whole fork/join replayed from one
+ * cached CUDA graph per maintenance kind.  Several handles ("chunks" of the replicas resident on this GPU) overlap the
+ * copies of one chunk with the kernels of the others.  The pipeline owns the device staging buffers; the caller needs
+ * no device memory at all.  Handles must outlive the pipeline and must not be stepped concurrently through atm_step. */
+typedef struct atm_host_pipeline atm_host_pipeline;
+
+typedef struct {
+    const void *posq_host;     /* [R][P] float4 (x, y, z, q), slot order; pinned host memory (cudaHostAlloc / cudaHostRegister) */
+    int64_t *force_host;       /* [R][3P] pinned host memory: receives the ATM force (2^32 fixed point, SoA x|y|z blocks) */
+    double *energies_host;     /* [R][ATM_NUM_ENERGY_SLOTS] pinned host memory, or NULL */
+    int32_t include_energy;    /* as atm_step_io.include_energy */
+    int32_t reserved;
+} atm_host_io;
+
+int atm_host_pipeline_create(int32_t num_handles, atm_handle *const *handles, atm_host_pipeline **out);
+int atm_host_pipeline_destroy(atm_host_pipeline *p);
+/* ios: one entry per handle, in the order given to _create.  maintenance: 0 = none, 1 = atm_nb_prune first,
+ * 2 = atm_nb_rebuild first (the very first step must pass 2; that one synchronises, see atm_nb_rebuild).
+ * Asynchronous: the host buffers hold the results once `stream` (non-default) has been synchronised. */
+int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t maintenance, void *stream);
+
 /* ------------------------------------------------------------------ Hamiltonian replica exchange (host) */
 
 /* Deterministic Metropolis sweep over neighbouring lambda-states, identical on every rank.

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libatm_b200.so")
-SOURCES = ["atm_capi.cu", "atm_copy_merge.cu", "atm_nb.cu", "atm_hrex.cu"]
+SOURCES = ["atm_capi.cu", "atm_copy_merge.cu", "atm_nb.cu", "atm_hrex.cu", "atm_host.cu"]
 HEADERS = [os.path.join(CSRC, "atm_common.cuh"), os.path.join(ROOT, "include", "atm_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

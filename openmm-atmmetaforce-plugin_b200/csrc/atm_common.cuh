@@ -107,6 +107,13 @@ int upload_params_if_dirty(atm_handle *h, cudaStream_t stream);
 int refresh_params_from_device(atm_handle *h);
 void hrex_destroy(atm_handle *h);
 
+// hooks of the host-buffer pipeline (atm_host.cu), implemented in atm_nb.cu
+int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *needs_sync_rebuild);
+int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream);
+int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream);
+uint64_t nb_alloc_generation(const atm_handle *h);
+const double *nb_energies_device(const atm_handle *h);
+
 // Tier-1 launchers implemented in atm_copy_merge.cu
 int launch_copy_state(atm_handle *h, const void *posq, const void *corr, void *posq1, void *corr1, void *posq2,
                       void *corr2, cudaStream_t stream);

@@ -43,6 +43,9 @@ constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
 constexpr int NUM_FLAGS = 40;
+#ifndef ATM_PRUNE_BLOCK
+#define ATM_PRUNE_BLOCK 1          // list steps per software-pipeline block of the prune kernel (1 = one-step loop)
+#endif
 constexpr int EACC_SLOTS = 8;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2), Urec(1), Urec(2)
 constexpr double PME_SCALE = 1099511627776.0;  // 2^40 fixed point of the charge-grid accumulation
 
@@ -602,6 +605,51 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
     const unsigned int *in = d.jlist_outer + li.offset;
     unsigned int *out = d.jlist + li.offset;
     int count = 0;
+#if ATM_PRUNE_BLOCK > 1
+    // software pipeline in blocks of PB list steps: the entries (streaming from DRAM) are loaded two blocks ahead, the
+    // partner coordinates (gathers from L2) one block ahead, so PB independent gathers are in flight per lane while
+    // the previous block is tested.  The kept entries are written in list order, exactly as the one-step loop did.
+    constexpr int PB = ATM_PRUNE_BLOCK;
+    unsigned int ea[PB], eb[PB];
+    float4 pa[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) ea[q] = q < nst_outer ? __ldg(in + q * 32 + lane) : 0xffu;
+#pragma unroll
+    for (int q = 0; q < PB; q++) eb[q] = PB + q < nst_outer ? __ldg(in + (PB + q) * 32 + lane) : 0xffu;
+#pragma unroll
+    for (int q = 0; q < PB; q++) pa[q] = __ldg(d.xs + rsite + (ea[q] >> 8));
+    for (int st0 = 0; st0 < nst_outer; st0 += PB) {
+        unsigned int ecur[PB], en[PB];
+        float4 pcur[PB];
+#pragma unroll
+        for (int q = 0; q < PB; q++) { ecur[q] = ea[q]; pcur[q] = pa[q]; ea[q] = eb[q]; }
+#pragma unroll
+        for (int q = 0; q < PB; q++) en[q] = st0 + 2 * PB + q < nst_outer ? __ldg(in + (st0 + 2 * PB + q) * 32 + lane) : 0xffu;
+        if (st0 + PB < nst_outer) {
+#pragma unroll
+            for (int q = 0; q < PB; q++) pa[q] = __ldg(d.xs + rsite + (ea[q] >> 8));
+        }
+#pragma unroll
+        for (int q = 0; q < PB; q++) eb[q] = en[q];
+#pragma unroll
+        for (int q = 0; q < PB; q++) {
+            const unsigned int ec = ecur[q];
+            bool keep = false;
+            if ((ec & 0xffu) != 0xffu) {
+                const float4 p = pcur[q];
+                const float px = wrap_delta(p.x - cA.x, L.x, iL.x), py = wrap_delta(p.y - cA.y, L.y, iL.y),
+                            pz = wrap_delta(p.z - cA.z, L.z, iL.z);
+                float d2min = 1e30f;
+#pragma unroll
+                for (int k = 0; k < CL; k++) d2min = fminf(d2min, fmaf(px, xa[k], fmaf(py, ya[k], fmaf(pz, za[k], a2[k]))));
+                keep = d2min + fmaf(pz, pz, fmaf(py, py, px * px)) <= rl2;
+            }
+            const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[count + __popc(kmask & ((1u << lane) - 1))] = ec;
+            count += __popc(kmask);
+        }
+    }
+#else
     // software pipeline: entries three steps ahead (they stream from DRAM), coordinates one step ahead
     unsigned int e0 = __ldg(in + lane);
     unsigned int e1 = nst_outer > 1 ? __ldg(in + 32 + lane) : 0xffu;
@@ -627,6 +675,7 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
         if (keep) out[count + __popc(kmask & ((1u << lane) - 1))] = ec;
         count += __popc(kmask);
     }
+#endif
     const int nsteps = (count + 31) >> 5;
     for (int p = count + lane; p < nsteps * 32; p += 32) out[p] = 0xffu;
     // work items of this list: (<= ITEM_STEPS)-step chunks, slots reserved with one atomic (their order only affects
@@ -2278,3 +2327,61 @@ int atm_nb_stats(atm_handle *h, int64_t out[8]) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Hooks of the host-buffer pipeline (atm_host.cu): the Tier-2 state is private to this file
+// ------------------------------------------------------------------------------------------------
+namespace atm {
+
+// Everything a pipeline step must settle on the host BEFORE it enqueues (or replays) the device work of one handle:
+// deferred capacity check of the last asynchronous rebuild, parameter / box uploads, box-size check of a rebuild.
+// *needs_sync_rebuild: the pair lists must first be (re)built through the synchronous, verified atm_nb_rebuild.
+int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *needs_sync_rebuild) {
+    ATM_REQUIRE(h && h->nb && h->nb->ready && h->nb->box_set, ATM_ERR_STATE, "atm_host_pipeline_step: call atm_nb_setup and atm_set_box first");
+    NbState *nb = h->nb;
+    int rc = check_pending_rebuild(h, false);
+    if (rc && !(maintenance == 2 && rc == ATM_ERR_STATE)) return rc;  // a capacity error is cured by the rebuild requested now
+    *needs_sync_rebuild = nb->needs_realloc || !nb->verified || !nb->list_valid;
+    ATM_REQUIRE(maintenance == 2 || !*needs_sync_rebuild, ATM_ERR_STATE,
+                "atm_host_pipeline_step: no valid neighbour structure (the first step must ask for a rebuild)");
+    if ((rc = upload_params_if_dirty(h, stream))) return rc;
+    if (!*needs_sync_rebuild && (rc = upload_box_if_dirty(h, stream))) return rc;
+    if (maintenance == 2)
+        for (int r = 0; r < h->R; r++)
+            ATM_REQUIRE(2.0 * nb->d.rlist_outer < std::min({nb->h_box[3 * r], nb->h_box[3 * r + 1], nb->h_box[3 * r + 2]}), ATM_ERR_UNSUPPORTED,
+                        "atm_host_pipeline_step: box edge smaller than 2*(cutoff+skin)");
+    return ATM_OK;
+}
+
+// The device work of one handle for one step on device staging buffers: [rebuild | prune] + the step itself.  No
+// validation, no uploads, no synchronisation: safe inside a stream capture.
+int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream) {
+    NbState *nb = h->nb;
+    int rc;
+    if (maintenance == 2) {
+        if ((rc = launch_rebuild(h, (const float4 *)posq, stream))) return rc;
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+    } else if (maintenance == 1) {
+        if ((rc = launch_prune_all(h, posq, stream))) return rc;
+    }
+    atm_step_io io{};
+    io.posq = posq;
+    io.force = (int64_t *)force;
+    io.include_energy = include_energy;
+    return launch_step(h, &io, stream, false);
+}
+
+// Bookkeeping after a replayed asynchronous rebuild: `stream` is ordered behind the copy of the capacity flags.
+int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream) {
+    NbState *nb = h->nb;
+    ATM_CUDA_CHECK(cudaEventRecord(nb->flags_event, stream));
+    nb->flags_pending = true;
+    nb->list_valid = true;
+    nb->generation++;
+    return ATM_OK;
+}
+
+uint64_t nb_alloc_generation(const atm_handle *h) { return h->nb ? h->nb->alloc_generation : 0; }
+const double *nb_energies_device(const atm_handle *h) { return h->nb ? h->nb->d.energies : nullptr; }
+
+}  // namespace atm

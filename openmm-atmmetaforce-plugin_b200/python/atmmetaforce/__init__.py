@@ -4,7 +4,7 @@ Same module name and public names as the reference's SWIG module (python/atmmeta
 ATMMetaForce, ATMMetaForceUtils, ATMMETAFORCE_VERSION.  The compute path is libatm_b200.so (CUDA, sm_100a).
 """
 from ._capi import ATMError, LIB_PATH  # noqa: F401
-from .backend import ATMBackend, softcore_softplus, hrex_sweep, hrex_reduced_energy  # noqa: F401
+from .backend import ATMBackend, HostPipeline, softcore_softplus, hrex_sweep, hrex_reduced_energy  # noqa: F401
 
 ATMMETAFORCE_VERSION = "0.3.1"  # reference openmmapi/include/ATMMetaForceVersion.h:4
 from .replica import ReplicaExchange  # noqa: F401,E402

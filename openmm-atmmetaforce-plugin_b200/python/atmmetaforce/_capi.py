@@ -25,6 +25,7 @@ SYMBOLS = (
     "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
     "atm_hrex_device_setup", "atm_hrex_device_pack", "atm_hrex_device_exchange", "atm_hrex_device_state",
+    "atm_host_pipeline_create", "atm_host_pipeline_destroy", "atm_host_pipeline_step",
 )
 
 
@@ -50,6 +51,11 @@ class StepIO(C.Structure):
                 ("force_state1_ext", C.c_void_p), ("force_state2_ext", C.c_void_p), ("energy_ext", C.c_void_p),
                 ("posq1", C.c_void_p), ("posq1_corr", C.c_void_p), ("posq2", C.c_void_p), ("posq2_corr", C.c_void_p),
                 ("include_energy", C.c_int32), ("collect_stats", C.c_int32)]
+
+
+class HostIO(C.Structure):
+    _fields_ = [("posq_host", C.c_void_p), ("force_host", C.c_void_p), ("energies_host", C.c_void_p),
+                ("include_energy", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -99,6 +105,9 @@ def lib():
     L.atm_hrex_device_exchange.argtypes = [vp, vp, C.c_uint64, vp]
     L.atm_hrex_device_state.argtypes = [vp, vp, vp, vp]
     L.atm_hrex_reduced_energy.restype = dbl
+    L.atm_host_pipeline_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp)]
+    L.atm_host_pipeline_destroy.argtypes = [vp]
+    L.atm_host_pipeline_step.argtypes = [vp, C.POINTER(HostIO), i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("atm_last_error", "atm_version", "atm_hrex_reduced_energy"):

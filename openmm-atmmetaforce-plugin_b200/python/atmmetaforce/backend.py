@@ -208,6 +208,61 @@ class ATMBackend:
         return dict(zip(keys, (int(x) for x in out)))
 
 
+class HostPipeline:
+    """atm_host_pipeline_* (include/atm_b200.h): the step with pinned HOST buffers on both sides, for one or more
+    back-ends ("chunks") whose copies and kernels overlap; one cached CUDA graph launch per step.
+
+    posq_host  : list of pinned CPU float32 tensors [R_c][P][4]   (this step's coordinates + charges)
+    force_host : list of pinned CPU int64 tensors   [R_c][3P]     (receives the ATM force, 2^32 fixed point)
+    energies_host : list of pinned CPU float64 tensors [R_c][NUM_ENERGY_SLOTS] or None
+    """
+    NONE, PRUNE, REBUILD = 0, 1, 2
+
+    def __init__(self, backends):
+        self.backends = list(backends)
+        arr = (C.c_void_p * len(self.backends))(*[b._h for b in self.backends])
+        self._p = C.c_void_p()
+        check(_capi.lib().atm_host_pipeline_create(len(self.backends), arr, C.byref(self._p)))
+        self._ios = None
+        self._key = None
+
+    def close(self):
+        if self._p:
+            _capi.lib().atm_host_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _hptr(t, what):
+        if t is None:
+            return None
+        if t.is_cuda or not t.is_contiguous() or not t.is_pinned():
+            raise ATMError(f"{what}: expected a contiguous pinned host tensor")
+        return t.data_ptr()
+
+    def step(self, posq_host, force_host, energies_host=None, maintenance=0, include_energy=True, stream=None):
+        n = len(self.backends)
+        if len(posq_host) != n or len(force_host) != n or (energies_host is not None and len(energies_host) != n):
+            raise ATMError("HostPipeline.step: one buffer per back-end is required")
+        key = (tuple(t.data_ptr() for t in posq_host), tuple(t.data_ptr() for t in force_host),
+               tuple(t.data_ptr() for t in energies_host) if energies_host is not None else None, bool(include_energy))
+        if key != self._key:
+            ios = (_capi.HostIO * n)()
+            for c, b in enumerate(self.backends):
+                if posq_host[c].numel() != b.R * b.P * 4 or force_host[c].numel() != b.R * b.P * 3:
+                    raise ATMError(f"HostPipeline.step: chunk {c}: buffer size does not match [R][P]")
+                ios[c] = _capi.HostIO(self._hptr(posq_host[c], "posq_host"), self._hptr(force_host[c], "force_host"),
+                                      self._hptr(energies_host[c], "energies_host") if energies_host is not None else None,
+                                      1 if include_energy else 0, 0)
+            self._ios, self._key = ios, key
+        check(_capi.lib().atm_host_pipeline_step(self._p, self._ios, int(maintenance), _stream_ptr(stream)))
+
+
 def softcore_softplus(params, U1, U2):
     """Host scalar stage of the library (same math the device runs)."""
     p = _np(params, np.float64)

@@ -1,0 +1,141 @@
+"""atm_host_pipeline_* (the step with pinned HOST buffers on both sides) against the device-buffer path.
+
+Every accumulation of the step is fixed point, so the forces the pipeline returns to the host must be BIT-IDENTICAL to
+what atm_step leaves on the device for the same coordinates and the same pair-list history (rebuild / prune / none),
+whatever the chunking of the replicas; the energy records likewise.  Parity of atm_step itself against the oracle is
+tests/test_gpu_nb2.py; one oracle check is repeated here through the host path.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(atm, s, params_rows, replicas):
+    n = s["pos"].shape[0]
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=replicas)
+    be.set_displacements(s["displ"])
+    be.set_box(s["box"])
+    for r in range(replicas):
+        be.set_parameters(params_rows[r], replica=r)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.1, skin_outer=0.3,
+                exclusions=s["excl"], exception_pairs=s["exc14"], exception_params=s["exc14_par"])
+    return be
+
+
+def _coords(s, P, replicas, seed, sigma):
+    n = s["pos"].shape[0]
+    rng = np.random.default_rng(seed)
+    posq = np.zeros((replicas, P, 4), np.float32)
+    for r in range(replicas):
+        posq[r, :n, :3] = s["pos"] + rng.normal(0, sigma, (n, 3))
+        posq[r, :n, 3] = s["charge"]
+    return posq
+
+
+@pytest.mark.parametrize("split", [(3,), (2, 1), (1, 1, 1)])
+def test_pipeline_matches_device_path(split):
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic, _capi
+    s = synthetic.water_box(12000)   # 4.9 nm box: half the box must hold cutoff + outer skin + a cluster's extent
+    sched = synthetic.atm_schedule_22()
+    R = sum(split)
+    rows = [sched[(5 * r + 3) % 22] for r in range(R)]
+    stream = torch.cuda.Stream()
+    # device-buffer path: one handle with all R replicas
+    ref = _setup(atm, s, rows, R)
+    P = ref.P
+    # host path: the same replicas split over len(split) handles
+    bounds = np.cumsum((0,) + tuple(split))
+    bes = [_setup(atm, s, rows[bounds[c]:bounds[c + 1]], split[c]) for c in range(len(split))]
+    pipe = atm.HostPipeline(bes)
+    posq_h = [torch.zeros((k, P, 4), dtype=torch.float32).pin_memory() for k in split]
+    force_h = [torch.full((k, 3 * P), 7, dtype=torch.int64).pin_memory() for k in split]
+    en_h = [torch.zeros((k, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory() for k in split]
+    plan = [pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.NONE, pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.REBUILD, pipe.NONE]
+    for it, maint in enumerate(plan):
+        x = _coords(s, P, R, seed=100 + it, sigma=0.002 * (1 + it % 3))
+        xd = torch.from_numpy(x).cuda()
+        force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+        with torch.cuda.stream(stream):
+            if maint == pipe.REBUILD:
+                ref.rebuild(xd, stream=stream)
+            elif maint == pipe.PRUNE:
+                ref.prune(xd, stream=stream)
+            ref.step(xd, force, include_energy=True, graph=(it % 2 == 1), stream=stream)
+        en_ref = ref.get_energies(stream=stream)
+        for c in range(len(split)):
+            posq_h[c].copy_(torch.from_numpy(x[bounds[c]:bounds[c + 1]]))
+        pipe.step(posq_h, force_h, en_h, maintenance=maint, stream=stream)
+        stream.synchronize()
+        got_f = torch.cat(force_h, 0)
+        got_e = torch.cat(en_h, 0).numpy()
+        assert torch.equal(got_f, force.cpu()), f"step {it} (maintenance {maint}): forces differ"
+        # U1, U2, u, u_sc, ebias, energy, sp are deterministic (fixed-point partial sums)
+        assert np.array_equal(got_e[:, :7], en_ref[:, :7]), f"step {it}: energy records differ"
+        assert np.abs(got_f.numpy()).max() > 0
+    # launches are accounted per handle: pack + nb2 + merge per plain step at least
+    assert all(b.launch_count() >= 3 * len(plan) for b in bes)
+    pipe.close()
+    for b in bes + [ref]:
+        b.close()
+
+
+def test_pipeline_against_oracle(abfe):
+    """The reference fixture through the host path: U1, u and the merged force against the CPU oracle."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import _capi
+    from helpers import oracle_system, force_from_fixed, rel_rms
+    s = dict(abfe)
+    s["cutoff"], s["ewald_alpha"] = 1.0, O.ewald_alpha(1.0)
+    n = s["pos"].shape[0]
+    be = _setup(atm, s, [s["params"]], 1)
+    P = be.P
+    pipe = atm.HostPipeline([be])
+    posq_h = torch.zeros((1, P, 4), dtype=torch.float32).pin_memory()
+    posq_h[0, :n, :3] = torch.from_numpy(s["pos"].astype(np.float32))
+    posq_h[0, :n, 3] = torch.from_numpy(s["charge"].astype(np.float32))
+    force_h = torch.zeros((1, 3 * P), dtype=torch.int64).pin_memory()
+    en_h = torch.zeros((1, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory()
+    stream = torch.cuda.Stream()
+    pipe.step([posq_h], [force_h], [en_h], maintenance=pipe.REBUILD, stream=stream)
+    stream.synchronize()
+    pos32 = s["pos"].astype(np.float32).astype(np.float64)
+    pos2_32 = (s["pos"].astype(np.float32) + s["displ"].astype(np.float32)).astype(np.float64)
+    S = oracle_system(O, s, 1.0, s["ewald_alpha"])
+    e1, _, f1 = S.nb_direct(pos32)
+    e2, _, f2 = S.nb_direct(pos2_32)
+    sc = O.scalars(s["params"], e1, e2)
+    f_ref = O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], s["params"][8])
+    en = en_h.numpy()[0]
+    assert abs(en[_capi.E_U1] - e1) <= 1e-6 * abs(e1)
+    assert abs(en[_capi.E_USC] - sc["u_sc"]) <= 5e-3
+    assert rel_rms(force_from_fixed(force_h.numpy()[0], n, P), f_ref) <= 1e-5
+    pipe.close()
+    be.close()
+
+
+def test_pipeline_errors():
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic
+    s = synthetic.water_box(12000)
+    be = _setup(atm, s, [synthetic.atm_schedule_22()[0]], 1)
+    P = be.P
+    with pytest.raises(atm.ATMError):
+        atm.HostPipeline([be, be])                      # the same handle twice
+    pipe = atm.HostPipeline([be])
+    posq_h = torch.zeros((1, P, 4), dtype=torch.float32).pin_memory()
+    force_h = torch.zeros((1, 3 * P), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.Stream()
+    with pytest.raises(atm.ATMError, match="rebuild"):  # no pair list yet and none asked for
+        pipe.step([posq_h], [force_h], maintenance=pipe.NONE, stream=stream)
+    with pytest.raises(atm.ATMError, match="pinned"):
+        pipe.step([torch.zeros((1, P, 4))], [force_h], maintenance=pipe.REBUILD, stream=stream)
+    with pytest.raises(atm.ATMError):
+        pipe.step([posq_h], [force_h], maintenance=5, stream=stream)
+    pipe.close()
+    be.close()
