@@ -44,7 +44,7 @@ constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energ
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
 constexpr int NUM_FLAGS = 40;
 #ifndef ATM_PRUNE_BLOCK
-#define ATM_PRUNE_BLOCK 1          // list steps per software-pipeline block of the prune kernel (1 = one-step loop)
+#define ATM_PRUNE_BLOCK 2          // list steps per software-pipeline block of the prune kernel (1 = one-step loop)
 #endif
 constexpr int EACC_SLOTS = 8;                  // Uc, U(S1), U(S2), pairs in cutoff per target (C, S1, S2), Urec(1), Urec(2)
 constexpr double PME_SCALE = 1099511627776.0;  // 2^40 fixed point of the charge-grid accumulation
@@ -570,19 +570,16 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
 
 // INNER list: the outer entries that are inside (cutoff + inner skin) of at least one ATOM of the cluster at the
 // current coordinates.  Cheap (coalesced reads of the outer list, no exclusion work), run every few steps.
-__global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
-    const int lane = threadIdx.x & 31;
-    const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int r = blockIdx.y;
-    const int nlists = d.Cmax + d.CLmax;
-    if (l >= nlists) return;
+// Prunes list l of replica r (one warp); returns the number of kept entries (0 for an empty / unused list).
+__device__ __forceinline__ int prune_one_list(const NbDev &d, int r, int l, int nlists, int lane, ListInfo &li, float4 *sa) {
+    if (l >= nlists) return 0;
     const int nst_outer = d.outer_nsteps[(size_t)r * nlists + l];
     int *nsteps_out = d.list_nsteps + (size_t)r * nlists + l;
     if (nst_outer == 0) {
         if (lane == 0) *nsteps_out = 0;
-        return;
+        return 0;
     }
-    const ListInfo li = decode_list(d, r, l);
+    li = decode_list(d, r, l);
     const int A = li.cluster;
     const size_t rcA = (size_t)r * d.Cmax + A;
     const size_t rsite = (size_t)r * d.Smax;
@@ -592,16 +589,15 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
     const float rl2 = d.rlist * d.rlist;
     // cluster atoms relative to the cluster centre as (-2a, |a|^2): |p - a|^2 = |p|^2 + (-2a).p + |a|^2 costs three
     // FFMAs and a min per atom; all coordinates are within ~1.5 nm of the centre, so the expansion loses nothing that
-    // matters for a skin test
-    float xa[CL], ya[CL], za[CL], a2[CL];
-#pragma unroll
-    for (int k = 0; k < CL; k++) {
-        const float4 p = __ldg(d.xs + rsite + (size_t)A * CL + k);
-        const bool ok = (validA >> k) & 1;
+    // matters for a skin test.  They live in shared memory (broadcast reads): 32 fewer registers per thread buy the
+    // occupancy this latency-bound kernel needs.
+    if (lane < CL) {
+        const float4 p = __ldg(d.xs + rsite + (size_t)A * CL + lane);
+        const bool ok = (validA >> lane) & 1;
         const float ax = wrap_delta(p.x - cA.x, L.x, iL.x), ay = wrap_delta(p.y - cA.y, L.y, iL.y), az = wrap_delta(p.z - cA.z, L.z, iL.z);
-        xa[k] = -2.f * ax; ya[k] = -2.f * ay; za[k] = -2.f * az;
-        a2[k] = ok ? fmaf(az, az, fmaf(ay, ay, ax * ax)) : 1e30f;
+        sa[lane] = make_float4(-2.f * ax, -2.f * ay, -2.f * az, ok ? fmaf(az, az, fmaf(ay, ay, ax * ax)) : 1e30f);
     }
+    __syncwarp();
     const unsigned int *in = d.jlist_outer + li.offset;
     unsigned int *out = d.jlist + li.offset;
     int count = 0;
@@ -641,7 +637,7 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
                             pz = wrap_delta(p.z - cA.z, L.z, iL.z);
                 float d2min = 1e30f;
 #pragma unroll
-                for (int k = 0; k < CL; k++) d2min = fminf(d2min, fmaf(px, xa[k], fmaf(py, ya[k], fmaf(pz, za[k], a2[k]))));
+                for (int k = 0; k < CL; k++) { const float4 a = sa[k]; d2min = fminf(d2min, fmaf(px, a.x, fmaf(py, a.y, fmaf(pz, a.z, a.w)))); }
                 keep = d2min + fmaf(pz, pz, fmaf(py, py, px * px)) <= rl2;
             }
             const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
@@ -668,7 +664,7 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
                         pz = wrap_delta(p.z - cA.z, L.z, iL.z);
             float d2min = 1e30f;
 #pragma unroll
-            for (int k = 0; k < CL; k++) d2min = fminf(d2min, fmaf(px, xa[k], fmaf(py, ya[k], fmaf(pz, za[k], a2[k]))));
+            for (int k = 0; k < CL; k++) { const float4 a = sa[k]; d2min = fminf(d2min, fmaf(px, a.x, fmaf(py, a.y, fmaf(pz, a.z, a.w)))); }
             keep = d2min + fmaf(pz, pz, fmaf(py, py, px * px)) <= rl2;
         }
         const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
@@ -678,21 +674,54 @@ __global__ void __launch_bounds__(128) nl_prune_kernel(NbDev d) {
 #endif
     const int nsteps = (count + 31) >> 5;
     for (int p = count + lane; p < nsteps * 32; p += 32) out[p] = 0xffu;
-    // work items of this list: (<= ITEM_STEPS)-step chunks, slots reserved with one atomic (their order only affects
-    // scheduling: every accumulation downstream is fixed point, hence order independent)
-    // Buckets by chunk length: the force kernel hands out the longest chunks first (longest-processing-time order keeps
-    // the tail of the launch short when only a few replicas share the GPU).
+    if (lane == 0) *nsteps_out = nsteps;
+    return count;
+}
+
+#ifndef ATM_PRUNE_WARPS
+#define ATM_PRUNE_WARPS 4
+#endif
+constexpr int PRUNE_WARPS = ATM_PRUNE_WARPS;   // lists per block of the prune kernel
+
+// Measured (B200, 22 / 3 replicas of the 23k-atom system, whole prune call): one-step loop with the cluster atoms in
+// registers (107 registers, 16 warps / SM) 315 / 62 us; blocks of 2 steps with the cluster atoms in shared memory at
+// <= 64 registers (32 warps / SM) 228 / 50 us; blocks of 4 at 80 registers 243 / 53 us; 48 / 40 / 32 registers: 272 /
+// 250 / 277 us (spills).
+#ifndef ATM_PRUNE_MIN_BLOCKS
+#define ATM_PRUNE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32 * PRUNE_WARPS, ATM_PRUNE_MIN_BLOCKS) nl_prune_kernel(NbDev d) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int l = blockIdx.x * PRUNE_WARPS + w;
+    const int r = blockIdx.y;
+    ListInfo li;
+    li.cluster = 0; li.target = TGT_C; li.offset = 0;
+    __shared__ float4 s_atoms[PRUNE_WARPS][CL];
+    const int count = prune_one_list(d, r, l, d.Cmax + d.CLmax, lane, li, s_atoms[w]);
+    const int A = li.cluster;
+    const int nsteps = (count + 31) >> 5;
+    // work items of this list: (<= ITEM_STEPS)-step chunks (their order only affects scheduling: every accumulation
+    // downstream is fixed point, hence order independent).  Buckets by chunk length: the force kernel hands out the
+    // longest chunks first (longest-processing-time order keeps the tail of the launch short when only a few replicas
+    // share the GPU).  The counters every list touches -- kept entries, live items, the bucket of full chunks -- are
+    // summed over the block first: same-address atomics serialise in the L2, one per block instead of one per list.
     const int nfull = nsteps / ITEM_STEPS, rem = nsteps - nfull * ITEM_STEPS;
-    int base_full = 0, base_rem = 0;
-    if (lane == 0) {
-        *nsteps_out = nsteps;
-        atomicAdd((unsigned long long *)&d.flags[6], (unsigned long long)count);
-        if (nfull > 0) base_full = atomicAdd(&d.flags[ITEM_BUCKET0 + ITEM_STEPS], nfull);
-        if (rem > 0) base_rem = atomicAdd(&d.flags[ITEM_BUCKET0 + rem], 1);
-        if (nfull + (rem > 0) > 0) atomicAdd(&d.flags[4], nfull + (rem > 0 ? 1 : 0));
+    __shared__ int s_count[PRUNE_WARPS], s_nfull[PRUNE_WARPS], s_items[PRUNE_WARPS], s_base_full;
+    if (lane == 0) { s_count[w] = count; s_nfull[w] = nfull; s_items[w] = nfull + (rem > 0 ? 1 : 0); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tc = 0, tf = 0, ti = 0;
+#pragma unroll
+        for (int k = 0; k < PRUNE_WARPS; k++) { tc += s_count[k]; tf += s_nfull[k]; ti += s_items[k]; }
+        if (tc > 0) atomicAdd((unsigned long long *)&d.flags[6], (unsigned long long)tc);
+        s_base_full = tf > 0 ? atomicAdd(&d.flags[ITEM_BUCKET0 + ITEM_STEPS], tf) : 0;
+        if (ti > 0) atomicAdd(&d.flags[4], ti);
     }
-    base_full = __shfl_sync(0xffffffffu, base_full, 0);
-    base_rem = __shfl_sync(0xffffffffu, base_rem, 0);
+    __syncthreads();
+    int base_full = s_base_full, base_rem = 0;
+#pragma unroll
+    for (int k = 0; k < PRUNE_WARPS; k++) base_full += k < w ? s_nfull[k] : 0;
+    if (lane == 0 && rem > 0) base_rem = atomicAdd(&d.flags[ITEM_BUCKET0 + rem], 1);
     for (int c = lane; c < nfull; c += 32)
         d.items[(size_t)ITEM_STEPS * d.max_items + base_full + c] =
             make_int4((int)(li.offset + (size_t)c * ITEM_STEPS * 32), A | (li.target << 28), r | (ITEM_STEPS << 8), c * ITEM_STEPS);
@@ -1719,9 +1748,8 @@ static int launch_prune(atm_handle *h, cudaStream_t stream, bool refresh_boxes) 
     const int nlists = d.Cmax + d.CLmax;
     if (refresh_boxes) nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
     ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 4, 0, sizeof(int), stream));      // live item count
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + ITEM_BUCKET0, 0, sizeof(int) * (ITEM_STEPS + 1), stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * 2, stream));  // pruned-entry counter
-    nl_prune_kernel<<<dim3((nlists + 3) / 4, d.R), 128, 0, stream>>>(d);
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * (NUM_FLAGS - 6), stream));  // pruned-entry counter [6,7], item buckets
+    nl_prune_kernel<<<dim3((nlists + PRUNE_WARPS - 1) / PRUNE_WARPS, d.R), 32 * PRUNE_WARPS, 0, stream>>>(d);
     h->launches += (refresh_boxes ? 1 : 0) + 1;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;

@@ -1,6 +1,7 @@
 """Small two-replica case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): rebuild, prune, two plain
 steps with statistics, one CUDA-graph step (programmatic dependent launches inside), PME on for the last step, the
-on-device replica exchange, energies read back.
+on-device replica exchange, energies read back; then the host-buffer pipeline (two handles forked / joined inside one
+captured graph) through its rebuild / prune / plain variants.
 
     compute-sanitizer --tool memcheck  python tools/sanitize_case.py
 """
@@ -47,3 +48,25 @@ with torch.cuda.stream(stream):
 en2 = be.get_energies(stream=stream)
 print("u:", en[:, 3], "u with PME:", en2[:, 3], "states:", rex.replica_state)
 be.close()
+
+# host-buffer pipeline: two one-replica handles, pinned buffers on both sides
+bes = []
+for r in range(R):
+    b = atm.ATMBackend(n, precision="mixed", num_replicas=1)
+    b.set_displacements(s["displ"])
+    b.set_box(s["box"])
+    b.set_parameters(sched[5 + 11 * r])
+    b.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.1, skin_outer=0.2, exclusions=s["excl"])
+    bes.append(b)
+pipe = atm.HostPipeline(bes)
+P = bes[0].P
+posq_h = [posq[r:r + 1].cpu().pin_memory() for r in range(R)]
+force_h = [torch.zeros((1, 3 * P), dtype=torch.int64).pin_memory() for _ in range(R)]
+en_h = [torch.zeros((1, 16), dtype=torch.float64).pin_memory() for _ in range(R)]
+for maint in (pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.REBUILD, pipe.NONE):
+    pipe.step(posq_h, force_h, en_h, maintenance=maint, stream=stream)
+    stream.synchronize()
+print("pipeline u:", [float(e[0, 3]) for e in en_h], "max |F| (fixed point):", [int(f.abs().max()) for f in force_h])
+pipe.close()
+for b in bes:
+    b.close()
