@@ -780,9 +780,11 @@ __device__ __forceinline__ float pair_interaction(float r2, float qq, float sig,
     poly = fmaf(poly, t, ERFC_A2);
     poly = fmaf(poly, t, ERFC_A1);
     poly = fmaf(poly, t, ERFC_A0);
-    const float erfc_ar = poly * t * ex;
-    const float ec = qq * rinv * erfc_ar;
-    const float fc = fmaf(qq * pc.two_a_sqrtpi, ex, ec);
+    // Coulomb: E = qq exp(-a^2 r^2) P(t) t / r,  F r = E + qq (2a/sqrt(pi)) exp(-a^2 r^2)  -- five instructions
+    const float g = poly * t * rinv;
+    const float qe = qq * ex;
+    const float ec = qe * g;
+    const float fc = fmaf(qe, pc.two_a_sqrtpi, ec);
     if (ENERGY) energy = fmaf(es6, s6, -es6) + ec;
     return (flj + fc) * rinv2;
 }
@@ -972,7 +974,6 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
         const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
         float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
-        bool any = false;
 #pragma unroll
         for (int k = 0; k < CL; k++) {
             const float4 xi = sm.xi[w][k];
@@ -981,16 +982,17 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
             float en = 0.f;
-            const float fsc = pair_interaction<ENERGY>(r2, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
-            const float fs = in ? fsc : 0.f;
-            if (ENERGY) e_step += in ? en : 0.f;
+            // a pair outside the cutoff (or excluded, or a padding slot) is evaluated at r^2 = 1e30: every term underflows
+            // to exactly zero (flush-to-zero MUFU paths, no inf/NaN even for r = 0), so ONE select on r^2 replaces the
+            // selects on the force scale and on the energy
+            const float fs = pair_interaction<ENERGY>(in ? r2 : 1e30f, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
+            if (ENERGY) e_step += en;
             if (STATS) npairs += in ? 1 : 0;
-            any |= in;
             fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
             fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
         }
         if (ENERGY) e_acc += (double)e_step;
-        if (any) {
+        if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {  // no partner atom in range (or an exactly zero force): nothing to add
             red_add_fixed(buf + j, fjx);
             red_add_fixed(buf + it.comp_stride + j, fjy);
             red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
