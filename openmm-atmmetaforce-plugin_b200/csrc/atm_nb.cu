@@ -974,6 +974,7 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
         const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
         float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
+        bool any = false;
 #pragma unroll
         for (int k = 0; k < CL; k++) {
             const float4 xi = sm.xi[w][k];
@@ -988,11 +989,12 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
             const float fs = pair_interaction<ENERGY>(in ? r2 : 1e30f, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
             if (ENERGY) e_step += en;
             if (STATS) npairs += in ? 1 : 0;
+            any |= in;
             fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
             fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
         }
         if (ENERGY) e_acc += (double)e_step;
-        if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {  // no partner atom in range (or an exactly zero force): nothing to add
+        if (any) {  // (deriving this from fj != 0 after the loop instead of 8 predicate ORs measured 2 % SLOWER per launch)
             red_add_fixed(buf + j, fjx);
             red_add_fixed(buf + it.comp_stride + j, fjy);
             red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
