@@ -65,6 +65,20 @@ def test_bad_arguments_raise():
         atm.hrex_sweep(np.zeros((2, 9)), np.array([[0.0, np.nan], [0, 0]]), [0, 1], 0.4, 1, 0)  # NaN guard
 
 
+def test_host_pipeline_rejects_bad_arguments_before_touching_the_device():
+    """atm_host_pipeline_*: argument checks come first, so they are testable without a GPU (no CPU fallback exists:
+    a valid call needs handles, and atm_create needs a CUDA device)."""
+    L = _capi.lib()
+    p = C.c_void_p()
+    assert L.atm_host_pipeline_create(0, None, C.byref(p)) != _capi.ATM_OK and not p.value
+    assert b"no handles" in L.atm_last_error()
+    handles = (C.c_void_p * 1)(None)
+    assert L.atm_host_pipeline_create(1, handles, C.byref(p)) != _capi.ATM_OK and not p.value
+    assert L.atm_host_pipeline_step(None, None, 0, None) != _capi.ATM_OK
+    assert L.atm_host_pipeline_destroy(None) == _capi.ATM_OK      # destroying nothing is not an error
+    assert C.sizeof(_capi.HostIO) == 32                           # 3 pointers + 2 int32, as declared in the header
+
+
 # ------------------------------------------------------------------ replica exchange decisions (host, deterministic)
 
 def _schedule():
