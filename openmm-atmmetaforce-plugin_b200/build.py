@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libatm_b200.so")
 SOURCES = ["atm_capi.cu", "atm_copy_merge.cu", "atm_nb.cu", "atm_hrex.cu", "atm_host.cu"]
-HEADERS = [os.path.join(CSRC, "atm_common.cuh"), os.path.join(ROOT, "include", "atm_b200.h")]
+HEADERS = [os.path.join(CSRC, f) for f in ("atm_common.cuh", "atm_nb_types.cuh", "atm_nb_lists.cuh", "atm_nb_force.cuh",
+                                            "atm_nb_pme.cuh")] + [os.path.join(ROOT, "include", "atm_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -1,0 +1,513 @@
+// atm_nb_force.cuh -- Tier 2 per-step kernels: the two-state direct-space force kernel (nb2_kernel: work items of the
+// pair lists, then excluded / 1-4 exception pairs) and the fused scalar stage + merge (nb_merge_kernel).
+// Included by atm_nb.cu only.
+#pragma once
+
+#include "atm_common.cuh"
+#include "atm_nb_types.cuh"
+
+namespace atm {
+
+// ------------------------------------------------------------------------------------------------
+// The force kernel.
+// ------------------------------------------------------------------------------------------------
+// erfc(x) = t (a0 + a1 t + ... + a6 t^6) exp(-x^2), t = 1/(1 + p x); max relative error 6.8e-8 on [0, 4.2]
+// (fit: DESIGN.md "erfc"); evaluated in fp32 the rounding error (~4e-7) dominates.
+#define ERFC_P 0.357431514f
+#define ERFC_A0 1.9957954259e-01f
+#define ERFC_A1 2.2717719300e-01f
+#define ERFC_A2 5.6467497521e-02f
+#define ERFC_A3 5.3674605718e-01f
+#define ERFC_A4 -4.8585730230e-01f
+#define ERFC_A5 6.4534500206e-01f
+#define ERFC_A6 -1.7945805777e-01f
+
+// MUFU wrappers without the denormal / range fix-up code the CUDA math library adds around them
+__device__ __forceinline__ float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// round to nearest integer for |x| < 2^22 without the (quarter-rate) FRND instruction
+__device__ __forceinline__ float fast_rint(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+
+struct PairConst {
+    float cutoff2;
+    float p_alpha;      // ERFC_P * alpha
+    float neg_a2_log2e; // -alpha^2 log2(e)
+    float two_a_sqrtpi; // 2 alpha / sqrt(pi)
+};
+
+// One pair.  qq = q_i q_j k_e (charges are stored pre-multiplied by sqrt(k_e)); sig = (s_i+s_j)/2; eps4 = 4 sqrt(e_i e_j).
+// Returns F/r (fscale) and, when ENERGY, the pair energy.
+template <bool ENERGY>
+__device__ __forceinline__ float pair_interaction(float r2, float qq, float sig, float eps4, const PairConst &pc, float &energy) {
+    float rinv = mufu_rsqrt(r2);
+#ifdef ATM_RSQRT_NEWTON  // A/B switch: measured force/energy parity is identical without the Newton step
+    rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);
+#endif
+    const float rinv2 = rinv * rinv;
+    const float r = r2 * rinv;
+    const float s2 = sig * sig * rinv2;
+    const float s6 = s2 * s2 * s2;
+    const float es6 = eps4 * s6;
+    const float flj = es6 * fmaf(12.0f, s6, -6.0f);
+    const float t = mufu_rcp(fmaf(pc.p_alpha, r, 1.0f));
+    const float ex = mufu_ex2(pc.neg_a2_log2e * r2);
+    float poly = fmaf(ERFC_A6, t, ERFC_A5);
+    poly = fmaf(poly, t, ERFC_A4);
+    poly = fmaf(poly, t, ERFC_A3);
+    poly = fmaf(poly, t, ERFC_A2);
+    poly = fmaf(poly, t, ERFC_A1);
+    poly = fmaf(poly, t, ERFC_A0);
+    // Coulomb: E = qq exp(-a^2 r^2) P(t) t / r,  F r = E + qq (2a/sqrt(pi)) exp(-a^2 r^2)  -- five instructions
+    const float g = poly * t * rinv;
+    const float qe = qq * ex;
+    const float ec = qe * g;
+    const float fc = fmaf(qe, pc.two_a_sqrtpi, ec);
+    if (ENERGY) energy = fmaf(es6, s6, -es6) + ec;
+    return (flj + fc) * rinv2;
+}
+
+struct ItemCtx {
+    int r, A, target, nst;
+    const unsigned int *list;
+    size_t rsite, comp_stride;
+};
+
+template <bool ENERGY, bool STATS>
+__device__ __forceinline__ void nb2_item_epilogue(const NbDev &d, const ItemCtx &it, int lane, unsigned long long *buf,
+                                                  float (&fix)[CL], float (&fiy)[CL], float (&fiz)[CL], double e_acc, int npairs) {
+    // transpose-reduce the 24 i-force accumulators: after three halving exchanges lane (l&7) owns atom l&7
+    {
+        const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+        float w[4][3];
+#pragma unroll
+        for (int mm = 0; mm < 4; mm++) {
+            const float kx = b0 ? fix[2 * mm + 1] : fix[2 * mm], sx = b0 ? fix[2 * mm] : fix[2 * mm + 1];
+            const float ky = b0 ? fiy[2 * mm + 1] : fiy[2 * mm], sy = b0 ? fiy[2 * mm] : fiy[2 * mm + 1];
+            const float kz = b0 ? fiz[2 * mm + 1] : fiz[2 * mm], sz = b0 ? fiz[2 * mm] : fiz[2 * mm + 1];
+            w[mm][0] = kx + __shfl_xor_sync(0xffffffffu, sx, 1);
+            w[mm][1] = ky + __shfl_xor_sync(0xffffffffu, sy, 1);
+            w[mm][2] = kz + __shfl_xor_sync(0xffffffffu, sz, 1);
+        }
+        float x2[2][3];
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float kk = b1 ? w[2 * mm + 1][c] : w[2 * mm][c], ss = b1 ? w[2 * mm][c] : w[2 * mm + 1][c];
+                x2[mm][c] = kk + __shfl_xor_sync(0xffffffffu, ss, 2);
+            }
+        float y[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float kk = b2 ? x2[1][c] : x2[0][c], ss = b2 ? x2[0][c] : x2[1][c];
+            y[c] = kk + __shfl_xor_sync(0xffffffffu, ss, 4);
+            y[c] += __shfl_xor_sync(0xffffffffu, y[c], 8);
+            y[c] += __shfl_xor_sync(0xffffffffu, y[c], 16);
+        }
+        // lane l (< 8) now holds atom index (b0 + 2 b1 + 4 b2) = l
+        if (lane < CL) {
+            const int i = it.A * CL + lane;
+            red_add_fixed(buf + i, y[0]);
+            red_add_fixed(buf + it.comp_stride + i, y[1]);
+            red_add_fixed(buf + 2 * it.comp_stride + i, y[2]);
+        }
+    }
+    // energies: warp sum in double, one fixed-point atomic per warp
+    if (ENERGY || STATS) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            if (ENERGY) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, off);
+            if (STATS) npairs += __shfl_xor_sync(0xffffffffu, npairs, off);
+        }
+        if (lane == 0) {
+            unsigned long long *ea = d.eacc + (size_t)it.r * EACC_SLOTS;
+            if (ENERGY) atomicAdd(ea + it.target, (unsigned long long)__double2ll_rn(e_acc * ENERGY_SCALE));
+            if (STATS) atomicAdd(ea + 3 + it.target, (unsigned long long)npairs);
+        }
+    }
+}
+
+// Partner data is staged through a per-lane shared-memory ring with cp.async (prefetch distance 3 steps); the cluster
+// atoms are broadcast from shared memory instead of living in 48 registers, which buys a fifth resident block per SM.
+constexpr int NB_WARPS = NB_THREADS / 32;
+#ifndef ATM_PF_DIST
+#define ATM_PF_DIST 3
+#endif
+#ifndef ATM_RING
+#define ATM_RING 4
+#endif
+constexpr int RING = ATM_RING;        // ring slots per lane (power of two, > PF_DIST)
+constexpr int PF_DIST = ATM_PF_DIST;  // coordinate steps in flight
+
+// The list entries of a work item (<= ITEM_STEPS x 128 B, contiguous, streaming from DRAM) are brought into shared
+// memory by ONE bulk asynchronous copy (the TMA unit: cp.async.bulk, SASS UBLKCP) that signals an mbarrier, instead of
+// a rolling register prefetch of one LDG per step.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_arm(unsigned long long *bar, void *smem, const void *gmem, unsigned int bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct __align__(128) Nb2Smem {
+    unsigned int el[NB_WARPS][ITEM_STEPS][32];  // the item's list entries (bulk copy destination)
+    float4 xj[NB_WARPS][RING][32];
+    float2 pj[NB_WARPS][RING][32];
+    float4 xi[NB_WARPS][CL];
+    float2 pi[NB_WARPS][CL];
+    unsigned long long bar[NB_WARPS];           // one mbarrier per warp
+};
+
+template <bool ENERGY, bool STATS>
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
+    const float4 L = d.box[it.r], iL = d.invbox[it.r];
+    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
+    PairConst pc;
+    pc.cutoff2 = d.cutoff2;
+    pc.p_alpha = ERFC_P * d.alpha;
+    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
+    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+
+    // the whole entry list of the item: one bulk copy, in flight while the cluster atoms are staged
+    if (lane == 0) bulk_load_arm(&sm.bar[w], &sm.el[w][0][0], it.list, (unsigned)it.nst * 128u);
+    // cluster atoms -> shared memory (lanes 0..7), shifted next to the cluster centre
+    if (lane < CL) {
+        float4 x = __ldg(d.xs + it.rsite + (size_t)it.A * CL + lane);
+        x.x -= L.x * fast_rint((x.x - cA.x) * iL.x);
+        x.y -= L.y * fast_rint((x.y - cA.y) * iL.y);
+        x.z -= L.z * fast_rint((x.z - cA.z) * iL.z);
+        sm.xi[w][lane] = x;
+        sm.pi[w][lane] = __ldg(d.par + it.rsite + (size_t)it.A * CL + lane);
+    }
+    mbar_wait(&sm.bar[w], parity);
+#pragma unroll
+    for (int q = 0; q < PF_DIST; q++) {
+        if (q < it.nst) {
+            const unsigned int eq = sm.el[w][q][lane];
+            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (eq >> 8));
+            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (eq >> 8));
+        }
+        cp_async_commit();
+    }
+    __syncwarp();
+
+    float fix[CL], fiy[CL], fiz[CL];
+#pragma unroll
+    for (int k = 0; k < CL; k++) fix[k] = fiy[k] = fiz[k] = 0.f;
+    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
+    double e_acc = 0.0;
+    int npairs = 0;
+
+    for (int st = 0; st < it.nst; st++) {
+        cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
+        const int slot = st & (RING - 1);
+        const float4 xjc = sm.xj[w][slot][lane];
+        const float2 pjc = sm.pj[w][slot][lane];
+        const unsigned int e = sm.el[w][st][lane];
+        // keep PF_DIST steps in flight
+        {
+            const int sp = st + PF_DIST;
+            if (sp < it.nst) {
+                const unsigned int e_next = sm.el[w][sp][lane];
+                const int ps = sp & (RING - 1);
+                cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
+                cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
+            }
+            cp_async_commit();
+        }
+        const int j = e >> 8;
+        const unsigned int m = e & 0xffu;
+        const float xjx = xjc.x - L.x * fast_rint((xjc.x - cA.x) * iL.x);
+        const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
+        const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < CL; k++) {
+            const float4 xi = sm.xi[w][k];
+            const float2 pi = sm.pi[w][k];
+            const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
+            float en = 0.f;
+            // a pair outside the cutoff (or excluded, or a padding slot) is evaluated at r^2 = 1e30: every term underflows
+            // to exactly zero (flush-to-zero MUFU paths, no inf/NaN even for r = 0), so ONE select on r^2 replaces the
+            // selects on the force scale and on the energy
+            const float fs = pair_interaction<ENERGY>(in ? r2 : 1e30f, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
+            if (ENERGY) e_step += en;
+            if (STATS) npairs += in ? 1 : 0;
+            any |= in;
+            fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
+            fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
+        }
+        if (ENERGY) e_acc += (double)e_step;
+        if (any) {  // (deriving this from fj != 0 after the loop instead of 8 predicate ORs measured 2 % SLOWER per launch)
+            red_add_fixed(buf + j, fjx);
+            red_add_fixed(buf + it.comp_stride + j, fjy);
+            red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
+        }
+    }
+    cp_async_wait<0>();
+    nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, fix, fiy, fiz, e_acc, npairs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Excluded pairs (Ewald correction -qq erf(ar)/r, minimum image) and 1-4 exceptions (plain Coulomb + LJ, no image).
+// One thread per (replica, pair).  Pairs whose atoms move together go to C, others are evaluated in both states.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add_pair_force(const NbDev &d, int r, int target, int si, int sj, float fx, float fy, float fz) {
+    unsigned long long *buf = d.buf + (size_t)target * 3 * d.R * d.Smax + (size_t)r * d.Smax;
+    const size_t cs = (size_t)d.R * d.Smax;
+    red_add_fixed(buf + si, fx); red_add_fixed(buf + cs + si, fy); red_add_fixed(buf + 2 * cs + si, fz);
+    red_add_fixed(buf + sj, -fx); red_add_fixed(buf + cs + sj, -fy); red_add_fixed(buf + 2 * cs + sj, -fz);
+}
+
+__device__ __forceinline__ void special_pairs_body(const NbDev &d, int t, int r, const int2 *__restrict__ excl, int n_excl,
+                                                   const int2 *__restrict__ exc, const float4 *__restrict__ exc_par, int n_exc) {
+    double e_tgt[3] = {0.0, 0.0, 0.0};
+    if (t < n_excl + n_exc) {
+        const bool is_exc = t >= n_excl;
+        const int2 pr = is_exc ? exc[t - n_excl] : excl[t];
+        const int ga = d.group_of_atom[pr.x], gb = d.group_of_atom[pr.y];
+        const float4 L = d.box[r], iL = d.invbox[r];
+        const int nstate = (ga == gb) ? 1 : 2;
+        for (int s = 0; s < nstate; s++) {
+            const int target = (ga == gb) ? TGT_C : (s == 0 ? TGT_S1 : TGT_S2);
+            int si = d.site_slot[(size_t)r * d.U + pr.x], sj = d.site_slot[(size_t)r * d.U + pr.y];
+            if (s == 1) {
+                if (ga != 0) si = d.site_slot[(size_t)r * d.U + d.N + d.ghost_of_atom[pr.x]];
+                if (gb != 0) sj = d.site_slot[(size_t)r * d.U + d.N + d.ghost_of_atom[pr.y]];
+            }
+            const float4 a = d.xs[(size_t)r * d.Smax + si], b = d.xs[(size_t)r * d.Smax + sj];
+            float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+            float fs, en;
+            if (!is_exc) {
+                dx = wrap_delta(dx, L.x, iL.x); dy = wrap_delta(dy, L.y, iL.y); dz = wrap_delta(dz, L.z, iL.z);
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float qq = a.w * b.w;
+                if (r2 > 0.f && qq != 0.f && d.alpha > 0.f) {
+                    const float rinv = 1.0f / sqrtf(r2), rr = r2 * rinv, ar = d.alpha * rr;
+                    const float erf_ar = erff(ar);
+                    en = -qq * rinv * erf_ar;
+                    fs = -qq * rinv * (erf_ar - ar * expf(-ar * ar) * 1.1283791670955126f) * rinv * rinv;
+                } else { en = 0.f; fs = 0.f; }
+            } else {
+                const float4 pp = exc_par[t - n_excl];  // ke*chargeProd, sigma, 4 eps
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float rinv = 1.0f / sqrtf(r2), rinv2 = rinv * rinv;
+                const float s2 = pp.y * pp.y * rinv2, s6 = s2 * s2 * s2;
+                en = pp.z * s6 * (s6 - 1.0f) + pp.x * rinv;
+                fs = (pp.z * s6 * (12.0f * s6 - 6.0f) + pp.x * rinv) * rinv2;
+            }
+            add_pair_force(d, r, target, si, sj, dx * fs, dy * fs, dz * fs);
+            e_tgt[target] += (double)en;
+        }
+    }
+    // block reduction of the three energies (warp shuffle, then one atomic per warp)
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double v = e_tgt[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && v != 0.0) {
+            unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;
+            atomicAdd(ea + k, (unsigned long long)__double2ll_rn(v * ENERGY_SCALE));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused scalar stage + merge.  Per replica: u = U(S2) - U(S1), soft-core, softplus, sp (double, once per block),
+// then  F[slot] += C + (1-sp) S1 + sp S2  gathered from cluster order, accumulators zeroed behind the read.
+// Semantics: CommonATMMetaForceKernels.cpp:182-201 + kernels/atmmetaforce.cc:8-16, blend in double.
+// ------------------------------------------------------------------------------------------------
+constexpr int MERGE2_THREADS = 256;
+
+// Scalar stage, one thread per replica: u = U(S2) - U(S1), soft-core, softplus, sp -- all in double on the device
+// (the reference does this on the host after two blocking energy downloads, CommonATMMetaForceKernels.cpp:164-199).
+__device__ double scalar_stage_replica(const NbDev &d, int r, const double *__restrict__ energy_ext, int include_energy,
+                                       bool write_record) {
+    volatile unsigned long long *ea = d.eacc + (size_t)r * EACC_SLOTS;  // written by atomics of other blocks: read through L2
+    const double uc = (double)(long long)ea[0] / ENERGY_SCALE, u1 = (double)(long long)ea[1] / ENERGY_SCALE,
+                 u2 = (double)(long long)ea[2] / ENERGY_SCALE;
+    double U1 = uc + u1, U2 = uc + u2, du = u2 - u1;
+    double *e = d.energies + (size_t)r * ATM_NUM_ENERGY_SLOTS;
+    double rec1 = 0.0, rec2 = 0.0, eself = 0.0;
+    if (d.pme_on) {
+        // reciprocal energies of the two states (accumulated in double, so their difference is as good as the sum)
+        const double r1 = (double)(long long)ea[6] / ENERGY_SCALE, r2 = (double)(long long)ea[7] / ENERGY_SCALE;
+        const double self = -d.pme_self_sum * (double)d.alpha * 0.5641895835477563;  // -alpha/sqrt(pi) sum q^2
+        const float4 Lb = d.box[r];
+        const double bg = -3.141592653589793 * d.pme_qtot2 /
+                          (2.0 * (double)Lb.x * (double)Lb.y * (double)Lb.z * (double)d.alpha * (double)d.alpha);
+        U1 += r1 + self + bg;
+        U2 += r2 + self + bg;
+        du += r2 - r1;
+        rec1 = r1; rec2 = r2; eself = self;
+    }
+    if (d.disp_coeff != 0.0) {  // same constant in both states: u is unaffected
+        const float4 Lb = d.box[r];
+        const double ed = d.disp_coeff / ((double)Lb.x * (double)Lb.y * (double)Lb.z);
+        U1 += ed;
+        U2 += ed;
+    }
+    if (energy_ext) {
+        U1 += energy_ext[2 * r];
+        U2 += energy_ext[2 * r + 1];
+        du += energy_ext[2 * r + 1] - energy_ext[2 * r];
+    }
+    const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
+    if (write_record) {
+        e[ATM_E_UREC1] = rec1; e[ATM_E_UREC2] = rec2; e[ATM_E_USELF] = eself;
+        e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;
+        e[ATM_E_ENERGY] = include_energy ? s.energy : 0.0; e[ATM_E_SP] = s.sp;
+        e[ATM_E_NPAIRS] = (double)(ea[3] + ea[4] + ea[5]);
+        e[ATM_E_NPAIRS_C] = (double)ea[3]; e[ATM_E_NPAIRS_S1] = (double)ea[4]; e[ATM_E_NPAIRS_S2] = (double)ea[5];
+    }
+    return s.sp;  // the accumulators are zeroed by the next step's pack kernel
+}
+
+// ------------------------------------------------------------------------------------------------
+// The per-step compute launch: work items of the pair lists (one warp each), then blocks of excluded / exception
+// pairs.
+// ------------------------------------------------------------------------------------------------
+struct SpecialArgs {
+    const int2 *excl;
+    const int2 *exc;
+    const float4 *exc_par;
+    int n_excl, n_exc;
+    int blocks_per_replica;  // ceil((n_excl + n_exc) / NB_THREADS)
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS)
+nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
+    pdl_trigger();  // the merge may be scheduled once every block of this grid has started (it waits for completion)
+    pdl_wait();     // cluster-order coordinates come from the pack kernel
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < n_item_blocks) {
+        // The pruned list's item count lives on the device; the grid is sized from the count the last verified build
+        // saw plus a margin, and this grid-stride loop picks up whatever a later prune added beyond it.
+        __shared__ Nb2Smem sm;
+        const int w = threadIdx.x >> 5;
+        if (lane == 0) mbar_init(&sm.bar[w], 1);
+        __syncwarp();
+        unsigned int parity = 0;  // phase of this warp's mbarrier: flips with every completed bulk copy
+        const int n_items = d.flags[4], stride = n_item_blocks * (NB_THREADS / 32);
+        for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
+            __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
+            int wi = warp, b = ITEM_STEPS;
+            for (; b > 1; --b) {  // longest chunks first
+                const int c = d.flags[ITEM_BUCKET0 + b];
+                if (wi < c) break;
+                wi -= c;
+            }
+            const int4 item = __ldg(d.items + (size_t)b * d.max_items + wi);
+            ItemCtx it;
+            it.r = item.z & 0xff;
+            it.A = item.y & 0x0fffffff;
+            it.target = (item.y >> 28) & 3;
+            it.nst = item.z >> 8;
+            it.list = d.jlist + (unsigned int)item.x;
+            it.rsite = (size_t)it.r * d.Smax;
+            it.comp_stride = (size_t)d.R * d.Smax;
+            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm, parity);
+            else nb2_item<true, STATS>(d, it, lane, w, sm, parity);
+        }
+    } else {
+        const int sb = blockIdx.x - n_item_blocks;
+        const int r = sb / sp.blocks_per_replica, chunk = sb - r * sp.blocks_per_replica;
+        special_pairs_body(d, chunk * NB_THREADS + threadIdx.x, r, sp.excl, sp.n_excl, sp.exc, sp.exc_par, sp.n_exc);
+    }
+}
+
+// Merge, one thread per cluster-order slot: the three accumulators are read (and zeroed) coalesced, only the final
+// read-modify-write of the caller's force buffer is a scatter.  The thread of a displaced atom also folds in (and
+// zeroes) the S2 accumulator of its ghost site; ghost and padding slots have no thread work.
+// F[slot] += C + llrint(sp * S2 + (1 - sp) * S1), blend in double (kernels/atmmetaforce.cc:8-16 semantics).
+// The scalar stage is fused in: thread 0 of every block forms u, the soft core, the softplus bias and sp = dW/du of the
+// block's replica in double (the reference does this on the host after two blocking energy downloads,
+// CommonATMMetaForceKernels.cpp:164-199); every block gets the same bits, block 0 of a replica writes the energy record.
+__global__ void __launch_bounds__(MERGE2_THREADS)
+nb_merge_kernel(NbDev d, long long *__restrict__ force, const long long *__restrict__ f1_ext,
+                const long long *__restrict__ f2_ext, const double *__restrict__ energy_ext, int include_energy) {
+    __shared__ double s_sp;
+    const int r = blockIdx.y;
+    const int s = blockIdx.x * MERGE2_THREADS + threadIdx.x;
+    const size_t rsite = (size_t)r * d.Smax;
+    // everything that does not depend on the force kernel first
+    const bool live = s < CL * d.nclusters[r];
+    const int i = live ? d.slot_out[rsite + s] : -1;  // caller's slot of this site's atom, -1 for ghosts and padding
+    const int gs = i >= 0 ? d.slot_ghost[rsite + s] : -1;
+    pdl_wait();
+    if (threadIdx.x == 0) s_sp = scalar_stage_replica(d, r, energy_ext, include_energy, blockIdx.x == 0);
+    __syncthreads();
+    if (i < 0) return;
+    const double sp = s_sp, sp1 = 1.0 - sp;
+    const size_t cs = (size_t)d.R * d.Smax;
+    long long *bufC = (long long *)d.buf + rsite, *buf1 = bufC + 3 * cs, *buf2 = bufC + 6 * cs;
+    long long fc[3], fa[3], fb[3], fg[3], fo_old[3];
+    size_t fo[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {  // every load first
+        fc[c] = bufC[c * cs + s];
+        fa[c] = buf1[c * cs + s];
+        fb[c] = buf2[c * cs + s];
+        fg[c] = gs >= 0 ? buf2[c * cs + gs] : 0;
+        fo[c] = (size_t)r * 3 * d.P + (size_t)c * d.P + i;
+        fo_old[c] = force[fo[c]];
+    }
+    bool nz1[3], nz2[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        nz1[c] = fa[c] != 0;
+        nz2[c] = fb[c] != 0;
+        if (f1_ext) fa[c] += f1_ext[fo[c]];
+        if (f2_ext) fb[c] += f2_ext[fo[c]];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // hand the accumulators back zeroed; the state-specific ones are zero already for every site that is not
+        // within the cutoff of a displaced atom or a ghost (96 % of them): skip those writes
+        bufC[c * cs + s] = 0;
+        if (nz1[c]) buf1[c * cs + s] = 0;
+        if (nz2[c]) buf2[c * cs + s] = 0;
+        if (gs >= 0) buf2[c * cs + gs] = 0;
+        const double v = __dadd_rn(__dmul_rn(sp, (double)(fb[c] + fg[c])), __dmul_rn(sp1, (double)fa[c]));
+        force[fo[c]] = fo_old[c] + fc[c] + __double2ll_rn(v);
+    }
+}
+
+}  // namespace atm
