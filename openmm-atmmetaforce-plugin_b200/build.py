@@ -57,7 +57,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
         if verbose:
             sys.stdout.write(out)
-    cmd = [NVCC, "--shared", "-ccbin", "/usr/bin/g++", "-o", lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    cmd = [NVCC, "--shared", "-ccbin", "/usr/bin/g++", "-o", lib] + objs + ["-lcufft", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return lib
 

@@ -119,6 +119,7 @@ int atm_destroy(atm_handle *h) {
 }
 
 int atm_set_displacements(atm_handle *h, const int32_t *atom_index, const double *dxyz, void *stream) {
+    ATM_NVTX_RANGE("atm_set_displacements");
     ATM_REQUIRE(h != nullptr && (dxyz != nullptr || h->N == 0), ATM_ERR_INVALID, "atm_set_displacements: null argument");
     const int N = h->N, P = h->P;
     if (atom_index != nullptr) {
@@ -173,6 +174,7 @@ int atm_get_parameters(atm_handle *h, int32_t replica, double p[ATM_NUM_PARAMS])
 
 int atm_copy_state(atm_handle *h, const void *posq, const void *posq_corr, void *posq1, void *posq1_corr, void *posq2,
                    void *posq2_corr, void *stream) {
+    ATM_NVTX_RANGE("atm_copy_state");
     ATM_REQUIRE(h != nullptr, ATM_ERR_INVALID, "atm_copy_state: null handle");
     if (h->N == 0) return ATM_OK;
     ATM_REQUIRE(posq && posq1 && posq2, ATM_ERR_INVALID, "atm_copy_state: null position buffer");
@@ -195,6 +197,7 @@ int atm_wrap_positions(atm_handle *h, const void *posq_in, void *posq_out, const
 }
 
 int atm_hybrid_force(atm_handle *h, int64_t *force, const int64_t *f1, const int64_t *f2, double sp, void *stream) {
+    ATM_NVTX_RANGE("atm_hybrid_force");
     ATM_REQUIRE(h != nullptr, ATM_ERR_INVALID, "atm_hybrid_force: null handle");
     if (h->N == 0) return ATM_OK;
     ATM_REQUIRE(force && f1 && f2, ATM_ERR_INVALID, "atm_hybrid_force: null force buffer");
@@ -213,6 +216,7 @@ int atm_softcore_softplus(const double p[ATM_NUM_PARAMS], double U1, double U2, 
 
 int atm_execute(atm_handle *h, int32_t replica, double U1, double U2, int64_t *force, const int64_t *f1,
                 const int64_t *f2, int32_t include_energy, double *energy, void *stream) {
+    ATM_NVTX_RANGE("atm_execute");
     ATM_REQUIRE(h != nullptr, ATM_ERR_INVALID, "atm_execute: null handle");
     ATM_REQUIRE(replica >= 0 && replica < h->R, ATM_ERR_INVALID, "atm_execute: replica %d out of range", replica);
     int rc0 = refresh_params_from_device(h);  // the on-device exchange may have rewritten the rows

@@ -10,6 +10,8 @@
 
 #include "atm_b200.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace atm {
 
 void set_error(const char *fmt, ...);
@@ -72,6 +74,16 @@ __host__ __device__ inline Scalars scalar_stage(const double *p, double U1, doub
     s.sp = dir > 0 ? s.bfp * s.fp : 1.0 - s.bfp * s.fp;
     return s;
 }
+
+// NVTX range around an entry point (host side; a no-op unless a profiler injects the NVTX library): the calls show up
+// as named spans above their kernels in a timeline (tracing).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define ATM_NVTX_RANGE(name) atm::NvtxRange atm_nvtx_range__(name)
 
 struct NbState;  // Tier-2 state (atm_nb.cu)
 

@@ -123,6 +123,7 @@ int atm_host_pipeline_destroy(atm_host_pipeline *p) {
 }
 
 int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t maintenance, void *stream_) {
+    ATM_NVTX_RANGE("atm_host_pipeline_step");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(p && ios, ATM_ERR_INVALID, "atm_host_pipeline_step: null argument");
     ATM_REQUIRE(maintenance >= 0 && maintenance <= 2, ATM_ERR_INVALID, "atm_host_pipeline_step: maintenance must be 0 (none), 1 (prune) or 2 (rebuild)");

@@ -154,6 +154,7 @@ int atm_hrex_device_setup(atm_handle *h, int32_t num_states, const double *state
 }
 
 int atm_hrex_device_pack(atm_handle *h, double *send, int32_t rows, void *stream_) {
+    ATM_NVTX_RANGE("atm_hrex_device_pack");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && send && rows >= 1, ATM_ERR_INVALID, "atm_hrex_device_pack: bad argument");
     const double *en = nullptr;
@@ -167,6 +168,7 @@ int atm_hrex_device_pack(atm_handle *h, double *send, int32_t rows, void *stream
 }
 
 int atm_hrex_device_exchange(atm_handle *h, const double *gathered, uint64_t cycle, void *stream_) {
+    ATM_NVTX_RANGE("atm_hrex_device_exchange");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && h->hrex, ATM_ERR_STATE, "atm_hrex_device_exchange: call atm_hrex_device_setup first");
     ATM_REQUIRE(gathered, ATM_ERR_INVALID, "atm_hrex_device_exchange: null argument");

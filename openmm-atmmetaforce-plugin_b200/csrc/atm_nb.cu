@@ -361,6 +361,7 @@ static int launch_prune_all(atm_handle *h, const void *posq, cudaStream_t stream
 }
 
 int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
+    ATM_NVTX_RANGE("atm_nb_prune");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && posq, ATM_ERR_INVALID, "atm_nb_prune: null argument");
     ATM_REQUIRE(h->nb && h->nb->ready, ATM_ERR_STATE, "atm_nb_prune: Tier 2 not set up");
@@ -399,6 +400,7 @@ int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
 }
 
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream_) {
+    ATM_NVTX_RANGE("atm_nb_setup");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && desc, ATM_ERR_INVALID, "atm_nb_setup: null argument");
     ATM_REQUIRE(h->cfg.precision != ATM_PREC_DOUBLE, ATM_ERR_UNSUPPORTED,
@@ -586,6 +588,7 @@ static int check_pending_rebuild(atm_handle *h, bool wait) {
 }
 
 int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
+    ATM_NVTX_RANGE("atm_nb_rebuild");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(h && posq_, ATM_ERR_INVALID, "atm_nb_rebuild: null argument");
     ATM_REQUIRE(h->nb && h->nb->ready && h->nb->box_set, ATM_ERR_STATE, "atm_nb_rebuild: call atm_nb_setup and atm_set_box first");
@@ -748,6 +751,7 @@ static int validate_step(atm_handle *h, const atm_step_io *io, const char *who) 
 }
 
 int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
+    ATM_NVTX_RANGE("atm_step");
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc;
     if (h && h->nb && (rc = check_pending_rebuild(h, false))) return rc;
@@ -762,6 +766,7 @@ int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
 // re-captured when the buffers, the flags or the pair-list generation change.  `stream` must be a real (non-legacy)
 // stream because it is put into capture mode.
 int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
+    ATM_NVTX_RANGE("atm_step_graph");
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc;
     if (h && h->nb && (rc = check_pending_rebuild(h, false))) return rc;
@@ -871,6 +876,7 @@ static void pme_moduli(int n, int order, std::vector<double> &mod) {
 }
 
 int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t order) {
+    ATM_NVTX_RANGE("atm_pme_setup");
     ATM_REQUIRE(h && h->nb && h->nb->ready, ATM_ERR_STATE, "atm_pme_setup: call atm_nb_setup first");
     NbState *nb = h->nb;
     NbDev &d = nb->d;
