@@ -23,6 +23,7 @@
 #ifndef ATM_B200_H_
 #define ATM_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -230,6 +231,18 @@ int atm_get_energies(atm_handle *h, double *out, void *stream);
 /* Diagnostics of the last rebuild: out = {sites per replica, clusters of replica 0, list entries per replica (mean),
  * env list capacity, ligand/ghost list capacity, displaced atoms M, displacement groups G, xy columns}. */
 int atm_nb_stats(atm_handle *h, int64_t out[8]);
+
+/* ------------------------------------------------------------------ runtime utilities for hosts without the CUDA toolkit */
+
+/* A C++ / Python host that drives the library through this header alone (no cuda_runtime.h) still needs a stream to
+ * issue work on and page-locked memory for the host-buffer step.  Thin wrappers of cudaStreamCreateWithFlags
+ * (non-blocking) / cudaStreamDestroy / cudaStreamSynchronize / cudaHostAlloc / cudaFreeHost on `device` (-1 = current).
+ * The reference gets all of these from OpenMM's CudaContext (cu.getCurrentStream(), CudaContext::getPinnedBuffer). */
+int atm_stream_create(int32_t device, void **stream);
+int atm_stream_destroy(void *stream);
+int atm_stream_synchronize(void *stream);
+int atm_host_alloc(size_t bytes, void **ptr);
+int atm_host_free(void *ptr);
 
 /* ------------------------------------------------------------------ the step with HOST buffers on both sides */
 

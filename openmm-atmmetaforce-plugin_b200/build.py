@@ -65,6 +65,7 @@ def build(force=False, verbose=False, defines=(), out=None):
 FACADE = os.path.join(HERE, "python", "atmmetaforce", "_atmmetaforce_core.so")
 FACADE_SRC = [os.path.join(HERE, "openmmapi", "src", "ATMMetaForce.cpp"),
               os.path.join(HERE, "openmmapi", "src", "ATMMetaForceB200Kernel.cpp"),
+              os.path.join(HERE, "openmmapi", "src", "ATMMetaForceImpl.cpp"),
               os.path.join(HERE, "serialization", "ATMMetaForceProxy.cpp"),
               os.path.join(HERE, "python", "src", "atmmetaforce_core.cpp")]
 
@@ -86,7 +87,7 @@ def build_facade(force=False):
     subprocess.check_call(cmd)
     test = os.path.join(HERE, "build", "TestSerializeATMMetaForce")
     os.makedirs(os.path.dirname(test), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:3] + \
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:4] + \
           [os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp"), "-L", HERE, "-latm_b200",
            "-Wl,-rpath,$ORIGIN/..", "-o", test]
     subprocess.check_call(cmd)

@@ -35,8 +35,7 @@ struct atm_host_pipeline {
     std::vector<Chunk> chunks;
     cudaEvent_t fork = nullptr;
     cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};   // maintenance 0 / 1 / 2
-    int exec_launches[3] = {0, 0, 0};                        // own kernels per replay (all chunks)
-    std::vector<uint64_t> exec_launches_chunk[3];            // ... per chunk
+    std::vector<uint64_t> exec_launches_chunk[3];            // own kernels per replay, per chunk
     std::vector<atm_host_io> ios;                            // the buffers the cached graphs were captured with
 };
 
@@ -68,6 +67,51 @@ static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int mainten
 }
 
 extern "C" {
+
+int atm_stream_create(int32_t device, void **stream) {
+    ATM_REQUIRE(stream, ATM_ERR_INVALID, "atm_stream_create: null argument");
+    *stream = nullptr;
+    int count = 0;
+    ATM_REQUIRE(cudaGetDeviceCount(&count) == cudaSuccess && count > 0, ATM_ERR_CUDA,
+                "atm_stream_create: no CUDA device available (this library has no CPU fallback)");
+    if (device >= 0) ATM_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    ATM_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return ATM_OK;
+}
+
+int atm_stream_destroy(void *stream) {
+    if (!stream) return ATM_OK;
+    ATM_CUDA_CHECK(cudaStreamDestroy((cudaStream_t)stream));
+    return ATM_OK;
+}
+
+int atm_stream_synchronize(void *stream) {
+    ATM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return ATM_OK;
+}
+
+int atm_host_alloc(size_t bytes, void **ptr) {
+    ATM_REQUIRE(ptr && bytes > 0, ATM_ERR_INVALID, "atm_host_alloc: null argument / zero size");
+    *ptr = nullptr;
+    int count = 0;
+    ATM_REQUIRE(cudaGetDeviceCount(&count) == cudaSuccess && count > 0, ATM_ERR_CUDA,
+                "atm_host_alloc: no CUDA device available (this library has no CPU fallback)");
+    cudaError_t err = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (err != cudaSuccess) {
+        *ptr = nullptr;
+        set_error("atm_host_alloc: %s", cudaGetErrorString(err));
+        return err == cudaErrorMemoryAllocation ? ATM_ERR_NOMEM : ATM_ERR_CUDA;
+    }
+    return ATM_OK;
+}
+
+int atm_host_free(void *ptr) {
+    if (!ptr) return ATM_OK;
+    ATM_CUDA_CHECK(cudaFreeHost(ptr));
+    return ATM_OK;
+}
 
 int atm_host_pipeline_create(int32_t num_handles, atm_handle *const *handles, atm_host_pipeline **out) {
     ATM_REQUIRE(out && handles && num_handles > 0, ATM_ERR_INVALID, "atm_host_pipeline_create: null argument / no handles");

@@ -66,11 +66,24 @@ public:
     double getDefaultDirection() const { return defaultDirection; }
     const std::vector<int> &getVariableForceGroups() const { return VariableForceGroups; }
 
+    /** Pushes changed per-particle displacements into an existing Context (the number of particles cannot change).
+     *  ref: ATMMetaForce::updateParametersInContext (openmmapi/include/ATMMetaForce.h:130, src/ATMMetaForce.cpp:38-40). */
+    void updateParametersInContext(OpenMM::Context &context);
+    /** Soft-core perturbation energy u_sc (kJ/mol) of the Context's last evaluation.
+     *  ref: ATMMetaForce::getPerturbationEnergy (ATMMetaForce.h:145, src/ATMMetaForce.cpp:42-44). */
+    double getPerturbationEnergy(const OpenMM::Context &context) const;
+
     /** The nine defaults in atm_b200.h parameter order (lambda1 ... direction). */
     void getDefaultParameters(double p[9]) const;
     /** Displacements as a dense [numParticles][3] array indexed by FORCE ENTRY (entry i == atom i; the 'particle'
      *  field is stored but, exactly like the reference's GPU platforms, not used for indexing). */
     std::vector<double> getDisplacementArray() const;
+
+#ifdef ATM_HAVE_OPENMM
+protected:
+#endif
+    /** ref: ATMMetaForce::createImpl (ATMMetaForce.h:300, src/ATMMetaForce.cpp:34-36). */
+    OpenMM::ForceImpl *createImpl() const;
 
 private:
     struct ParticleInfo {

@@ -1,0 +1,86 @@
+// ATMMetaForceImpl.h -- the per-Context implementation object of ATMMetaForce, with the surface of the reference's
+// ATMMetaForceImpl (ref: openmmapi/include/internal/ATMMetaForceImpl.h:24-60): initialize, calcForcesAndEnergy,
+// getDefaultParameters, getKernelNames, updateParametersInContext, getPerturbationEnergy.
+//
+// Build WITHOUT OpenMM (this image): the Impl is the whole orchestration of the Tier-2 path.  Where the reference
+// creates two inner Contexts and evaluates them one after the other (ref: openmmapi/src/ATMMetaForceImpl.cpp:90-128),
+// this Impl describes the variable-group NonbondedForce to the back-end once (atm_nb_setup) and then, per evaluation,
+// hands the Context's host positions to atm_host_pipeline_step -- H2D, [rebuild | prune], copy-state/pack, the two-state
+// direct-space kernel, the device scalar stage, the merge, D2H of forces and energy record -- one CUDA-graph launch.
+// Direct space only: PME reciprocal space and bonded terms stay in OpenMM's inner contexts, which
+// do not exist in this build.  With OpenMM present the adapter in INTEGRATION.md section 2-4 is used instead.
+#ifndef ATMMETAFORCE_IMPL_H_
+#define ATMMETAFORCE_IMPL_H_
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ATMMetaForce.h"
+#include "atm_b200.h"
+#ifndef ATM_HAVE_OPENMM
+#include "openmm_standin_context.h"
+#endif
+
+namespace ATMMetaForcePlugin {
+
+#ifndef ATM_HAVE_OPENMM
+
+class ATMMetaForceImpl : public OpenMM::ForceImpl {
+public:
+    explicit ATMMetaForceImpl(const ATMMetaForce &owner);
+    ~ATMMetaForceImpl();
+    ATMMetaForceImpl(const ATMMetaForceImpl &) = delete;
+    ATMMetaForceImpl &operator=(const ATMMetaForceImpl &) = delete;
+
+    /** ref: ATMMetaForceImpl::initialize (:69-88): the variable-force-group mask (the ATM group itself cannot be
+     *  variable), and which Forces of the System the two states evaluate.  No device work yet. */
+    void initialize(OpenMM::ContextImpl &context) override;
+    const ATMMetaForce &getOwner() const { return owner; }
+    void updateContextState(OpenMM::ContextImpl &, bool & /*forcesInvalid*/) {}
+    /** ref: ATMMetaForceImpl::calcForcesAndEnergy (:90-128).  Adds the ATM force to context.getForces(); returns
+     *  e0 + W(u_sc) when includeEnergy, else 0; 0 without any work when the ATM group is not in `groups`. */
+    double calcForcesAndEnergy(OpenMM::ContextImpl &context, bool includeForces, bool includeEnergy, int groups) override;
+    /** ref: :130-142 */
+    std::map<std::string, double> getDefaultParameters() override;
+    std::vector<std::string> getKernelNames() override;
+    /** ref: :150-152 -> kernel copyParametersToContext (CommonATMMetaForceKernels.cpp:229-251). */
+    void updateParametersInContext(OpenMM::ContextImpl &context);
+    double getPerturbationEnergy() const { return PerturbationEnergy; }
+
+    // knobs of this back-end (no reference counterpart)
+    void setPairListSkins(double inner_nm, double outer_nm);
+    void setDevice(int ordinal) { device = ordinal; }
+    int getVariableForceGroupsMask() const { return variable_force_groups_mask; }
+    /** The full energy record of the last evaluation (atm_energy_slot order). */
+    const std::vector<double> &getEnergyRecord() const { return energyRecord; }
+
+private:
+    void createBackend(OpenMM::ContextImpl &context);
+    void releaseBackend();
+
+    const ATMMetaForce &owner;
+    const OpenMM::NonbondedForce *nonbonded;
+    double PerturbationEnergy;
+    int variable_force_groups_mask;
+    int device;
+    double skin, skinOuter;
+    // back-end objects (created at the first evaluation, so that a Context can be built and configured on any host)
+    atm_handle *handle;
+    atm_host_pipeline *pipeline;
+    void *stream;
+    float *posqHost;       // pinned [P][4]
+    int64_t *forceHost;    // pinned [3P]
+    double *energyHost;    // pinned [ATM_NUM_ENERGY_SLOTS]
+    int paddedNumAtoms;
+    bool displacementsDirty;
+    unsigned long boxVersionSeen;
+    std::vector<OpenMM::Vec3> refRebuild, refPrune;
+    std::vector<double> energyRecord;
+};
+
+#endif  // !ATM_HAVE_OPENMM
+
+}  // namespace ATMMetaForcePlugin
+
+#endif

@@ -49,6 +49,10 @@ public:
     const std::string &getName() const { return name; }
     void setName(const std::string &n) { name = n; }
     virtual bool usesPeriodicBoundaryConditions() const { return false; }
+    /** The per-Context implementation object, or NULL for a Force that is only data for another Force's Impl (here:
+     *  NonbondedForce, evaluated by ATMMetaForceImpl).  OpenMM declares this protected and lets Context call it as a
+     *  friend; the stand-in keeps it public. */
+    virtual ForceImpl *createImpl() const { return nullptr; }
 
 private:
     int forceGroup;

@@ -1,0 +1,234 @@
+// ATMMetaForceImpl.cpp -- see ATMMetaForceImpl.h.  Host logic only; every number comes from libatm_b200.so.
+#include "ATMMetaForceImpl.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "ATMMetaForceB200Kernel.h"
+
+using namespace ATMMetaForcePlugin;
+using OpenMM::OpenMMException;
+
+#ifndef ATM_HAVE_OPENMM
+
+namespace {
+
+void check(int rc, const char *what) {
+    if (rc != ATM_OK) throw OpenMMException(std::string(what) + ": " + atm_last_error());
+}
+
+// largest displacement of any particle since `ref` (upper bound: sqrt(3) * largest component)
+double maxMove(const std::vector<OpenMM::Vec3> &pos, const std::vector<OpenMM::Vec3> &ref) {
+    double m = 0.0;
+    for (size_t i = 0; i < pos.size(); i++)
+        for (int c = 0; c < 3; c++) m = std::max(m, std::fabs(pos[i][c] - ref[i][c]));
+    return m * 1.7320508075688772;
+}
+
+}  // namespace
+
+ATMMetaForceImpl::ATMMetaForceImpl(const ATMMetaForce &owner)
+    : owner(owner), nonbonded(nullptr), PerturbationEnergy(0.0), variable_force_groups_mask(0), device(-1), skin(0.05),
+      skinOuter(0.3), handle(nullptr), pipeline(nullptr), stream(nullptr), posqHost(nullptr), forceHost(nullptr),
+      energyHost(nullptr), paddedNumAtoms(0), displacementsDirty(false), boxVersionSeen(0),
+      energyRecord(ATM_NUM_ENERGY_SLOTS, 0.0) {}
+
+ATMMetaForceImpl::~ATMMetaForceImpl() { releaseBackend(); }
+
+void ATMMetaForceImpl::releaseBackend() {
+    if (pipeline) atm_host_pipeline_destroy(pipeline);
+    if (handle) atm_destroy(handle);
+    if (posqHost) atm_host_free(posqHost);
+    if (forceHost) atm_host_free(forceHost);
+    if (energyHost) atm_host_free(energyHost);
+    if (stream) atm_stream_destroy(stream);
+    pipeline = nullptr; handle = nullptr; posqHost = nullptr; forceHost = nullptr; energyHost = nullptr; stream = nullptr;
+}
+
+void ATMMetaForceImpl::setPairListSkins(double inner_nm, double outer_nm) {
+    if (!(inner_nm > 0.0) || outer_nm < inner_nm) throw OpenMMException("ATMMetaForce: pair-list skins must satisfy 0 < inner <= outer");
+    if (handle) throw OpenMMException("ATMMetaForce: the pair-list skins must be set before the first evaluation");
+    skin = inner_nm;
+    skinOuter = outer_nm;
+}
+
+void ATMMetaForceImpl::initialize(OpenMM::ContextImpl &context) {
+    const OpenMM::System &system = context.getSystem();
+    variable_force_groups_mask = variableForceGroupsMask(owner);   // throws when the ATM group itself is listed
+    if (owner.getNumParticles() != system.getNumParticles())
+        throw OpenMMException("ATMMetaForce must have exactly as many particles as the System it belongs to.");
+    // which Forces the two states evaluate: everything outside the ATM group that sits in a variable force group
+    // (ref: copysystem :51-65 clones every non-ATM force; the mask :75-81 selects the variable ones at evaluation time)
+    nonbonded = nullptr;
+    for (int i = 0; i < system.getNumForces(); i++) {
+        const OpenMM::Force &f = system.getForce(i);
+        if (&f == &owner || f.getForceGroup() == owner.getForceGroup()) continue;
+        if (!((variable_force_groups_mask >> f.getForceGroup()) & 1)) continue;
+        const OpenMM::NonbondedForce *nb = dynamic_cast<const OpenMM::NonbondedForce *>(&f);
+        if (!nb) throw OpenMMException("ATMMetaForce: a variable force group holds a Force this OpenMM-free build cannot evaluate "
+                                       "(only NonbondedForce direct space is evaluated by the Blackwell back-end)");
+        if (nonbonded) throw OpenMMException("ATMMetaForce: more than one NonbondedForce in the variable force groups");
+        if (nb->getNumParticles() != system.getNumParticles())
+            throw OpenMMException("NonbondedForce must have exactly as many particles as the System it belongs to.");
+        if (nb->getNonbondedMethod() != OpenMM::NonbondedForce::PME && nb->getNonbondedMethod() != OpenMM::NonbondedForce::Ewald)
+            throw OpenMMException("ATMMetaForce: this back-end evaluates periodic Ewald / PME direct space only");
+        nonbonded = nb;
+    }
+}
+
+std::map<std::string, double> ATMMetaForceImpl::getDefaultParameters() {
+    return ATMMetaForceB200Kernel::getDefaultParameters(owner);
+}
+
+std::vector<std::string> ATMMetaForceImpl::getKernelNames() { return {ATMMetaForceB200Kernel::Name()}; }
+
+void ATMMetaForceImpl::updateParametersInContext(OpenMM::ContextImpl &context) {
+    if (owner.getNumParticles() != context.getSystem().getNumParticles())
+        throw OpenMMException("copyParametersToContext: The number of ATMMetaForce particles has changed");
+    displacementsDirty = true;   // uploaded (and the pair lists rebuilt) by the next evaluation
+}
+
+void ATMMetaForceImpl::createBackend(OpenMM::ContextImpl &context) {
+    if (!nonbonded)
+        throw OpenMMException("ATMMetaForce: no NonbondedForce in the variable force groups: nothing to evaluate");
+    const int n = owner.getNumParticles();
+    try {
+        atm_config cfg;
+        cfg.num_particles = n;
+        cfg.padded_num_particles = 0;
+        cfg.precision = ATM_PREC_MIXED;
+        cfg.num_replicas = 1;
+        cfg.device = device;
+        check(atm_create(&cfg, &handle), "ATMMetaForce: creating the Blackwell back-end");
+        paddedNumAtoms = 32 * ((n + 31) / 32);
+        check(atm_stream_create(device, &stream), "ATMMetaForce: stream");
+        std::vector<double> d = owner.getDisplacementArray();
+        check(atm_set_displacements(handle, nullptr, d.data(), stream), "ATMMetaForce: uploading the displacement table");
+        {   // the box goes in before the NonbondedForce description, so that every allocation and upload of the set-up is
+            // issued on `stream`
+            OpenMM::Vec3 a, b, c;
+            context.getPeriodicBoxVectors(a, b, c);
+            const double box[9] = {a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2]};
+            check(atm_set_box(handle, -1, box), "ATMMetaForce: periodic box");
+        }
+        // NonbondedForce -> atm_nonbonded_desc: every exception excludes its pair; one with a non-zero chargeProd or
+        // epsilon is a scaled 1-4 interaction with its own parameters
+        std::vector<double> q(n), sig(n), eps(n);
+        for (int i = 0; i < n; i++) nonbonded->getParticleParameters(i, q[i], sig[i], eps[i]);
+        std::vector<int32_t> excl, excPairs;
+        std::vector<double> excParams;
+        for (int e = 0; e < nonbonded->getNumExceptions(); e++) {
+            int a, b;
+            double cp, s, ep;
+            nonbonded->getExceptionParameters(e, a, b, cp, s, ep);
+            if (a < 0 || a >= n || b < 0 || b >= n || a == b) throw OpenMMException("NonbondedForce: Illegal particle index for an exception");
+            excl.push_back(a); excl.push_back(b);
+            if (cp != 0.0 || ep != 0.0) {
+                excPairs.push_back(a); excPairs.push_back(b);
+                excParams.push_back(cp); excParams.push_back(s); excParams.push_back(ep);
+            }
+        }
+        atm_nonbonded_desc desc;
+        std::memset(&desc, 0, sizeof(desc));
+        desc.charge = q.data(); desc.sigma = sig.data(); desc.epsilon = eps.data();
+        desc.num_exclusions = (int32_t)(excl.size() / 2); desc.exclusions = excl.data();
+        desc.num_exceptions = (int32_t)(excPairs.size() / 2); desc.exception_pairs = excPairs.data(); desc.exception_params = excParams.data();
+        desc.cutoff = nonbonded->getCutoffDistance();
+        // OpenMM's rule for the Ewald splitting parameter: alpha = sqrt(-ln(2 tol)) / r_c
+        desc.ewald_alpha = std::sqrt(-std::log(2.0 * nonbonded->getEwaldErrorTolerance())) / desc.cutoff;
+        desc.skin = skin;
+        desc.skin_outer = skinOuter;
+        check(atm_nb_setup(handle, &desc, stream), "ATMMetaForce: describing the NonbondedForce to the back-end");
+        check(atm_host_alloc(sizeof(float) * 4 * (size_t)paddedNumAtoms, (void **)&posqHost), "ATMMetaForce: pinned coordinates");
+        check(atm_host_alloc(sizeof(int64_t) * 3 * (size_t)paddedNumAtoms, (void **)&forceHost), "ATMMetaForce: pinned forces");
+        check(atm_host_alloc(sizeof(double) * ATM_NUM_ENERGY_SLOTS, (void **)&energyHost), "ATMMetaForce: pinned energy record");
+        std::memset(posqHost, 0, sizeof(float) * 4 * (size_t)paddedNumAtoms);
+        for (int i = 0; i < n; i++) posqHost[4 * i + 3] = (float)q[i];
+        check(atm_host_pipeline_create(1, &handle, &pipeline), "ATMMetaForce: host pipeline");
+        check(atm_stream_synchronize(nullptr), "ATMMetaForce: set-up");   // nothing of the set-up is left in flight on the
+        check(atm_stream_synchronize(stream), "ATMMetaForce: set-up");    // legacy stream or on ours
+    } catch (...) {
+        releaseBackend();
+        throw;
+    }
+    displacementsDirty = false;
+    boxVersionSeen = context.getBoxVersion();
+    refRebuild.clear();
+    refPrune.clear();
+}
+
+double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool includeForces, bool includeEnergy, int groups) {
+    if ((groups & (1 << owner.getForceGroup())) == 0) return 0.0;
+    if (!handle) createBackend(context);
+    const int n = owner.getNumParticles();
+    const std::vector<OpenMM::Vec3> &pos = context.positionsRef();
+    // the nine global parameters, by name (ref: CommonATMMetaForceKernels.cpp:165-181 reads them from the context)
+    double p[ATM_NUM_PARAMS] = {context.getParameter(ATMMetaForce::Lambda1()), context.getParameter(ATMMetaForce::Lambda2()),
+                                context.getParameter(ATMMetaForce::Alpha()),   context.getParameter(ATMMetaForce::U0()),
+                                context.getParameter(ATMMetaForce::W0()),      context.getParameter(ATMMetaForce::Umax()),
+                                context.getParameter(ATMMetaForce::Ubcore()),  context.getParameter(ATMMetaForce::Acore()),
+                                context.getParameter(ATMMetaForce::Direction())};
+    check(atm_set_parameters(handle, 0, p), "ATMMetaForce: parameters");
+    bool rebuild = refRebuild.empty();
+    if (displacementsDirty) {
+        std::vector<double> d = owner.getDisplacementArray();
+        check(atm_set_displacements(handle, nullptr, d.data(), stream), "ATMMetaForce: uploading the displacement table");
+        displacementsDirty = false;
+        rebuild = true;
+    }
+    if (boxVersionSeen != context.getBoxVersion()) {
+        OpenMM::Vec3 a, b, c;
+        context.getPeriodicBoxVectors(a, b, c);
+        const double box[9] = {a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2]};
+        check(atm_set_box(handle, -1, box), "ATMMetaForce: periodic box");
+        boxVersionSeen = context.getBoxVersion();
+        rebuild = true;
+    }
+    // pair lists: rebuild / prune when some atom may have moved by more than half the respective skin
+    int maintenance = 0;
+    if (rebuild || maxMove(pos, refRebuild) > 0.5 * skinOuter) {
+        maintenance = 2;
+        refRebuild = pos;
+        refPrune = pos;
+    } else if (maxMove(pos, refPrune) > 0.5 * skin) {
+        maintenance = 1;
+        refPrune = pos;
+    }
+    for (int i = 0; i < n; i++) {
+        posqHost[4 * i] = (float)pos[i][0];
+        posqHost[4 * i + 1] = (float)pos[i][1];
+        posqHost[4 * i + 2] = (float)pos[i][2];
+    }
+    atm_host_io io;
+    io.posq_host = posqHost;
+    io.force_host = forceHost;
+    io.energies_host = energyHost;
+    io.include_energy = 1;   // the reference always evaluates the inner energies (do_energy = true, :104)
+    io.reserved = 0;
+    check(atm_host_pipeline_step(pipeline, &io, maintenance, stream), "ATMMetaForce: evaluating the alchemical force");
+    check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
+    energyRecord.assign(energyHost, energyHost + ATM_NUM_ENERGY_SLOTS);
+    PerturbationEnergy = energyRecord[ATM_E_USC];
+    if (includeForces) {
+        std::vector<OpenMM::Vec3> &f = context.getForces();
+        const double inv = 1.0 / 4294967296.0;   // 2^32 fixed point of the long force buffers
+        for (int i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++) f[i][c] += (double)forceHost[(size_t)c * paddedNumAtoms + i] * inv;
+    }
+    return includeEnergy ? energyRecord[ATM_E_ENERGY] : 0.0;
+}
+
+// ---- the three members of ATMMetaForce that need the Impl (ref: openmmapi/src/ATMMetaForce.cpp:34-44)
+
+OpenMM::ForceImpl *ATMMetaForce::createImpl() const { return new ATMMetaForceImpl(*this); }
+
+void ATMMetaForce::updateParametersInContext(OpenMM::Context &context) {
+    dynamic_cast<ATMMetaForceImpl &>(context.getForceImpl(*this)).updateParametersInContext(context.getImpl());
+}
+
+double ATMMetaForce::getPerturbationEnergy(const OpenMM::Context &context) const {
+    return dynamic_cast<const ATMMetaForceImpl &>(context.getForceImpl(*this)).getPerturbationEnergy();
+}
+
+#endif  // !ATM_HAVE_OPENMM

@@ -26,6 +26,7 @@ SYMBOLS = (
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
     "atm_hrex_device_setup", "atm_hrex_device_pack", "atm_hrex_device_exchange", "atm_hrex_device_state",
     "atm_host_pipeline_create", "atm_host_pipeline_destroy", "atm_host_pipeline_step",
+    "atm_stream_create", "atm_stream_destroy", "atm_stream_synchronize", "atm_host_alloc", "atm_host_free",
 )
 
 
@@ -108,6 +109,11 @@ def lib():
     L.atm_host_pipeline_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp)]
     L.atm_host_pipeline_destroy.argtypes = [vp]
     L.atm_host_pipeline_step.argtypes = [vp, C.POINTER(HostIO), i32, vp]
+    L.atm_stream_create.argtypes = [i32, C.POINTER(vp)]
+    L.atm_stream_destroy.argtypes = [vp]
+    L.atm_stream_synchronize.argtypes = [vp]
+    L.atm_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.atm_host_free.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("atm_last_error", "atm_version", "atm_hrex_reduced_energy"):

@@ -37,12 +37,18 @@ class ATMMetaForce(_core.ATMMetaForce):
     def getPerturbationEnergy(self, context):
         """Soft-core perturbation energy of the context's last evaluation, kJ/mol
         (ref: ATMMetaForce::getPerturbationEnergy, openmmapi/src/ATMMetaForce.cpp:42-44; .i:47-49 adds the unit)."""
-        val = context._atm_perturbation_energy(self)
+        if isinstance(context, _core.Context):      # the C++ Context of this build: ATMMetaForceImpl answers
+            val = super().getPerturbationEnergy(context)
+        else:
+            val = context._atm_perturbation_energy(self)
         return val * _unit.kilojoules_per_mole if _unit is not None else val
 
     def updateParametersInContext(self, context):
         """Push changed displacements to the device (ref: ATMMetaForce.cpp:38-40)."""
-        context._atm_update_parameters(self)
+        if isinstance(context, _core.Context):
+            super().updateParametersInContext(context)
+        else:
+            context._atm_update_parameters(self)
 
     @staticmethod
     def cast(force):

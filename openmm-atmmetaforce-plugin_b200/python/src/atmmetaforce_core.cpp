@@ -2,6 +2,7 @@
 // which cannot be generated here: SWIG and OpenMM's swig headers are absent).  Same method names and argument order;
 // getParticleParameters returns the tuple (particle, dx, dy, dz) like the SWIG OUTPUT typemaps (.i:79-87);
 // std::exception is mapped to a Python exception like the %exception block (.i:54-61).
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -9,12 +10,18 @@
 
 #include "ATMMetaForce.h"
 #include "ATMMetaForceB200Kernel.h"
+#include "ATMMetaForceImpl.h"
 #include "ATMMetaForceProxy.h"
 
 namespace py = pybind11;
 using namespace ATMMetaForcePlugin;
 
 static void *ptr(uintptr_t p) { return reinterpret_cast<void *>(p); }
+
+static OpenMM::Vec3 vec3(const std::vector<double> &v) {
+    if (v.size() != 3) throw OpenMM::OpenMMException("expected a vector of three numbers");
+    return OpenMM::Vec3(v[0], v[1], v[2]);
+}
 
 PYBIND11_MODULE(_atmmetaforce_core, m) {
     m.doc() = "C++ facade of the Blackwell ATM Meta-Force back-end";
@@ -60,6 +67,8 @@ PYBIND11_MODULE(_atmmetaforce_core, m) {
         .def("getDefaultAcore", &ATMMetaForce::getDefaultAcore)
         .def("getDefaultDirection", &ATMMetaForce::getDefaultDirection)
         .def("getVariableForceGroups", &ATMMetaForce::getVariableForceGroups)
+        .def("getPerturbationEnergy", &ATMMetaForce::getPerturbationEnergy, py::arg("context"))
+        .def("updateParametersInContext", &ATMMetaForce::updateParametersInContext, py::arg("context"))
         .def("getDisplacementArray", &ATMMetaForce::getDisplacementArray)
         .def("getDefaultParameterArray", [](const ATMMetaForce &f) {
             std::vector<double> p(9);
@@ -77,6 +86,68 @@ PYBIND11_MODULE(_atmmetaforce_core, m) {
         return std::unique_ptr<ATMMetaForce>(OpenMM::XmlSerializer::deserialize<ATMMetaForce>(ss));
     });
     m.def("variableForceGroupsMask", &variableForceGroupsMask);
+
+    // ---- the OpenMM-free System / Context of this build (openmm_standin_context.h) and the C++ ATMMetaForceImpl behind it
+    py::class_<OpenMM::System>(m, "System")
+        .def(py::init<>())
+        .def("addParticle", &OpenMM::System::addParticle, py::arg("mass"))
+        .def("getNumParticles", &OpenMM::System::getNumParticles)
+        .def("getNumForces", &OpenMM::System::getNumForces)
+        .def("setDefaultPeriodicBoxVectors", [](OpenMM::System &s, const std::vector<double> &a, const std::vector<double> &b,
+                                                const std::vector<double> &c) { s.setDefaultPeriodicBoxVectors(vec3(a), vec3(b), vec3(c)); })
+        .def("addNonbondedForce", [](OpenMM::System &s, const std::vector<double> &charge, const std::vector<double> &sigma,
+                                     const std::vector<double> &epsilon, const std::vector<int> &exceptionPairs,
+                                     const std::vector<double> &exceptionParams, double cutoff, double ewaldTolerance, int group) {
+            if (charge.size() != sigma.size() || charge.size() != epsilon.size() || exceptionPairs.size() % 2 != 0 ||
+                exceptionParams.size() / 3 != exceptionPairs.size() / 2)
+                throw OpenMM::OpenMMException("addNonbondedForce: inconsistent array lengths");
+            auto *nb = new OpenMM::NonbondedForce();
+            for (size_t i = 0; i < charge.size(); i++) nb->addParticle(charge[i], sigma[i], epsilon[i]);
+            for (size_t e = 0; e < exceptionPairs.size() / 2; e++)
+                nb->addException(exceptionPairs[2 * e], exceptionPairs[2 * e + 1], exceptionParams[3 * e], exceptionParams[3 * e + 1],
+                                 exceptionParams[3 * e + 2]);
+            nb->setNonbondedMethod(OpenMM::NonbondedForce::PME);
+            nb->setCutoffDistance(cutoff);
+            nb->setEwaldErrorTolerance(ewaldTolerance);
+            nb->setForceGroup(group);
+            return s.addForce(nb);
+        }, py::arg("charge"), py::arg("sigma"), py::arg("epsilon"), py::arg("exceptionPairs"), py::arg("exceptionParams"),
+           py::arg("cutoff"), py::arg("ewaldTolerance") = 5e-4, py::arg("forceGroup") = 0)
+        .def("addATMMetaForce", [](OpenMM::System &s, const ATMMetaForce &f) {
+            auto *copy = new ATMMetaForce(f);     // the System owns its forces
+            s.addForce(copy);
+            return copy;
+        }, py::return_value_policy::reference_internal, py::arg("force"));
+
+    py::class_<OpenMM::Context>(m, "Context")
+        .def(py::init<const OpenMM::System &>(), py::keep_alive<1, 2>(), py::arg("system"))
+        .def("setPositions", [](OpenMM::Context &c, py::array_t<double, py::array::c_style | py::array::forcecast> pos) {
+            if (pos.ndim() != 2 || pos.shape(1) != 3) throw OpenMM::OpenMMException("setPositions: expected an (N, 3) array in nm");
+            std::vector<OpenMM::Vec3> v(pos.shape(0));
+            auto r = pos.unchecked<2>();
+            for (py::ssize_t i = 0; i < pos.shape(0); i++) v[i] = OpenMM::Vec3(r(i, 0), r(i, 1), r(i, 2));
+            c.setPositions(v);
+        })
+        .def("setPeriodicBoxVectors", [](OpenMM::Context &c, const std::vector<double> &a, const std::vector<double> &b,
+                                         const std::vector<double> &cc) { c.setPeriodicBoxVectors(vec3(a), vec3(b), vec3(cc)); })
+        .def("setParameter", &OpenMM::Context::setParameter)
+        .def("getParameter", &OpenMM::Context::getParameter)
+        .def("getParameters", &OpenMM::Context::getParameters)
+        .def("setPairListSkins", [](OpenMM::Context &c, const ATMMetaForce &f, double inner, double outer) {
+            dynamic_cast<ATMMetaForceImpl &>(c.getForceImpl(f)).setPairListSkins(inner, outer);
+        }, py::arg("force"), py::arg("inner"), py::arg("outer"))
+        .def("getEnergyRecord", [](OpenMM::Context &c, const ATMMetaForce &f) {
+            return dynamic_cast<ATMMetaForceImpl &>(c.getForceImpl(f)).getEnergyRecord();
+        }, py::arg("force"))
+        .def("calcForcesAndEnergy", [](OpenMM::Context &c, bool includeForces, bool includeEnergy, int groups) {
+            const double e = c.calcForcesAndEnergy(includeForces, includeEnergy, groups);
+            const auto &f = c.getForces();
+            py::array_t<double> out({(py::ssize_t)f.size(), (py::ssize_t)3});
+            auto w = out.mutable_unchecked<2>();
+            for (size_t i = 0; i < f.size(); i++)
+                for (int k = 0; k < 3; k++) w(i, k) = f[i][k];
+            return py::make_tuple(e, out);
+        }, py::arg("includeForces") = true, py::arg("includeEnergy") = true, py::arg("groups") = -1);
 
     py::class_<ATMMetaForceB200Kernel>(m, "ATMMetaForceB200Kernel")
         .def(py::init<>())

@@ -82,3 +82,64 @@ def test_cpp_serialization_test_binary():
         pytest.skip("C++ test binary not built (run __graft_entry__.build())")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "Done" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------- the C++ ATMMetaForceImpl behind the OpenMM-free Context
+
+def _cpp_system(n=64, atm_group=3, var_groups=(1,), nb_group=1, n_atm_particles=None):
+    from atmmetaforce import _atmmetaforce_core as core
+    s = core.System()
+    for _ in range(n):
+        s.addParticle(12.0)
+    s.setDefaultPeriodicBoxVectors([4.0, 0, 0], [0, 4.0, 0], [0, 0, 4.0])
+    s.addNonbondedForce([0.1 * (-1) ** i for i in range(n)], [0.3] * n, [0.5] * n, [0, 1, 2, 3], [0.0, 0.3, 0.0, 0.05, 0.3, 0.2],
+                        cutoff=0.9, forceGroup=nb_group)
+    f = atm.ATMMetaForce(0.1, 0.6, 0.2, 1.5, 0.25, 200.0, 100.0, 0.0625, 1.0, list(var_groups))
+    f.setForceGroup(atm_group)
+    for i in range(n if n_atm_particles is None else n_atm_particles):
+        f.addParticle(i, 1.0 if i < 4 else 0.0, 0.0, 0.0)
+    return core, s, s.addATMMetaForce(f)
+
+
+def test_cpp_impl_registers_the_nine_parameters_and_validates():
+    """ATMMetaForceImpl::initialize / getDefaultParameters (ref: openmmapi/src/ATMMetaForceImpl.cpp:69-88,130-142):
+    runs on any host -- no device work happens before the first evaluation."""
+    core, s, f = _cpp_system()
+    ctx = core.Context(s)
+    assert ctx.getParameters() == {"ATMLambda1": 0.1, "ATMLambda2": 0.6, "ATMAlpha": 0.2, "ATMU0": 1.5, "ATMW0": 0.25,
+                                   "ATMUmax": 200.0, "ATMUbcore": 100.0, "ATMAcore": 0.0625, "ATMDirection": 1.0}
+    ctx.setParameter("ATMLambda1", 0.3)
+    assert ctx.getParameter("ATMLambda1") == 0.3
+    with pytest.raises(atm.OpenMMException, match="invalid parameter name"):
+        ctx.setParameter("ATMLambda3", 1.0)
+    with pytest.raises(atm.OpenMMException, match="invalid parameter name"):
+        ctx.getParameter("nope")
+    assert core.ATMMetaForce.getPerturbationEnergy(f, ctx) == 0.0          # nothing evaluated yet
+    core.ATMMetaForce.updateParametersInContext(f, ctx)                      # legal at any time
+    with pytest.raises(atm.OpenMMException, match="positions have not been set"):
+        ctx.calcForcesAndEnergy()
+    with pytest.raises(atm.OpenMMException, match="wrong number of positions"):
+        ctx.setPositions(np.zeros((3, 3)))
+
+
+def test_cpp_impl_rejects_bad_systems():
+    core, s, _ = _cpp_system(atm_group=1, var_groups=(1,), nb_group=2)
+    with pytest.raises(atm.OpenMMException, match="cannot be one of the variable force groups"):
+        core.Context(s)
+    core, s, _ = _cpp_system(n_atm_particles=10)
+    with pytest.raises(atm.OpenMMException, match="exactly as many particles"):
+        core.Context(s)
+
+
+def test_cpp_impl_skips_other_groups_and_fails_loudly_without_gpu():
+    import torch
+    core, s, f = _cpp_system()
+    ctx = core.Context(s)
+    rng = np.random.default_rng(0)
+    ctx.setPositions(rng.uniform(0, 4.0, (64, 3)))
+    e, frc = ctx.calcForcesAndEnergy(True, True, 1 << 1)    # the ATM group (3) is not requested: no work, no device needed
+    assert e == 0.0 and frc.shape == (64, 3) and not frc.any()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (the evaluation itself is covered by tests/test_gpu_facade.py)")
+    with pytest.raises(atm.OpenMMException, match="CUDA"):  # no CPU fallback: the first real evaluation needs the device
+        ctx.calcForcesAndEnergy(True, True, -1)

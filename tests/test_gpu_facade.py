@@ -97,3 +97,93 @@ def test_kernel_object_matches_reference_seam(abfe):
     assert abs(energy - sc["energy"]) < 1e-9 and abs(k.getPerturbationEnergy() - sc["u_sc"]) < 1e-9
     exp = O.hybrid_force_i64(n, P, f0c.cpu().numpy(), f1.cpu().numpy(), f2.cpu().numpy(), sc["sp"])
     assert np.array_equal(f0.cpu().numpy(), exp)
+
+
+def test_cpp_impl_matches_python_context_and_oracle(abfe):
+    """The C++ orchestration (ATMMetaForceImpl behind the OpenMM-free System / Context, evaluating through
+    atm_host_pipeline_step) on the reference fixture: same numbers as the Python Context on device buffers (both drive
+    the same kernels with the same pair-list settings) and the oracle's direct-space energies and forces."""
+    import atmmetaforce as atm
+    from atmmetaforce import _atmmetaforce_core as core, _capi
+    import oracle_py as O
+    from helpers import oracle_system, rel_rms
+    kcal = 4.184
+    n = abfe["pos"].shape[0]
+    params = (0.5, 0.5, 0.0, 0.0, 0.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0)
+    atm_group, nb_group = 2, 1
+
+    def make_force():
+        f = atm.ATMMetaForce(*params, [nb_group])
+        for i in range(n):
+            f.addParticle(i, *abfe["displ"][i])
+        f.setForceGroup(atm_group)
+        return f
+
+    # C++ path
+    s = core.System()
+    for m in abfe["mass"]:
+        s.addParticle(float(m))
+    L = abfe["box"]
+    s.setDefaultPeriodicBoxVectors([L[0], 0, 0], [0, L[1], 0], [0, 0, L[2]])
+    # OpenMM convention: every exception excludes its pair; non-zero parameters make it a 1-4 interaction
+    exc = {(int(a), int(b)): (0.0, 0.3, 0.0) for a, b in abfe["excl"]}
+    for (a, b), p in zip(abfe["exc14"], abfe["exc14_par"]):
+        exc[(int(a), int(b))] = tuple(float(x) for x in p)
+    pairs = [x for ab in exc for x in ab]
+    pars = [x for ab in exc for x in exc[ab]]
+    s.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), pairs, pars,
+                        cutoff=1.0, ewaldTolerance=5e-4, forceGroup=nb_group)
+    fc = s.addATMMetaForce(make_force())
+    ctx = core.Context(s)
+    ctx.setPairListSkins(fc, 0.1, 0.3)
+    ctx.setPositions(abfe["pos"])
+    e_cpp, f_cpp = ctx.calcForcesAndEnergy(True, True, -1)
+    u_cpp = core.ATMMetaForce.getPerturbationEnergy(fc, ctx)
+    rec = np.array(ctx.getEnergyRecord(fc))
+
+    # Python Context on device buffers, same skins
+    nonbonded = atm.NonbondedDirect(abfe["charge"], abfe["sigma"], abfe["epsilon"], cutoff=1.0, ewald_tolerance=5e-4,
+                                    exclusions=abfe["excl"], exception_pairs=abfe["exc14"], exception_params=abfe["exc14_par"],
+                                    force_group=nb_group)
+    fp = make_force()
+    pctx = atm.Context(fp, nonbonded, abfe["box"], precision="mixed", skin=0.1, skin_outer=0.3)
+    pctx.setPositions(abfe["pos"])
+    st = pctx.getState(getEnergy=True, getForces=True)
+    # same kernels, same pair-list settings, fixed-point accumulation: equal up to the order of the excluded / 1-4 pair
+    # lists (their double-precision energy partial sums are grouped per warp), i.e. far below any physical tolerance
+    assert abs(e_cpp - st.getPotentialEnergy()) <= 1e-11 * abs(e_cpp)
+    assert abs(u_cpp - fp.getPerturbationEnergy(pctx)) <= 1e-8
+    assert np.abs(f_cpp - st.getForces()).max() <= 1e-6
+
+    # oracle (direct space of both states on the float-rounded coordinates)
+    S = oracle_system(O, abfe, 1.0, nonbonded.ewald_alpha)
+    pos32 = abfe["pos"].astype(np.float32).astype(np.float64)
+    pos2_32 = (abfe["pos"].astype(np.float32) + abfe["displ"].astype(np.float32)).astype(np.float64)
+    e1, _, f1 = S.nb_direct(pos32)
+    e2, _, f2 = S.nb_direct(pos2_32)
+    sc = O.scalars(params, e1, e2)
+    assert abs(rec[_capi.E_U1] - e1) <= 1e-6 * abs(e1)
+    assert abs(u_cpp - sc["u_sc"]) <= 5e-3
+    assert abs(e_cpp - sc["energy"]) <= 1e-6 * abs(sc["energy"])
+    assert rel_rms(f_cpp, O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], params[8])) <= 1e-5
+
+    # a second evaluation of moved coordinates (prune path), a parameter change, and a group mask without the ATM group
+    rng = np.random.default_rng(5)
+    moved = abfe["pos"] + rng.normal(0, 0.012, abfe["pos"].shape)   # > skin/2 for some atom, < skin_outer/2: prune
+    ctx.setPositions(moved)
+    ctx.setParameter("ATMLambda2", 0.75)
+    e2_cpp, f2_cpp = ctx.calcForcesAndEnergy(True, True, 1 << atm_group)
+    pctx.setPositions(moved)
+    pctx.setParameter("ATMLambda2", 0.75)
+    st2 = pctx.getState(getEnergy=True, getForces=True)
+    assert abs(e2_cpp - st2.getPotentialEnergy()) <= 1e-9 * abs(e2_cpp)
+    assert rel_rms(f2_cpp, st2.getForces()) <= 1e-6
+    assert ctx.calcForcesAndEnergy(True, True, 1 << nb_group)[0] == 0.0
+
+    # updateParametersInContext: zero displacements -> u == 0 (ref test idea: python/tests/test_abfe.py + ATMMetaForce.cpp:38-40)
+    for i in abfe["lig1"]:
+        fc.setParticleParameters(int(i), int(i), 0.0, 0.0, 0.0)
+    core.ATMMetaForce.updateParametersInContext(fc, ctx)
+    ctx.calcForcesAndEnergy(True, True, -1)
+    assert core.ATMMetaForce.getPerturbationEnergy(fc, ctx) == 0.0
+    pctx.close()
