@@ -77,7 +77,9 @@ def build_facade(force=False):
     import pybind11
     build(force=False)
     deps = FACADE_SRC + [os.path.join(HERE, "openmmapi", "include", f) for f in os.listdir(os.path.join(HERE, "openmmapi", "include"))]
-    deps += [os.path.join(HERE, "serialization", "ATMMetaForceProxy.h"), LIB]
+    deps += [os.path.join(HERE, "serialization", "ATMMetaForceProxy.h"), LIB,
+             os.path.join(HERE, "openmmapi", "tests", "TestATMMetaForceImpl.cpp"),
+             os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp")]
     if not force and os.path.exists(FACADE) and all(os.path.getmtime(d) <= os.path.getmtime(FACADE) for d in deps):
         return FACADE
     inc = ["-I", os.path.join(HERE, "openmmapi", "include"), "-I", os.path.join(HERE, "serialization"),
@@ -89,6 +91,11 @@ def build_facade(force=False):
     os.makedirs(os.path.dirname(test), exist_ok=True)
     cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:4] + \
           [os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp"), "-L", HERE, "-latm_b200",
+           "-Wl,-rpath,$ORIGIN/..", "-o", test]
+    subprocess.check_call(cmd)
+    test = os.path.join(HERE, "build", "TestATMMetaForceImpl")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:4] + \
+          [os.path.join(HERE, "openmmapi", "tests", "TestATMMetaForceImpl.cpp"), "-L", HERE, "-latm_b200",
            "-Wl,-rpath,$ORIGIN/..", "-o", test]
     subprocess.check_call(cmd)
     return FACADE

@@ -143,3 +143,16 @@ def test_cpp_impl_skips_other_groups_and_fails_loudly_without_gpu():
         pytest.skip("a GPU is present (the evaluation itself is covered by tests/test_gpu_facade.py)")
     with pytest.raises(atm.OpenMMException, match="CUDA"):  # no CPU fallback: the first real evaluation needs the device
         ctx.calcForcesAndEnergy(True, True, -1)
+
+
+def test_cpp_impl_test_binary():
+    """openmmapi/tests/TestATMMetaForceImpl.cpp, host-logic part (parameters, names, mask rule, group skip, loud failure
+    without a device)."""
+    import torch
+    exe = os.path.join(ROOT, "openmm-atmmetaforce-plugin_b200", "build", "TestATMMetaForceImpl")
+    if not os.path.exists(exe):
+        pytest.skip("C++ test binary not built (run __graft_entry__.build())")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: tests/test_gpu_facade.py runs the binary in its gpu mode")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "Done" in out.stdout, out.stdout + out.stderr

@@ -187,3 +187,16 @@ def test_cpp_impl_matches_python_context_and_oracle(abfe):
     ctx.calcForcesAndEnergy(True, True, -1)
     assert core.ATMMetaForce.getPerturbationEnergy(fc, ctx) == 0.0
     pctx.close()
+
+
+def test_cpp_impl_test_binary_gpu():
+    """openmmapi/tests/TestATMMetaForceImpl.cpp in its gpu mode: a pure C++ host (no Python, no CUDA headers) builds a
+    System, evaluates it through ATMMetaForceImpl, and checks translation invariance and u == 0 at zero displacement."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "openmm-atmmetaforce-plugin_b200", "build", "TestATMMetaForceImpl")
+    if not os.path.exists(exe):
+        pytest.skip("C++ test binary not built (run __graft_entry__.build())")
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and "Done" in out.stdout, out.stdout + out.stderr
