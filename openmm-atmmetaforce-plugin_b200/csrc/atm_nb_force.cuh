@@ -184,11 +184,18 @@ struct __align__(128) Nb2Smem {
     unsigned int el[NB_WARPS][ITEM_STEPS][32];  // the item's list entries (bulk copy destination)
     float4 xj[NB_WARPS][RING][32];
     float2 pj[NB_WARPS][RING][32];
+#ifdef ATM_NB2_SCALAR
     float4 xi[NB_WARPS][CL];
     float2 pi[NB_WARPS][CL];
+#else
+    // cluster atoms in PAIRS (atoms 2p, 2p+1) for the packed f32x2 inner loop: three 128-bit broadcast reads per pair --
+    // (x0,x1,y0,y1), (z0,z1,q0,q1), (hs0,hs1,se0,se1)
+    float4 ci[NB_WARPS][CL / 2][3];
+#endif
     unsigned long long bar[NB_WARPS];           // one mbarrier per warp
 };
 
+#ifdef ATM_NB2_SCALAR  // round-1 scalar inner loop, kept for A/B builds (-DATM_NB2_SCALAR)
 template <bool ENERGY, bool STATS>
 __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
     const float4 L = d.box[it.r], iL = d.invbox[it.r];
@@ -281,6 +288,157 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     cp_async_wait<0>();
     nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, fix, fiy, fiz, e_acc, npairs);
 }
+#endif  // ATM_NB2_SCALAR
+
+#ifndef ATM_NB2_SCALAR
+// ------------------------------------------------------------------------------------------------
+// Packed inner loop (sm_100 only): Blackwell executes two fp32 operations per lane in ONE issued instruction
+// (fma/mul/add.rn.f32x2 -> SASS FFMA2 / FMUL2 / FADD2, operands in aligned 64-bit register pairs, the second source
+// optionally a broadcast scalar, constants as broadcast immediates).  The kernel is bound by instruction issue, not by
+// the FMA pipe (round 1: issue slots 80 % busy, FMA pipe 52 %), so the 8 cluster atoms of a list step are processed as
+// 4 PAIRS (atoms 2p, 2p+1 against the lane's partner): every arithmetic instruction of pair_interaction, the distance
+// and the force accumulation is issued once per two pair slots.  Only the MUFU ops (rsqrt, rcp, ex2) and the
+// cutoff / mask selects stay scalar.  The algebra is that of pair_interaction() with the multiplications folded into
+// FMAs where that does not lengthen the dependent chain:
+//     fs = (es6 (12 s6 - 6) + fc) rinv^2  ->  h = fma(12, s6, -6); fs = fma(es6, h, fc) * rinv2
+// f_j is accumulated with the sign of f_i (dx * fs) and negated once per step.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+template <bool ENERGY>
+__device__ __forceinline__ float2 pair_interaction_x2(float2 r2, float2 qq, float2 sig, float2 eps4, const PairConst &pc, float2 &energy) {
+    const float2 rinv = f2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 rinv2 = __fmul2_rn(rinv, rinv);
+    const float2 r = __fmul2_rn(r2, rinv);
+    const float2 sr = __fmul2_rn(sig, rinv);
+    const float2 s2 = __fmul2_rn(sr, sr);
+    const float2 s6 = __fmul2_rn(__fmul2_rn(s2, s2), s2);
+    const float2 es6 = __fmul2_rn(eps4, s6);
+    const float2 h = __ffma2_rn(s6, f2(12.0f), f2(-6.0f));
+    const float2 ta = __ffma2_rn(r, f2(pc.p_alpha), f2(1.0f));
+    const float2 t = f2(mufu_rcp(ta.x), mufu_rcp(ta.y));
+    const float2 ea = __fmul2_rn(r2, f2(pc.neg_a2_log2e));
+    const float2 ex = f2(mufu_ex2(ea.x), mufu_ex2(ea.y));
+    float2 poly = __ffma2_rn(t, f2(ERFC_A6), f2(ERFC_A5));
+    poly = __ffma2_rn(poly, t, f2(ERFC_A4));
+    poly = __ffma2_rn(poly, t, f2(ERFC_A3));
+    poly = __ffma2_rn(poly, t, f2(ERFC_A2));
+    poly = __ffma2_rn(poly, t, f2(ERFC_A1));
+    poly = __ffma2_rn(poly, t, f2(ERFC_A0));
+    const float2 g = __fmul2_rn(__fmul2_rn(poly, t), rinv);
+    const float2 qe = __fmul2_rn(qq, ex);
+    const float2 ec = __fmul2_rn(qe, g);
+    const float2 fc = __ffma2_rn(qe, f2(pc.two_a_sqrtpi), ec);
+    if (ENERGY) energy = __fadd2_rn(__ffma2_rn(es6, s6, f2(-es6.x, -es6.y)), ec);
+    return __fmul2_rn(__ffma2_rn(es6, h, fc), rinv2);
+}
+
+template <bool ENERGY, bool STATS>
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
+    const float4 L = d.box[it.r], iL = d.invbox[it.r];
+    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
+    PairConst pc;
+    pc.cutoff2 = d.cutoff2;
+    pc.p_alpha = ERFC_P * d.alpha;
+    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
+    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+
+    // the whole entry list of the item: one bulk copy, in flight while the cluster atoms are staged
+    if (lane == 0) bulk_load_arm(&sm.bar[w], &sm.el[w][0][0], it.list, (unsigned)it.nst * 128u);
+    // cluster atoms -> shared memory (lanes 0..7), shifted next to the cluster centre, interleaved in pairs
+    if (lane < CL) {
+        float4 x = __ldg(d.xs + it.rsite + (size_t)it.A * CL + lane);
+        const float2 pp = __ldg(d.par + it.rsite + (size_t)it.A * CL + lane);
+        x.x -= L.x * fast_rint((x.x - cA.x) * iL.x);
+        x.y -= L.y * fast_rint((x.y - cA.y) * iL.y);
+        x.z -= L.z * fast_rint((x.z - cA.z) * iL.z);
+        float *c = reinterpret_cast<float *>(&sm.ci[w][lane >> 1][0]) + (lane & 1);
+        c[0] = x.x; c[2] = x.y; c[4] = x.z; c[6] = x.w; c[8] = pp.x; c[10] = pp.y;
+    }
+    mbar_wait(&sm.bar[w], parity);
+#pragma unroll
+    for (int q = 0; q < PF_DIST; q++) {
+        if (q < it.nst) {
+            const unsigned int eq = sm.el[w][q][lane];
+            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (eq >> 8));
+            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (eq >> 8));
+        }
+        cp_async_commit();
+    }
+    __syncwarp();
+
+    float2 fix[CL / 2], fiy[CL / 2], fiz[CL / 2];
+#pragma unroll
+    for (int p = 0; p < CL / 2; p++) fix[p] = fiy[p] = fiz[p] = f2(0.f);
+    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
+    double e_acc = 0.0;
+    int npairs = 0;
+
+    for (int st = 0; st < it.nst; st++) {
+        cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
+        const int slot = st & (RING - 1);
+        const float4 xjc = sm.xj[w][slot][lane];
+        const float2 pjc = sm.pj[w][slot][lane];
+        const unsigned int e = sm.el[w][st][lane];
+        // keep PF_DIST steps in flight
+        {
+            const int sp = st + PF_DIST;
+            if (sp < it.nst) {
+                const unsigned int e_next = sm.el[w][sp][lane];
+                const int ps = sp & (RING - 1);
+                cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
+                cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
+            }
+            cp_async_commit();
+        }
+        const int j = e >> 8;
+        const unsigned int m = e & 0xffu;
+        // minus the partner's coordinates, shifted next to the cluster centre
+        const float nxj = fmaf(L.x, fast_rint((xjc.x - cA.x) * iL.x), -xjc.x);
+        const float nyj = fmaf(L.y, fast_rint((xjc.y - cA.y) * iL.y), -xjc.y);
+        const float nzj = fmaf(L.z, fast_rint((xjc.z - cA.z) * iL.z), -xjc.z);
+        float2 fjx = f2(0.f), fjy = f2(0.f), fjz = f2(0.f), e_step = f2(0.f);
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < CL / 2; p++) {
+            const float4 cxy = sm.ci[w][p][0], czq = sm.ci[w][p][1], cps = sm.ci[w][p][2];
+            const float2 dx = __fadd2_rn(f2(cxy.x, cxy.y), f2(nxj));
+            const float2 dy = __fadd2_rn(f2(cxy.z, cxy.w), f2(nyj));
+            const float2 dz = __fadd2_rn(f2(czq.x, czq.y), f2(nzj));
+            const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            const bool in0 = (r2.x < pc.cutoff2) && !(m & (1u << (2 * p)));
+            const bool in1 = (r2.y < pc.cutoff2) && !(m & (2u << (2 * p)));
+            // a pair outside the cutoff (or excluded, or a padding slot) is evaluated at r^2 = 1e30: every term underflows
+            // to exactly zero (flush-to-zero MUFU paths, no inf/NaN even for r = 0)
+            const float2 r2s = f2(in0 ? r2.x : 1e30f, in1 ? r2.y : 1e30f);
+            float2 en = f2(0.f);
+            const float2 fs = pair_interaction_x2<ENERGY>(r2s, __fmul2_rn(f2(czq.z, czq.w), f2(xjc.w)), __fadd2_rn(f2(cps.x, cps.y), f2(pjc.x)),
+                                                          __fmul2_rn(f2(cps.z, cps.w), f2(pjc.y)), pc, en);
+            if (ENERGY) e_step = __fadd2_rn(e_step, en);
+            if (STATS) npairs += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+            any |= in0 | in1;
+            fix[p] = __ffma2_rn(dx, fs, fix[p]); fiy[p] = __ffma2_rn(dy, fs, fiy[p]); fiz[p] = __ffma2_rn(dz, fs, fiz[p]);
+            fjx = __ffma2_rn(dx, fs, fjx); fjy = __ffma2_rn(dy, fs, fjy); fjz = __ffma2_rn(dz, fs, fjz);
+        }
+        if (ENERGY) e_acc += (double)(e_step.x + e_step.y);
+        if (any) {
+            red_add_fixed(buf + j, -(fjx.x + fjx.y));
+            red_add_fixed(buf + it.comp_stride + j, -(fjy.x + fjy.y));
+            red_add_fixed(buf + 2 * it.comp_stride + j, -(fjz.x + fjz.y));
+        }
+    }
+    cp_async_wait<0>();
+    float ax[CL], ay[CL], az[CL];
+#pragma unroll
+    for (int p = 0; p < CL / 2; p++) {
+        ax[2 * p] = fix[p].x; ax[2 * p + 1] = fix[p].y;
+        ay[2 * p] = fiy[p].x; ay[2 * p + 1] = fiy[p].y;
+        az[2 * p] = fiz[p].x; az[2 * p + 1] = fiz[p].y;
+    }
+    nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, ax, ay, az, e_acc, npairs);
+}
+#endif  // !ATM_NB2_SCALAR
 
 // ------------------------------------------------------------------------------------------------
 // Excluded pairs (Ewald correction -qq erf(ar)/r, minimum image) and 1-4 exceptions (plain Coulomb + LJ, no image).
