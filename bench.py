@@ -32,6 +32,7 @@ DT_FS = 1.0
 NUM_REPLICAS = 22
 FP32_PEAK_TFLOPS = None  # derived from the device at run time: SMs * 128 lanes * 2 flop * max SM clock
 FLOP_PER_PAIR = 60.0
+JITTER_NM = 0.005        # per-step seeded Gaussian position noise around the base coordinates, clipped at 2.5 sigma
 
 
 def parse_args():
@@ -56,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=200, help="upper bound of the CPU-baseline sample (also capped at ~15 s)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: time budget of the whole run; a step "
+                    "covers fewer replicas when K steps of all of them would not fit")
     ap.add_argument("--skip-two-separate", action="store_true")
     ap.add_argument("--skip-tier1", action="store_true", help="skip the 8M-atom HBM roofline probe of copy-state / hybrid-force")
     ap.add_argument("--e2e-chunks", type=int, default=6)
@@ -151,13 +154,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(s, sched, steps, budget_s=15.0):
-    """Times the CPU restatement of the same hot path (oracle port, OpenMP) on one replica; returns
-    (replica-ns/day, seconds per step, threads, steps done)."""
+def _oracle_system(s):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
+    # every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"], s["cutoff"], s["ewald_alpha"], s["excl"],
                  s["exc14"], s["exc14_par"])
+    return O, S
+
+
+def cpu_oracle_rate(s, sched, steps, budget_s=15.0):
+    """cpu_baseline leg: the CPU restatement of the same hot path (oracle port, OpenMP, all host threads) on ONE
+    replica; returns (replica-ns/day, seconds per replica-step, threads, steps done)."""
+    O, S = _oracle_system(s)
     pos = replica_positions(s, 0)
     S.step(sched[0], pos, s["displ"])  # warm-up (page-in, OpenMP pool)
     t0 = time.perf_counter()
@@ -208,25 +218,62 @@ def tier1_hbm_probe(torch, atm, dev, flush, atoms=8_000_000):
     return out
 
 
+def workload_config(args, label, s, replicas_per_rank, exchange, use_graph, pme_grid, flush_note):
+    """The `config` object of the JSON line; both arms print the same keys."""
+    return {"workload": label, "replicas": args.replicas, "replicas_per_rank": replicas_per_rank, "atoms": int(s["pos"].shape[0]),
+            "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
+            "prune_every": args.prune_every, "rebuild_every": args.rebuild_every, "exchange_every": args.exchange_every,
+            "exchange": exchange, "cuda_graph": use_graph, "pme_grid": pme_grid, "l2": flush_note,
+            "jitter_nm": JITTER_NM}
+
+
 def run_reference(args):
     """The reference arm: the reference's own CPU path cannot be built here (every translation unit needs OpenMM,
     which is absent from the image), so this times the oracle port -- a C/OpenMP restatement of the same path -- with
-    all host threads, replicas evaluated one after another."""
+    all host threads.  One step = every replica of the schedule evaluated once (two full direct-space evaluations +
+    scalar stage + merge each), one after another: the same whole-job step the GPU arm times.  When K steps of all
+    replicas would not fit the time budget, a step covers the first `sample` replicas only and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     s, sched, label = load_workload(args.workload)
-    steps = max(1, min(args.steps, args.cpu_steps))
-    rate, sec, threads, steps = cpu_oracle_rate(s, sched, steps)
+    O, S = _oracle_system(s)
+    R = args.replicas
+    pos = [replica_positions(s, g) for g in range(R)]
+    t0 = time.perf_counter()
+    S.step(sched[0], pos[0], s["displ"])          # page-in + OpenMP pool + a first estimate of the cost
+    S.step(sched[0], pos[0], s["displ"])
+    est = (time.perf_counter() - t0) / 2
+    W, K = max(0, args.warmup), max(1, args.steps)
+    budget = args.cpu_budget_s
+    sample = R
+    if est * R * (K + W) > budget:                # bounded sample: fewer replicas per step, never fewer steps
+        sample = max(1, min(R, int(budget / (est * (K + W)))))
+    rng = np.random.default_rng(2022)
+
+    def one_step(k):
+        for g in range(sample):
+            x = pos[g] + np.clip(rng.normal(0.0, JITTER_NM, pos[g].shape), -2.5 * JITTER_NM, 2.5 * JITTER_NM)
+            S.step(sched[g % len(sched)], x, s["displ"])
+
+    for k in range(W):
+        one_step(k)
+    t0 = time.perf_counter()
+    for k in range(K):
+        one_step(k)
+    sec = (time.perf_counter() - t0) / K          # seconds per step of `sample` replicas
+    rate = sample * DT_FS * 1e-6 * 86400.0 / sec  # replicas are evaluated one after another: aggregate == per-replica rate
+    threads = O.num_threads()
     line = {
         "impl": "reference", "metric": "aggregate replica-ns/day (ATM hot path)", "value": rate, "unit": "replica-ns/day",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3 * args.replicas,
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": label, "replicas": args.replicas, "atoms": int(s["pos"].shape[0]), "dt_fs": DT_FS,
-                   "cutoff_nm": s["cutoff"]},
+        "config": workload_config(args, label, s, None, None, None, None, None),
+        "replicas_per_step_timed": sample,
+        "ms_per_step_all_replicas": sec * 1e3 * R / sample,
         "cpu_baseline": {"value": rate, "unit": "replica-ns/day", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps of 1 replica (two full direct-space evaluations + merge per step), "
-                                   f"replicas run sequentially so the aggregate rate equals the per-replica rate"},
+                         "sample": f"{K} steps (+{W} warm-up) of {sample} of the {R} replicas, evaluated one after another with "
+                                   f"{threads} OpenMP threads (two full direct-space evaluations + scalar stage + merge per replica-step)"},
         "e2e": {"value": rate, "unit": "replica-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle/_ref (the reference compiled in place) is not buildable: OpenMM is absent; kind=port",
     }
@@ -307,31 +354,65 @@ def run_b200(args):
         for k, row in rex.exchange(en[:, 0:2].contiguous()):
             be.set_parameters(row, replica=k)
 
+    # ---- per-step position jitter: x = base + clipped N(0, 0.005 nm), a seeded set of NJ noise
+    #      fields cycled through, applied on the device OUTSIDE the event pairs; the prune / rebuild therefore see
+    #      different coordinates every time (round 1 re-evaluated identical coordinates)
+    NJ = 8
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2022 + rank)
+    base = posq.clone()
+    noise = []
+    for j in range(NJ):
+        z = torch.zeros_like(posq)
+        z[:, :n, :3] = torch.clamp(torch.randn((max(R, 1), n, 3), generator=gen, device=dev) * JITTER_NM, -2.5 * JITTER_NM, 2.5 * JITTER_NM)
+        noise.append(z)
+
+    # steady-state frequencies of the step kinds over one period of the declared cadences
+    period = int(np.lcm(args.prune_every, args.rebuild_every))
+    n_reb = sum(1 for k in range(period) if k % args.rebuild_every == 0)
+    n_pru = sum(1 for k in range(period) if k % args.rebuild_every != 0 and k % args.prune_every == 0)
+    freq = {"rebuild": n_reb / period, "prune": n_pru / period, "exchange": 1.0 / args.exchange_every if total_replicas > 1 else 0.0}
+
     step_no = [0]
 
-    def one_step(timed_events=None):
+    def one_step(ev=None, kind=None, do_ex=None):
+        """One pass of the hot path for every resident replica.  ev = 4 events: start | after pair-list maintenance |
+        after the step | after the exchange cycle."""
         with torch.cuda.stream(stream):
+            k = step_no[0]
+            torch.add(base, noise[k % NJ], out=posq)
             if flush is not None:
                 flush.zero_()
-            if timed_events is not None:
-                timed_events[0].record(stream)
-            k = step_no[0]
-            if k % args.rebuild_every == 0:
+            if kind is None:
+                kind = "rebuild" if k % args.rebuild_every == 0 else ("prune" if k % args.prune_every == 0 else "plain")
+            if do_ex is None:
+                do_ex = (k + 1) % args.exchange_every == 0
+            if ev is not None:
+                ev[0].record(stream)
+            if kind == "rebuild":
                 be.rebuild(posq, stream=stream)
-            elif k % args.prune_every == 0:
+            elif kind == "prune":
                 be.prune(posq, stream=stream)
+            if ev is not None:
+                ev[1].record(stream)
             be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream)
-            if (k + 1) % args.exchange_every == 0:
+            if ev is not None:
+                ev[2].record(stream)
+            if do_ex:
                 exchange((k + 1) // args.exchange_every)
-            if timed_events is not None:
-                timed_events[1].record(stream)
+            if ev is not None:
+                ev[3].record(stream)
             step_no[0] += 1
+        return kind, do_ex
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def new_events():
+        return [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     # ---- warm-up (>= 3 steps), then one statistics step (pair counts; not timed)
     W = max(3, args.warmup)
@@ -350,30 +431,86 @@ def run_b200(args):
         stats_en = np.zeros((1, _capi.NUM_ENERGY_SLOTS))
     nb_stats = be.nb_stats() if R > 0 else {}
 
-    # ---- timed region: exactly K steps, per-step CUDA events on the launching stream (the L2 flush between steps
-    #      stays outside the event pairs), barrier + synchronize on both sides, max over ranks
+    # ---- timed region: exactly K steps, per-step CUDA events on the launching stream (jitter and L2 flush stay outside
+    #      the event pairs), barrier + synchronize on both sides, max over ranks
     K = args.steps
-    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    records = []
     launches0 = be.launch_count()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     t_wall0 = time.perf_counter()
-    if R > 0:
-        for k in range(K):
-            one_step(events[k])
+    for k in range(K):
+        ev = new_events()
+        if R > 0:
+            kind, ex = one_step(ev)
+        else:  # a rank without replicas still takes part in the exchange collective
+            kind, ex = "plain", (step_no[0] + 1) % args.exchange_every == 0
+            with torch.cuda.stream(stream):
+                for e in ev[:3]:
+                    e.record(stream)
+                if ex:
+                    exchange(0)
+                ev[3].record(stream)
+            step_no[0] += 1
+        records.append((kind, ex, ev))
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
+    launches = be.launch_count() - launches0
+    window_ms = sum(ev[0].elapsed_time(ev[3]) for _, _, ev in records)
+
+    # ---- the K-step window holds whatever maintenance / exchange calls fall on its step numbers (a 20-step window:
+    #      4 prunes, at most one rebuild, no exchange), so the reported step time is the STEADY-STATE one:
+    #          plain step + sum over kinds of (mean cost of that call) * (its frequency on the declared cadence),
+    #      every term measured in this run with the same events; kinds the window saw fewer than 3 times are sampled
+    #      right after it (outside the window, same stream, same jitter/flush discipline)
+    extra = []
+    for kind_x in ("prune", "rebuild"):
+        have = sum(1 for kd, _, _ in records if kd == kind_x)
+        for _ in range(max(0, 3 - have) if freq[kind_x] > 0 else 0):
+            ev = new_events()
+            if R > 0:
+                one_step(ev, kind=kind_x, do_ex=False)
+                one_step(None, kind="plain", do_ex=False)
+                extra.append((kind_x, False, ev))
+    have_ex = sum(1 for _, ex, _ in records if ex)
+    for _ in range(max(0, 3 - have_ex) if freq["exchange"] > 0 else 0):
+        ev = new_events()
+        if R > 0:
+            one_step(ev, kind="plain", do_ex=True)
+        else:
+            with torch.cuda.stream(stream):
+                for e in ev[:3]:
+                    e.record(stream)
+                exchange(0)
+                ev[3].record(stream)
+        extra.append(("plain", True, ev))
+    barrier()
     if device_exchange:
         rex.sync_from_device(stream=stream)   # bookkeeping only (raises on a non-finite energy), outside the timed region
-    launches = be.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in events) if R > 0 else 0.0
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    allrec = records + extra
+
+    def mean_ms(sel, a, b):
+        v = [ev[a].elapsed_time(ev[b]) for kd, ex, ev in allrec if sel(kd, ex)]
+        return (sum(v) / len(v), len(v)) if v else (0.0, 0)
+
+    t_plain, n_plain = mean_ms(lambda kd, ex: True, 1, 2) if R > 0 else (0.0, 0)
+    comp = {"step": {"ms": t_plain, "samples": n_plain, "per_step": 1.0}}
+    steady = t_plain
+    for kind_x in ("prune", "rebuild"):
+        t, c = mean_ms(lambda kd, ex, kx=kind_x: kd == kx, 0, 1)
+        comp[kind_x] = {"ms": t, "samples": c, "per_step": freq[kind_x]}
+        steady += t * freq[kind_x]
+    t, c = mean_ms(lambda kd, ex: ex, 2, 3)
+    comp["exchange"] = {"ms": t, "samples": c, "per_step": freq["exchange"]}
+    steady += t * freq["exchange"]
+    tt = torch.tensor([steady, window_ms / K], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / K
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt[0].item())
+    window_ms_per_step = float(tt[1].item())
     value = total_replicas * DT_FS * 1e-6 * 86400.0 / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (nb2): CUDA events around the launch, 20 more steps right after the timed region
@@ -385,6 +522,7 @@ def run_b200(args):
                 if flush is not None:
                     flush.zero_()
                 be.step(posq, force, posq_corr=corr, include_energy=True, graph=False, stream=stream)
+            torch.add(base, noise[0], out=posq)
         tot, cnt = be.profile_read()
         be.profile_enable(False)
         nb2_ms = tot / max(cnt, 1)
@@ -481,34 +619,67 @@ def run_b200(args):
         pq_c = [posq_h[lo:hi] for _, lo, hi in chunks]
         f_c = [force_h[lo:hi] for _, lo, hi in chunks]
         en_c = [en_h[lo:hi] for _, lo, hi in chunks]
+        # per-step jitter of the HOST coordinates: NJ pinned snapshots cycled through (the copy into the caller's pinned
+        # buffer happens outside the event pair, like the integrator's position update it stands for)
+        base_h = posq_h.clone()
+        snaps = []
+        rng_h = np.random.default_rng(3033 + rank)
+        for j in range(4):
+            z = base_h.clone()
+            z[:, :n, :3] += torch.from_numpy(np.clip(rng_h.normal(0.0, JITTER_NM, (R, n, 3)), -2.5 * JITTER_NM, 2.5 * JITTER_NM).astype(np.float32))
+            snaps.append(z)
         KE = min(K, 200)
         WE = 5
-        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
+        kinds_e = []
+        ee = []
         with torch.cuda.stream(stream):
             pipe.step(pq_c, f_c, en_c, maintenance=pipe.REBUILD, stream=stream)   # first build: synchronous, verified
+        schedule_e = [None] * (KE + WE)
+        seen = {"plain": 0, "prune": 0, "rebuild": 0}
         for k in range(KE + WE):
+            kd = "rebuild" if k % args.rebuild_every == 0 else ("prune" if k % args.prune_every == 0 else "plain")
+            schedule_e[k] = kd
+            if k >= WE:
+                seen[kd] += 1
+        for kd in ("prune", "rebuild", "plain"):      # kinds the window holds fewer than 3 times: sampled after it
+            for _ in range(max(0, 3 - seen[kd])):
+                schedule_e += [kd, "plain"]
+        for k, kd in enumerate(schedule_e):
+            posq_h.copy_(snaps[k % len(snaps)])
             with torch.cuda.stream(stream):
                 if flush is not None:
                     flush.zero_()
-                if k >= WE:
-                    ee[k - WE][0].record(stream)
-                maint = pipe.REBUILD if k % args.rebuild_every == 0 else (pipe.PRUNE if k % args.prune_every == 0 else pipe.NONE)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                maint = {"rebuild": pipe.REBUILD, "prune": pipe.PRUNE, "plain": pipe.NONE}[kd]
                 pipe.step(pq_c, f_c, en_c, maintenance=maint, stream=stream)
+                b.record(stream)
                 if k >= WE:
-                    ee[k - WE][1].record(stream)
+                    ee.append((kd, k < KE + WE, a, b))
             stream.synchronize()  # the step's result (forces, energies) is on the host before the next step starts
         pipe.close()
         torch.cuda.synchronize()
-        e2e_ms = sum(a.elapsed_time(b) for a, b in ee) / KE
+        e2e_comp = {}
+        e2e_ms = 0.0
+        f_e = {"rebuild": freq["rebuild"], "prune": freq["prune"], "plain": 1.0 - freq["rebuild"] - freq["prune"]}
+        for kd in ("plain", "prune", "rebuild"):
+            v = [a.elapsed_time(b) for kk, _, a, b in ee if kk == kd]
+            t_kd = sum(v) / len(v) if v else 0.0
+            e2e_comp[kd] = {"ms": t_kd, "samples": len(v), "per_step": f_e[kd]}
+            e2e_ms += t_kd * f_e[kd]
+        e2e_window_ms = sum(a.elapsed_time(b) for _, inw, a, b in ee if inw) / KE
+        posq_h.copy_(base_h)
         h2d = posq_h.numel() * 4
         d2h = force_h.numel() * 8 + R * _capi.NUM_ENERGY_SLOTS * 8
         for bc, *_ in chunks:
             if bc is not be:
                 bc.close()
-    t = torch.tensor([e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    if e2e_ms is None:
+        e2e_comp, e2e_window_ms = {}, 0.0
+    t = torch.tensor([e2e_ms or 0.0, e2e_window_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms, e2e_window_ms = float(t[0].item()), float(t[1].item())
     e2e_value = total_replicas * DT_FS * 1e-6 * 86400.0 / (e2e_ms * 1e-3) if e2e_ms > 0 else None
 
     if rank == 0:
@@ -525,16 +696,21 @@ def run_b200(args):
         pairs_computed = pc + p1 + p2
         roofline = None
         traffic = None
-        try:  # DRAM bytes of one nb2 launch from the committed ncu --set full capture (same workload / replica count only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_nb2_traffic.json")))
-            if tj["workload"] == args.workload and tj["replicas"] == R and world == 1:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_src = None
+        try:  # DRAM bytes of one nb2 launch: ncu cannot run inside a bench run, so this is the newest committed
+            # `ncu --set full` capture of the same workload / replica count (profiles/r*_nb2_traffic.json), N = 1 only
+            import glob
+            for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_nb2_traffic.json"))):
+                tj = json.load(open(fn))
+                if tj["workload"] == args.workload and tj["replicas"] == R and world == 1:
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    traffic_src = os.path.relpath(fn, ROOT)
         except Exception:
             pass
         if nb2_ms:
             ach = pairs_two_state * FLOP_PER_PAIR / (nb2_ms * 1e-3) / 1e12
             roofline = {"kernel": "nb2_kernel (two-state direct space)", "bound": "fp32", "achieved": ach,
-                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": traffic,
+                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": "derived: SMs*128 lanes*2 flop*max SM clock (no measured fp32 peak in MEASURED_PEAKS.json)",
                         "flop_per_pair": FLOP_PER_PAIR, "pairs_two_state_equivalent": pairs_two_state,
                         "pairs_computed": pairs_computed, "nb2_ms": nb2_ms,
@@ -561,15 +737,15 @@ def run_b200(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 pair math, int64 fixed-point accumulation, f64 scalar stage",
             "data": "synthetic",
-            "config": {"workload": label, "replicas": total_replicas, "replicas_per_rank": max_per_rank, "atoms": int(n),
-                       "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
-                       "prune_every": args.prune_every, "rebuild_every": args.rebuild_every,
-                       "exchange_every": args.exchange_every, "exchange": "device" if device_exchange else "host", "cuda_graph": use_graph, "pme_grid": pme_grid,
-                       "l2": "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)",
-                       "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank},
+            "config": workload_config(args, label, s, max_per_rank, "device" if device_exchange else "host", use_graph, pme_grid,
+                                      "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)"),
+            "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank,
+            "ms_per_step_is": "steady state on the declared cadences: plain step + sum(component ms * per_step), every component "
+                              "timed in this run with CUDA events (max over ranks); window_ms_per_step is the raw K-step window",
+            "components": comp, "window_ms_per_step": window_ms_per_step,
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "chunks": e2e_chunks,
+                    "ms_per_step": e2e_ms, "window_ms_per_step": e2e_window_ms, "components": e2e_comp, "chunks": e2e_chunks,
                     "call": "atm_host_pipeline_step (pinned host coordinates in, pinned host forces + energy records out, "
                             "one cached CUDA graph per step; pair-list maintenance on the bench cadence)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,

@@ -170,11 +170,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
         : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+__device__ __forceinline__ void cp_async16(void *smem, unsigned long long gaddr) {  // gaddr: global state space
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gaddr));
 }
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+__device__ __forceinline__ void cp_async8(void *smem, unsigned long long gaddr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gaddr));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -183,114 +183,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct __align__(128) Nb2Smem {
     unsigned int el[NB_WARPS][ITEM_STEPS][32];  // the item's list entries (bulk copy destination)
     float4 xj[NB_WARPS][RING][32];
-    float2 pj[NB_WARPS][RING][32];
-#ifdef ATM_NB2_SCALAR
-    float4 xi[NB_WARPS][CL];
-    float2 pi[NB_WARPS][CL];
-#else
+    float4 pj[NB_WARPS][RING][32];              // .xy = (sigma/2, 2 sqrt(eps)); float4 stride so that ONE offset addresses xj and pj
     // cluster atoms in PAIRS (atoms 2p, 2p+1) for the packed f32x2 inner loop: three 128-bit broadcast reads per pair --
     // (x0,x1,y0,y1), (z0,z1,q0,q1), (hs0,hs1,se0,se1)
     float4 ci[NB_WARPS][CL / 2][3];
-#endif
     unsigned long long bar[NB_WARPS];           // one mbarrier per warp
 };
+constexpr int PJ_OFF = NB_WARPS * RING * 32;    // float4 elements between a lane's xj slot and its pj slot
 
-#ifdef ATM_NB2_SCALAR  // round-1 scalar inner loop, kept for A/B builds (-DATM_NB2_SCALAR)
-template <bool ENERGY, bool STATS>
-__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
-    const float4 L = d.box[it.r], iL = d.invbox[it.r];
-    const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
-    PairConst pc;
-    pc.cutoff2 = d.cutoff2;
-    pc.p_alpha = ERFC_P * d.alpha;
-    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
-    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+// Pins a value in a register: the compiler can no longer rematerialise it from kernel arguments / thread ids inside the
+// list-step loop (at 96 registers it re-derived the ring, accumulator and site-array addresses in every step: ~35 of
+// the loop's 336 instructions).
+template <typename T>
+__device__ __forceinline__ void pin64(T *&p) { asm volatile("" : "+l"(p)); }
+__device__ __forceinline__ void pin64(unsigned long long &v) { asm volatile("" : "+l"(v)); }
 
-    // the whole entry list of the item: one bulk copy, in flight while the cluster atoms are staged
-    if (lane == 0) bulk_load_arm(&sm.bar[w], &sm.el[w][0][0], it.list, (unsigned)it.nst * 128u);
-    // cluster atoms -> shared memory (lanes 0..7), shifted next to the cluster centre
-    if (lane < CL) {
-        float4 x = __ldg(d.xs + it.rsite + (size_t)it.A * CL + lane);
-        x.x -= L.x * fast_rint((x.x - cA.x) * iL.x);
-        x.y -= L.y * fast_rint((x.y - cA.y) * iL.y);
-        x.z -= L.z * fast_rint((x.z - cA.z) * iL.z);
-        sm.xi[w][lane] = x;
-        sm.pi[w][lane] = __ldg(d.par + it.rsite + (size_t)it.A * CL + lane);
-    }
-    mbar_wait(&sm.bar[w], parity);
-#pragma unroll
-    for (int q = 0; q < PF_DIST; q++) {
-        if (q < it.nst) {
-            const unsigned int eq = sm.el[w][q][lane];
-            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (eq >> 8));
-            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (eq >> 8));
-        }
-        cp_async_commit();
-    }
-    __syncwarp();
-
-    float fix[CL], fiy[CL], fiz[CL];
-#pragma unroll
-    for (int k = 0; k < CL; k++) fix[k] = fiy[k] = fiz[k] = 0.f;
-    unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
-    double e_acc = 0.0;
-    int npairs = 0;
-
-    for (int st = 0; st < it.nst; st++) {
-        cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
-        const int slot = st & (RING - 1);
-        const float4 xjc = sm.xj[w][slot][lane];
-        const float2 pjc = sm.pj[w][slot][lane];
-        const unsigned int e = sm.el[w][st][lane];
-        // keep PF_DIST steps in flight
-        {
-            const int sp = st + PF_DIST;
-            if (sp < it.nst) {
-                const unsigned int e_next = sm.el[w][sp][lane];
-                const int ps = sp & (RING - 1);
-                cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
-                cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
-            }
-            cp_async_commit();
-        }
-        const int j = e >> 8;
-        const unsigned int m = e & 0xffu;
-        const float xjx = xjc.x - L.x * fast_rint((xjc.x - cA.x) * iL.x);
-        const float xjy = xjc.y - L.y * fast_rint((xjc.y - cA.y) * iL.y);
-        const float xjz = xjc.z - L.z * fast_rint((xjc.z - cA.z) * iL.z);
-        float fjx = 0.f, fjy = 0.f, fjz = 0.f, e_step = 0.f;
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < CL; k++) {
-            const float4 xi = sm.xi[w][k];
-            const float2 pi = sm.pi[w][k];
-            const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const bool in = (r2 < pc.cutoff2) && !(m & (1u << k));
-            float en = 0.f;
-            // a pair outside the cutoff (or excluded, or a padding slot) is evaluated at r^2 = 1e30: every term underflows
-            // to exactly zero (flush-to-zero MUFU paths, no inf/NaN even for r = 0), so ONE select on r^2 replaces the
-            // selects on the force scale and on the energy
-            const float fs = pair_interaction<ENERGY>(in ? r2 : 1e30f, xi.w * xjc.w, pi.x + pjc.x, pi.y * pjc.y, pc, en);
-            if (ENERGY) e_step += en;
-            if (STATS) npairs += in ? 1 : 0;
-            any |= in;
-            fix[k] = fmaf(dx, fs, fix[k]); fiy[k] = fmaf(dy, fs, fiy[k]); fiz[k] = fmaf(dz, fs, fiz[k]);
-            fjx = fmaf(-dx, fs, fjx); fjy = fmaf(-dy, fs, fjy); fjz = fmaf(-dz, fs, fjz);
-        }
-        if (ENERGY) e_acc += (double)e_step;
-        if (any) {  // (deriving this from fj != 0 after the loop instead of 8 predicate ORs measured 2 % SLOWER per launch)
-            red_add_fixed(buf + j, fjx);
-            red_add_fixed(buf + it.comp_stride + j, fjy);
-            red_add_fixed(buf + 2 * it.comp_stride + j, fjz);
-        }
-    }
-    cp_async_wait<0>();
-    nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, fix, fiy, fiz, e_acc, npairs);
-}
-#endif  // ATM_NB2_SCALAR
-
-#ifndef ATM_NB2_SCALAR
 // ------------------------------------------------------------------------------------------------
 // Packed inner loop (sm_100 only): Blackwell executes two fp32 operations per lane in ONE issued instruction
 // (fma/mul/add.rn.f32x2 -> SASS FFMA2 / FMUL2 / FADD2, operands in aligned 64-bit register pairs, the second source
@@ -320,12 +227,20 @@ __device__ __forceinline__ float2 pair_interaction_x2(float2 r2, float2 qq, floa
     const float2 t = f2(mufu_rcp(ta.x), mufu_rcp(ta.y));
     const float2 ea = __fmul2_rn(r2, f2(pc.neg_a2_log2e));
     const float2 ex = f2(mufu_ex2(ea.x), mufu_ex2(ea.y));
+#ifdef ATM_NB2_ESTRIN  // A/B: Estrin's scheme, dependent depth 4 instead of 6 at the price of two more multiplications
+    const float2 t2 = __fmul2_rn(t, t), t4 = __fmul2_rn(t2, t2);
+    const float2 p01 = __ffma2_rn(t, f2(ERFC_A1), f2(ERFC_A0)), p23 = __ffma2_rn(t, f2(ERFC_A3), f2(ERFC_A2));
+    const float2 p45 = __ffma2_rn(t, f2(ERFC_A5), f2(ERFC_A4));
+    const float2 p456 = __ffma2_rn(t2, f2(ERFC_A6), p45), p0123 = __ffma2_rn(p23, t2, p01);
+    float2 poly = __ffma2_rn(p456, t4, p0123);
+#else
     float2 poly = __ffma2_rn(t, f2(ERFC_A6), f2(ERFC_A5));
     poly = __ffma2_rn(poly, t, f2(ERFC_A4));
     poly = __ffma2_rn(poly, t, f2(ERFC_A3));
     poly = __ffma2_rn(poly, t, f2(ERFC_A2));
     poly = __ffma2_rn(poly, t, f2(ERFC_A1));
     poly = __ffma2_rn(poly, t, f2(ERFC_A0));
+#endif
     const float2 g = __fmul2_rn(__fmul2_rn(poly, t), rinv);
     const float2 qe = __fmul2_rn(qq, ex);
     const float2 ec = __fmul2_rn(qe, g);
@@ -335,14 +250,15 @@ __device__ __forceinline__ float2 pair_interaction_x2(float2 r2, float2 qq, floa
 }
 
 template <bool ENERGY, bool STATS>
-__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity) {
+__device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int lane, int w, Nb2Smem &sm, unsigned int parity,
+                                         const PairConst &pc) {
     const float4 L = d.box[it.r], iL = d.invbox[it.r];
     const float4 cA = d.cc[(size_t)it.r * d.Cmax + it.A];
-    PairConst pc;
-    pc.cutoff2 = d.cutoff2;
-    pc.p_alpha = ERFC_P * d.alpha;
-    pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
-    pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+    // per-replica bases of the site arrays, pinned: the gather address of a partner is one IMAD.WIDE from them
+    unsigned long long xs_g = (unsigned long long)__cvta_generic_to_global(d.xs + it.rsite);
+    unsigned long long par_g = (unsigned long long)__cvta_generic_to_global(d.par + it.rsite);
+    pin64(xs_g);
+    pin64(par_g);
 
     // the whole entry list of the item: one bulk copy, in flight while the cluster atoms are staged
     if (lane == 0) bulk_load_arm(&sm.bar[w], &sm.el[w][0][0], it.list, (unsigned)it.nst * 128u);
@@ -356,13 +272,15 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         float *c = reinterpret_cast<float *>(&sm.ci[w][lane >> 1][0]) + (lane & 1);
         c[0] = x.x; c[2] = x.y; c[4] = x.z; c[6] = x.w; c[8] = pp.x; c[10] = pp.y;
     }
+    const unsigned int *elp = &sm.el[w][0][lane];
+    float4 *ring = &sm.xj[w][0][lane];  // the lane's ring: slot s of xj at ring[32 s], of pj at ring[32 s + PJ_OFF]
     mbar_wait(&sm.bar[w], parity);
 #pragma unroll
     for (int q = 0; q < PF_DIST; q++) {
         if (q < it.nst) {
-            const unsigned int eq = sm.el[w][q][lane];
-            cp_async16(&sm.xj[w][q][lane], d.xs + it.rsite + (eq >> 8));
-            cp_async8(&sm.pj[w][q][lane], d.par + it.rsite + (eq >> 8));
+            const unsigned int eq = elp[q * 32] >> 8;
+            cp_async16(ring + q * 32, xs_g + (unsigned long long)eq * 16ull);
+            cp_async8(ring + q * 32 + PJ_OFF, par_g + (unsigned long long)eq * 8ull);
         }
         cp_async_commit();
     }
@@ -371,38 +289,47 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     float2 fix[CL / 2], fiy[CL / 2], fiz[CL / 2];
 #pragma unroll
     for (int p = 0; p < CL / 2; p++) fix[p] = fiy[p] = fiz[p] = f2(0.f);
+    // accumulator base of this (target, replica) and the byte stride between the x / y / z blocks, pinned
     unsigned long long *buf = d.buf + (size_t)it.target * 3 * it.comp_stride + it.rsite;
+    unsigned long long buf_g = (unsigned long long)__cvta_generic_to_global(buf);
+    unsigned long long cs8 = (unsigned long long)it.comp_stride * 8ull;
+    pin64(buf_g);
+    pin64(cs8);
     double e_acc = 0.0;
     int npairs = 0;
+    // periodic shift of the partner in packed form (x, y) + scalar z
+    const float2 ncA_xy = f2(-cA.x, -cA.y), iL_xy = f2(iL.x, iL.y), L_xy = f2(L.x, L.y);
+    const float4 *ci = &sm.ci[w][0][0];
 
     for (int st = 0; st < it.nst; st++) {
         cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
-        const int slot = st & (RING - 1);
-        const float4 xjc = sm.xj[w][slot][lane];
-        const float2 pjc = sm.pj[w][slot][lane];
-        const unsigned int e = sm.el[w][st][lane];
+        const int slot = (st & (RING - 1)) * 32;
+        const float4 xjc = ring[slot];
+        const float2 pjc = *reinterpret_cast<const float2 *>(ring + slot + PJ_OFF);
+        const unsigned int e = elp[st * 32];
         // keep PF_DIST steps in flight
         {
             const int sp = st + PF_DIST;
             if (sp < it.nst) {
-                const unsigned int e_next = sm.el[w][sp][lane];
-                const int ps = sp & (RING - 1);
-                cp_async16(&sm.xj[w][ps][lane], d.xs + it.rsite + (e_next >> 8));
-                cp_async8(&sm.pj[w][ps][lane], d.par + it.rsite + (e_next >> 8));
+                const unsigned int e_next = elp[sp * 32] >> 8;
+                const int ps = (sp & (RING - 1)) * 32;
+                cp_async16(ring + ps, xs_g + (unsigned long long)e_next * 16ull);
+                cp_async8(ring + ps + PJ_OFF, par_g + (unsigned long long)e_next * 8ull);
             }
             cp_async_commit();
         }
-        const int j = e >> 8;
-        const unsigned int m = e & 0xffu;
+        const unsigned int m = e;  // low 8 bits: exclusion / padding mask
         // minus the partner's coordinates, shifted next to the cluster centre
-        const float nxj = fmaf(L.x, fast_rint((xjc.x - cA.x) * iL.x), -xjc.x);
-        const float nyj = fmaf(L.y, fast_rint((xjc.y - cA.y) * iL.y), -xjc.y);
+        float2 tq = __fmul2_rn(__fadd2_rn(f2(xjc.x, xjc.y), ncA_xy), iL_xy);
+        tq = __fadd2_rn(__fadd2_rn(tq, f2(12582912.0f)), f2(-12582912.0f));
+        const float2 nxy = __ffma2_rn(L_xy, tq, f2(-xjc.x, -xjc.y));
+        const float nxj = nxy.x, nyj = nxy.y;
         const float nzj = fmaf(L.z, fast_rint((xjc.z - cA.z) * iL.z), -xjc.z);
         float2 fjx = f2(0.f), fjy = f2(0.f), fjz = f2(0.f), e_step = f2(0.f);
         bool any = false;
 #pragma unroll
         for (int p = 0; p < CL / 2; p++) {
-            const float4 cxy = sm.ci[w][p][0], czq = sm.ci[w][p][1], cps = sm.ci[w][p][2];
+            const float4 cxy = ci[3 * p], czq = ci[3 * p + 1], cps = ci[3 * p + 2];
             const float2 dx = __fadd2_rn(f2(cxy.x, cxy.y), f2(nxj));
             const float2 dy = __fadd2_rn(f2(cxy.z, cxy.w), f2(nyj));
             const float2 dz = __fadd2_rn(f2(czq.x, czq.y), f2(nzj));
@@ -422,10 +349,18 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
             fjx = __ffma2_rn(dx, fs, fjx); fjy = __ffma2_rn(dy, fs, fjy); fjz = __ffma2_rn(dz, fs, fjz);
         }
         if (ENERGY) e_acc += (double)(e_step.x + e_step.y);
+#ifdef ATM_NB2_ALWAYS_RED  // A/B: no per-lane "any pair in range" predicate, a zero is added instead
+        (void)any;
+        {
+#else
         if (any) {
-            red_add_fixed(buf + j, -(fjx.x + fjx.y));
-            red_add_fixed(buf + it.comp_stride + j, -(fjy.x + fjy.y));
-            red_add_fixed(buf + 2 * it.comp_stride + j, -(fjz.x + fjz.y));
+#endif
+            unsigned long long bj = buf_g + (unsigned long long)(e >> 8) * 8ull;
+            red_add_fixed_global(bj, -(fjx.x + fjx.y));
+            bj += cs8;
+            red_add_fixed_global(bj, -(fjy.x + fjy.y));
+            bj += cs8;
+            red_add_fixed_global(bj, -(fjz.x + fjz.y));
         }
     }
     cp_async_wait<0>();
@@ -438,7 +373,6 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     }
     nb2_item_epilogue<ENERGY, STATS>(d, it, lane, buf, ax, ay, az, e_acc, npairs);
 }
-#endif  // !ATM_NB2_SCALAR
 
 // ------------------------------------------------------------------------------------------------
 // Excluded pairs (Ewald correction -qq erf(ar)/r, minimum image) and 1-4 exceptions (plain Coulomb + LJ, no image).
@@ -583,15 +517,29 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
         if (lane == 0) mbar_init(&sm.bar[w], 1);
         __syncwarp();
         unsigned int parity = 0;  // phase of this warp's mbarrier: flips with every completed bulk copy
+        PairConst pc;
+        pc.cutoff2 = d.cutoff2;
+        pc.p_alpha = ERFC_P * d.alpha;
+        pc.neg_a2_log2e = -d.alpha * d.alpha * 1.4426950408889634f;
+        pc.two_a_sqrtpi = d.two_alpha_over_sqrtpi;
+        // Work items live in ITEM_STEPS length buckets and are handed out longest first.  Lane l keeps the inclusive
+        // prefix count of the buckets ITEM_STEPS, ITEM_STEPS-1, ..., ITEM_STEPS-l (one load + a warp scan per WARP);
+        // an item index is then turned into (bucket, index in bucket) by a ballot instead of a chain of up to 16
+        // dependent loads per ITEM.
+        const int cnt = (lane < ITEM_STEPS) ? d.flags[ITEM_BUCKET0 + ITEM_STEPS - lane] : 0;
+        int pre = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, off);
+            if (lane >= off) pre += v;
+        }
         const int n_items = d.flags[4], stride = n_item_blocks * (NB_THREADS / 32);
         for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
             __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
-            int wi = warp, b = ITEM_STEPS;
-            for (; b > 1; --b) {  // longest chunks first
-                const int c = d.flags[ITEM_BUCKET0 + b];
-                if (wi < c) break;
-                wi -= c;
-            }
+            const unsigned int below = __ballot_sync(0xffffffffu, warp < pre);  // lanes whose prefix covers this item
+            const int l = below ? __ffs(below) - 1 : ITEM_STEPS - 1;
+            const int b = ITEM_STEPS - l;
+            const int wi = warp - __shfl_sync(0xffffffffu, pre - cnt, l);
             const int4 item = __ldg(d.items + (size_t)b * d.max_items + wi);
             ItemCtx it;
             it.r = item.z & 0xff;
@@ -601,8 +549,8 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
             it.list = d.jlist + (unsigned int)item.x;
             it.rsite = (size_t)it.r * d.Smax;
             it.comp_stride = (size_t)d.R * d.Smax;
-            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm, parity);
-            else nb2_item<true, STATS>(d, it, lane, w, sm, parity);
+            if (it.target == TGT_C && !energy_common) nb2_item<false, STATS>(d, it, lane, w, sm, parity, pc);
+            else nb2_item<true, STATS>(d, it, lane, w, sm, parity, pc);
         }
     } else {
         const int sb = blockIdx.x - n_item_blocks;

@@ -156,5 +156,11 @@ __device__ __forceinline__ void red_add_fixed(unsigned long long *addr, float f)
     long long v = __float2ll_rn(f * 4294967296.0f);
     atomicAdd(addr, (unsigned long long)v);
 }
+// same, for an address the compiler cannot prove to be global (a pointer pinned in a register, see pin64 in
+// atm_nb_force.cuh): names the state space so that no generic-address ATOM + QSPC sequence is emitted
+__device__ __forceinline__ void red_add_fixed_global(unsigned long long addr, float f) {
+    const long long v = __float2ll_rn(f * 4294967296.0f);
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
 
 }  // namespace atm

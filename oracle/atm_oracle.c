@@ -19,6 +19,15 @@ int atm_oracle_num_threads(void) {
 #endif
 }
 
+/* bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1, the CPU arm wants every core it may run on */
+void atm_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Scalar stage
  * ---------------------------------------------------------------------------------------------- */

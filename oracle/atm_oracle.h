@@ -94,6 +94,7 @@ void atm_oracle_step(const atm_oracle_system *sys, const double p[9], const doub
                      double du_ext, double *force_out, double energies[5]);
 
 int atm_oracle_num_threads(void);
+void atm_oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -192,3 +192,7 @@ def hybrid_force_i64(n, padded, force, f1, f2, sp):
 
 def num_threads():
     return lib().atm_oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().atm_oracle_set_num_threads(int(n))
