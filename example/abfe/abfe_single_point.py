@@ -59,7 +59,8 @@ if "--cpp" in sys.argv:
     context.setPositions(g["pos"])
     pot_energy, forces = context.calcForcesAndEnergy(True, True, (1 << 0) | (1 << atmforcegroup))
     pert_energy = core.ATMMetaForce.getPerturbationEnergy(force, context)
-    print("C++ ATMMetaForceImpl: PE(ATM group, direct space) = %.3f kJ/mol, u = %.4f kJ/mol, max |F| = %.1f kJ/mol/nm"
+    print("C++ ATMMetaForceImpl: PE(ATM group: whole NonbondedForce of state 1 + lambda2 u) = %.3f kJ/mol, u = %.4f kJ/mol "
+          "(reference pin 58.2 +- 0.1), max |F| = %.1f kJ/mol/nm"
           % (pot_energy, pert_energy, np.abs(forces).max()))
     print(io.format_sample_line(temperature, lmbd, lambda1, lambda2, alpha, u0, w0coeff, pot_energy, pert_energy))
     sys.exit(0)
@@ -77,8 +78,9 @@ for name, value in ((atmforce.Lambda1(), lambda1), (atmforce.Lambda2(), lambda2)
 state = context.getState(getEnergy=True, getForces=True, groups={0, atmforcegroup})
 pot_energy = state.getPotentialEnergy()
 pert_energy = atmforce.getPerturbationEnergy(context)
-print("direct-space PE of the ATM group = %.3f kJ/mol, perturbation energy u = %.4f kJ/mol (the reference's pin 58.2 adds "
-      "the reciprocal-space difference -13.65), max |F| = %.1f kJ/mol/nm" % (pot_energy, float(pert_energy), np.abs(state.getForces()).max()))
+print("PE of the ATM group (direct + reciprocal space + dispersion correction of state 1, + lambda2 u) = %.3f kJ/mol, "
+      "perturbation energy u = %.4f kJ/mol (reference pin: 58.2 +- 0.1), max |F| = %.1f kJ/mol/nm"
+      % (pot_energy, float(pert_energy), np.abs(state.getForces()).max()))
 
 with tempfile.TemporaryDirectory() as tmp:
     out = io.SampleWriter(os.path.join(tmp, "temoa-g1.out"), temperature)

@@ -188,6 +188,14 @@ int atm_set_box(atm_handle *h, int32_t replica, const double box[9]);
  * outgrew its capacity then surfaces as ATM_ERR_STATE from that call (and is cured by calling atm_nb_rebuild again). */
 int atm_nb_rebuild(atm_handle *h, const void *posq, void *stream);
 
+/* Verification of the last asynchronous rebuild (wait != 0: block until its capacity flags have arrived).
+ * ATM_OK: the lists are complete.  ATM_ERR_STATE: a list outgrew its capacity -- every step since that rebuild has
+ * returned NaN energies and NaN-poisoned forces (never silently truncated sums); atm_nb_rebuild again reallocates
+ * with larger capacities (synchronously) and the caller repeats those steps.  A list that merely came within 20 % of
+ * its capacity makes the NEXT atm_nb_rebuild reallocate ahead of time; that is not an error.
+ * No reference counterpart: OpenMM's own neighbour list handles this inside its inner contexts. */
+int atm_nb_check(atm_handle *h, int32_t wait);
+
 /* Re-prunes the INNER list from the outer one at the current coordinates (cheap, asynchronous, capturable).
  * Needed whenever any atom has moved by more than skin/2 since the last prune or rebuild. */
 int atm_nb_prune(atm_handle *h, const void *posq, void *stream);
@@ -270,6 +278,9 @@ int atm_host_pipeline_destroy(atm_host_pipeline *p);
  * 2 = atm_nb_rebuild first (the very first step must pass 2; that one synchronises, see atm_nb_rebuild).
  * Asynchronous: the host buffers hold the results once `stream` (non-default) has been synchronised. */
 int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t maintenance, void *stream);
+/* atm_nb_check(wait = 1) over every handle of the pipeline: call after synchronising a maintenance = 2 step and, on
+ * ATM_ERR_STATE, repeat that step (its rebuild then takes the synchronous, capacity-growing path). */
+int atm_host_pipeline_check(atm_host_pipeline *p);
 
 /* ------------------------------------------------------------------ Hamiltonian replica exchange (host) */
 

@@ -63,41 +63,58 @@ def build(force=False, verbose=False, defines=(), out=None):
 
 
 FACADE = os.path.join(HERE, "python", "atmmetaforce", "_atmmetaforce_core.so")
-FACADE_SRC = [os.path.join(HERE, "openmmapi", "src", "ATMMetaForce.cpp"),
-              os.path.join(HERE, "openmmapi", "src", "ATMMetaForceB200Kernel.cpp"),
-              os.path.join(HERE, "openmmapi", "src", "ATMMetaForceImpl.cpp"),
-              os.path.join(HERE, "serialization", "ATMMetaForceProxy.cpp"),
-              os.path.join(HERE, "python", "src", "atmmetaforce_core.cpp")]
+API = os.path.join(HERE, "openmmapi")
+STANDIN_LIB = os.path.join(HERE, "libOpenMMStandin.so")          # plays libOpenMM.so (+ libOpenMMCUDA.so): Platform registry, Context, CUDA platform
+API_LIB = os.path.join(HERE, "libATMMetaForcePlugin.so")          # ref: the API library of the same name (ATMMetaForce, Impl, proxy)
+PLUGIN_LIB = os.path.join(HERE, "libATMMetaForcePluginCUDA.so")   # ref: the CUDA plugin library of the same name (kernel factory + kernel)
+STANDIN_SRC = [os.path.join(API, "src", "openmm_standin_context.cpp"), os.path.join(API, "src", "openmm_standin_cuda.cpp")]
+API_SRC = [os.path.join(API, "src", "ATMMetaForce.cpp"), os.path.join(API, "src", "ATMMetaForceB200Kernel.cpp"),
+           os.path.join(API, "src", "ATMMetaForceImpl.cpp"), os.path.join(HERE, "serialization", "ATMMetaForceProxy.cpp")]
+PLUGIN_SRC = [os.path.join(HERE, "platforms", "b200", "src", "B200ATMMetaForceKernels.cpp"),
+              os.path.join(HERE, "platforms", "b200", "src", "B200ATMMetaForceKernelFactory.cpp")]
+BINDING_SRC = [os.path.join(HERE, "python", "src", "atmmetaforce_core.cpp")]
+TESTS = [("TestSerializeATMMetaForce", os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp")),
+         ("TestATMMetaForceImpl", os.path.join(API, "tests", "TestATMMetaForceImpl.cpp")),
+         ("TestB200ATMMetaForcePlugin", os.path.join(HERE, "platforms", "b200", "tests", "TestB200ATMMetaForcePlugin.cpp"))]
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+
+def _headers():
+    out = []
+    for d in (os.path.join(API, "include"), os.path.join(HERE, "platforms", "b200", "include"), os.path.join(HERE, "serialization")):
+        out += [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".h")]
+    return out
 
 
 def build_facade(force=False):
-    """g++: the C++ facade (ATMMetaForce class, XML proxy, kernel object) + its pybind11 binding, linked against
-    libatm_b200.so, plus the stand-alone C++ serialization test."""
+    """g++: the host side above the C ABI, laid out like the reference's build products --
+    libOpenMMStandin.so (stand-in of libOpenMM: Platform registry, Context, the CUDA-platform stand-in),
+    libATMMetaForcePlugin.so (the API library: ATMMetaForce, ATMMetaForceImpl, XML proxy, kernel object),
+    libATMMetaForcePluginCUDA.so (the plugin library: kernel factory + B200CalcATMMetaForceKernel, with the three
+    extern "C" registration symbols), the pybind11 module and the stand-alone C++ tests."""
     import sysconfig
     import pybind11
     build(force=False)
-    deps = FACADE_SRC + [os.path.join(HERE, "openmmapi", "include", f) for f in os.listdir(os.path.join(HERE, "openmmapi", "include"))]
-    deps += [os.path.join(HERE, "serialization", "ATMMetaForceProxy.h"), LIB,
-             os.path.join(HERE, "openmmapi", "tests", "TestATMMetaForceImpl.cpp"),
-             os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp")]
-    if not force and os.path.exists(FACADE) and all(os.path.getmtime(d) <= os.path.getmtime(FACADE) for d in deps):
+    products = [STANDIN_LIB, API_LIB, PLUGIN_LIB, FACADE] + [os.path.join(HERE, "build", t) for t, _ in TESTS]
+    deps = STANDIN_SRC + API_SRC + PLUGIN_SRC + BINDING_SRC + [src for _, src in TESTS] + _headers() + [LIB, os.path.abspath(__file__)]
+    if not force and all(os.path.exists(x) for x in products) and \
+            max(os.path.getmtime(d) for d in deps) <= min(os.path.getmtime(x) for x in products):
         return FACADE
-    inc = ["-I", os.path.join(HERE, "openmmapi", "include"), "-I", os.path.join(HERE, "serialization"),
-           "-I", os.path.join(ROOT, "include"), "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]]
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-fvisibility=hidden"] + inc + FACADE_SRC + \
-          ["-L", HERE, "-latm_b200", "-Wl,-rpath,$ORIGIN/../..", "-o", FACADE]
-    subprocess.check_call(cmd)
-    test = os.path.join(HERE, "build", "TestSerializeATMMetaForce")
-    os.makedirs(os.path.dirname(test), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:4] + \
-          [os.path.join(HERE, "serialization", "TestSerializeATMMetaForce.cpp"), "-L", HERE, "-latm_b200",
-           "-Wl,-rpath,$ORIGIN/..", "-o", test]
-    subprocess.check_call(cmd)
-    test = os.path.join(HERE, "build", "TestATMMetaForceImpl")
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2"] + inc[:6] + FACADE_SRC[:4] + \
-          [os.path.join(HERE, "openmmapi", "tests", "TestATMMetaForceImpl.cpp"), "-L", HERE, "-latm_b200",
-           "-Wl,-rpath,$ORIGIN/..", "-o", test]
-    subprocess.check_call(cmd)
+    inc = ["-I", os.path.join(API, "include"), "-I", os.path.join(HERE, "platforms", "b200", "include"),
+           "-I", os.path.join(HERE, "serialization"), "-I", os.path.join(ROOT, "include")]
+    cxx = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-reorder"]
+    subprocess.check_call(cxx + ["-shared"] + inc + ["-I", os.path.join(CUDA_HOME, "include")] + STANDIN_SRC +
+                          ["-L", HERE, "-latm_b200", "-L", os.path.join(CUDA_HOME, "lib64"), "-lcudart", "-ldl",
+                           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.join(CUDA_HOME, "lib64"), "-o", STANDIN_LIB])
+    subprocess.check_call(cxx + ["-shared"] + inc + API_SRC + ["-L", HERE, "-lOpenMMStandin", "-latm_b200", "-Wl,-rpath,$ORIGIN", "-o", API_LIB])
+    subprocess.check_call(cxx + ["-shared"] + inc + PLUGIN_SRC + ["-L", HERE, "-lATMMetaForcePlugin", "-lOpenMMStandin", "-latm_b200",
+                                                                  "-Wl,-rpath,$ORIGIN", "-o", PLUGIN_LIB])
+    subprocess.check_call(cxx + ["-shared"] + inc + ["-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]] + BINDING_SRC +
+                          ["-L", HERE, "-lATMMetaForcePlugin", "-lOpenMMStandin", "-latm_b200", "-Wl,-rpath,$ORIGIN/../..", "-o", FACADE])
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for name, src in TESTS:
+        subprocess.check_call(cxx + inc + [src, "-L", HERE, "-lATMMetaForcePlugin", "-lOpenMMStandin", "-latm_b200", "-ldl",
+                                           "-Wl,-rpath,$ORIGIN/..", "-o", os.path.join(HERE, "build", name)])
     return FACADE
 
 

@@ -227,4 +227,14 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
     return ATM_OK;
 }
 
+int atm_host_pipeline_check(atm_host_pipeline *p) {
+    ATM_REQUIRE(p, ATM_ERR_INVALID, "atm_host_pipeline_check: null argument");
+    int first = ATM_OK;
+    for (Chunk &k : p->chunks) {
+        const int rc = atm_nb_check(k.h, 1);
+        if (rc != ATM_OK && first == ATM_OK) first = rc;   // every handle is checked: each raises its own capacities
+    }
+    return first;
+}
+
 }  // extern "C"

@@ -187,7 +187,9 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     nb->alloc_generation++;
     nb->verified = false;
     nb->flags_pending = false;
-    if (!nb->h_flags) ATM_CUDA_CHECK(cudaMallocHost(&nb->h_flags, sizeof(int) * 8));
+    nb->grow_pending = false;
+    nb->overflowed = false;
+    if (!nb->h_flags) ATM_CUDA_CHECK(cudaMallocHost(&nb->h_flags, sizeof(int) * NUM_HOST_FLAGS));
     if (!nb->flags_event) ATM_CUDA_CHECK(cudaEventCreateWithFlags(&nb->flags_event, cudaEventDisableTiming));
     free_owned(nb);
     int rc = derive_groups(h);
@@ -525,7 +527,7 @@ static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.par, 0, sizeof(float2) * (size_t)d.R * d.Smax, stream));  // padding slots are read (masked)
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * 8, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * NUM_HOST_FLAGS, stream));
     nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
     nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
     size_t tmp_bytes = nb->sort_tmp_bytes;
@@ -558,6 +560,11 @@ static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
         d.capC = std::max(d.capC, 32 * ((int)(need * 1.25) / 32 + 1));
         d.capX = std::max(d.capX, 32 * ((int)(need * 1.25) / 32 + 1));
         *grow = true;
+    } else {
+        // head-room: a list within 20 % of its capacity raises that capacity (by half) at the NEXT rebuild, while the
+        // lists in use are still complete
+        if (flags[FLAG_MAXLEN_C] > (int)(0.8 * d.capC)) { nb->grow_capC = 32 * ((int)(flags[FLAG_MAXLEN_C] * 1.5) / 32 + 1); nb->grow_pending = true; }
+        if (flags[FLAG_MAXLEN_X] > (int)(0.8 * d.capX)) { nb->grow_capX = 32 * ((int)(flags[FLAG_MAXLEN_X] * 1.5) / 32 + 1); nb->grow_pending = true; }
     }
     unsigned long long inner_entries = 0;
     memcpy(&inner_entries, &flags[6], 8);
@@ -580,11 +587,22 @@ static int check_pending_rebuild(atm_handle *h, bool wait) {
     if (grow) {
         nb->list_valid = false;
         nb->needs_realloc = true;
-        set_error("a pair list outgrew its capacity during the last asynchronous atm_nb_rebuild; steps since then dropped "
-                  "interactions -- call atm_nb_rebuild again (capacities were raised)");
+        nb->overflowed = true;
+        set_error("a pair list outgrew its capacity during the last asynchronous atm_nb_rebuild; the energies and forces of "
+                  "the steps since then are NaN -- call atm_nb_rebuild again (capacities were raised) and repeat them");
         return ATM_ERR_STATE;
     }
     return ATM_OK;
+}
+
+int atm_nb_check(atm_handle *h, int32_t wait) {
+    ATM_REQUIRE(h, ATM_ERR_INVALID, "atm_nb_check: null handle");
+    if (!h->nb) return ATM_OK;
+    if (h->nb->overflowed && !h->nb->flags_pending) {
+        set_error("the pair lists of the last atm_nb_rebuild are incomplete (capacity overflow): call atm_nb_rebuild again");
+        return ATM_ERR_STATE;
+    }
+    return check_pending_rebuild(h, wait != 0);
 }
 
 int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
@@ -597,7 +615,11 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
     const float4 *posq = (const float4 *)posq_;
     int rc;
     if ((rc = check_pending_rebuild(h, false)) && rc != ATM_ERR_STATE) return rc;  // a capacity error is cured right here
-    if (nb->needs_realloc) {
+    if (nb->needs_realloc || nb->grow_pending) {
+        if (nb->grow_pending) {
+            nb->d.capC = std::max(nb->d.capC, nb->grow_capC);
+            nb->d.capX = std::max(nb->d.capX, nb->grow_capX);
+        }
         if ((rc = nb_allocate(h, stream))) return rc;
         nb->needs_realloc = false;
         nb->verified = false;
@@ -634,7 +656,7 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         } else if ((rc = launch_rebuild(h, posq, stream))) {
             return rc;
         }
-        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * NUM_HOST_FLAGS, cudaMemcpyDeviceToHost, stream));
         ATM_CUDA_CHECK(cudaEventRecord(nb->flags_event, stream));
         nb->flags_pending = true;
         nb->list_valid = true;
@@ -645,7 +667,7 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
     for (int attempt = 0; attempt < 4; attempt++) {
         NbDev &d = nb->d;
         if ((rc = launch_rebuild(h, posq, stream))) return rc;
-        int flags[8];
+        int flags[NUM_HOST_FLAGS];
         ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream));
         ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
         bool grow = false;
@@ -965,7 +987,7 @@ int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *n
     NbState *nb = h->nb;
     int rc = check_pending_rebuild(h, false);
     if (rc && !(maintenance == 2 && rc == ATM_ERR_STATE)) return rc;  // a capacity error is cured by the rebuild requested now
-    *needs_sync_rebuild = nb->needs_realloc || !nb->verified || !nb->list_valid;
+    *needs_sync_rebuild = nb->needs_realloc || !nb->verified || !nb->list_valid || (maintenance == 2 && nb->grow_pending);
     ATM_REQUIRE(maintenance == 2 || !*needs_sync_rebuild, ATM_ERR_STATE,
                 "atm_host_pipeline_step: no valid neighbour structure (the first step must ask for a rebuild)");
     if ((rc = upload_params_if_dirty(h, stream))) return rc;
@@ -984,7 +1006,7 @@ int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int inclu
     int rc;
     if (maintenance == 2) {
         if ((rc = launch_rebuild(h, (const float4 *)posq, stream))) return rc;
-        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * NUM_HOST_FLAGS, cudaMemcpyDeviceToHost, stream));
     } else if (maintenance == 1) {
         if ((rc = launch_prune_all(h, posq, stream))) return rc;
     }

@@ -480,7 +480,14 @@ __device__ double scalar_stage_replica(const NbDev &d, int r, const double *__re
         U2 += energy_ext[2 * r + 1];
         du += energy_ext[2 * r + 1] - energy_ext[2 * r];
     }
-    const Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
+    Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
+    if (d.flags[0] & 3) {
+        // the pair lists of the last rebuild are incomplete (a list outgrew its capacity, or the box is too small for
+        // the list radius): nothing computed from them may look like a result
+        const double bad = __longlong_as_double(0x7ff8000000000000ll);
+        U1 = U2 = bad;
+        s.u = s.usc = s.ebias = s.energy = s.sp = bad;
+    }
     if (write_record) {
         e[ATM_E_UREC1] = rec1; e[ATM_E_UREC2] = rec2; e[ATM_E_USELF] = eself;
         e[ATM_E_U1] = U1; e[ATM_E_U2] = U2; e[ATM_E_U] = s.u; e[ATM_E_USC] = s.usc; e[ATM_E_EBIAS] = s.ebias;

@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
             __syncwarp();
         }
     }
+    // longest list of each capacity class, every build: the host grows a capacity BEFORE a list can outgrow it
+    if (lane == 0) atomicMax(&d.flags[li.cap == d.capC ? FLAG_MAXLEN_C : FLAG_MAXLEN_X], count);
     if (count > li.cap) {
+        // the list does not fit: flag it.  The scalar stage of every later step sees the flag and poisons the energy
+        // record and the merged forces with NaN until the next rebuild clears it -- a truncated list never yields
+        // silently wrong numbers
         if (lane == 0) {
             atomicOr(&d.flags[0], 1);
             atomicMax(&d.flags[1], count);

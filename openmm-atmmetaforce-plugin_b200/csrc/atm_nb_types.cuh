@@ -25,6 +25,11 @@ constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
 constexpr int NUM_FLAGS = 40;
+// flags[0] bit 0: a list outgrew its capacity, bit 1: box too small; [1] longest overflowing list; [2,3] outer entries
+// (64 bit); [4] live work items; [5] outer work items; [6,7] pruned entries (64 bit); [8], [9] longest list of the
+// environment / ligand-ghost capacity class at the last build
+constexpr int FLAG_MAXLEN_C = 8, FLAG_MAXLEN_X = 9;
+constexpr int NUM_HOST_FLAGS = 16;   // what a rebuild copies to pinned host memory
 #ifndef ATM_PRUNE_BLOCK
 #define ATM_PRUNE_BLOCK 2          // list steps per software-pipeline block of the prune kernel (1 = one-step loop)
 #endif
@@ -108,6 +113,9 @@ struct NbState {
     uint64_t generation = 0;        // bumped by every rebuild
     uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
     bool verified = false, needs_realloc = false, flags_pending = false;
+    int grow_capC = 0, grow_capX = 0;
+    bool grow_pending = false;      // a list came within 20 % of its capacity: reallocate (larger) at the next rebuild
+    bool overflowed = false;        // the last asynchronous rebuild truncated a list (results since then are NaN-poisoned)
     int *h_flags = nullptr;         // pinned
     cudaEvent_t flags_event = nullptr;
     cudaGraphExec_t rebuild_graph = nullptr, prune_graph = nullptr;

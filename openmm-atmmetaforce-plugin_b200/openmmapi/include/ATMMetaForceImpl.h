@@ -7,8 +7,14 @@
 // this Impl describes the variable-group NonbondedForce to the back-end once (atm_nb_setup) and then, per evaluation,
 // hands the Context's host positions to atm_host_pipeline_step -- H2D, [rebuild | prune], copy-state/pack, the two-state
 // direct-space kernel, the device scalar stage, the merge, D2H of forces and energy record -- one CUDA-graph launch.
-// Direct space only: PME reciprocal space and bonded terms stay in OpenMM's inner contexts, which
-// do not exist in this build.  With OpenMM present the adapter in INTEGRATION.md section 2-4 is used instead.
+// The NonbondedForce is evaluated as a whole -- direct space, PME reciprocal space of both states and the dispersion
+// correction, as the reference's inner contexts do -- unless its reciprocal space was moved to a non-variable group.
+//
+// When the Context's Platform has a "CalcATMMetaForce" kernel registered (libATMMetaForcePluginCUDA.so on the "CUDA"
+// platform), the Impl instead runs the REFERENCE's orchestration, unchanged in structure: every non-ATM Force of the
+// System is cloned into two inner Systems (ref: copysystem, ATMMetaForceImpl.cpp:33-67), two linked inner Contexts
+// evaluate whatever sits in the variable force groups at x and at x + d, and the kernel seam does copyState and the
+// hybrid merge (ref: :90-128).  That is the generic path: any Force with an Impl on that platform can be variable.
 #ifndef ATMMETAFORCE_IMPL_H_
 #define ATMMETAFORCE_IMPL_H_
 
@@ -21,6 +27,7 @@
 #ifndef ATM_HAVE_OPENMM
 #include "openmm_standin_context.h"
 #endif
+#include <memory>
 
 namespace ATMMetaForcePlugin {
 
@@ -54,10 +61,23 @@ public:
     int getVariableForceGroupsMask() const { return variable_force_groups_mask; }
     /** The full energy record of the last evaluation (atm_energy_slot order). */
     const std::vector<double> &getEnergyRecord() const { return energyRecord; }
+    /** True when the platform's CalcATMMetaForce kernel and two inner Contexts are used (the reference's path). */
+    bool usesPlatformKernel() const { return (bool)kernel; }
+    OpenMM::Context *getInnerContext(int state) { return state == 1 ? innerContext1.get() : innerContext2.get(); }
 
 private:
     void createBackend(OpenMM::ContextImpl &context);
     void releaseBackend();
+    /** ref: ATMMetaForceImpl::copysystem (:33-67). */
+    void copysystem(const OpenMM::System &system, OpenMM::System &innerSystem);
+    double calcWithPlatformKernel(OpenMM::ContextImpl &context, bool includeForces, bool includeEnergy, int groups);
+
+    // the reference's orchestration (platform kernel + two linked inner contexts)
+    OpenMM::Kernel kernel;
+    OpenMM::System innerSystem1, innerSystem2;
+    OpenMM::VerletIntegrator innerIntegrator1, innerIntegrator2;
+    std::unique_ptr<OpenMM::Context> innerContext1, innerContext2;
+    bool hasInitializedInnerContexts;
 
     const ATMMetaForce &owner;
     const OpenMM::NonbondedForce *nonbonded;
@@ -73,7 +93,7 @@ private:
     int64_t *forceHost;    // pinned [3P]
     double *energyHost;    // pinned [ATM_NUM_ENERGY_SLOTS]
     int paddedNumAtoms;
-    bool displacementsDirty;
+    bool displacementsDirty, reciprocalOn;
     unsigned long boxVersionSeen;
     std::vector<OpenMM::Vec3> refRebuild, refPrune;
     std::vector<double> energyRecord;

@@ -53,6 +53,8 @@ public:
      *  NonbondedForce, evaluated by ATMMetaForceImpl).  OpenMM declares this protected and lets Context call it as a
      *  friend; the stand-in keeps it public. */
     virtual ForceImpl *createImpl() const { return nullptr; }
+    /** A deep copy (what OpenMM's XmlSerializer::clone<Force> gives ATMMetaForceImpl::copysystem); NULL = not clonable. */
+    virtual Force *clone() const { return nullptr; }
 
 private:
     int forceGroup;

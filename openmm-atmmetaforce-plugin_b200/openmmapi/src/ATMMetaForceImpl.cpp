@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "ATMMetaForceB200Kernel.h"
+#include "ATMMetaForceKernels.h"
 
 using namespace ATMMetaForcePlugin;
 using OpenMM::OpenMMException;
@@ -29,12 +30,42 @@ double maxMove(const std::vector<OpenMM::Vec3> &pos, const std::vector<OpenMM::V
 }  // namespace
 
 ATMMetaForceImpl::ATMMetaForceImpl(const ATMMetaForce &owner)
-    : owner(owner), nonbonded(nullptr), PerturbationEnergy(0.0), variable_force_groups_mask(0), device(-1), skin(0.05),
+    : innerIntegrator1(1.0), innerIntegrator2(1.0), hasInitializedInnerContexts(false), owner(owner), nonbonded(nullptr),
+      PerturbationEnergy(0.0), variable_force_groups_mask(0), device(-1), skin(0.05),
       skinOuter(0.3), handle(nullptr), pipeline(nullptr), stream(nullptr), posqHost(nullptr), forceHost(nullptr),
-      energyHost(nullptr), paddedNumAtoms(0), displacementsDirty(false), boxVersionSeen(0),
+      energyHost(nullptr), paddedNumAtoms(0), displacementsDirty(false), reciprocalOn(false), boxVersionSeen(0),
       energyRecord(ATM_NUM_ENERGY_SLOTS, 0.0) {}
 
-ATMMetaForceImpl::~ATMMetaForceImpl() { releaseBackend(); }
+ATMMetaForceImpl::~ATMMetaForceImpl() {
+    innerContext1.reset();
+    innerContext2.reset();
+    releaseBackend();
+}
+
+void ATMMetaForceImpl::copysystem(const OpenMM::System &system, OpenMM::System &innerSystem) {
+    for (int i = 0; i < system.getNumParticles(); i++) innerSystem.addParticle(system.getParticleMass(i));
+    for (int i = 0; i < system.getNumConstraints(); i++) {
+        int p1, p2;
+        double distance;
+        system.getConstraintParameters(i, p1, p2, distance);
+        innerSystem.addConstraint(p1, p2, distance);
+    }
+    OpenMM::Vec3 a, b, c;
+    system.getDefaultPeriodicBoxVectors(a, b, c);
+    innerSystem.setDefaultPeriodicBoxVectors(a, b, c);
+    // every Force outside the ATM force group goes into the inner systems, keeping its group; which of them are
+    // evaluated is decided per call by the variable-force-group mask.  A NonbondedForce keeps its reciprocal space in
+    // its own group.
+    for (int i = 0; i < system.getNumForces(); i++) {
+        const OpenMM::Force &force = system.getForce(i);
+        if (force.getForceGroup() == owner.getForceGroup()) continue;
+        OpenMM::Force *copy = force.clone();
+        if (!copy) throw OpenMMException("ATMMetaForce: a Force of the System cannot be cloned into the inner contexts");
+        copy->setForceGroup(force.getForceGroup());
+        if (auto *nb = dynamic_cast<OpenMM::NonbondedForce *>(copy)) nb->setReciprocalSpaceForceGroup(-1);
+        innerSystem.addForce(copy);
+    }
+}
 
 void ATMMetaForceImpl::releaseBackend() {
     if (pipeline) atm_host_pipeline_destroy(pipeline);
@@ -56,6 +87,14 @@ void ATMMetaForceImpl::setPairListSkins(double inner_nm, double outer_nm) {
 void ATMMetaForceImpl::initialize(OpenMM::ContextImpl &context) {
     const OpenMM::System &system = context.getSystem();
     variable_force_groups_mask = variableForceGroupsMask(owner);   // throws when the ATM group itself is listed
+    if (context.getPlatform().supportsKernels(getKernelNames())) {
+        // a platform back-end is registered: the reference's own orchestration (ref: initialize :83-87)
+        copysystem(system, innerSystem1);
+        copysystem(system, innerSystem2);
+        kernel = context.getPlatform().createKernel(CalcATMMetaForceKernel::Name(), context);
+        kernel.getAs<CalcATMMetaForceKernel>().initialize(system, owner);
+        return;
+    }
     if (owner.getNumParticles() != system.getNumParticles())
         throw OpenMMException("ATMMetaForce must have exactly as many particles as the System it belongs to.");
     // which Forces the two states evaluate: everything outside the ATM group that sits in a variable force group
@@ -86,6 +125,10 @@ std::vector<std::string> ATMMetaForceImpl::getKernelNames() { return {ATMMetaFor
 void ATMMetaForceImpl::updateParametersInContext(OpenMM::ContextImpl &context) {
     if (owner.getNumParticles() != context.getSystem().getNumParticles())
         throw OpenMMException("copyParametersToContext: The number of ATMMetaForce particles has changed");
+    if (kernel) {
+        kernel.getAs<CalcATMMetaForceKernel>().copyParametersToContext(context, owner);   // ref: :150-152
+        return;
+    }
     displacementsDirty = true;   // uploaded (and the pair lists rebuilt) by the next evaluation
 }
 
@@ -140,6 +183,20 @@ void ATMMetaForceImpl::createBackend(OpenMM::ContextImpl &context) {
         desc.skin = skin;
         desc.skin_outer = skinOuter;
         check(atm_nb_setup(handle, &desc, stream), "ATMMetaForce: describing the NonbondedForce to the back-end");
+        // The reference's inner contexts evaluate the cloned NonbondedForce as a whole (copysystem puts its reciprocal
+        // space into the force's own group, ref: :60-62): reciprocal space (smooth PME on OpenMM's mesh rule, order 5)
+        // and the long-range dispersion correction are part of U1 / U2 -- unless the caller moved the reciprocal space
+        // into a force group that is not variable, i.e. evaluates it elsewhere.
+        const int rg = nonbonded->getReciprocalSpaceForceGroup();
+        if (rg < 0 || ((variable_force_groups_mask >> rg) & 1)) {
+            OpenMM::Vec3 box[3];
+            context.getPeriodicBoxVectors(box[0], box[1], box[2]);
+            int grid[3];
+            OpenMM::pmeGridDimensions(desc.ewald_alpha, nonbonded->getEwaldErrorTolerance(), box, grid);
+            check(atm_pme_setup(handle, grid[0], grid[1], grid[2], 5), "ATMMetaForce: PME mesh");
+            reciprocalOn = true;
+        }
+        check(atm_nb_set_dispersion_correction(handle, nonbonded->getUseDispersionCorrection() ? 1 : 0), "ATMMetaForce: dispersion correction");
         check(atm_host_alloc(sizeof(float) * 4 * (size_t)paddedNumAtoms, (void **)&posqHost), "ATMMetaForce: pinned coordinates");
         check(atm_host_alloc(sizeof(int64_t) * 3 * (size_t)paddedNumAtoms, (void **)&forceHost), "ATMMetaForce: pinned forces");
         check(atm_host_alloc(sizeof(double) * ATM_NUM_ENERGY_SLOTS, (void **)&energyHost), "ATMMetaForce: pinned energy record");
@@ -158,7 +215,37 @@ void ATMMetaForceImpl::createBackend(OpenMM::ContextImpl &context) {
     refPrune.clear();
 }
 
+// The reference's calcForcesAndEnergy (ref: :90-128): inner contexts on first use, copyState, the two inner evaluations
+// of the variable force groups, the kernel's scalar stage + hybrid merge.
+double ATMMetaForceImpl::calcWithPlatformKernel(OpenMM::ContextImpl &context, bool includeForces, bool includeEnergy, int groups) {
+    if (!hasInitializedInnerContexts) {
+        hasInitializedInnerContexts = true;
+        innerContext1.reset(context.createLinkedContext(innerSystem1, innerIntegrator1));
+        innerContext2.reset(context.createLinkedContext(innerSystem2, innerIntegrator2));
+        std::vector<OpenMM::Vec3> pos;
+        context.getPositions(pos);
+        innerContext1->setPositions(pos);
+        innerContext2->setPositions(pos);
+    }
+    if ((groups & (1 << owner.getForceGroup())) == 0) return 0.0;
+    OpenMM::ContextImpl &inner1 = OpenMM::getContextImpl(*innerContext1), &inner2 = OpenMM::getContextImpl(*innerContext2);
+    CalcATMMetaForceKernel &k = kernel.getAs<CalcATMMetaForceKernel>();
+    k.copyState(context, inner1, inner2);
+    const double State1Energy = inner1.calcForcesAndEnergy(true, true, variable_force_groups_mask);
+    const double State2Energy = inner2.calcForcesAndEnergy(true, true, variable_force_groups_mask);
+    const double energy = k.execute(context, inner1, inner2, State1Energy, State2Energy, includeForces, includeEnergy);
+    PerturbationEnergy = k.getPerturbationEnergy();
+    std::fill(energyRecord.begin(), energyRecord.end(), 0.0);
+    energyRecord[ATM_E_U1] = State1Energy;
+    energyRecord[ATM_E_U2] = State2Energy;
+    energyRecord[ATM_E_U] = context.getParameter(ATMMetaForce::Direction()) > 0 ? State2Energy - State1Energy : State1Energy - State2Energy;
+    energyRecord[ATM_E_USC] = PerturbationEnergy;
+    energyRecord[ATM_E_ENERGY] = energy;
+    return includeEnergy ? energy : 0.0;
+}
+
 double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool includeForces, bool includeEnergy, int groups) {
+    if (kernel) return calcWithPlatformKernel(context, includeForces, includeEnergy, groups);
     if ((groups & (1 << owner.getForceGroup())) == 0) return 0.0;
     if (!handle) createBackend(context);
     const int n = owner.getNumParticles();
@@ -182,6 +269,14 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
         context.getPeriodicBoxVectors(a, b, c);
         const double box[9] = {a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2]};
         check(atm_set_box(handle, -1, box), "ATMMetaForce: periodic box");
+        if (reciprocalOn) {   // the mesh follows the box
+            OpenMM::Vec3 bv[3] = {a, b, c};
+            int grid[3];
+            OpenMM::pmeGridDimensions(std::sqrt(-std::log(2.0 * nonbonded->getEwaldErrorTolerance())) / nonbonded->getCutoffDistance(),
+                                      nonbonded->getEwaldErrorTolerance(), bv, grid);
+            check(atm_stream_synchronize(stream), "ATMMetaForce: waiting before the mesh change");
+            check(atm_pme_setup(handle, grid[0], grid[1], grid[2], 5), "ATMMetaForce: PME mesh");
+        }
         boxVersionSeen = context.getBoxVersion();
         rebuild = true;
     }
@@ -208,6 +303,18 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
     io.reserved = 0;
     check(atm_host_pipeline_step(pipeline, &io, maintenance, stream), "ATMMetaForce: evaluating the alchemical force");
     check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
+    if (maintenance == 2) {
+        // the rebuild inside that step was asynchronous: if a pair list outgrew its capacity the step returned NaN;
+        // repeat it (the rebuild now reallocates and verifies synchronously) before anything reaches the integrator
+        const int rc = atm_host_pipeline_check(pipeline);
+        if (rc == ATM_ERR_STATE) {
+            check(atm_host_pipeline_step(pipeline, &io, 2, stream), "ATMMetaForce: repeating the step after a pair-list capacity change");
+            check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
+            check(atm_host_pipeline_check(pipeline), "ATMMetaForce: pair lists");
+        } else {
+            check(rc, "ATMMetaForce: pair lists");
+        }
+    }
     energyRecord.assign(energyHost, energyHost + ATM_NUM_ENERGY_SLOTS);
     PerturbationEnergy = energyRecord[ATM_E_USC];
     if (includeForces) {

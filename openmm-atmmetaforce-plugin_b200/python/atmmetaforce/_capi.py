@@ -22,10 +22,10 @@ PARAM_NAMES = ("lambda1", "lambda2", "alpha", "u0", "w0", "umax", "ubcore", "aco
 SYMBOLS = (
     "atm_last_error", "atm_version", "atm_create", "atm_destroy", "atm_set_displacements", "atm_set_parameters",
     "atm_get_parameters", "atm_copy_state", "atm_wrap_positions", "atm_hybrid_force", "atm_softcore_softplus",
-    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
+    "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_check", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
     "atm_hrex_device_setup", "atm_hrex_device_pack", "atm_hrex_device_exchange", "atm_hrex_device_state",
-    "atm_host_pipeline_create", "atm_host_pipeline_destroy", "atm_host_pipeline_step",
+    "atm_host_pipeline_create", "atm_host_pipeline_destroy", "atm_host_pipeline_step", "atm_host_pipeline_check",
     "atm_stream_create", "atm_stream_destroy", "atm_stream_synchronize", "atm_host_alloc", "atm_host_free",
 )
 
@@ -91,6 +91,7 @@ def lib():
     L.atm_nb_set_dispersion_correction.argtypes = [vp, i32]
     L.atm_nb_rebuild.argtypes = [vp, vp, vp]
     L.atm_nb_prune.argtypes = [vp, vp, vp]
+    L.atm_nb_check.argtypes = [vp, i32]
     L.atm_step.argtypes = [vp, C.POINTER(StepIO), vp]
     L.atm_step_graph.argtypes = [vp, C.POINTER(StepIO), vp]
     L.atm_profile_enable.argtypes = [vp, i32]
@@ -109,6 +110,7 @@ def lib():
     L.atm_host_pipeline_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp)]
     L.atm_host_pipeline_destroy.argtypes = [vp]
     L.atm_host_pipeline_step.argtypes = [vp, C.POINTER(HostIO), i32, vp]
+    L.atm_host_pipeline_check.argtypes = [vp]
     L.atm_stream_create.argtypes = [i32, C.POINTER(vp)]
     L.atm_stream_destroy.argtypes = [vp]
     L.atm_stream_synchronize.argtypes = [vp]

@@ -131,6 +131,11 @@ class ATMBackend:
     def rebuild(self, posq, stream=None):
         check(_capi.lib().atm_nb_rebuild(self._h, _dptr(posq), _stream_ptr(stream)))
 
+    def nb_check(self, wait=True):
+        """Verification of the last asynchronous rebuild; raises ATMError when a pair list outgrew its capacity (the
+        steps since then returned NaN: rebuild again and repeat them)."""
+        check(_capi.lib().atm_nb_check(self._h, 1 if wait else 0))
+
     def prune(self, posq, stream=None):
         check(_capi.lib().atm_nb_prune(self._h, _dptr(posq), _stream_ptr(stream)))
 
@@ -261,6 +266,10 @@ class HostPipeline:
                                       1 if include_energy else 0, 0)
             self._ios, self._key = ios, key
         check(_capi.lib().atm_host_pipeline_step(self._p, self._ios, int(maintenance), _stream_ptr(stream)))
+
+    def check(self):
+        """atm_host_pipeline_check: after synchronising a REBUILD step; raises ATMError if that rebuild overflowed."""
+        check(_capi.lib().atm_host_pipeline_check(self._p))
 
 
 def softcore_softplus(params, U1, U2):

@@ -4,7 +4,10 @@ It plays the role OpenMM's Context + ATMMetaForceImpl play around the reference 
 (ref: openmmapi/src/ATMMetaForceImpl.cpp:69-142): it owns the nine global parameters under their ATM* names,
 positions, box, and runs  copy-state -> two-state direct space -> scalar stage -> merge  on the GPU through the
 C ABI.  The variable force group is a NonbondedForce-like description (charges, sigma, epsilon, exclusions,
-exceptions, cutoff, Ewald alpha) of the System -- direct space only; see DESIGN.md section 1 for what stays in OpenMM.
+exceptions, cutoff, Ewald alpha) of the System.  As in the reference's inner contexts the NonbondedForce is evaluated as a
+whole by default: direct space, PME reciprocal space of both states (OpenMM's mesh rule, order 5) and the long-range
+dispersion correction; `reciprocal_space=False` leaves the reciprocal part to an external evaluator
+(setExternalStateEnergies), which is what north_star's Tier-2 integration does with OpenMM's own PME.
 """
 import numpy as np
 
@@ -18,7 +21,7 @@ class NonbondedDirect:
     space).  Arrays by atom; exceptions are (i, j, chargeProd, sigma, epsilon) rows and imply an exclusion."""
 
     def __init__(self, charge, sigma, epsilon, cutoff, ewald_alpha=None, ewald_tolerance=5e-4, exclusions=None,
-                 exception_pairs=None, exception_params=None, force_group=0):
+                 exception_pairs=None, exception_params=None, force_group=0, reciprocal_space=True, dispersion_correction=True):
         self.charge = np.ascontiguousarray(charge, np.float64)
         self.sigma = np.ascontiguousarray(sigma, np.float64)
         self.epsilon = np.ascontiguousarray(epsilon, np.float64)
@@ -28,6 +31,9 @@ class NonbondedDirect:
         self.exception_pairs = np.zeros((0, 2), np.int32) if exception_pairs is None else np.ascontiguousarray(exception_pairs, np.int32)
         self.exception_params = np.zeros((0, 3)) if exception_params is None else np.ascontiguousarray(exception_params, np.float64)
         self.force_group = int(force_group)
+        self.ewald_tolerance = float(ewald_tolerance)
+        self.reciprocal_space = bool(reciprocal_space)            # NonbondedForce.setReciprocalSpaceForceGroup(-1): part of the force
+        self.dispersion_correction = bool(dispersion_correction)  # NonbondedForce.setUseDispersionCorrection (OpenMM default: on)
 
     def getForceGroup(self):
         return self.force_group
@@ -81,6 +87,7 @@ class Context:
                           skin=skin, skin_outer=skin_outer, exclusions=nonbonded.exclusions,
                           exception_pairs=nonbonded.exception_pairs, exception_params=nonbonded.exception_params)
         self._skin, self._skin_outer = skin, skin_outer
+        self._setup_reciprocal()
         self._dev = torch.device("cuda", device)
         self._posq = torch.zeros((1, self._P, 4), dtype=torch.float32, device=self._dev)
         self._corr = torch.zeros((1, self._P, 4), dtype=torch.float32, device=self._dev)
@@ -89,6 +96,13 @@ class Context:
         self._ref_prune = None
         self._energy_ext = None
         self._last = None
+
+    def _setup_reciprocal(self):
+        from .synthetic import pme_grid
+        if self._nb.reciprocal_space:
+            self._be.pme_setup(pme_grid(np.diag(self._box) if self._box.ndim == 2 else self._box, self._nb.ewald_alpha,
+                                        self._nb.ewald_tolerance), 5)
+        self._be.set_dispersion_correction(self._nb.dispersion_correction)
 
     # -- OpenMM-like surface ------------------------------------------------------------------------------------
     def setPositions(self, positions):
@@ -108,6 +122,7 @@ class Context:
         box = np.asarray(a, np.float64) if b is None else np.array([a, b, c], np.float64)
         self._box = box
         self._be.set_box(box)
+        self._setup_reciprocal()
         self._ref_rebuild = None
 
     def setParameter(self, name, value):

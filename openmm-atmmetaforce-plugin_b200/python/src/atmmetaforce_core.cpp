@@ -12,6 +12,7 @@
 #include "ATMMetaForceB200Kernel.h"
 #include "ATMMetaForceImpl.h"
 #include "ATMMetaForceProxy.h"
+#include "openmm_standin_cuda.h"
 
 namespace py = pybind11;
 using namespace ATMMetaForcePlugin;
@@ -97,7 +98,8 @@ PYBIND11_MODULE(_atmmetaforce_core, m) {
                                                 const std::vector<double> &c) { s.setDefaultPeriodicBoxVectors(vec3(a), vec3(b), vec3(c)); })
         .def("addNonbondedForce", [](OpenMM::System &s, const std::vector<double> &charge, const std::vector<double> &sigma,
                                      const std::vector<double> &epsilon, const std::vector<int> &exceptionPairs,
-                                     const std::vector<double> &exceptionParams, double cutoff, double ewaldTolerance, int group) {
+                                     const std::vector<double> &exceptionParams, double cutoff, double ewaldTolerance, int group,
+                                     int reciprocalSpaceForceGroup, bool useDispersionCorrection) {
             if (charge.size() != sigma.size() || charge.size() != epsilon.size() || exceptionPairs.size() % 2 != 0 ||
                 exceptionParams.size() / 3 != exceptionPairs.size() / 2)
                 throw OpenMM::OpenMMException("addNonbondedForce: inconsistent array lengths");
@@ -110,17 +112,65 @@ PYBIND11_MODULE(_atmmetaforce_core, m) {
             nb->setCutoffDistance(cutoff);
             nb->setEwaldErrorTolerance(ewaldTolerance);
             nb->setForceGroup(group);
+            nb->setReciprocalSpaceForceGroup(reciprocalSpaceForceGroup);
+            nb->setUseDispersionCorrection(useDispersionCorrection);
             return s.addForce(nb);
         }, py::arg("charge"), py::arg("sigma"), py::arg("epsilon"), py::arg("exceptionPairs"), py::arg("exceptionParams"),
-           py::arg("cutoff"), py::arg("ewaldTolerance") = 5e-4, py::arg("forceGroup") = 0)
+           py::arg("cutoff"), py::arg("ewaldTolerance") = 5e-4, py::arg("forceGroup") = 0, py::arg("reciprocalSpaceForceGroup") = -1,
+           py::arg("useDispersionCorrection") = true)
         .def("addATMMetaForce", [](OpenMM::System &s, const ATMMetaForce &f) {
             auto *copy = new ATMMetaForce(f);     // the System owns its forces
             s.addForce(copy);
             return copy;
         }, py::return_value_policy::reference_internal, py::arg("force"));
 
+    // ---- platforms: the kernel-less host platform is built in; "CUDA" (the stand-in of OpenMM's CUDA platform) appears
+    //      once a plugin library has been loaded / registerATMMetaForceCudaKernelFactories has run
+    m.def("loadPluginLibrary", &OpenMM::Platform::loadPluginLibrary, py::arg("file"));
+    m.def("registerCudaPlatform", []() {
+        try {
+            OpenMM::Platform::getPlatformByName("CUDA");
+        } catch (const OpenMM::OpenMMException &) {
+            OpenMM::Platform::registerPlatform(new OpenMM::CudaPlatform());
+        }
+    });
+    m.def("getPlatformNames", []() {
+        std::vector<std::string> names;
+        for (int i = 0; i < OpenMM::Platform::getNumPlatforms(); i++) names.push_back(OpenMM::Platform::getPlatform(i).getName());
+        return names;
+    });
+    m.def("platformSupportsKernels", [](const std::string &platform, const std::vector<std::string> &kernels) {
+        return OpenMM::Platform::getPlatformByName(platform).supportsKernels(kernels);
+    });
+
     py::class_<OpenMM::Context>(m, "Context")
         .def(py::init<const OpenMM::System &>(), py::keep_alive<1, 2>(), py::arg("system"))
+        .def(py::init([](const OpenMM::System &system, const std::string &platform, const std::map<std::string, std::string> &properties) {
+            return new OpenMM::Context(system, OpenMM::Platform::getPlatformByName(platform), properties);
+        }), py::keep_alive<1, 2>(), py::arg("system"), py::arg("platform"), py::arg("properties") = std::map<std::string, std::string>())
+        .def("getPlatformName", [](OpenMM::Context &c) { return c.getPlatform().getName(); })
+        .def("usesPlatformKernel", [](OpenMM::Context &c, const ATMMetaForce &f) {
+            return dynamic_cast<ATMMetaForceImpl &>(c.getForceImpl(f)).usesPlatformKernel();
+        }, py::arg("force"))
+        .def("getAtomIndex", [](OpenMM::Context &c) { return OpenMM::CudaPlatform::cudaContext(c.getImpl()).getAtomIndex(); })
+        .def("reorderAtoms", [](OpenMM::Context &c, const std::vector<int> &order) {
+            OpenMM::CudaPlatform::cudaContext(c.getImpl()).reorderAtoms(order);
+        }, py::arg("order"))
+        .def("getInnerPosq", [](OpenMM::Context &c, const ATMMetaForce &f, int state) {
+            // posq (float4 per slot) of inner context 1 or 2, or of the outer context (state 0): what copyState wrote
+            OpenMM::ContextImpl *ci = &c.getImpl();
+            if (state != 0) {
+                OpenMM::Context *inner = dynamic_cast<ATMMetaForceImpl &>(c.getForceImpl(f)).getInnerContext(state);
+                if (!inner) throw OpenMM::OpenMMException("the inner contexts do not exist yet");
+                ci = &inner->getImpl();
+            }
+            OpenMM::CudaContext &cu = OpenMM::CudaPlatform::cudaContext(*ci);
+            if (cu.getUseDoublePrecision()) throw OpenMM::OpenMMException("getInnerPosq: single / mixed precision only");
+            cu.synchronize();
+            py::array_t<float> out({(py::ssize_t)cu.getPaddedNumAtoms(), (py::ssize_t)4});
+            cu.getPosq().download(out.mutable_data());
+            return out;
+        }, py::arg("force"), py::arg("state"))
         .def("setPositions", [](OpenMM::Context &c, py::array_t<double, py::array::c_style | py::array::forcecast> pos) {
             if (pos.ndim() != 2 || pos.shape(1) != 3) throw OpenMM::OpenMMException("setPositions: expected an (N, 3) array in nm");
             std::vector<OpenMM::Vec3> v(pos.shape(0));

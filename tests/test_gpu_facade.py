@@ -21,7 +21,7 @@ def test_BindingEnergy(abfe):
     atmforcegroup, nonbonded_force_group = 2, 1
     nonbonded = atm.NonbondedDirect(abfe["charge"], abfe["sigma"], abfe["epsilon"], cutoff=1.0, ewald_tolerance=5e-4,
                                     exclusions=abfe["excl"], exception_pairs=abfe["exc14"], exception_params=abfe["exc14_par"],
-                                    force_group=nonbonded_force_group)
+                                    force_group=nonbonded_force_group, reciprocal_space=False, dispersion_correction=False)
     atmforce = atm.ATMMetaForce(lambda1, lambda2, alpha, u0, w0coeff, umsc, ubcore, acore, direction, [nonbonded_force_group])
     for i in range(n):
         atmforce.addParticle(i, 0., 0., 0.)
@@ -60,6 +60,59 @@ def test_BindingEnergy(abfe):
     context.getState(getEnergy=True)
     assert atmforce.getPerturbationEnergy(context) == 0.0
     context.close()
+
+
+def test_whole_nonbonded_force_by_default(abfe):
+    """Reference semantics by default (ref: copysystem keeps the reciprocal space in the cloned NonbondedForce,
+    openmmapi/src/ATMMetaForceImpl.cpp:60-62; OpenMM's dispersion correction is on by default): the Python Context and the
+    C++ Impl evaluate direct + reciprocal space + dispersion correction of both states without any external input, and
+    reproduce both reference pins (python/tests/test_abfe.py:147-150)."""
+    import atmmetaforce as atm
+    from atmmetaforce import _atmmetaforce_core as core
+    import oracle_bonded as B
+    kcal = 4.184
+    params = (0.5, 0.5, 0.0, 0.0, 0.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0)
+    n = abfe["pos"].shape[0]
+    g0, _ = B.group0_energy(abfe)
+
+    def make_force():
+        f = atm.ATMMetaForce(*params, [1])
+        for i in range(n):
+            f.addParticle(i, *abfe["displ"][i])
+        f.setForceGroup(2)
+        return f
+
+    nonbonded = atm.NonbondedDirect(abfe["charge"], abfe["sigma"], abfe["epsilon"], cutoff=1.0, ewald_tolerance=5e-4,
+                                    exclusions=abfe["excl"], exception_pairs=abfe["exc14"], exception_params=abfe["exc14_par"],
+                                    force_group=1)
+    fp = make_force()
+    pctx = atm.Context(fp, nonbonded, abfe["box"], precision="mixed")
+    pctx.setPositions(abfe["pos"])
+    st = pctx.getState(getEnergy=True, getForces=True)
+    assert abs(fp.getPerturbationEnergy(pctx) - 58.2) <= 0.1
+    assert abs(g0 + st.getPotentialEnergy() - float(abfe["pin_pe"])) <= 0.1
+
+    s = core.System()
+    for m in abfe["mass"]:
+        s.addParticle(float(m))
+    L = abfe["box"]
+    s.setDefaultPeriodicBoxVectors([L[0], 0, 0], [0, L[1], 0], [0, 0, L[2]])
+    exc = {(int(a), int(b)): (0.0, 0.3, 0.0) for a, b in abfe["excl"]}
+    for (a, b), p in zip(abfe["exc14"], abfe["exc14_par"]):
+        exc[(int(a), int(b))] = tuple(float(x) for x in p)
+    s.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), [x for ab in exc for x in ab],
+                        [x for ab in exc for x in exc[ab]], cutoff=1.0, ewaldTolerance=5e-4, forceGroup=1)
+    fc = s.addATMMetaForce(make_force())
+    ctx = core.Context(s)
+    ctx.setPositions(abfe["pos"])
+    e_cpp, f_cpp = ctx.calcForcesAndEnergy(True, True, 1 << 2)
+    assert abs(core.ATMMetaForce.getPerturbationEnergy(fc, ctx) - 58.2) <= 0.1
+    assert abs(g0 + e_cpp - float(abfe["pin_pe"])) <= 0.1
+    # the two contexts use different pair-list skins (0.05 / 0.1 nm): the same pairs are summed in a different order
+    from helpers import rel_rms
+    assert abs(e_cpp - st.getPotentialEnergy()) <= 1e-8 * abs(e_cpp)
+    assert rel_rms(f_cpp, st.getForces()) <= 2e-6
+    pctx.close()
 
 
 def test_kernel_object_matches_reference_seam(abfe):
@@ -132,7 +185,8 @@ def test_cpp_impl_matches_python_context_and_oracle(abfe):
     pairs = [x for ab in exc for x in ab]
     pars = [x for ab in exc for x in exc[ab]]
     s.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), pairs, pars,
-                        cutoff=1.0, ewaldTolerance=5e-4, forceGroup=nb_group)
+                        cutoff=1.0, ewaldTolerance=5e-4, forceGroup=nb_group,
+                        reciprocalSpaceForceGroup=31, useDispersionCorrection=False)   # direct space only: group 31 is not variable
     fc = s.addATMMetaForce(make_force())
     ctx = core.Context(s)
     ctx.setPairListSkins(fc, 0.1, 0.3)
@@ -144,7 +198,7 @@ def test_cpp_impl_matches_python_context_and_oracle(abfe):
     # Python Context on device buffers, same skins
     nonbonded = atm.NonbondedDirect(abfe["charge"], abfe["sigma"], abfe["epsilon"], cutoff=1.0, ewald_tolerance=5e-4,
                                     exclusions=abfe["excl"], exception_pairs=abfe["exc14"], exception_params=abfe["exc14_par"],
-                                    force_group=nb_group)
+                                    force_group=nb_group, reciprocal_space=False, dispersion_correction=False)
     fp = make_force()
     pctx = atm.Context(fp, nonbonded, abfe["box"], precision="mixed", skin=0.1, skin_outer=0.3)
     pctx.setPositions(abfe["pos"])

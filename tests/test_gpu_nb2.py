@@ -449,3 +449,88 @@ def test_config5_500k_water_box():
     assert np.abs(f.sum(0)).max() <= 1e-7 * np.abs(f).sum()
     print("500k: N %d u %.4f force rel rms %.2e |sum F|/sum|F| %.1e" % (f.shape[0], res["en"][E_U], err,
           np.abs(f.sum(0)).max() / np.abs(f).sum()))
+
+
+def test_async_rebuild_overflow_is_never_silent():
+    """A pair list that outgrows its capacity during an ASYNCHRONOUS rebuild (a droplet contracting to several times its
+    density after the verified first build sized the lists): the steps computed from the truncated lists return NaN
+    energies and NaN-poisoned forces, atm_nb_check / the next API call report ATM_ERR_STATE, and the rebuild that
+    follows reallocates, after which results match the oracle again.  A list that only comes close to its capacity
+    makes the next rebuild reallocate ahead of time without any error."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic, _capi
+    from helpers import oracle_system, rel_rms, force_from_fixed
+    s = synthetic.water_box(6000, n_lig=12, seed=11)
+    n = s["pos"].shape[0]
+    params = synthetic.atm_schedule_22()[5]
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=1)
+    P = be.P
+    be.set_displacements(s["displ"])
+    be.set_box(s["box"])
+    be.set_parameters(params)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.05, skin_outer=0.1, exclusions=s["excl"])
+    stream = torch.cuda.Stream()
+
+    def posq_of(pos):
+        q = np.zeros((1, P, 4), np.float32)
+        q[0, :n, :3] = pos
+        q[0, :n, 3] = s["charge"]
+        return torch.from_numpy(q).cuda()
+
+    posq0 = posq_of(s["pos"])
+    force = torch.zeros((1, 3 * P), dtype=torch.int64, device="cuda")
+    with torch.cuda.stream(stream):
+        be.rebuild(posq0, stream=stream)                      # first build: synchronous, verified, sizes the lists
+        be.step(posq0, force, stream=stream)
+    en0 = be.get_energies(stream=stream)[0].copy()
+    assert np.isfinite(en0[_capi.E_U1])
+    cap_before = be.nb_stats()["cap_env"]
+
+    # contract everything inside a sphere towards its centre: ~4x the partners within the list radius of a central
+    # cluster, far beyond the capacity margin of the verified first build (1.6x the mean-density expectation)
+    c = 0.5 * np.asarray(s["box"], np.float64).reshape(-1)[:3]
+    pos = s["pos"].copy()
+    d = pos - c
+    rr = np.linalg.norm(d, axis=1)
+    inside = rr < 1.5
+    pos[inside] = c + d[inside] * 0.55
+    posq1 = posq_of(pos)
+    force1 = torch.zeros_like(force)
+    with torch.cuda.stream(stream):
+        be.rebuild(posq1, stream=stream)                      # asynchronous now: truncates at least one list
+        be.step(posq1, force1, stream=stream)
+    stream.synchronize()
+    with pytest.raises(atm.ATMError, match="capacity"):
+        be.nb_check(wait=True)
+    en_raw = torch.as_tensor(_DevView(be.energies_device_ptr(), (1, _capi.NUM_ENERGY_SLOTS), "<f8"), device="cuda").cpu().numpy()[0]
+    assert np.isnan(en_raw[_capi.E_U1]) and np.isnan(en_raw[_capi.E_U]) and np.isnan(en_raw[_capi.E_ENERGY]) and np.isnan(en_raw[_capi.E_SP])
+    f_bad = force_from_fixed(force1.cpu().numpy()[0], n, P)
+    assert np.abs(f_bad).min() > 1e8                          # every atom's force is poisoned, none looks plausible
+    with pytest.raises(atm.ATMError):                         # further steps are refused until the lists are rebuilt
+        be.step(posq1, force1, stream=stream)
+
+    # cure: rebuild again (reallocates with the raised capacity, synchronous + verified), repeat the step
+    force2 = torch.zeros_like(force)
+    with torch.cuda.stream(stream):
+        be.rebuild(posq1, stream=stream)
+        be.step(posq1, force2, stream=stream)
+    en = be.get_energies(stream=stream)[0]
+    be.nb_check(wait=True)
+    assert be.nb_stats()["cap_env"] > cap_before
+    S = oracle_system(O, s, s["cutoff"], s["ewald_alpha"])
+    x1 = pos.astype(np.float32).astype(np.float64)
+    x2 = (pos.astype(np.float32) + s["displ"].astype(np.float32)).astype(np.float64)
+    e1, _, f1 = S.nb_direct(x1)
+    e2, _, f2 = S.nb_direct(x2)
+    sc = O.scalars(params, e1, e2)
+    assert abs(en[_capi.E_U1] - e1) <= 1e-6 * abs(e1)
+    f_ok = force_from_fixed(force2.cpu().numpy()[0], n, P)
+    assert rel_rms(f_ok, O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], params[8])) <= 1e-5
+    be.close()
+
+
+class _DevView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}

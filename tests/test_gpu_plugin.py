@@ -1,0 +1,175 @@
+"""The reference's own orchestration on the GPU, through the compiled plugin glue: ATMMetaForceImpl on the "CUDA"
+platform clones the NonbondedForce into two linked inner contexts, B200CalcATMMetaForceKernel (created by
+Platform::createKernel("CalcATMMetaForce") from the factory libATMMetaForcePluginCUDA.so registered) does copyState and
+the hybrid merge on the contexts' own device buffers (ref: openmmapi/src/ATMMetaForceImpl.cpp:90-128,
+platforms/common/src/CommonATMMetaForceKernels.cpp:111-226)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "openmm-atmmetaforce-plugin_b200")
+PLUGIN = os.path.join(PKG, "libATMMetaForcePluginCUDA.so")
+
+
+def test_plugin_cpp_binary_gpu():
+    exe = os.path.join(PKG, "build", "TestB200ATMMetaForcePlugin")
+    out = subprocess.run([exe, "gpu", PKG], capture_output=True, text=True)
+    assert out.returncode == 0 and "Done" in out.stdout, out.stdout + out.stderr
+
+
+def _cuda_context(core, abfe, params, nb_group, atm_group, precision="mixed"):
+    import atmmetaforce as atm
+    if "CUDA" not in core.getPlatformNames():
+        core.registerCudaPlatform()
+    core.loadPluginLibrary(PLUGIN)
+    n = abfe["pos"].shape[0]
+    f = atm.ATMMetaForce(*params, [nb_group])
+    for i in range(n):
+        f.addParticle(i, *abfe["displ"][i])
+    f.setForceGroup(atm_group)
+    s = core.System()
+    for m in abfe["mass"]:
+        s.addParticle(float(m))
+    L = abfe["box"]
+    s.setDefaultPeriodicBoxVectors([L[0], 0, 0], [0, L[1], 0], [0, 0, L[2]])
+    exc = {(int(a), int(b)): (0.0, 0.3, 0.0) for a, b in abfe["excl"]}
+    for (a, b), p in zip(abfe["exc14"], abfe["exc14_par"]):
+        exc[(int(a), int(b))] = tuple(float(x) for x in p)
+    s.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), [x for ab in exc for x in ab],
+                        [x for ab in exc for x in exc[ab]], cutoff=1.0, ewaldTolerance=5e-4, forceGroup=nb_group)
+    fc = s.addATMMetaForce(f)
+    ctx = core.Context(s, "CUDA", {"Precision": precision})
+    return s, fc, ctx
+
+
+def test_reference_orchestration_reproduces_the_pins(abfe):
+    """Both golden vectors of the reference (python/tests/test_abfe.py:147-150) through the kernel seam: the inner
+    contexts evaluate the complete NonbondedForce (direct + reciprocal space + dispersion correction) of each state."""
+    from atmmetaforce import _atmmetaforce_core as core, _capi
+    import oracle_py as O
+    import oracle_bonded as B
+    from helpers import oracle_system, rel_rms
+    kcal = 4.184
+    params = (0.5, 0.5, 0.0, 0.0, 0.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0)
+    atm_group, nb_group = 2, 1
+    s, fc, ctx = _cuda_context(core, abfe, params, nb_group, atm_group)
+    assert ctx.getPlatformName() == "CUDA" and ctx.usesPlatformKernel(fc)
+    n = abfe["pos"].shape[0]
+    ctx.setPositions(abfe["pos"])
+    e, f = ctx.calcForcesAndEnergy(True, True, 1 << atm_group)
+    u = core.ATMMetaForce.getPerturbationEnergy(fc, ctx)
+    rec = np.array(ctx.getEnergyRecord(fc))
+    assert abs(u - 58.2) <= 0.1                                              # pin 1
+    g0, _ = B.group0_energy(abfe)
+    assert abs(g0 + e - float(abfe["pin_pe"])) <= 0.1                        # pin 2: PE of groups {0, ATM}
+
+    # copyState wrote the inner coordinates bit-exactly (float add of the float-rounded displacement)
+    p0, p1, p2 = (ctx.getInnerPosq(fc, k) for k in (0, 1, 2))
+    table = O.displ_table(n, p0.shape[0], None, abfe["displ"])
+    e1, _, e2, _ = O.copy_state_f32(p0[:n], np.zeros_like(p0[:n]), table[:n])
+    assert np.array_equal(p1[:n].view(np.uint32), e1.view(np.uint32))
+    assert np.array_equal(p2[:n].view(np.uint32), e2.view(np.uint32))
+
+    # oracle: full NonbondedForce of both states at the float-rounded coordinates, merged with the Reference-platform rule
+    alpha = O.ewald_alpha(1.0)
+    grid = O.pme_grid(abfe["box"], alpha)
+    S = oracle_system(O, abfe, 1.0, alpha)
+    x1, x2 = e1[:, :3].astype(np.float64), e2[:, :3].astype(np.float64)
+    d1, _, f1 = S.nb_direct(x1)
+    d2, _, f2 = S.nb_direct(x2)
+    r1, g1 = S.pme_recip(x1, grid, 5, want_force=True)
+    r2, g2 = S.pme_recip(x2, grid, 5, want_force=True)
+    const = -138.935456 * alpha / np.sqrt(np.pi) * float((abfe["charge"] ** 2).sum()) + \
+        B.dispersion_correction(abfe["sigma"], abfe["epsilon"], 1.0, float(abfe["box"].prod()))
+    U1, U2 = d1 + r1 + const, d2 + r2 + const
+    sc = O.scalars(params, U1, U2)
+    assert abs(rec[_capi.E_U1] - U1) <= 1e-6 * abs(U1) and abs(rec[_capi.E_U2] - U2) <= 1e-6 * abs(U2)
+    assert abs(e - sc["energy"]) <= 1e-6 * abs(sc["energy"])
+    f_ref = O.merge_ref(np.zeros_like(f1), f1 + g1, f2 + g2, sc["sp_ref"], params[8])
+    assert rel_rms(f, f_ref) <= 1e-5
+
+    # the variable group evaluated directly in the OUTER context is the state-1 NonbondedForce (same kernel, same numbers)
+    e_nb, f_nb = ctx.calcForcesAndEnergy(True, True, 1 << nb_group)
+    assert abs(e_nb - rec[_capi.E_U1]) <= 1e-9 * abs(e_nb)
+    assert ctx.calcForcesAndEnergy(True, True, 1 << 5)[0] == 0.0
+
+    # OpenMM re-sorts atoms: the reorder listeners re-upload the displacement table (and the stand-in NonbondedForce its
+    # own order); every observable is unchanged and copyState stays bit-exact in the new slot order
+    perm = np.random.default_rng(3).permutation(n).astype(np.int32)
+    ctx.reorderAtoms(perm.tolist())
+    assert ctx.getAtomIndex() == perm.tolist()
+    e_b, f_b = ctx.calcForcesAndEnergy(True, True, 1 << atm_group)
+    assert abs(e_b - e) <= 1e-9 * abs(e) and np.abs(f_b - f).max() <= 1e-6
+    p0, p2 = ctx.getInnerPosq(fc, 0), ctx.getInnerPosq(fc, 2)
+    table = O.displ_table(n, p0.shape[0], perm, abfe["displ"])
+    _, _, e2b, _ = O.copy_state_f32(p0[:n], np.zeros_like(p0[:n]), table[:n])
+    assert np.array_equal(p2[:n].view(np.uint32), e2b.view(np.uint32))
+
+    # parameters are read from the context at every evaluation; direction -1 swaps the roles of the states
+    ctx.setParameter("ATMDirection", -1.0)
+    ctx.setParameter("ATMLambda1", 0.1)
+    ctx.setParameter("ATMLambda2", 0.4)
+    e_c, f_c = ctx.calcForcesAndEnergy(True, True, 1 << atm_group)
+    p_c = (0.1, 0.4) + params[2:8] + (-1.0,)
+    sc_c = O.scalars(p_c, U1, U2)
+    assert abs(e_c - sc_c["energy"]) <= 1e-6 * abs(sc_c["energy"])
+    assert abs(core.ATMMetaForce.getPerturbationEnergy(fc, ctx) - sc_c["u_sc"]) <= 5e-3
+    assert rel_rms(f_c, O.merge_ref(np.zeros_like(f1), f1 + g1, f2 + g2, sc_c["sp_ref"], -1.0)) <= 1e-5
+
+
+def test_fused_host_path_and_kernel_path_agree(abfe):
+    """Same System on the kernel-less host platform (ONE fused two-state launch + two-state PME) and on the CUDA platform
+    (two inner evaluations + kernel seam): same perturbation energy, same energy, same forces.  With the reciprocal
+    space moved to a non-variable force group the fused path leaves it out, and u changes by exactly that difference."""
+    from atmmetaforce import _atmmetaforce_core as core
+    import oracle_py as O
+    from helpers import oracle_system, rel_rms
+    kcal = 4.184
+    params = (0.5, 0.5, 0.0, 0.0, 0.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0)
+    s, fc, ctx = _cuda_context(core, abfe, params, 1, 2)
+    ctx.setPositions(abfe["pos"])
+    e_k, f_k = ctx.calcForcesAndEnergy(True, True, 1 << 2)
+    u_kernel = core.ATMMetaForce.getPerturbationEnergy(fc, ctx)
+    host = core.Context(s)
+    assert host.getPlatformName() == "HostB200" and not host.usesPlatformKernel(fc)
+    host.setPositions(abfe["pos"])
+    e_h, f_h = host.calcForcesAndEnergy(True, True, 1 << 2)
+    u_fused = core.ATMMetaForce.getPerturbationEnergy(fc, host)
+    assert abs(u_kernel - u_fused) <= 5e-3
+    assert abs(e_k - e_h) <= 1e-6 * abs(e_h)
+    assert rel_rms(f_k, f_h) <= 1e-5
+
+    import atmmetaforce as atm
+    n = abfe["pos"].shape[0]
+    s2 = core.System()
+    for m in abfe["mass"]:
+        s2.addParticle(float(m))
+    L = abfe["box"]
+    s2.setDefaultPeriodicBoxVectors([L[0], 0, 0], [0, L[1], 0], [0, 0, L[2]])
+    exc = {(int(a), int(b)): (0.0, 0.3, 0.0) for a, b in abfe["excl"]}
+    for (a, b), p in zip(abfe["exc14"], abfe["exc14_par"]):
+        exc[(int(a), int(b))] = tuple(float(x) for x in p)
+    s2.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), [x for ab in exc for x in ab],
+                         [x for ab in exc for x in exc[ab]], cutoff=1.0, ewaldTolerance=5e-4, forceGroup=1, reciprocalSpaceForceGroup=31)
+    f2 = atm.ATMMetaForce(*params, [1])
+    for i in range(n):
+        f2.addParticle(i, *abfe["displ"][i])
+    f2.setForceGroup(2)
+    fc2 = s2.addATMMetaForce(f2)
+    host2 = core.Context(s2)
+    host2.setPositions(abfe["pos"])
+    host2.calcForcesAndEnergy(True, True, 1 << 2)
+    u_direct = core.ATMMetaForce.getPerturbationEnergy(fc2, host2)
+    alpha = O.ewald_alpha(1.0)
+    S = oracle_system(O, abfe, 1.0, alpha)
+    grid = O.pme_grid(abfe["box"], alpha)
+    x1 = abfe["pos"].astype(np.float32).astype(np.float64)
+    x2 = (abfe["pos"].astype(np.float32) + abfe["displ"].astype(np.float32)).astype(np.float64)
+    r1, _ = S.pme_recip(x1, grid, 5)
+    r2, _ = S.pme_recip(x2, grid, 5)
+    assert abs((u_fused - u_direct) - (r2 - r1)) <= 5e-3
