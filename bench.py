@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--skin-outer", type=float, default=0.3)
     ap.add_argument("--host-exchange", action="store_true", help="run the replica-exchange sweep on the host (D2H copy + "
                     "synchronisation per cycle) instead of the on-device cycle")
+    ap.add_argument("--prune-mode", default="concurrent", choices=["concurrent", "before"], help="concurrent: the prune of step "
+                    "k's coordinates runs on the back-end's side stream during step k and serves steps k+1... (atm_step_io."
+                    "concurrent_prune); before: atm_nb_prune on the launching stream before the step (round 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=200, help="upper bound of the CPU-baseline sample (also capped at ~15 s)")
@@ -223,7 +226,7 @@ def workload_config(args, label, s, replicas_per_rank, exchange, use_graph, pme_
     return {"workload": label, "replicas": args.replicas, "replicas_per_rank": replicas_per_rank, "atoms": int(s["pos"].shape[0]),
             "dt_fs": DT_FS, "cutoff_nm": s["cutoff"], "skin_nm": args.skin, "skin_outer_nm": args.skin_outer,
             "prune_every": args.prune_every, "rebuild_every": args.rebuild_every, "exchange_every": args.exchange_every,
-            "exchange": exchange, "cuda_graph": use_graph, "pme_grid": pme_grid, "l2": flush_note,
+            "prune_mode": args.prune_mode, "exchange": exchange, "cuda_graph": use_graph, "pme_grid": pme_grid, "l2": flush_note,
             "jitter_nm": JITTER_NM}
 
 
@@ -389,13 +392,14 @@ def run_b200(args):
                 do_ex = (k + 1) % args.exchange_every == 0
             if ev is not None:
                 ev[0].record(stream)
+            conc = kind == "prune" and args.prune_mode == "concurrent"
             if kind == "rebuild":
                 be.rebuild(posq, stream=stream)
-            elif kind == "prune":
+            elif kind == "prune" and not conc:
                 be.prune(posq, stream=stream)
             if ev is not None:
                 ev[1].record(stream)
-            be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream)
+            be.step(posq, force, posq_corr=corr, include_energy=True, graph=use_graph, stream=stream, concurrent_prune=conc)
             if ev is not None:
                 ev[2].record(stream)
             if do_ex:
@@ -496,12 +500,20 @@ def run_b200(args):
         v = [ev[a].elapsed_time(ev[b]) for kd, ex, ev in allrec if sel(kd, ex)]
         return (sum(v) / len(v), len(v)) if v else (0.0, 0)
 
-    t_plain, n_plain = mean_ms(lambda kd, ex: True, 1, 2) if R > 0 else (0.0, 0)
+    concurrent = args.prune_mode == "concurrent"
+    # the step itself: every step, or -- with concurrent prunes, whose cost sits INSIDE the step interval -- the steps
+    # without a prune; a prune step is then charged the difference
+    t_plain, n_plain = mean_ms((lambda kd, ex: kd != "prune") if concurrent else (lambda kd, ex: True), 1, 2) if R > 0 else (0.0, 0)
     comp = {"step": {"ms": t_plain, "samples": n_plain, "per_step": 1.0}}
     steady = t_plain
     for kind_x in ("prune", "rebuild"):
-        t, c = mean_ms(lambda kd, ex, kx=kind_x: kd == kx, 0, 1)
-        comp[kind_x] = {"ms": t, "samples": c, "per_step": freq[kind_x]}
+        if kind_x == "prune" and concurrent:
+            t, c = mean_ms(lambda kd, ex: kd == "prune", 0, 2)
+            t = max(0.0, t - t_plain)
+            comp[kind_x] = {"ms": t, "samples": c, "per_step": freq[kind_x], "note": "concurrent with the step: (prune step) - (plain step)"}
+        else:
+            t, c = mean_ms(lambda kd, ex, kx=kind_x: kd == kx, 0, 1)
+            comp[kind_x] = {"ms": t, "samples": c, "per_step": freq[kind_x]}
         steady += t * freq[kind_x]
     t, c = mean_ms(lambda kd, ex: ex, 2, 3)
     comp["exchange"] = {"ms": t, "samples": c, "per_step": freq["exchange"]}
@@ -651,7 +663,8 @@ def run_b200(args):
                     flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                maint = {"rebuild": pipe.REBUILD, "prune": pipe.PRUNE, "plain": pipe.NONE}[kd]
+                maint = {"rebuild": pipe.REBUILD, "prune": pipe.PRUNE_CONCURRENT if args.prune_mode == "concurrent" else pipe.PRUNE,
+                         "plain": pipe.NONE}[kd]
                 pipe.step(pq_c, f_c, en_c, maintenance=maint, stream=stream)
                 b.record(stream)
                 if k >= WE:

@@ -213,6 +213,11 @@ typedef struct {
     int32_t include_energy;    /* also evaluate the shared (env-env) pair energies so that U1,U2,E are valid;
                                   0 = forces and u only (u, u_sc, W, sp remain exact) */
     int32_t collect_stats;     /* also count the pairs inside the cutoff (ATM_E_NPAIRS); costs a few percent */
+    int32_t concurrent_prune;  /* 1 = re-prune the inner list from THESE coordinates on the handle's side stream while
+                                  the step runs on the list in use; `stream` joins at the end of the step and the NEXT
+                                  step uses the new list (the inner skin must cover one more step than with
+                                  atm_nb_prune).  Needs a non-default stream. */
+    int32_t reserved;
 } atm_step_io;
 
 /* One pass of the hot path for all R replicas: copy-state -> two-state direct space -> device scalar
@@ -275,7 +280,8 @@ typedef struct {
 int atm_host_pipeline_create(int32_t num_handles, atm_handle *const *handles, atm_host_pipeline **out);
 int atm_host_pipeline_destroy(atm_host_pipeline *p);
 /* ios: one entry per handle, in the order given to _create.  maintenance: 0 = none, 1 = atm_nb_prune first,
- * 2 = atm_nb_rebuild first (the very first step must pass 2; that one synchronises, see atm_nb_rebuild).
+ * 2 = atm_nb_rebuild first (the very first step must pass 2; that one synchronises, see atm_nb_rebuild),
+ * 3 = re-prune CONCURRENTLY with this step (atm_step_io.concurrent_prune: the new list serves the next step).
  * Asynchronous: the host buffers hold the results once `stream` (non-default) has been synchronised. */
 int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t maintenance, void *stream);
 /* atm_nb_check(wait = 1) over every handle of the pipeline: call after synchronising a maintenance = 2 step and, on
@@ -311,6 +317,23 @@ int atm_hrex_device_setup(atm_handle *h, int32_t num_states, const double *state
 int atm_hrex_device_pack(atm_handle *h, double *send, int32_t rows, void *stream);
 int atm_hrex_device_exchange(atm_handle *h, const double *gathered, uint64_t cycle, void *stream);
 int atm_hrex_device_state(atm_handle *h, int32_t *replica_state, int64_t counters[3], void *stream);
+
+/* The communicator of the replica layer (no reference counterpart): one rank per GPU of a node,
+ * NCCL over NVLink.  NCCL is resolved at RUN time (the libnccl.so.2 the process already carries, e.g. torch's, else the
+ * system library); a build without NCCL still loads and only these entry points report ATM_ERR_UNSUPPORTED.
+ *   atm_re_unique_id      rank 0 fills 128 bytes (an ncclUniqueId) and shares them by any side channel (MPI, a file,
+ *                         torch.distributed.broadcast_object_list ...)
+ *   atm_re_comm_create    every rank, collectively: ncclCommInitRank.  world == 1 needs neither id nor NCCL.
+ *   atm_re_comm_from_nccl borrows an ncclComm_t the host created itself (not destroyed by _destroy)
+ *   atm_hrex_device_cycle one whole exchange cycle on `stream`: pack kernel -> ncclAllGather of 2 doubles per replica
+ *                         slot -> sweep kernel (new lambda states, parameter rows rewritten in place).  No host
+ *                         synchronisation; capturable into a CUDA graph; every rank must call it with the same cycle. */
+typedef struct atm_re_comm atm_re_comm;
+int atm_re_unique_id(void *id128);
+int atm_re_comm_create(const void *id128, int32_t world, int32_t rank, int32_t device, atm_re_comm **out);
+int atm_re_comm_from_nccl(void *nccl_comm, int32_t rank, atm_re_comm **out);
+int atm_re_comm_destroy(atm_re_comm *c);
+int atm_hrex_device_cycle(atm_handle *h, atm_re_comm *comm, uint64_t cycle, void *stream);
 
 /* Reduced energy beta*E_s(x) of coordinates with energies (U1,U2) under state parameters p (host). */
 double atm_hrex_reduced_energy(const double p[ATM_NUM_PARAMS], double U1, double U2, double beta);

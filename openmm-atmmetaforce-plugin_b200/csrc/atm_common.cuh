@@ -123,6 +123,8 @@ void hrex_destroy(atm_handle *h);
 int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *needs_sync_rebuild);
 int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream);
 int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream);
+int nb_host_inner_copy(const atm_handle *h);     // which copy of the pruned list is in use (0 / 1)
+void nb_host_flip_inner(atm_handle *h);          // after a maintenance = 3 step has been enqueued / replayed
 uint64_t nb_alloc_generation(const atm_handle *h);
 const double *nb_energies_device(const atm_handle *h);
 

@@ -34,13 +34,14 @@ struct atm_host_pipeline {
     int device = 0;
     std::vector<Chunk> chunks;
     cudaEvent_t fork = nullptr;
-    cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};   // maintenance 0 / 1 / 2
-    std::vector<uint64_t> exec_launches_chunk[3];            // own kernels per replay, per chunk
+    // maintenance 0 / 1 / 2 / 3 (3 = concurrent prune), times the copy of the pruned list the chunks read (0 / 1)
+    cudaGraphExec_t exec[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<uint64_t> exec_launches_chunk[8];            // own kernels per replay, per chunk
     std::vector<atm_host_io> ios;                            // the buffers the cached graphs were captured with
 };
 
 static void drop_graphs(atm_host_pipeline *p) {
-    for (int v = 0; v < 3; v++)
+    for (int v = 0; v < 8; v++)
         if (p->exec[v]) { cudaGraphExecDestroy(p->exec[v]); p->exec[v] = nullptr; }
 }
 
@@ -170,7 +171,8 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
     ATM_NVTX_RANGE("atm_host_pipeline_step");
     cudaStream_t stream = (cudaStream_t)stream_;
     ATM_REQUIRE(p && ios, ATM_ERR_INVALID, "atm_host_pipeline_step: null argument");
-    ATM_REQUIRE(maintenance >= 0 && maintenance <= 2, ATM_ERR_INVALID, "atm_host_pipeline_step: maintenance must be 0 (none), 1 (prune) or 2 (rebuild)");
+    ATM_REQUIRE(maintenance >= 0 && maintenance <= 3, ATM_ERR_INVALID,
+                "atm_host_pipeline_step: maintenance must be 0 (none), 1 (prune), 2 (rebuild) or 3 (prune concurrently with the step)");
     ATM_REQUIRE(stream != nullptr, ATM_ERR_INVALID, "atm_host_pipeline_step: needs a non-default stream (it is captured)");
     const size_t nc = p->chunks.size();
     for (size_t c = 0; c < nc; c++)
@@ -199,13 +201,18 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
         p->ios.assign(ios, ios + nc);
         for (size_t c = 0; c < nc; c++) p->chunks[c].generation = nb_alloc_generation(p->chunks[c].h);
     }
-    const int v = maintenance;
+    const int copy = nb_host_inner_copy(p->chunks[0].h);
+    for (size_t c = 1; c < nc; c++)
+        ATM_REQUIRE(nb_host_inner_copy(p->chunks[c].h) == copy || maintenance == 2, ATM_ERR_STATE,
+                    "atm_host_pipeline_step: the handles of a pipeline must be stepped together (pruned-list copies differ)");
+    const int m = maintenance;
+    const int v = 2 * maintenance + (maintenance == 2 ? 0 : copy);   // a rebuild always writes copy 0
     if (!p->exec[v]) {
         std::vector<uint64_t> before(nc);
         for (size_t c = 0; c < nc; c++) before[c] = p->chunks[c].h->launches;
         cudaGraph_t graph = nullptr;
         ATM_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_all(p, ios, v, stream);
+        rc = enqueue_all(p, ios, m, stream);
         cudaError_t err = cudaStreamEndCapture(stream, &graph);
         p->exec_launches_chunk[v].assign(nc, 0);
         for (size_t c = 0; c < nc; c++) {
@@ -222,7 +229,8 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
     ATM_CUDA_CHECK(cudaGraphLaunch(p->exec[v], stream));
     for (size_t c = 0; c < nc; c++) {
         p->chunks[c].h->launches += p->exec_launches_chunk[v][c];
-        if (v == 2 && (rc = nb_host_rebuild_enqueued(p->chunks[c].h, stream))) return rc;
+        if (m == 2 && (rc = nb_host_rebuild_enqueued(p->chunks[c].h, stream))) return rc;
+        if (m == 3) nb_host_flip_inner(p->chunks[c].h);
     }
     return ATM_OK;
 }

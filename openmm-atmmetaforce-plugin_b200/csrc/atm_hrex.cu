@@ -14,6 +14,7 @@
 // The host reads the bookkeeping (state permutation, acceptance count) only when it asks for it.
 // The sweep is the same function the host entry point atm_hrex_sweep runs (atm_capi.cu); tests compare the two.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstring>
@@ -32,7 +33,47 @@ struct HrexState {
     int *d_gather_slot = nullptr;    // [num_replicas] row of replica g in the gathered array
     int *d_local_global = nullptr;   // [R] global replica id of local replica k, -1 = unused slot
     long long *d_counters = nullptr; // accepted swaps, cycles, error flag (non-finite energy)
+    double *d_send = nullptr;        // [rows_per_rank][2] (atm_hrex_device_cycle)
+    double *d_gathered = nullptr;    // [gathered_rows][2]
 };
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time: the library has no link-time dependency on it.  A process that already carries a
+// libnccl.so.2 (e.g. through torch) keeps using THAT instance; otherwise the system library is loaded.  Only the five
+// entry points below are used; their signatures are NCCL's public C API (nccl.h), with ncclComm_t / ncclUniqueId
+// treated as an opaque pointer / 128 opaque bytes.
+// ------------------------------------------------------------------------------------------------
+struct NcclId128 { char b[128]; };   // ncclUniqueId is passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *id) = nullptr;
+    int (*CommInitRank)(void **comm, int nranks, NcclId128 id, int rank) = nullptr;
+    int (*CommDestroy)(void *comm) = nullptr;
+    int (*CommCount)(void *comm, int *count) = nullptr;
+    int (*AllGather)(const void *send, void *recv, size_t count, int dtype, void *comm, cudaStream_t stream) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi &nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the instance the process already uses, if any
+        if (!a.lib) a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) return a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+        a.CommCount = reinterpret_cast<decltype(a.CommCount)>(dlsym(a.lib, "ncclCommCount"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.lib, "ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.CommCount && a.AllGather && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble / ncclFloat64 in nccl.h
 
 __host__ __device__ inline uint64_t hrex_splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -109,6 +150,7 @@ void hrex_destroy(atm_handle *h) {
     if (!x) return;
     cudaFree(x->d_schedule); cudaFree(x->d_replica_state); cudaFree(x->d_gather_slot); cudaFree(x->d_local_global);
     cudaFree(x->d_counters);
+    cudaFree(x->d_send); cudaFree(x->d_gathered);
     delete x;
     h->hrex = nullptr;
 }
@@ -144,6 +186,9 @@ int atm_hrex_device_setup(atm_handle *h, int32_t num_states, const double *state
     ATM_CUDA_CHECK(cudaMalloc(&x->d_gather_slot, sizeof(int) * num_replicas));
     ATM_CUDA_CHECK(cudaMalloc(&x->d_local_global, sizeof(int) * h->R));
     ATM_CUDA_CHECK(cudaMalloc(&x->d_counters, sizeof(long long) * 4));
+    ATM_CUDA_CHECK(cudaMalloc(&x->d_send, sizeof(double) * 2 * gathered_rows));
+    ATM_CUDA_CHECK(cudaMalloc(&x->d_gathered, sizeof(double) * 2 * gathered_rows));
+    ATM_CUDA_CHECK(cudaMemsetAsync(x->d_send, 0, sizeof(double) * 2 * gathered_rows, stream));
     ATM_CUDA_CHECK(cudaMemcpyAsync(x->d_schedule, state_params, sizeof(double) * num_states * ATM_NUM_PARAMS, cudaMemcpyHostToDevice, stream));
     ATM_CUDA_CHECK(cudaMemcpyAsync(x->d_replica_state, replica_state, sizeof(int) * num_replicas, cudaMemcpyHostToDevice, stream));
     ATM_CUDA_CHECK(cudaMemcpyAsync(x->d_gather_slot, gather_slot, sizeof(int) * num_replicas, cudaMemcpyHostToDevice, stream));
@@ -183,6 +228,94 @@ int atm_hrex_device_exchange(atm_handle *h, const double *gathered, uint64_t cyc
     h->params_device_newer = true;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
+}
+
+// ---- the communicator of the replica layer and the whole cycle in one call
+}  // extern "C"
+
+struct atm_re_comm {
+    void *comm = nullptr;   // ncclComm_t
+    int world = 1, rank = 0;
+    bool owned = false;
+};
+
+extern "C" {
+
+int atm_re_unique_id(void *id128) {
+    ATM_REQUIRE(id128, ATM_ERR_INVALID, "atm_re_unique_id: null argument");
+    NcclApi &n = nccl();
+    ATM_REQUIRE(n.ok, ATM_ERR_UNSUPPORTED, "atm_re_unique_id: no usable libnccl.so.2 in this process or on the library path");
+    const int rc = n.GetUniqueId(id128);
+    ATM_REQUIRE(rc == 0, ATM_ERR_CUDA, "ncclGetUniqueId: %s", n.GetErrorString(rc));
+    return ATM_OK;
+}
+
+int atm_re_comm_create(const void *id128, int32_t world, int32_t rank, int32_t device, atm_re_comm **out) {
+    ATM_REQUIRE(out, ATM_ERR_INVALID, "atm_re_comm_create: null argument");
+    *out = nullptr;
+    ATM_REQUIRE(world >= 1 && rank >= 0 && rank < world, ATM_ERR_INVALID, "atm_re_comm_create: bad rank %d of %d", rank, world);
+    atm_re_comm *c = new atm_re_comm();
+    c->world = world;
+    c->rank = rank;
+    if (world > 1) {
+        ATM_REQUIRE(id128, ATM_ERR_INVALID, "atm_re_comm_create: a unique id is needed for more than one rank");
+        NcclApi &n = nccl();
+        if (!n.ok) { delete c; set_error("atm_re_comm_create: no usable libnccl.so.2 in this process or on the library path"); return ATM_ERR_UNSUPPORTED; }
+        if (device >= 0) ATM_CUDA_CHECK(cudaSetDevice(device));
+        NcclId128 id;
+        memcpy(id.b, id128, sizeof(id.b));
+        const int rc = n.CommInitRank(&c->comm, world, id, rank);
+        if (rc != 0) { delete c; set_error("ncclCommInitRank: %s", n.GetErrorString(rc)); return ATM_ERR_CUDA; }
+        c->owned = true;
+    }
+    *out = c;
+    return ATM_OK;
+}
+
+int atm_re_comm_from_nccl(void *nccl_comm, int32_t rank, atm_re_comm **out) {
+    ATM_REQUIRE(out && nccl_comm, ATM_ERR_INVALID, "atm_re_comm_from_nccl: null argument");
+    NcclApi &n = nccl();
+    ATM_REQUIRE(n.ok, ATM_ERR_UNSUPPORTED, "atm_re_comm_from_nccl: no usable libnccl.so.2");
+    int count = 0;
+    const int rc = n.CommCount(nccl_comm, &count);
+    ATM_REQUIRE(rc == 0, ATM_ERR_CUDA, "ncclCommCount: %s", n.GetErrorString(rc));
+    atm_re_comm *c = new atm_re_comm();
+    c->comm = nccl_comm;
+    c->world = count;
+    c->rank = rank;
+    *out = c;
+    return ATM_OK;
+}
+
+int atm_re_comm_destroy(atm_re_comm *c) {
+    if (!c) return ATM_OK;
+    if (c->owned && c->comm) nccl().CommDestroy(c->comm);
+    delete c;
+    return ATM_OK;
+}
+
+// pack -> all-gather over NVLink -> sweep, all on `stream`, no host synchronisation, capturable into a CUDA graph.
+// comm == NULL or a one-rank communicator: the local rows are the gathered rows.
+int atm_hrex_device_cycle(atm_handle *h, atm_re_comm *comm, uint64_t cycle, void *stream_) {
+    ATM_NVTX_RANGE("atm_hrex_device_cycle");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ATM_REQUIRE(h && h->hrex, ATM_ERR_STATE, "atm_hrex_device_cycle: call atm_hrex_device_setup first");
+    HrexState *x = (HrexState *)h->hrex;
+    const int world = comm ? comm->world : 1;
+    ATM_REQUIRE(x->gathered_rows % world == 0, ATM_ERR_INVALID, "atm_hrex_device_cycle: %d gathered rows do not divide over %d ranks",
+                x->gathered_rows, world);
+    const int rows = x->gathered_rows / world;
+    int rc;
+    if ((rc = atm_hrex_device_pack(h, x->d_send, rows, stream))) return rc;
+    const double *gathered = x->d_send;
+    if (world > 1) {
+        NcclApi &n = nccl();
+        ATM_REQUIRE(n.ok && comm->comm, ATM_ERR_STATE, "atm_hrex_device_cycle: the communicator has no NCCL handle");
+        const int nrc = n.AllGather(x->d_send, x->d_gathered, (size_t)2 * rows, NCCL_FLOAT64, comm->comm, stream);
+        ATM_REQUIRE(nrc == 0, ATM_ERR_CUDA, "ncclAllGather: %s", n.GetErrorString(nrc));
+        gathered = x->d_gathered;
+    }
+    return atm_hrex_device_exchange(h, gathered, cycle, stream);
 }
 
 int atm_hrex_device_state(atm_handle *h, int32_t *replica_state, int64_t counters[3], void *stream_) {

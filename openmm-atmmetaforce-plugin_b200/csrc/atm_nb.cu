@@ -119,7 +119,12 @@ static int dev_upload(NbState *nb, T **ptr, const std::vector<T> &v, cudaStream_
 
 void nb_destroy(atm_handle *h) {
     if (!h->nb) return;
-    if (h->nb->graph_exec) cudaGraphExecDestroy(h->nb->graph_exec);
+    for (StepGraph &g : h->nb->step_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->nb->prune_graph_alt) cudaGraphExecDestroy(h->nb->prune_graph_alt);
+    if (h->nb->side_stream) { cudaStreamSynchronize(h->nb->side_stream); cudaStreamDestroy(h->nb->side_stream); }
+    if (h->nb->ev_fork) cudaEventDestroy(h->nb->ev_fork);
+    if (h->nb->ev_join) cudaEventDestroy(h->nb->ev_join);
     if (h->nb->rebuild_graph) cudaGraphExecDestroy(h->nb->rebuild_graph);
     if (h->nb->prune_graph) cudaGraphExecDestroy(h->nb->prune_graph);
     for (void *p : h->nb->pme_owned) cudaFree(p);
@@ -167,6 +172,13 @@ static int derive_groups(atm_handle *h) {
 
 static int nb_allocate(atm_handle *h, cudaStream_t stream);
 
+static void use_inner(NbDev &d, const InnerBuf &b) {
+    d.jlist = b.jlist;
+    d.list_nsteps = b.list_nsteps;
+    d.items = b.items;
+    d.iflags = b.iflags;
+}
+
 int nb_on_displacements_changed(atm_handle *h, cudaStream_t stream) {
     if (!h->nb || !h->nb->ready) return ATM_OK;
     // the site layout depends on the displacement groups and on the slot order: reallocate and require a rebuild
@@ -189,7 +201,7 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     nb->flags_pending = false;
     nb->grow_pending = false;
     nb->overflowed = false;
-    if (!nb->h_flags) ATM_CUDA_CHECK(cudaMallocHost(&nb->h_flags, sizeof(int) * NUM_HOST_FLAGS));
+    if (!nb->h_flags) ATM_CUDA_CHECK(cudaMallocHost(&nb->h_flags, sizeof(int) * (NUM_HOST_FLAGS + 8)));
     if (!nb->flags_event) ATM_CUDA_CHECK(cudaEventCreateWithFlags(&nb->flags_event, cudaEventDisableTiming));
     free_owned(nb);
     int rc = derive_groups(h);
@@ -283,16 +295,34 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     if ((rc = dev_alloc(nb, &d.cmeta, RC))) return rc;
     const size_t per_replica = (size_t)d.CenvMax * d.capC + (size_t)d.CXmax * d.capX + (size_t)d.CLmax * d.capC;
     nb->jlist_entries = per_replica * R;
-    if ((rc = dev_alloc(nb, &d.jlist, nb->jlist_entries))) return rc;
     if ((rc = dev_alloc(nb, &d.jlist_outer, nb->jlist_entries))) return rc;
     if ((rc = dev_alloc(nb, &d.outer_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
-    if ((rc = dev_alloc(nb, &d.list_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
     {
         const int chunksC = (d.capC / 32 + ITEM_STEPS - 1) / ITEM_STEPS, chunksX = (d.capX / 32 + ITEM_STEPS - 1) / ITEM_STEPS;
         nb->max_items = R * (d.CenvMax * chunksC + d.CXmax * chunksX + d.CLmax * chunksC);
         d.max_items = nb->max_items;
-        if ((rc = dev_alloc(nb, &d.items, (size_t)nb->max_items * (ITEM_STEPS + 1)))) return rc;
         nb->n_items = 0;
+    }
+    for (InnerBuf &b : nb->inner) {   // two copies of the pruned list (concurrent prune)
+        if ((rc = dev_alloc(nb, &b.jlist, nb->jlist_entries))) return rc;
+        if ((rc = dev_alloc(nb, &b.list_nsteps, (size_t)R * (d.Cmax + d.CLmax)))) return rc;
+        if ((rc = dev_alloc(nb, &b.items, (size_t)nb->max_items * (ITEM_STEPS + 1)))) return rc;
+        if ((rc = dev_alloc(nb, &b.iflags, NUM_FLAGS))) return rc;
+        ATM_CUDA_CHECK(cudaMemsetAsync(b.iflags, 0, sizeof(int) * NUM_FLAGS, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(b.list_nsteps, 0, (size_t)R * (d.Cmax + d.CLmax) * sizeof(int), stream));
+    }
+    nb->cur = 0;
+    use_inner(d, nb->inner[0]);
+    if ((rc = dev_alloc(nb, &nb->xs_side, RS))) return rc;
+    if (!nb->side_stream) {
+        // ATM_B200_SIDE_PRIORITY=1: the side stream gets the highest priority, so that the prune's blocks are placed
+        // ahead of the force kernel's pending ones instead of filling its tail (experiment switch)
+        static const bool high = [] { const char *e = getenv("ATM_B200_SIDE_PRIORITY"); return e && e[0] == '1'; }();
+        int least = 0, greatest = 0;
+        ATM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        ATM_CUDA_CHECK(cudaStreamCreateWithPriority(&nb->side_stream, cudaStreamNonBlocking, high ? greatest : least));
+        ATM_CUDA_CHECK(cudaEventCreateWithFlags(&nb->ev_fork, cudaEventDisableTiming));
+        ATM_CUDA_CHECK(cudaEventCreateWithFlags(&nb->ev_join, cudaEventDisableTiming));
     }
     if ((rc = dev_alloc(nb, &d.flags, NUM_FLAGS))) return rc;
     ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * NUM_FLAGS, stream));
@@ -302,7 +332,6 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     ATM_CUDA_CHECK(cudaMemsetAsync(d.buf, 0, 9 * RS * sizeof(unsigned long long), stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.eacc, 0, (size_t)R * EACC_SLOTS * sizeof(unsigned long long), stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.energies, 0, (size_t)R * ATM_NUM_ENERGY_SLOTS * sizeof(double), stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.list_nsteps, 0, (size_t)R * (d.Cmax + d.CLmax) * sizeof(int), stream));
 
     // radix sort scratch
     int key_bits = 16;
@@ -333,16 +362,13 @@ static int upload_box_if_dirty(atm_handle *h, cudaStream_t stream) {
     return ATM_OK;
 }
 
-// pack must have run on the current coordinates; optionally refresh the cluster boxes/centres first
-static int launch_prune(atm_handle *h, cudaStream_t stream, bool refresh_boxes) {
-    NbState *nb = h->nb;
-    NbDev &d = nb->d;
-    const int nlists = d.Cmax + d.CLmax;
-    if (refresh_boxes) nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 4, 0, sizeof(int), stream));      // live item count
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.flags + 6, 0, sizeof(int) * (NUM_FLAGS - 6), stream));  // pruned-entry counter [6,7], item buckets
-    nl_prune_kernel<<<dim3((nlists + PRUNE_WARPS - 1) / PRUNE_WARPS, d.R), 32 * PRUNE_WARPS, 0, stream>>>(d);
-    h->launches += (refresh_boxes ? 1 : 0) + 1;
+// Prunes the outer list at the cluster-order coordinates dv.xs into the inner-list copy dv points at.  The cluster
+// centres stay those of the last rebuild (they are only the origin of the minimum-image shifts, see nl_bbox_kernel).
+static int launch_prune(atm_handle *h, cudaStream_t stream, const NbDev &dv) {
+    const int nlists = dv.Cmax + dv.CLmax;
+    ATM_CUDA_CHECK(cudaMemsetAsync(dv.iflags, 0, sizeof(int) * NUM_FLAGS, stream));   // live items, kept entries, item buckets
+    nl_prune_kernel<<<dim3((nlists + PRUNE_WARPS - 1) / PRUNE_WARPS, dv.R), 32 * PRUNE_WARPS, 0, stream>>>(dv);
+    h->launches += 1;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
 }
@@ -357,9 +383,9 @@ static int check_pending_rebuild(atm_handle *h, bool wait);
 
 static int launch_prune_all(atm_handle *h, const void *posq, cudaStream_t stream) {
     NbDev &d = h->nb->d;
-    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)posq);
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)posq, 1);
     h->launches++;
-    return launch_prune(h, stream, /*refresh_boxes=*/true);
+    return launch_prune(h, stream, d);
 }
 
 int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
@@ -374,8 +400,14 @@ int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
     NbState *nb = h->nb;
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
     if (stream == nullptr) return launch_prune_all(h, posq, stream);
-    if (!nb->prune_graph || nb->prune_graph_posq != posq || nb->prune_graph_generation != nb->alloc_generation) {
+    if (nb->prune_graph_posq != posq || nb->prune_graph_generation != nb->alloc_generation) {   // both cached graphs are stale
         if (nb->prune_graph) { cudaGraphExecDestroy(nb->prune_graph); nb->prune_graph = nullptr; }
+        if (nb->prune_graph_alt) { cudaGraphExecDestroy(nb->prune_graph_alt); nb->prune_graph_alt = nullptr; }
+        nb->prune_graph_posq = posq;
+        nb->prune_graph_generation = nb->alloc_generation;
+    }
+    cudaGraphExec_t &pg = nb->cur == 0 ? nb->prune_graph : nb->prune_graph_alt;   // the graph that prunes into the copy in use
+    if (!pg) {
         cudaGraph_t graph = nullptr;
         const uint64_t before = h->launches;
         if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -383,18 +415,15 @@ int atm_nb_prune(atm_handle *h, const void *posq, void *stream_) {
             cudaError_t err = cudaStreamEndCapture(stream, &graph);
             nb->prune_graph_launches = (int)(h->launches - before);
             h->launches = before;
-            if (rc == ATM_OK && err == cudaSuccess && graph && cudaGraphInstantiate(&nb->prune_graph, graph, 0) == cudaSuccess) {
-                nb->prune_graph_posq = posq;
-                nb->prune_graph_generation = nb->alloc_generation;
-            } else {
-                nb->prune_graph = nullptr;
+            if (!(rc == ATM_OK && err == cudaSuccess && graph && cudaGraphInstantiate(&pg, graph, 0) == cudaSuccess)) {
+                pg = nullptr;
                 cudaGetLastError();
             }
             if (graph) cudaGraphDestroy(graph);
         }
     }
-    if (nb->prune_graph) {
-        ATM_CUDA_CHECK(cudaGraphLaunch(nb->prune_graph, stream));
+    if (pg) {
+        ATM_CUDA_CHECK(cudaGraphLaunch(pg, stream));
         h->launches += nb->prune_graph_launches;
         return ATM_OK;
     }
@@ -522,6 +551,8 @@ static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream
     NbDev &d = nb->d;
     int rc;
     const int RU = d.R * d.U;
+    nb->cur = 0;   // a rebuild always leaves the pruned list in copy 0 (its cached graph holds that copy's pointers)
+    use_inner(d, nb->inner[0]);
     ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
     ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
@@ -534,12 +565,12 @@ static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream
     cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
     nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
     if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
-    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq);
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq, 1);
     nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
     const int nlists = d.Cmax + d.CLmax;
     nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
     h->launches += 6 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox, build
-    if ((rc = launch_prune(h, stream, /*refresh_boxes=*/false))) return rc;
+    if ((rc = launch_prune(h, stream, d))) return rc;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
 }
@@ -567,9 +598,9 @@ static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
         if (flags[FLAG_MAXLEN_X] > (int)(0.8 * d.capX)) { nb->grow_capX = 32 * ((int)(flags[FLAG_MAXLEN_X] * 1.5) / 32 + 1); nb->grow_pending = true; }
     }
     unsigned long long inner_entries = 0;
-    memcpy(&inner_entries, &flags[6], 8);
+    memcpy(&inner_entries, &flags[NUM_HOST_FLAGS + 6], 8);   // the inner-list counters travel behind the rebuild flags
     nb->stats[2] = (int64_t)(inner_entries / d.R);
-    nb->items_seen = flags[4];
+    nb->items_seen = flags[NUM_HOST_FLAGS + 4];
     return ATM_OK;
 }
 
@@ -653,10 +684,13 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         if (nb->rebuild_graph) {
             ATM_CUDA_CHECK(cudaGraphLaunch(nb->rebuild_graph, stream));
             h->launches += nb->rebuild_graph_launches;
+            nb->cur = 0;   // what launch_rebuild did when the graph was captured: the pruned list is in copy 0
+            use_inner(nb->d, nb->inner[0]);
         } else if ((rc = launch_rebuild(h, posq, stream))) {
             return rc;
         }
         ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * NUM_HOST_FLAGS, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags + NUM_HOST_FLAGS, nb->d.iflags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
         ATM_CUDA_CHECK(cudaEventRecord(nb->flags_event, stream));
         nb->flags_pending = true;
         nb->list_valid = true;
@@ -664,14 +698,20 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         return ATM_OK;
     }
     // first build after (re)allocation: synchronous, verified, grows the capacities until everything fits
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0; attempt < 6; attempt++) {
         NbDev &d = nb->d;
         if ((rc = launch_rebuild(h, posq, stream))) return rc;
-        int flags[NUM_HOST_FLAGS];
-        ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+        int flags[NUM_HOST_FLAGS + 8];
+        ATM_CUDA_CHECK(cudaMemcpyAsync(flags, d.flags, sizeof(int) * NUM_HOST_FLAGS, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaMemcpyAsync(flags + NUM_HOST_FLAGS, d.iflags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
         ATM_CUDA_CHECK(cudaStreamSynchronize(stream));
         bool grow = false;
         if ((rc = inspect_rebuild_flags(h, flags, &grow))) return rc;
+        if (nb->grow_pending) {   // the head-room rule applies to the verified build as well: steady state starts with margin
+            d.capC = std::max(d.capC, nb->grow_capC);
+            d.capX = std::max(d.capX, nb->grow_capX);
+            grow = true;
+        }
         if (grow) {
             if ((rc = nb_allocate(h, stream))) return rc;
             if ((rc = upload_box_if_dirty(h, stream))) return rc;
@@ -689,7 +729,7 @@ int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {
         nb->generation++;
         return ATM_OK;
     }
-    set_error("atm_nb_rebuild: neighbour list capacity could not be satisfied after 4 attempts");
+    set_error("atm_nb_rebuild: neighbour list capacity could not be satisfied after 6 attempts");
     return ATM_ERR_NOMEM;
 }
 
@@ -702,7 +742,21 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         if ((rc = launch_copy_state(h, io->posq, io->posq_corr, io->posq1, io->posq1_corr, io->posq2, io->posq2_corr, stream))) return rc;
         h->launches++;
     }
-    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq);
+    if (io->concurrent_prune) {
+        // Re-prune from THESE coordinates on the side stream while the step runs on the copy in use: its own pack into
+        // xs_side, then the prune into the other copy.  The caller's stream joins at the end of the step (the side
+        // stream reads posq), and the next step switches copies (flip_inner, called by the entry points per launch).
+        NbDev ds = d;
+        ds.xs = nb->xs_side;
+        use_inner(ds, nb->inner[nb->cur ^ 1]);
+        ATM_CUDA_CHECK(cudaEventRecord(nb->ev_fork, stream));
+        ATM_CUDA_CHECK(cudaStreamWaitEvent(nb->side_stream, nb->ev_fork, 0));
+        nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, nb->side_stream>>>(ds, (const float4 *)io->posq, 0);
+        h->launches++;
+        if ((rc = launch_prune(h, nb->side_stream, ds))) return rc;
+        ATM_CUDA_CHECK(cudaEventRecord(nb->ev_join, nb->side_stream));
+    }
+    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, (const float4 *)io->posq, 1);
     const int warps_per_block = NB_THREADS / 32;
     int item_blocks = (nb->n_items + warps_per_block - 1) / warps_per_block;
     {   // ATM_B200_NB2_WAVES=k: cap the grid at k resident waves and let the grid-stride loop do the rest (experiment)
@@ -755,8 +809,15 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
                                     !profile && !d.pme_on && nblocks > 0, d, (long long *)io->force, (const long long *)io->force_state1_ext,
                                     (const long long *)io->force_state2_ext, io->energy_ext, (int)io->include_energy));
     h->launches += 2;  // pack, merge
+    if (io->concurrent_prune) ATM_CUDA_CHECK(cudaStreamWaitEvent(stream, nb->ev_join, 0));
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
+}
+
+// after a step with a concurrent prune has been ENQUEUED (or its graph replayed): later work uses the other copy
+static void flip_inner(NbState *nb) {
+    nb->cur ^= 1;
+    use_inner(nb->d, nb->inner[nb->cur]);
 }
 
 static int validate_step(atm_handle *h, const atm_step_io *io, const char *who) {
@@ -781,7 +842,10 @@ int atm_step(atm_handle *h, const atm_step_io *io, void *stream_) {
     ATM_CUDA_CHECK(cudaSetDevice(h->device));
     if ((rc = upload_params_if_dirty(h, stream))) return rc;
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
-    return launch_step(h, io, stream, h->nb->profiling);
+    ATM_REQUIRE(!(io->concurrent_prune && stream == nullptr), ATM_ERR_INVALID, "atm_step: a concurrent prune needs a non-default stream");
+    if ((rc = launch_step(h, io, stream, h->nb->profiling))) return rc;
+    if (io->concurrent_prune) flip_inner(h->nb);
+    return ATM_OK;
 }
 
 // Same step, replayed from a cached CUDA graph (one driver call per step instead of 5-6 launches).  The graph is
@@ -798,26 +862,44 @@ int atm_step_graph(atm_handle *h, const atm_step_io *io, void *stream_) {
     NbState *nb = h->nb;
     if ((rc = upload_params_if_dirty(h, stream))) return rc;
     if ((rc = upload_box_if_dirty(h, stream))) return rc;
-    const bool same = nb->graph_exec && memcmp(&nb->graph_io, io, sizeof(*io)) == 0 && nb->graph_generation == nb->alloc_generation;
-    if (!same) {
-        if (nb->graph_exec) { cudaGraphExecDestroy(nb->graph_exec); nb->graph_exec = nullptr; }
+    // cached graphs: one per (io block, inner-list copy in use); all of them die with the allocation they were captured on
+    if (!nb->step_graphs.empty() && nb->step_graphs[0].generation != nb->alloc_generation) {
+        for (StepGraph &g : nb->step_graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        nb->step_graphs.clear();
+    }
+    StepGraph *sg = nullptr;
+    for (StepGraph &g : nb->step_graphs)
+        if (g.cur == nb->cur && memcmp(&g.io, io, sizeof(*io)) == 0) sg = &g;
+    if (!sg) {
+        if (nb->step_graphs.size() >= 16) {   // a caller cycling through many buffers: start over
+            for (StepGraph &g : nb->step_graphs)
+                if (g.exec) cudaGraphExecDestroy(g.exec);
+            nb->step_graphs.clear();
+        }
         cudaGraph_t graph = nullptr;
         const uint64_t launches_before = h->launches;
         ATM_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         rc = launch_step(h, io, stream, false);
         cudaError_t err = cudaStreamEndCapture(stream, &graph);
+        const int nodes = (int)(h->launches - launches_before);
         h->launches = launches_before;
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         ATM_REQUIRE(err == cudaSuccess && graph, ATM_ERR_CUDA, "atm_step_graph: capture failed: %s", cudaGetErrorString(err));
-        err = cudaGraphInstantiate(&nb->graph_exec, graph, 0);
+        StepGraph g;
+        err = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         ATM_REQUIRE(err == cudaSuccess, ATM_ERR_CUDA, "atm_step_graph: instantiate failed: %s", cudaGetErrorString(err));
-        nb->graph_io = *io;
-        nb->graph_generation = nb->alloc_generation;
-        nb->graph_nodes = 3 + (io->posq1 ? 1 : 0) + (nb->d.pme_on ? 4 : 0);  // pack, nb2 (+special pairs), [PME x4], scalar stage + merge
+        g.io = *io;
+        g.cur = nb->cur;
+        g.generation = nb->alloc_generation;
+        g.nodes = nodes;   // own kernels of one replay: [copy-state], [side pack, prune], pack, nb2, [PME x4], merge
+        nb->step_graphs.push_back(g);
+        sg = &nb->step_graphs.back();
     }
-    ATM_CUDA_CHECK(cudaGraphLaunch(nb->graph_exec, stream));
-    h->launches += nb->graph_nodes;
+    ATM_CUDA_CHECK(cudaGraphLaunch(sg->exec, stream));
+    h->launches += sg->nodes;
+    if (io->concurrent_prune) flip_inner(nb);
     return ATM_OK;
 }
 
@@ -1007,6 +1089,7 @@ int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int inclu
     if (maintenance == 2) {
         if ((rc = launch_rebuild(h, (const float4 *)posq, stream))) return rc;
         ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags, nb->d.flags, sizeof(int) * NUM_HOST_FLAGS, cudaMemcpyDeviceToHost, stream));
+        ATM_CUDA_CHECK(cudaMemcpyAsync(nb->h_flags + NUM_HOST_FLAGS, nb->d.iflags, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
     } else if (maintenance == 1) {
         if ((rc = launch_prune_all(h, posq, stream))) return rc;
     }
@@ -1014,8 +1097,12 @@ int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int inclu
     io.posq = posq;
     io.force = (int64_t *)force;
     io.include_energy = include_energy;
+    io.concurrent_prune = maintenance == 3;
     return launch_step(h, &io, stream, false);
 }
+
+int nb_host_inner_copy(const atm_handle *h) { return h->nb ? h->nb->cur : 0; }
+void nb_host_flip_inner(atm_handle *h) { flip_inner(h->nb); }
 
 // Bookkeeping after a replayed asynchronous rebuild: `stream` is ordered behind the copy of the capacity flags.
 int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream) {
@@ -1024,6 +1111,8 @@ int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream) {
     nb->flags_pending = true;
     nb->list_valid = true;
     nb->generation++;
+    nb->cur = 0;   // a (replayed) rebuild leaves the pruned list in copy 0
+    use_inner(nb->d, nb->inner[0]);
     return ATM_OK;
 }
 

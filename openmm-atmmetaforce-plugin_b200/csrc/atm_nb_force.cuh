@@ -533,14 +533,14 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
         // prefix count of the buckets ITEM_STEPS, ITEM_STEPS-1, ..., ITEM_STEPS-l (one load + a warp scan per WARP);
         // an item index is then turned into (bucket, index in bucket) by a ballot instead of a chain of up to 16
         // dependent loads per ITEM.
-        const int cnt = (lane < ITEM_STEPS) ? d.flags[ITEM_BUCKET0 + ITEM_STEPS - lane] : 0;
+        const int cnt = (lane < ITEM_STEPS) ? d.iflags[ITEM_BUCKET0 + ITEM_STEPS - lane] : 0;
         int pre = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, pre, off);
             if (lane >= off) pre += v;
         }
-        const int n_items = d.flags[4], stride = n_item_blocks * (NB_THREADS / 32);
+        const int n_items = d.iflags[4], stride = n_item_blocks * (NB_THREADS / 32);
         for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
             __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
             const unsigned int below = __ballot_sync(0xffffffffu, warp < pre);  // lanes whose prefix covers this item

@@ -115,12 +115,13 @@ __global__ void nl_link_ghosts_kernel(NbDev d) {
 
 // Every step: gather current coordinates into cluster order; ghosts get posq + displ (the same float add as
 // CopyState, so a ghost sits exactly at the reference's posq2).
-__global__ void nb_pack_kernel(NbDev d, const float4 *__restrict__ posq) {
+// zero_eacc = 0: the side-stream pack of a concurrent prune (it must not touch the accumulators of the step in flight).
+__global__ void nb_pack_kernel(NbDev d, const float4 *__restrict__ posq, int zero_eacc) {
     pdl_trigger();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     // first kernel of a step: the energy / pair-count accumulators of the previous step have been consumed by its merge
-    if (blockIdx.x == 0 && threadIdx.x < EACC_SLOTS) d.eacc[(size_t)r * EACC_SLOTS + threadIdx.x] = 0ull;
+    if (zero_eacc && blockIdx.x == 0 && threadIdx.x < EACC_SLOTS) d.eacc[(size_t)r * EACC_SLOTS + threadIdx.x] = 0ull;
     if (t >= CL * d.nclusters[r]) return;
     const size_t rs = (size_t)r * d.Smax + t;
     const int src = d.slot_src[rs];
@@ -168,9 +169,11 @@ __global__ void nl_bbox_kernel(NbDev d) {
     d.cc[rc] = make_float4(x0.x + 0.5f * (lo.x + hi.x), x0.y + 0.5f * (lo.y + hi.y), x0.z + 0.5f * (lo.z + hi.z), 0.f);
     d.ch[rc] = make_float4(0.5f * (hi.x - lo.x), 0.5f * (hi.y - lo.y), 0.5f * (hi.z - lo.z), 0.f);
     d.cmeta[rc] = cls | (valid << 16);
-    // the per-step image shift of a partner relative to the cluster centre needs half extent + list radius <= L/2
-    const float hmax_x = 0.5f * (hi.x - lo.x) + d.rlist_outer, hmax_y = 0.5f * (hi.y - lo.y) + d.rlist_outer,
-                hmax_z = 0.5f * (hi.z - lo.z) + d.rlist_outer;
+    // the per-step image shift of a partner relative to the cluster centre needs half extent + list radius <= L/2; the
+    // centres stay those of the rebuild until the next one (atoms drift by up to half the outer skin, partners too:
+    // the outer skin is in rlist_outer, the inner skin is added for the pruned list built from drifted coordinates)
+    const float rl = d.rlist_outer + (d.rlist - sqrtf(d.cutoff2));
+    const float hmax_x = 0.5f * (hi.x - lo.x) + rl, hmax_y = 0.5f * (hi.y - lo.y) + rl, hmax_z = 0.5f * (hi.z - lo.z) + rl;
     if (hmax_x > 0.5f * L.x || hmax_y > 0.5f * L.y || hmax_z > 0.5f * L.z) atomicOr(&d.flags[0], 2);
 }
 
@@ -552,15 +555,15 @@ __global__ void __launch_bounds__(32 * PRUNE_WARPS, ATM_PRUNE_MIN_BLOCKS) nl_pru
         int tc = 0, tf = 0, ti = 0;
 #pragma unroll
         for (int k = 0; k < PRUNE_WARPS; k++) { tc += s_count[k]; tf += s_nfull[k]; ti += s_items[k]; }
-        if (tc > 0) atomicAdd((unsigned long long *)&d.flags[6], (unsigned long long)tc);
-        s_base_full = tf > 0 ? atomicAdd(&d.flags[ITEM_BUCKET0 + ITEM_STEPS], tf) : 0;
-        if (ti > 0) atomicAdd(&d.flags[4], ti);
+        if (tc > 0) atomicAdd((unsigned long long *)&d.iflags[6], (unsigned long long)tc);
+        s_base_full = tf > 0 ? atomicAdd(&d.iflags[ITEM_BUCKET0 + ITEM_STEPS], tf) : 0;
+        if (ti > 0) atomicAdd(&d.iflags[4], ti);
     }
     __syncthreads();
     int base_full = s_base_full, base_rem = 0;
 #pragma unroll
     for (int k = 0; k < PRUNE_WARPS; k++) base_full += k < w ? s_nfull[k] : 0;
-    if (lane == 0 && rem > 0) base_rem = atomicAdd(&d.flags[ITEM_BUCKET0 + rem], 1);
+    if (lane == 0 && rem > 0) base_rem = atomicAdd(&d.iflags[ITEM_BUCKET0 + rem], 1);
     for (int c = lane; c < nfull; c += 32)
         d.items[(size_t)ITEM_STEPS * d.max_items + base_full + c] =
             make_int4((int)(li.offset + (size_t)c * ITEM_STEPS * 32), A | (li.target << 28), r | (ITEM_STEPS << 8), c * ITEM_STEPS);

@@ -63,7 +63,8 @@ struct NbDev {  // everything the kernels need, passed by value
     unsigned int *jlist, *jlist_outer;
     int *list_nsteps, *outer_nsteps;
     int4 *items;  // work items: {list offset in entries, cluster | target << 28, replica | steps << 8, first entry step}
-    int *flags;
+    int *flags;   // rebuild flags (layout below)
+    int *iflags;  // counters of the INNER list in use: [4] live work items, [6,7] kept entries, [ITEM_BUCKET0 + n] items of n steps
     // accumulators
     unsigned long long *buf;
     unsigned long long *eacc;
@@ -78,6 +79,23 @@ struct NbDev {  // everything the kernels need, passed by value
     double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms
     double pme_qtot2;              // (sum of q sqrt(ke))^2: neutralising-background term -pi Q^2 / (2 V alpha^2)
     double disp_coeff;             // long-range dispersion correction = disp_coeff / V (0 = off)
+};
+
+// The pruned (inner) pair list exists twice: a prune that runs CONCURRENTLY with a step (on the handle's side stream)
+// writes the copy that is not in use; the next step switches over.
+struct InnerBuf {
+    unsigned int *jlist = nullptr;
+    int *list_nsteps = nullptr;
+    int4 *items = nullptr;
+    int *iflags = nullptr;
+};
+
+struct StepGraph {   // one cached CUDA graph of a step: keyed by the io block, the inner-list copy in use and the allocation
+    atm_step_io io{};
+    int cur = 0;
+    uint64_t generation = 0;
+    cudaGraphExec_t exec = nullptr;
+    int nodes = 0;
 };
 
 struct NbState {
@@ -125,10 +143,14 @@ struct NbState {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
-    cudaGraphExec_t graph_exec = nullptr;
-    atm_step_io graph_io{};
-    uint64_t graph_generation = 0;
-    int graph_nodes = 0;
+    std::vector<StepGraph> step_graphs;
+    // concurrent prune (atm_step_io.concurrent_prune)
+    InnerBuf inner[2];
+    int cur = 0;                    // which copy the force kernel reads
+    float4 *xs_side = nullptr;      // cluster-order coordinates packed by the side stream
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t prune_graph_alt = nullptr;   // synchronous prune into copy 1
     int64_t stats[8] = {0};
 };
 

@@ -25,6 +25,7 @@ SYMBOLS = (
     "atm_execute", "atm_get_perturbation_energy", "atm_nb_setup", "atm_pme_setup", "atm_nb_set_dispersion_correction", "atm_set_box", "atm_nb_rebuild", "atm_nb_check", "atm_nb_prune", "atm_step", "atm_step_graph", "atm_profile_enable", "atm_profile_read", "atm_launch_count",
     "atm_energies_device", "atm_get_energies", "atm_nb_stats", "atm_hrex_sweep", "atm_hrex_reduced_energy",
     "atm_hrex_device_setup", "atm_hrex_device_pack", "atm_hrex_device_exchange", "atm_hrex_device_state",
+    "atm_re_unique_id", "atm_re_comm_create", "atm_re_comm_from_nccl", "atm_re_comm_destroy", "atm_hrex_device_cycle",
     "atm_host_pipeline_create", "atm_host_pipeline_destroy", "atm_host_pipeline_step", "atm_host_pipeline_check",
     "atm_stream_create", "atm_stream_destroy", "atm_stream_synchronize", "atm_host_alloc", "atm_host_free",
 )
@@ -51,7 +52,7 @@ class StepIO(C.Structure):
     _fields_ = [("posq", C.c_void_p), ("posq_corr", C.c_void_p), ("force", C.c_void_p),
                 ("force_state1_ext", C.c_void_p), ("force_state2_ext", C.c_void_p), ("energy_ext", C.c_void_p),
                 ("posq1", C.c_void_p), ("posq1_corr", C.c_void_p), ("posq2", C.c_void_p), ("posq2_corr", C.c_void_p),
-                ("include_energy", C.c_int32), ("collect_stats", C.c_int32)]
+                ("include_energy", C.c_int32), ("collect_stats", C.c_int32), ("concurrent_prune", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HostIO(C.Structure):
@@ -109,6 +110,11 @@ def lib():
     L.atm_hrex_reduced_energy.restype = dbl
     L.atm_host_pipeline_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp)]
     L.atm_host_pipeline_destroy.argtypes = [vp]
+    L.atm_re_unique_id.argtypes = [vp]
+    L.atm_re_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    L.atm_re_comm_from_nccl.argtypes = [vp, i32, C.POINTER(vp)]
+    L.atm_re_comm_destroy.argtypes = [vp]
+    L.atm_hrex_device_cycle.argtypes = [vp, vp, C.c_uint64, vp]
     L.atm_host_pipeline_step.argtypes = [vp, C.POINTER(HostIO), i32, vp]
     L.atm_host_pipeline_check.argtypes = [vp]
     L.atm_stream_create.argtypes = [i32, C.POINTER(vp)]

@@ -140,12 +140,15 @@ class ATMBackend:
         check(_capi.lib().atm_nb_prune(self._h, _dptr(posq), _stream_ptr(stream)))
 
     def step(self, posq, force, posq_corr=None, f1_ext=None, f2_ext=None, energy_ext=None, posq1=None, posq1_corr=None,
-             posq2=None, posq2_corr=None, include_energy=True, collect_stats=False, graph=False, stream=None):
+             posq2=None, posq2_corr=None, include_energy=True, collect_stats=False, graph=False, stream=None, concurrent_prune=False):
+        """atm_step / atm_step_graph.  concurrent_prune: re-prune the inner pair list from these coordinates on the
+        back-end's side stream while the step runs; the next step uses the new list."""
         def v(t):
             p = _dptr(t)
             return p.value if p is not None else None
         io = _capi.StepIO(v(posq), v(posq_corr), v(force), v(f1_ext), v(f2_ext), v(energy_ext), v(posq1), v(posq1_corr),
-                          v(posq2), v(posq2_corr), 1 if include_energy else 0, 1 if collect_stats else 0)
+                          v(posq2), v(posq2_corr), 1 if include_energy else 0, 1 if collect_stats else 0,
+                          1 if concurrent_prune else 0, 0)
         fn = _capi.lib().atm_step_graph if graph else _capi.lib().atm_step
         check(fn(self._h, C.byref(io), _stream_ptr(stream)))
 
@@ -167,6 +170,10 @@ class ATMBackend:
 
     def hrex_exchange(self, gathered, cycle, stream=None):
         check(_capi.lib().atm_hrex_device_exchange(self._h, _dptr(gathered), int(cycle), _stream_ptr(stream)))
+
+    def hrex_cycle(self, comm, cycle, stream=None):
+        """atm_hrex_device_cycle: pack -> ncclAllGather (inside the library) -> sweep, on `stream`.  comm: ReplicaComm or None."""
+        check(_capi.lib().atm_hrex_device_cycle(self._h, comm._c if comm is not None else None, int(cycle), _stream_ptr(stream)))
 
     def hrex_state(self, num_replicas, stream=None):
         """Synchronises.  Returns (replica_state[num_replicas], accepted swaps, cycles, error flag)."""
@@ -213,6 +220,35 @@ class ATMBackend:
         return dict(zip(keys, (int(x) for x in out)))
 
 
+class ReplicaComm:
+    """atm_re_comm_*: the NCCL communicator of the replica layer, owned by the library.  `share` is any callable that
+    takes the 128-byte id from rank 0 and returns it on every rank (e.g. a torch.distributed broadcast)."""
+
+    def __init__(self, rank, world_size, device, share=None):
+        self.rank, self.world = int(rank), int(world_size)
+        self._c = C.c_void_p()
+        idbuf = (C.c_char * 128)()
+        if self.world > 1:
+            if share is None:
+                raise ATMError("ReplicaComm: a `share` callable is needed to distribute the NCCL unique id")
+            if self.rank == 0:
+                check(_capi.lib().atm_re_unique_id(idbuf))
+            raw = share(bytes(idbuf.raw) if self.rank == 0 else None)
+            idbuf = (C.c_char * 128).from_buffer_copy(raw)
+        check(_capi.lib().atm_re_comm_create(idbuf, self.world, self.rank, int(device), C.byref(self._c)))
+
+    def close(self):
+        if self._c:
+            _capi.lib().atm_re_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostPipeline:
     """atm_host_pipeline_* (include/atm_b200.h): the step with pinned HOST buffers on both sides, for one or more
     back-ends ("chunks") whose copies and kernels overlap; one cached CUDA graph launch per step.
@@ -221,7 +257,7 @@ class HostPipeline:
     force_host : list of pinned CPU int64 tensors   [R_c][3P]     (receives the ATM force, 2^32 fixed point)
     energies_host : list of pinned CPU float64 tensors [R_c][NUM_ENERGY_SLOTS] or None
     """
-    NONE, PRUNE, REBUILD = 0, 1, 2
+    NONE, PRUNE, REBUILD, PRUNE_CONCURRENT = 0, 1, 2, 3
 
     def __init__(self, backends):
         self.backends = list(backends)

@@ -69,12 +69,26 @@ class ReplicaExchange:
         return changed
 
     # ---- the same cycle without a host round trip (GPU back-end only)
-    def attach_device(self, backend, stream=None):
+    def attach_device(self, backend, stream=None, collective="library"):
         """Move the exchange bookkeeping onto the device of `backend` (an ATMBackend holding this rank's replicas in the
         order of self.mine).  After this, exchange_device() runs a whole cycle asynchronously on the stream:
-        pack kernel -> all-gather (NCCL) -> sweep kernel that rewrites the local parameter rows in place."""
+        pack kernel -> all-gather (NCCL) -> sweep kernel that rewrites the local parameter rows in place.
+        collective = "library": the all-gather is issued inside libatm_b200 on a communicator of its own
+        (atm_re_comm_create / atm_hrex_device_cycle; the NCCL unique id travels through torch.distributed once);
+        "torch": torch.distributed.all_gather_into_tensor between the library's pack and sweep kernels."""
         import torch
         self._be = backend
+        self._collective = collective
+        self._comm = None
+        if collective == "library":
+            from .backend import ReplicaComm
+
+            def share(raw):
+                import torch.distributed as dist
+                box = [raw]
+                dist.broadcast_object_list(box, src=0, group=self.group)
+                return box[0]
+            self._comm = ReplicaComm(self.rank, self.world, torch.cuda.current_device(), share if self.world > 1 else None)
         rows = self.world * self.max_per_rank
         gather_slot = np.array([self._slot[g] for g in range(self.num_replicas)], np.int32)
         backend.hrex_setup(self.schedule, self.replica_state, self.mine, gather_slot, rows, self.beta, self.seed, stream=stream)
@@ -84,13 +98,19 @@ class ReplicaExchange:
 
     def exchange_device(self, stream=None):
         """One cycle, fully asynchronous (no .cpu(), no synchronisation).  Bookkeeping: sync_from_device()."""
+        self.cycle += 1
+        self.attempted_cycles += 1
+        if self._collective == "library":
+            self._be.hrex_cycle(self._comm, self.cycle, stream=stream)
+            return
+        import torch
         self._be.hrex_pack(self._send, stream=stream)
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
-        self.cycle += 1
+            # the collective is ordered on torch's CURRENT stream: make that the stream of the pack and sweep kernels
+            with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+                dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
         self._be.hrex_exchange(self._recv, self.cycle, stream=stream)
-        self.attempted_cycles += 1
 
     def sync_from_device(self, stream=None):
         """Pull the state permutation and the acceptance count back (synchronises the stream)."""
@@ -102,10 +122,20 @@ class ReplicaExchange:
         return rs
 
     def state_dict(self):
-        """Checkpoint of the exchange bookkeeping (state permutation, RNG counter)."""
+        """Checkpoint of the exchange bookkeeping (state permutation, RNG counter).  With the bookkeeping on the device
+        the permutation is pulled back first (synchronises)."""
+        if getattr(self, "_be", None) is not None:
+            self.sync_from_device()
         return {"replica_state": self.replica_state.tolist(), "cycle": self.cycle, "seed": self.seed,
                 "accepted": self.accepted}
 
     def load_state_dict(self, d):
         self.replica_state[:] = np.asarray(d["replica_state"], np.int32)
         self.cycle, self.seed, self.accepted = int(d["cycle"]), int(d["seed"]), int(d.get("accepted", 0))
+        if getattr(self, "_be", None) is not None:
+            # the device holds its own copy of the permutation and the parameter rows: upload the restored ones
+            gather_slot = np.array([self._slot[g] for g in range(self.num_replicas)], np.int32)
+            self._be.hrex_setup(self.schedule, self.replica_state, self.mine, gather_slot, self.world * self.max_per_rank,
+                                self.beta, self.seed)
+            for k, row in enumerate(self.local_parameters()):
+                self._be.set_parameters(row, replica=k)

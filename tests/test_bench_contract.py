@@ -30,7 +30,7 @@ def test_reference_arm_json_line():
     import inspect
     keys = set(d["config"])
     assert {"workload", "replicas", "replicas_per_rank", "atoms", "dt_fs", "cutoff_nm", "skin_nm", "skin_outer_nm", "prune_every",
-            "rebuild_every", "exchange_every", "exchange", "cuda_graph", "pme_grid", "l2", "jitter_nm"} == keys
+            "rebuild_every", "exchange_every", "prune_mode", "exchange", "cuda_graph", "pme_grid", "l2", "jitter_nm"} == keys
     assert "workload_config(args, label, s, max_per_rank" in inspect.getsource(bench.run_b200)
     # what was timed is what is printed: a step = every replica once (or a stated sample of them), threads = the cores
     # this process may use even when the launcher exported OMP_NUM_THREADS=1

@@ -53,7 +53,9 @@ def test_pipeline_matches_device_path(split):
     posq_h = [torch.zeros((k, P, 4), dtype=torch.float32).pin_memory() for k in split]
     force_h = [torch.full((k, 3 * P), 7, dtype=torch.int64).pin_memory() for k in split]
     en_h = [torch.zeros((k, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory() for k in split]
-    plan = [pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.NONE, pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.REBUILD, pipe.NONE]
+    C = pipe.PRUNE_CONCURRENT   # the prune runs on the side stream during the step and serves the NEXT step
+    plan = [pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.NONE, C, pipe.NONE, C, C, pipe.PRUNE, pipe.NONE, pipe.REBUILD, pipe.NONE,
+            pipe.PRUNE, pipe.REBUILD, C, pipe.NONE, pipe.REBUILD, pipe.NONE, C, C, C, pipe.REBUILD, pipe.NONE, pipe.PRUNE]
     for it, maint in enumerate(plan):
         x = _coords(s, P, R, seed=100 + it, sigma=0.002 * (1 + it % 3))
         xd = torch.from_numpy(x).cuda()
@@ -63,7 +65,7 @@ def test_pipeline_matches_device_path(split):
                 ref.rebuild(xd, stream=stream)
             elif maint == pipe.PRUNE:
                 ref.prune(xd, stream=stream)
-            ref.step(xd, force, include_energy=True, graph=(it % 2 == 1), stream=stream)
+            ref.step(xd, force, include_energy=True, graph=(it % 2 == 1), stream=stream, concurrent_prune=(maint == C))
         en_ref = ref.get_energies(stream=stream)
         for c in range(len(split)):
             posq_h[c].copy_(torch.from_numpy(x[bounds[c]:bounds[c + 1]]))

@@ -451,6 +451,52 @@ def test_config5_500k_water_box():
           np.abs(f.sum(0)).max() / np.abs(f).sum()))
 
 
+def test_concurrent_prune_serves_the_next_step(abfe):
+    """atm_step_io.concurrent_prune: the step that carries the prune still runs on the list in use (complete, so the
+    result is right); the NEXT step runs on the list pruned from the carried coordinates -- bit-identical to
+    atm_nb_prune + atm_step on those coordinates (same list, fixed-point accumulation)."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from helpers import make_backend, oracle_system, force_from_fixed, rel_rms
+    alpha = O.ewald_alpha(1.0)
+    rng = np.random.default_rng(8)
+    n = abfe["pos"].shape[0]
+    moved = abfe["pos"] + rng.normal(0, 0.01, abfe["pos"].shape)
+    out = {}
+    for mode in ("concurrent", "before"):
+        be, posq0, _ = make_backend(atm, abfe, 1.0, alpha, abfe["params"], skin=0.1)
+        P = be.P
+        posq1 = posq0.clone()
+        posq1[0, :n, :3] = torch.from_numpy(moved.astype(np.float32)).cuda()
+        stream = torch.cuda.Stream()
+        fa, fb = (torch.zeros((1, 3 * P), dtype=torch.int64, device="cuda") for _ in range(2))
+        with torch.cuda.stream(stream):
+            be.rebuild(posq0, stream=stream)
+            if mode == "concurrent":
+                be.step(posq1, fa, stream=stream, concurrent_prune=True, graph=True)   # old list, prune of posq1 alongside
+                be.step(posq1, fb, stream=stream, graph=True)                          # new list
+            else:
+                be.step(posq1, fa, stream=stream)                                      # old list
+                be.prune(posq1, stream=stream)
+                be.step(posq1, fb, stream=stream)                                      # new list
+        en = be.get_energies(stream=stream)[0].copy()
+        out[mode] = (fa.cpu(), fb.cpu(), en)
+        be.close()
+    assert torch.equal(out["concurrent"][1], out["before"][1])
+    assert torch.equal(out["concurrent"][0], out["before"][0])
+    assert np.array_equal(out["concurrent"][2][:7], out["before"][2][:7])
+    S = oracle_system(O, abfe, 1.0, alpha)
+    x1 = moved.astype(np.float32).astype(np.float64)
+    x2 = (moved.astype(np.float32) + abfe["displ"].astype(np.float32)).astype(np.float64)
+    e1, _, f1 = S.nb_direct(x1)
+    e2, _, f2 = S.nb_direct(x2)
+    sc = O.scalars(abfe["params"], e1, e2)
+    f_ref = O.merge_ref(np.zeros_like(f1), f1, f2, sc["sp_ref"], abfe["params"][8])
+    for k in (0, 1):
+        assert rel_rms(force_from_fixed(out["concurrent"][k].numpy()[0], n, be.P), f_ref) <= 1e-5
+
+
 def test_async_rebuild_overflow_is_never_silent():
     """A pair list that outgrows its capacity during an ASYNCHRONOUS rebuild (a droplet contracting to several times its
     density after the verified first build sized the lists): the steps computed from the truncated lists return NaN
@@ -462,7 +508,7 @@ def test_async_rebuild_overflow_is_never_silent():
     import oracle_py as O
     from atmmetaforce import synthetic, _capi
     from helpers import oracle_system, rel_rms, force_from_fixed
-    s = synthetic.water_box(6000, n_lig=12, seed=11)
+    s = synthetic.water_box(20000, n_lig=12, seed=11)   # 5.8 nm box: the stretched clusters of the depleted shell still fit
     n = s["pos"].shape[0]
     params = synthetic.atm_schedule_22()[5]
     be = atm.ATMBackend(n, precision="mixed", num_replicas=1)
