@@ -269,12 +269,18 @@ int atm_host_free(void *ptr);
  * no device memory at all.  Handles must outlive the pipeline and must not be stepped concurrently through atm_step. */
 typedef struct atm_host_pipeline atm_host_pipeline;
 
+/* What comes back in force_host: the fixed-point long force buffer as OpenMM keeps it (24 B per atom), the same values as
+ * float32 kJ/mol/nm (12 B per atom: half the PCIe traffic; a host caller converts to floating point anyway, as
+ * Context.getState does), or nothing (a caller that only samples energies). */
+enum { ATM_FORCE_I64 = 0, ATM_FORCE_F32 = 1, ATM_FORCE_NONE = 2 };
+
 typedef struct {
     const void *posq_host;     /* [R][P] float4 (x, y, z, q), slot order; pinned host memory (cudaHostAlloc / cudaHostRegister) */
-    int64_t *force_host;       /* [R][3P] pinned host memory: receives the ATM force (2^32 fixed point, SoA x|y|z blocks) */
+    void *force_host;          /* [R][3P] pinned host memory, SoA x|y|z blocks per replica: int64 (2^32 fixed point) or float32
+                                  according to force_format; may be NULL with ATM_FORCE_NONE */
     double *energies_host;     /* [R][ATM_NUM_ENERGY_SLOTS] pinned host memory, or NULL */
     int32_t include_energy;    /* as atm_step_io.include_energy */
-    int32_t reserved;
+    int32_t force_format;      /* ATM_FORCE_I64 (0, default) | ATM_FORCE_F32 | ATM_FORCE_NONE */
 } atm_host_io;
 
 int atm_host_pipeline_create(int32_t num_handles, atm_handle *const *handles, atm_host_pipeline **out);

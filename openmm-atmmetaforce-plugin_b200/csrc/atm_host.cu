@@ -23,6 +23,7 @@ struct Chunk {
     atm_handle *h = nullptr;
     float4 *posq = nullptr;        // device staging [R][P]
     long long *force = nullptr;    // device staging [R][3P]
+    float *force_f32 = nullptr;    // device staging [R][3P] for force_format 1 (allocated on first use)
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     uint64_t generation = 0;       // alloc generation the cached graphs were captured against
@@ -45,6 +46,12 @@ static void drop_graphs(atm_host_pipeline *p) {
         if (p->exec[v]) { cudaGraphExecDestroy(p->exec[v]); p->exec[v] = nullptr; }
 }
 
+// force_format 1: the merged fixed-point force as float32 kJ/mol/nm, same [R][3][P] layout: half the D2H bytes
+__global__ void force_to_f32_kernel(const long long *__restrict__ in, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)((double)in[i] * (1.0 / 4294967296.0));
+}
+
 // enqueue one step of every chunk (fork from `stream`, join back into it); capturable
 static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int maintenance, cudaStream_t stream) {
     ATM_CUDA_CHECK(cudaEventRecord(p->fork, stream));
@@ -57,7 +64,13 @@ static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int mainten
         ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * np, cudaMemcpyHostToDevice, k.stream));
         ATM_CUDA_CHECK(cudaMemsetAsync(k.force, 0, sizeof(long long) * 3 * np, k.stream));
         if ((rc = nb_host_enqueue(h, k.posq, k.force, ios[c].include_energy, maintenance, k.stream))) return rc;
-        ATM_CUDA_CHECK(cudaMemcpyAsync(ios[c].force_host, k.force, sizeof(long long) * 3 * np, cudaMemcpyDeviceToHost, k.stream));
+        if (ios[c].force_format == ATM_FORCE_F32) {
+            force_to_f32_kernel<<<(unsigned)((3 * np + 255) / 256), 256, 0, k.stream>>>(k.force, k.force_f32, 3 * np);
+            h->launches++;
+            ATM_CUDA_CHECK(cudaMemcpyAsync(ios[c].force_host, k.force_f32, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, k.stream));
+        } else if (ios[c].force_format == ATM_FORCE_I64) {
+            ATM_CUDA_CHECK(cudaMemcpyAsync(ios[c].force_host, k.force, sizeof(long long) * 3 * np, cudaMemcpyDeviceToHost, k.stream));
+        }   // ATM_FORCE_NONE: energies only
         if (ios[c].energies_host)
             ATM_CUDA_CHECK(cudaMemcpyAsync(ios[c].energies_host, nb_energies_device(h), sizeof(double) * (size_t)h->R * ATM_NUM_ENERGY_SLOTS,
                                            cudaMemcpyDeviceToHost, k.stream));
@@ -161,6 +174,7 @@ int atm_host_pipeline_destroy(atm_host_pipeline *p) {
         if (k.done) cudaEventDestroy(k.done);
         if (k.posq) cudaFree(k.posq);
         if (k.force) cudaFree(k.force);
+        if (k.force_f32) cudaFree(k.force_f32);
     }
     if (p->fork) cudaEventDestroy(p->fork);
     delete p;
@@ -175,8 +189,19 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
                 "atm_host_pipeline_step: maintenance must be 0 (none), 1 (prune), 2 (rebuild) or 3 (prune concurrently with the step)");
     ATM_REQUIRE(stream != nullptr, ATM_ERR_INVALID, "atm_host_pipeline_step: needs a non-default stream (it is captured)");
     const size_t nc = p->chunks.size();
-    for (size_t c = 0; c < nc; c++)
-        ATM_REQUIRE(ios[c].posq_host && ios[c].force_host, ATM_ERR_INVALID, "atm_host_pipeline_step: chunk %d: posq_host and force_host are required", (int)c);
+    for (size_t c = 0; c < nc; c++) {
+        ATM_REQUIRE(ios[c].posq_host, ATM_ERR_INVALID, "atm_host_pipeline_step: chunk %d: posq_host is required", (int)c);
+        ATM_REQUIRE(ios[c].force_format >= ATM_FORCE_I64 && ios[c].force_format <= ATM_FORCE_NONE, ATM_ERR_INVALID,
+                    "atm_host_pipeline_step: chunk %d: unknown force_format %d", (int)c, (int)ios[c].force_format);
+        ATM_REQUIRE(ios[c].force_host || ios[c].force_format == ATM_FORCE_NONE, ATM_ERR_INVALID,
+                    "atm_host_pipeline_step: chunk %d: force_host is required unless force_format is ATM_FORCE_NONE", (int)c);
+        ATM_REQUIRE(ios[c].force_format != ATM_FORCE_NONE || ios[c].energies_host, ATM_ERR_INVALID,
+                    "atm_host_pipeline_step: chunk %d: nothing to return (no forces, no energies)", (int)c);
+        if (ios[c].force_format == ATM_FORCE_F32 && !p->chunks[c].force_f32) {
+            ATM_CUDA_CHECK(cudaSetDevice(p->device));
+            ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].force_f32, sizeof(float) * 3 * (size_t)p->chunks[c].h->R * p->chunks[c].h->P));
+        }
+    }
     ATM_CUDA_CHECK(cudaSetDevice(p->device));
     int rc;
     bool any_sync = false;

@@ -300,7 +300,7 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
     io.force_host = forceHost;
     io.energies_host = energyHost;
     io.include_energy = 1;   // the reference always evaluates the inner energies (do_energy = true, :104)
-    io.reserved = 0;
+    io.force_format = ATM_FORCE_I64;
     check(atm_host_pipeline_step(pipeline, &io, maintenance, stream), "ATMMetaForce: evaluating the alchemical force");
     check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
     if (maintenance == 2) {

@@ -254,7 +254,8 @@ class HostPipeline:
     back-ends ("chunks") whose copies and kernels overlap; one cached CUDA graph launch per step.
 
     posq_host  : list of pinned CPU float32 tensors [R_c][P][4]   (this step's coordinates + charges)
-    force_host : list of pinned CPU int64 tensors   [R_c][3P]     (receives the ATM force, 2^32 fixed point)
+    force_host : list of pinned CPU tensors [R_c][3P]: int64 (2^32 fixed point, OpenMM's long force layout) or float32
+                 (kJ/mol/nm, half the D2H bytes); the dtype selects the format.  None = energies only
     energies_host : list of pinned CPU float64 tensors [R_c][NUM_ENERGY_SLOTS] or None
     """
     NONE, PRUNE, REBUILD, PRUNE_CONCURRENT = 0, 1, 2, 3
@@ -288,18 +289,30 @@ class HostPipeline:
 
     def step(self, posq_host, force_host, energies_host=None, maintenance=0, include_energy=True, stream=None):
         n = len(self.backends)
+        import torch
+        if force_host is None:
+            force_host = [None] * n
         if len(posq_host) != n or len(force_host) != n or (energies_host is not None and len(energies_host) != n):
             raise ATMError("HostPipeline.step: one buffer per back-end is required")
-        key = (tuple(t.data_ptr() for t in posq_host), tuple(t.data_ptr() for t in force_host),
+        key = (tuple(t.data_ptr() for t in posq_host), tuple(t.data_ptr() if t is not None else 0 for t in force_host),
                tuple(t.data_ptr() for t in energies_host) if energies_host is not None else None, bool(include_energy))
         if key != self._key:
             ios = (_capi.HostIO * n)()
             for c, b in enumerate(self.backends):
-                if posq_host[c].numel() != b.R * b.P * 4 or force_host[c].numel() != b.R * b.P * 3:
+                f = force_host[c]
+                if posq_host[c].numel() != b.R * b.P * 4 or (f is not None and f.numel() != b.R * b.P * 3):
                     raise ATMError(f"HostPipeline.step: chunk {c}: buffer size does not match [R][P]")
-                ios[c] = _capi.HostIO(self._hptr(posq_host[c], "posq_host"), self._hptr(force_host[c], "force_host"),
+                if f is None:
+                    fmt = _capi.FORCE_NONE
+                elif f.dtype == torch.int64:
+                    fmt = _capi.FORCE_I64
+                elif f.dtype == torch.float32:
+                    fmt = _capi.FORCE_F32
+                else:
+                    raise ATMError("HostPipeline.step: force_host must be int64 (fixed point) or float32")
+                ios[c] = _capi.HostIO(self._hptr(posq_host[c], "posq_host"), self._hptr(f, "force_host"),
                                       self._hptr(energies_host[c], "energies_host") if energies_host is not None else None,
-                                      1 if include_energy else 0, 0)
+                                      1 if include_energy else 0, fmt)
             self._ios, self._key = ios, key
         check(_capi.lib().atm_host_pipeline_step(self._p, self._ios, int(maintenance), _stream_ptr(stream)))
 

@@ -120,6 +120,38 @@ def test_pipeline_against_oracle(abfe):
     be.close()
 
 
+def test_force_formats():
+    """ATM_FORCE_F32: exactly the fixed-point force converted to float32 ((float)(f / 2^32)); ATM_FORCE_NONE: energies only."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic, _capi
+    s = synthetic.water_box(12000)
+    sched = synthetic.atm_schedule_22()
+    be = _setup(atm, s, [sched[4], sched[17]], 2)
+    P = be.P
+    pipe = atm.HostPipeline([be])
+    posq_h = torch.from_numpy(_coords(s, P, 2, seed=3, sigma=0.003)).pin_memory()
+    f64 = torch.zeros((2, 3 * P), dtype=torch.int64).pin_memory()
+    f32 = torch.zeros((2, 3 * P), dtype=torch.float32).pin_memory()
+    en_a, en_b, en_c = (torch.zeros((2, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory() for _ in range(3))
+    stream = torch.cuda.Stream()
+    pipe.step([posq_h], [f64], [en_a], maintenance=pipe.REBUILD, stream=stream)
+    stream.synchronize()
+    pipe.step([posq_h], [f32], [en_b], maintenance=pipe.NONE, stream=stream)
+    stream.synchronize()
+    pipe.step([posq_h], None, [en_c], maintenance=pipe.NONE, stream=stream)
+    stream.synchronize()
+    expect = (f64.numpy().astype(np.float64) / 4294967296.0).astype(np.float32)
+    assert np.array_equal(f32.numpy(), expect) and np.abs(expect).max() > 0
+    assert np.array_equal(en_a.numpy()[:, :7], en_b.numpy()[:, :7]) and np.array_equal(en_a.numpy()[:, :7], en_c.numpy()[:, :7])
+    with pytest.raises(atm.ATMError, match="nothing to return"):
+        pipe.step([posq_h], None, None, maintenance=pipe.NONE, stream=stream)
+    with pytest.raises(atm.ATMError, match="int64"):
+        pipe.step([posq_h], [torch.zeros((2, 3 * P), dtype=torch.float64).pin_memory()], [en_a], maintenance=pipe.NONE, stream=stream)
+    pipe.close()
+    be.close()
+
+
 def test_pipeline_errors():
     import torch
     import atmmetaforce as atm
