@@ -473,6 +473,7 @@ def run_b200(args):
     #      every term measured in this run with the same events; kinds the window saw fewer than 3 times are sampled
     #      right after it (outside the window, same stream, same jitter/flush discipline)
     extra = []
+    barrier()   # rank 0 has just spent 0.15 s stopping the clock sampler: line the ranks up again before the collectives below
     for kind_x in ("prune", "rebuild"):
         have = sum(1 for kd, _, _ in records if kd == kind_x)
         for _ in range(max(0, 3 - have) if freq[kind_x] > 0 else 0):
@@ -499,8 +500,13 @@ def run_b200(args):
     allrec = records + extra
 
     def mean_ms(sel, a, b):
+        """Typical cost of one component: the mean over the plain steps' many samples; the MEDIAN for the few samples of
+        a maintenance / exchange call, so that a one-off event (a capacity growth that reallocates the lists, a graph
+        re-capture, NCCL's lazy connection set-up) does not pass for steady state."""
         v = [ev[a].elapsed_time(ev[b]) for kd, ex, ev in allrec if sel(kd, ex)]
-        return (sum(v) / len(v), len(v)) if v else (0.0, 0)
+        if not v:
+            return 0.0, 0
+        return (float(np.median(v)) if len(v) < 50 else sum(v) / len(v)), len(v)
 
     concurrent = args.prune_mode == "concurrent"
     # the step itself: every step, or -- with concurrent prunes, whose cost sits INSIDE the step interval -- the steps
@@ -520,6 +526,9 @@ def run_b200(args):
     t, c = mean_ms(lambda kd, ex: ex, 2, 3)
     comp["exchange"] = {"ms": t, "samples": c, "per_step": freq["exchange"]}
     steady += t * freq["exchange"]
+    if os.environ.get("ATM_BENCH_DEBUG"):
+        print(f"[bench rank {rank}] steady {steady:.4f} window {window_ms / K:.4f} " +
+              " ".join(f"{k}={v['ms']:.4f}x{v['samples']}" for k, v in comp.items()), file=sys.stderr, flush=True)
     tt = torch.tensor([steady, window_ms / K], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -680,7 +689,7 @@ def run_b200(args):
         f_e = {"rebuild": freq["rebuild"], "prune": freq["prune"], "plain": 1.0 - freq["rebuild"] - freq["prune"]}
         for kd in ("plain", "prune", "rebuild"):
             v = [a.elapsed_time(b) for kk, _, a, b in ee if kk == kd]
-            t_kd = sum(v) / len(v) if v else 0.0
+            t_kd = (float(np.median(v)) if len(v) < 50 else sum(v) / len(v)) if v else 0.0
             e2e_comp[kd] = {"ms": t_kd, "samples": len(v), "per_step": f_e[kd]}
             e2e_ms += t_kd * f_e[kd]
         e2e_window_ms = sum(a.elapsed_time(b) for _, inw, a, b in ee if inw) / KE
@@ -757,7 +766,8 @@ def run_b200(args):
                                       "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)"),
             "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank,
             "ms_per_step_is": "steady state on the declared cadences: plain step + sum(component ms * per_step), every component "
-                              "timed in this run with CUDA events (max over ranks); window_ms_per_step is the raw K-step window",
+                              "timed in this run with CUDA events (mean of the plain steps, median of the few maintenance / "
+                              "exchange samples; max over ranks); window_ms_per_step is the raw K-step window",
             "components": comp, "window_ms_per_step": window_ms_per_step,
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -542,11 +542,42 @@ __global__ void __launch_bounds__(32 * PRUNE_WARPS, ATM_PRUNE_MIN_BLOCKS) nl_pru
     const int count = prune_one_list(d, r, l, d.Cmax + d.CLmax, lane, li, s_atoms[w]);
     const int A = li.cluster;
     const int nsteps = (count + 31) >> 5;
+    (void)A;
     // work items of this list: (<= ITEM_STEPS)-step chunks (their order only affects scheduling: every accumulation
     // downstream is fixed point, hence order independent).  Buckets by chunk length: the force kernel hands out the
     // longest chunks first (longest-processing-time order keeps the tail of the launch short when only a few replicas
     // share the GPU).  The counters every list touches -- kept entries, live items, the bucket of full chunks -- are
     // summed over the block first: same-address atomics serialise in the L2, one per block instead of one per list.
+#ifdef ATM_EVEN_SPLIT
+    // A list longer than ITEM_STEPS is cut into EQUAL chunks (17 steps -> 9 + 8 instead of 16 + 1): no work item is
+    // mostly prologue.  Chunk lengths differ from list to list, so every chunk length has its own bucket counter.
+    const int nch = (nsteps + ITEM_STEPS - 1) / ITEM_STEPS;
+    const int len_lo = nch > 0 ? nsteps / nch : 0, n_hi = nch > 0 ? nsteps - len_lo * nch : 0;   // n_hi chunks of len_lo + 1 first
+    __shared__ int s_count[PRUNE_WARPS], s_items[PRUNE_WARPS];
+    if (lane == 0) { s_count[w] = count; s_items[w] = nch; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tc = 0, ti = 0;
+#pragma unroll
+        for (int k = 0; k < PRUNE_WARPS; k++) { tc += s_count[k]; ti += s_items[k]; }
+        if (tc > 0) atomicAdd((unsigned long long *)&d.iflags[6], (unsigned long long)tc);
+        if (ti > 0) atomicAdd(&d.iflags[4], ti);
+    }
+    int base_hi = 0, base_lo = 0;
+    if (lane == 0) {
+        if (n_hi > 0) base_hi = atomicAdd(&d.iflags[ITEM_BUCKET0 + len_lo + 1], n_hi);
+        if (nch - n_hi > 0 && len_lo > 0) base_lo = atomicAdd(&d.iflags[ITEM_BUCKET0 + len_lo], nch - n_hi);
+    }
+    base_hi = __shfl_sync(0xffffffffu, base_hi, 0);
+    base_lo = __shfl_sync(0xffffffffu, base_lo, 0);
+    for (int c = lane; c < nch; c += 32) {
+        const bool hi = c < n_hi;
+        const int len = hi ? len_lo + 1 : len_lo;
+        const int first = hi ? c * (len_lo + 1) : n_hi * (len_lo + 1) + (c - n_hi) * len_lo;
+        d.items[(size_t)len * d.max_items + (hi ? base_hi + c : base_lo + (c - n_hi))] =
+            make_int4((int)(li.offset + (size_t)first * 32), A | (li.target << 28), r | (len << 8), first);
+    }
+#else
     const int nfull = nsteps / ITEM_STEPS, rem = nsteps - nfull * ITEM_STEPS;
     __shared__ int s_count[PRUNE_WARPS], s_nfull[PRUNE_WARPS], s_items[PRUNE_WARPS], s_base_full;
     if (lane == 0) { s_count[w] = count; s_nfull[w] = nfull; s_items[w] = nfull + (rem > 0 ? 1 : 0); }
@@ -570,6 +601,7 @@ __global__ void __launch_bounds__(32 * PRUNE_WARPS, ATM_PRUNE_MIN_BLOCKS) nl_pru
     if (lane == 0 && rem > 0)
         d.items[(size_t)rem * d.max_items + base_rem] =
             make_int4((int)(li.offset + (size_t)nfull * ITEM_STEPS * 32), A | (li.target << 28), r | (rem << 8), nfull * ITEM_STEPS);
+#endif
 }
 
 }  // namespace atm

@@ -24,7 +24,7 @@ constexpr int NB_MIN_BLOCKS = ATM_NB_MIN_BLOCKS;   // 5 -> 20 warps / SM at <= 1
 constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
-constexpr int NUM_FLAGS = 40;
+constexpr int NUM_FLAGS = ITEM_BUCKET0 + ITEM_STEPS + 8;   // rebuild flags, then one bucket counter per item length
 // flags[0] bit 0: a list outgrew its capacity, bit 1: box too small; [1] longest overflowing list; [2,3] outer entries
 // (64 bit); [4] live work items; [5] outer work items; [6,7] pruned entries (64 bit); [8], [9] longest list of the
 // environment / ligand-ghost capacity class at the last build

@@ -46,6 +46,10 @@ _FB_DIST = "0.5*kf*step(dd)*dd^2; dd = d - tol; "
 # periodic angle variable (period 2 pi): (k/2) max(0, |wrap(x - x0)| - tol)^2
 _FB_ANGLE = ("0.5*kf*step(da)*da^2; da = abs(dw) - tol; dw = dx - twopi*floor(dx/twopi + 0.5); dx = ang - x0; "
              "twopi = %.17g; " % (2.0 * math.pi))
+# the same well written with its two edges a0 = x0 - tol, b0 = x0 + tol (the reference's per-bond parameters of the phi / psi
+# restraints, ref: python/ATMMetaForceUtils.py:638-640, 684-686: code that edits the bonds afterwards relies on them)
+_FB_ANGLE_AB = ("0.5*kf*step(da)*da^2; da = abs(dw) - 0.5*(b0 - a0); dw = dx - twopi*floor(dx/twopi + 0.5); dx = ang - 0.5*(a0 + b0); "
+                "twopi = %.17g; " % (2.0 * math.pi))
 # cosine variable:                        (k/2) max(0, |c - c0| - ctol)^2
 _FB_COS = "0.5*kf*step(dc)*dc^2; dc = abs(cost - cos0) - ctol; "
 
@@ -199,43 +203,97 @@ class ATMMetaForceUtils(object):
                 thetaforce.addGroup(g)
             t0, tt = float(_val(theta0)), float(_val(thetatol))
             cos0 = math.cos(t0)
-            lo, hi = max(0.0, t0 - tt), min(math.pi, t0 + tt)
-            ctol = max(abs(math.cos(lo) - cos0), abs(math.cos(hi) - cos0))  # tolerance of cos(theta) over theta0 +- thetatol
+            # the reference's tolerance is the full span of cos(theta) over [theta0 - tol, theta0 + tol] clipped to [0, pi]
+            # (ref: python/ATMMetaForceUtils.py:612-614)
+            a0, b0 = max(0.0, t0 - tt), min(math.pi, t0 + tt)
+            ctol = abs(math.cos(a0) - math.cos(b0))
             thetaforce.addBond([g0, g0 + 1, g0 + 2, g0 + 3], [float(_val(ktheta)), cos0, ctol])
 
-        def dihedral_force(attr, groups, k, x0, tol):
-            # the two frames are translated to a common origin: points are (A, B, B + (D - C) ...) built from differences,
-            # so the dihedral is written with explicit vectors instead of dihedral(g1..g4)
+        def dihedral_force(attr, groups, points, k, x0, tol):
+            # Group order and per-bond parameters (kf, a0 = x0 - tol, b0 = x0 + tol) are the reference's
+            # (ref: :642-656 phi: r1, r2, r3, l1, l2; :688-702 psi: r1, r2, l1, l2, l3).  `points` names, in terms of the
+            # five centroids p1..p5, the three bond vectors b1, b2, b3 of the dihedral once the two frames share an origin.
             f = getattr(self, attr)
             if f is None:
-                expr = _FB_ANGLE + (
+                # (upstream's phi expression tests the variable `psi` instead of `phi`, ref: :638-641 -- a typo that makes its
+                # phi restraint fail to compile; the intended dihedral is implemented here)
+                expr = _FB_ANGLE_AB + (
                     "ang = atan2(sy, cx); "
-                    # IUPAC dihedral atan2(|b2| b1.(b2 x b3), (b1 x b2).(b2 x b3)) with b1 = p2-p1, b2 = p3-p2 and, the two
-                    # origins (p3, p4) being superimposed, b3 = p5-p4
+                    # IUPAC dihedral atan2(|b2| b1.(b2 x b3), (b1 x b2).(b2 x b3))
                     "sy = bn*(b1x*n2x + b1y*n2y + b1z*n2z); cx = n1x*n2x + n1y*n2y + n1z*n2z; "
                     "n1x = b1y*b2z-b1z*b2y; n1y = b1z*b2x-b1x*b2z; n1z = b1x*b2y-b1y*b2x; "
                     "n2x = b2y*b3z-b2z*b3y; n2y = b2z*b3x-b2x*b3z; n2z = b2x*b3y-b2y*b3x; "
-                    "bn = sqrt(b2x^2+b2y^2+b2z^2); "
-                    "b1x = x2-x1; b1y = y2-y1; b1z = z2-z1; b2x = x3-x2; b2y = y3-y2; b2z = z3-z2; "
-                    "b3x = x5-x4; b3y = y5-y4; b3z = z5-z4")
+                    "bn = sqrt(b2x^2+b2y^2+b2z^2); " + points)
                 f = mm.CustomCentroidBondForce(5, expr)
-                for name in ("kf", "x0", "tol"):
+                for name in ("kf", "a0", "b0"):
                     f.addPerBondParameter(name)
                 self.system.addForce(f)
                 setattr(self, attr, f)
             g0 = f.getNumGroups()
             for g in groups:
                 f.addGroup(g)
-            f.addBond([g0 + i for i in range(5)], [float(_val(k)), float(_val(x0)), float(_val(tol))])
+            c, t = float(_val(x0)), float(_val(tol))
+            f.addBond([g0 + i for i in range(5)], [float(_val(k)), c - t, c + t])
             return f
 
+        def vec(name, a, b):   # name = p_a - p_b, component-wise
+            return "; ".join(f"{name}{c} = {c}{a}-{c}{b}" for c in "xyz")
+
         if kphi is not None:
-            # r3 - r2 - r1 | l1 - l2  with r1 and l1 superimposed: points (r3, r2, r1) and the bond l1 -> l2
-            phiforce = dihedral_force("CMAnglePhiForce", (r3, r2, r1, l1, l2), kphi, phi0, phitol)
+            # groups (r1, r2, r3, l1, l2); dihedral r3 - r2 - (r1 = l1) - l2: b1 = r2 - r3, b2 = r1 - r2, b3 = l2 - l1
+            phiforce = dihedral_force("CMAnglePhiForce", (r1, r2, r3, l1, l2),
+                                      "; ".join((vec("b1", 2, 3), vec("b2", 1, 2), vec("b3", 5, 4))), kphi, phi0, phitol)
         if kpsi is not None:
-            # r2 - r1 | l1 - l2 - l3 mirrored: walk from the ligand side, points (l3, l2, l1) and the bond r1 -> r2
-            psiforce = dihedral_force("CMAnglePsiForce", (l3, l2, l1, r1, r2), kpsi, psi0, psitol)
+            # groups (r1, r2, l1, l2, l3); dihedral r2 - (r1 = l1) - l2 - l3: b1 = r1 - r2, b2 = l2 - l1, b3 = l3 - l2
+            psiforce = dihedral_force("CMAnglePsiForce", (r1, r2, l1, l2, l3),
+                                      "; ".join((vec("b1", 1, 2), vec("b2", 4, 3), vec("b3", 5, 4))), kpsi, psi0, psitol)
         return (thetaforce, phiforce, psiforce)
+
+    # -- Boresch-style restraints between three receptor atoms (a, b, c) and three ligand atoms (A, B, C) ---------------------
+    def _addVsiteRestraintForceBoresch(self, lig_ref_particles, rcpt_ref_particles, kfrA, rA0, rAtol, kfthA, thA0, thAtol,
+                                       kfphA, phA0, phAtol, kfthB, thB0, thBtol, kfphB, phB0, phBtol, kfphC, phC0, phCtol):
+        """Flat-bottom wells on the six Boresch coordinates (ref: python/ATMMetaForceUtils.py:280-384; private and unused
+        upstream, kept for API parity): rA = |a A|, thetaA = angle(b, a, A), thetaB = angle(a, A, B),
+        phiA = dihedral(c, b, a, A), phiB = dihedral(b, a, A, B), phiC = dihedral(a, A, B, C).  A term whose force
+        constant is None is skipped.  Returns (CustomBondForce, CustomAngleForce, CustomTorsionForce), None where unused.
+        Per-term parameters as upstream: (kf, r0, tol) for the distance, (kf, a0, b0) = centre -+ tolerance for the rest.
+        Angles use period pi in the wrap, dihedrals 2 pi, as upstream."""
+        assert len(lig_ref_particles) == 3 and len(rcpt_ref_particles) == 3
+        mm = _mm()
+        A, B, C = lig_ref_particles
+        a, b, c = rcpt_ref_particles
+        bondforce = angleforce = torsforce = None
+        if kfrA is not None:
+            bondforce = mm.CustomBondForce("0.5*kf*step(dd)*dd^2; dd = abs(r - r0) - tol")
+            for name in ("kf", "r0", "tol"):
+                bondforce.addPerBondParameter(name)
+            bondforce.addBond(a, A, [float(_val(kfrA)), float(_val(rA0)), float(_val(rAtol))])
+            self.system.addForce(bondforce)
+
+        def edges(x0, tol):
+            x0, tol = float(_val(x0)), float(_val(tol))
+            return x0 - tol, x0 + tol
+
+        angles = [(kfthA, thA0, thAtol, (b, a, A)), (kfthB, thB0, thBtol, (a, A, B))]
+        if any(k is not None for k, *_ in angles):
+            angleforce = mm.CustomAngleForce(_FB_ANGLE_AB.replace("ang", "theta").replace("twopi = %.17g" % (2.0 * math.pi),
+                                                                                            "twopi = %.17g" % math.pi))
+            for name in ("kf", "a0", "b0"):
+                angleforce.addPerAngleParameter(name)
+            for k, x0, tol, (p0, p1, p2) in angles:
+                if k is not None:
+                    angleforce.addAngle(p0, p1, p2, [float(_val(k)), *edges(x0, tol)])
+            self.system.addForce(angleforce)
+        torsions = [(kfphA, phA0, phAtol, (c, b, a, A)), (kfphB, phB0, phBtol, (b, a, A, B)), (kfphC, phC0, phCtol, (a, A, B, C))]
+        if any(k is not None for k, *_ in torsions):
+            torsforce = mm.CustomTorsionForce(_FB_ANGLE_AB.replace("ang", "theta"))
+            for name in ("kf", "a0", "b0"):
+                torsforce.addPerTorsionParameter(name)
+            for k, x0, tol, (p0, p1, p2, p3) in torsions:
+                if k is not None:
+                    torsforce.addTorsion(p0, p1, p2, p3, [float(_val(k)), *edges(x0, tol)])
+            self.system.addForce(torsforce)
+        return (bondforce, angleforce, torsforce)
 
     # -- positional restraints -------------------------------------------------------------------------------------------
     def addPosRestraints(self, particles, refpos, fc=25.0 * 4.184 * 100.0, tol=0.05, periodic=True):

@@ -16,7 +16,8 @@ class _Rec:
         self.group = 0
 
     def addPerBondParameter(self, n): self.params.append(n)
-    addPerParticleParameter = addPerTorsionParameter = addPerBondParameter
+    addPerParticleParameter = addPerTorsionParameter = addPerAngleParameter = addPerBondParameter
+    def addAngle(self, a, b, c, v): self.bonds.append(((a, b, c), list(v)))
     def addGroup(self, g): self.groups.append(list(g)); return len(self.groups) - 1
     def getNumGroups(self): return len(self.groups)
     def addBond(self, p, v): self.bonds.append((list(p), list(v)))
@@ -48,6 +49,11 @@ def fake_openmm(monkeypatch):
     for kind in ("CustomCentroidBondForce", "CustomCompoundBondForce"):
         setattr(mod, kind, (lambda k: (lambda n, expr: _Rec(k, n, expr)))(kind))
     mod.CustomTorsionForce = lambda expr: _Rec("CustomTorsionForce", 4, expr)
+    mod.CustomAngleForce = lambda expr: _Rec("CustomAngleForce", 3, expr)
+
+    class _Bond(_Rec):   # CustomBondForce.addBond(p1, p2, parameters)
+        def addBond(self, p1, p2, v): self.bonds.append(((p1, p2), list(v)))
+    mod.CustomBondForce = lambda expr: _Bond("CustomBondForce", 2, expr)
     mod.CustomExternalForce = lambda expr: _Rec("CustomExternalForce", 1, expr)
     monkeypatch.setitem(sys.modules, "openmm", mod)
     return mod
@@ -144,13 +150,49 @@ def test_cm_angle_restraints(fake_openmm):
     assert th.groups == [[0, 1], [2], [10], [11, 12]]
     k, cos0, ctol = th.bonds[0][1]
     assert k == 100.0 and cos0 == pytest.approx(math.cos(math.radians(30)))
-    assert ctol == pytest.approx(max(abs(math.cos(math.radians(20)) - cos0), abs(math.cos(math.radians(40)) - cos0)))
-    assert ph.groups == [[3], [2], [0, 1], [10], [11, 12]] and ph.bonds[0][1] == [10.0, 0.5, 0.2]
-    # the dihedral expression reproduces a textbook dihedral: points (1,0,0),(0,0,0),(0,0,1) and bond direction (cos a, sin a, 0)
+    # the reference's tolerance: the full span |cos(theta0 - tol) - cos(theta0 + tol)| (ref: ATMMetaForceUtils.py:612-614)
+    assert ctol == pytest.approx(abs(math.cos(math.radians(20)) - math.cos(math.radians(40))))
+    # the reference's group order (r1, r2, r3, l1, l2) and per-bond parameters (kf, a0 = phi0 - tol, b0 = phi0 + tol)
+    assert ph.groups == [[0, 1], [2], [3], [10], [11, 12]] and ph.bonds[0][1] == pytest.approx([10.0, 0.3, 0.7])
+    assert ph.params == ["kf", "a0", "b0"] and th.params == ["kf", "cos0", "ctol"]
+    # phi = dihedral r3 - r2 - (r1 = l1) - l2: with r3 = (1,0,1), r2 = (0,0,1), r1 = (0,0,0) the ligand axis l2 - l1 =
+    # (cos a, sin a, 0.4) has azimuth a
+    ang_expr = "ang; " + ph.expr.split("ang = ", 1)[0].split("; ", 1)[1] + "ang = " + ph.expr.split("ang = ", 1)[1]
     for a in (0.3, -1.2, 2.8):
-        val = _eval("ang; " + ph.expr.split("; ", 1)[1].split("ang = ", 1)[0] + "ang = " + ph.expr.split("ang = ", 1)[1],
-                    x1=1, y1=0, z1=0, x2=0, y2=0, z2=0, x3=0, y3=0, z3=1, x4=7, y4=7, z4=7,
-                    x5=7 + math.cos(a), y5=7 + math.sin(a), z5=7 + 0.4, kf=0, x0=0, tol=0)
-        assert val == pytest.approx(a, abs=1e-12)
+        val = _eval(ang_expr, x1=0, y1=0, z1=0, x2=0, y2=0, z2=1, x3=1, y3=0, z3=1, x4=7, y4=7, z4=7,
+                    x5=7 + math.cos(a), y5=7 + math.sin(a), z5=7 - 0.4, kf=0, a0=0, b0=0)
+        assert abs(val) == pytest.approx(abs(a), abs=1e-12)
+    # flat bottom between a0 and b0, periodic: inside -> 0, outside -> (kf/2)(distance to the nearer edge)^2
+    well = lambda ang: _eval(ph.expr.split("ang = ", 1)[0] + "ang = %r" % ang, kf=10.0, a0=0.3, b0=0.7)
+    assert well(0.5) == 0.0 and well(0.31) == 0.0
+    assert well(0.9) == pytest.approx(5.0 * 0.2 ** 2) and well(0.1) == pytest.approx(5.0 * 0.2 ** 2)
+    assert well(0.9 + 2 * math.pi) == pytest.approx(5.0 * 0.2 ** 2)
     th2, _, ps2 = u.addVsiteRestraintForceCMAngles(lig, rcpt, ktheta=1.0, theta0=0.1, thetatol=0.1, kpsi=5.0, psi0=1.0, psitol=0.1)
-    assert th2 is th and len(th.bonds) == 2 and ps2.groups == [[13], [11, 12], [10], [0, 1], [2]]
+    assert th2 is th and len(th.bonds) == 2 and ps2.groups == [[0, 1], [2], [10], [11, 12], [13]]
+    assert ps2.bonds[0][1] == pytest.approx([5.0, 0.9, 1.1]) and ps2.params == ["kf", "a0", "b0"]
+
+
+def test_boresch_restraints(fake_openmm):
+    """_addVsiteRestraintForceBoresch (ref: python/ATMMetaForceUtils.py:288-384): which atoms define each of the six
+    coordinates, the (kf, a0, b0) parameters, skipped terms."""
+    from atmmetaforce import ATMMetaForceUtils
+    system = _System([])
+    u = ATMMetaForceUtils(system, fix_zero_LJparams=False)
+    lig, rcpt = [10, 11, 12], [0, 1, 2]       # (A, B, C), (a, b, c)
+    bond, ang, tors = u._addVsiteRestraintForceBoresch(lig, rcpt, 1000.0, 0.5, 0.1, 50.0, 1.2, 0.2, 20.0, 0.4, 0.3,
+                                                       None, None, None, 21.0, -1.0, 0.25, 22.0, 2.0, 0.5)
+    assert system.forces == [bond, ang, tors]
+    assert bond.bonds == [((0, 10), [1000.0, 0.5, 0.1])] and bond.params == ["kf", "r0", "tol"]
+    assert ang.params == tors.params == ["kf", "a0", "b0"]
+    assert len(ang.bonds) == 1 and ang.bonds[0][0] == (1, 0, 10) and ang.bonds[0][1] == pytest.approx([50.0, 1.0, 1.4])   # thetaA only
+    assert [t[0] for t in tors.torsions] == [(2, 1, 0, 10), (1, 0, 10, 11), (0, 10, 11, 12)]
+    assert tors.torsions[1][1] == pytest.approx([21.0, -1.25, -0.75])
+    # distance well: flat inside r0 +- tol, harmonic outside
+    assert _eval(bond.expr, r=0.55, kf=1000.0, r0=0.5, tol=0.1) == 0.0
+    assert _eval(bond.expr, r=0.8, kf=1000.0, r0=0.5, tol=0.1) == pytest.approx(500.0 * 0.2 ** 2)
+    assert _eval(bond.expr, r=0.3, kf=1000.0, r0=0.5, tol=0.1) == pytest.approx(500.0 * 0.1 ** 2)
+    # dihedral well is 2 pi periodic
+    assert _eval(tors.expr, theta=-1.0 + 2 * math.pi, kf=21.0, a0=-1.25, b0=-0.75) == pytest.approx(0.0, abs=1e-12)
+    assert _eval(tors.expr, theta=-0.5, kf=21.0, a0=-1.25, b0=-0.75) == pytest.approx(10.5 * 0.25 ** 2)
+    none = u._addVsiteRestraintForceBoresch(lig, rcpt, *([None] * 18))
+    assert none == (None, None, None) and len(system.forces) == 3
