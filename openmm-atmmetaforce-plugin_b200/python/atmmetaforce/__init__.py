@@ -8,7 +8,8 @@ from .backend import ATMBackend, HostPipeline, softcore_softplus, hrex_sweep, hr
 
 ATMMETAFORCE_VERSION = "0.3.1"  # reference openmmapi/include/ATMMetaForceVersion.h:4
 from .replica import ReplicaExchange  # noqa: F401,E402
-from .force import ATMMetaForce, OpenMMException, serialize, deserialize  # noqa: F401,E402
+from .force import ATMMetaForce, OpenMMException, serialize, deserialize, vectord, vectori  # noqa: F401,E402
 from .context import Context, NonbondedDirect, State  # noqa: F401,E402
 from . import io  # noqa: F401,E402
+from .driver import ReplicaExchangeDriver, JitterPropagator  # noqa: F401,E402
 from .utils import ATMMetaForceUtils  # noqa: F401,E402

@@ -20,6 +20,41 @@ def _strip(x):
     return float(x)
 
 
+class vectord(list):
+    """std::vector<double> as SWIG exposes it (ref: python/atmmetaforceplugin.i:16 %template(vectord)): a sequence of
+    floats with push_back / size besides the list protocol."""
+
+    _conv = float
+
+    def __init__(self, values=()):
+        if isinstance(values, int) and not isinstance(values, bool):   # vectord(n): n default-constructed elements
+            values = [self._conv(0)] * values
+        super().__init__(self._conv(_strip(v) if self._conv is float else v) for v in values)
+
+    def append(self, v):
+        super().append(self._conv(_strip(v) if self._conv is float else v))
+
+    push_back = append
+
+    def __setitem__(self, i, v):
+        if isinstance(i, slice):
+            super().__setitem__(i, [self._conv(x) for x in v])
+        else:
+            super().__setitem__(i, self._conv(_strip(v) if self._conv is float else v))
+
+    def size(self):
+        return len(self)
+
+    def empty(self):
+        return len(self) == 0
+
+
+class vectori(vectord):
+    """std::vector<int> (ref: .i:17 %template(vectori)); what getVariableForceGroups() hands back."""
+
+    _conv = int
+
+
 class ATMMetaForce(_core.ATMMetaForce):
     """See openmmapi/include/ATMMetaForce.h.  Constructor order (ref: ATMMetaForce.h:79-83):
     (Lambda1, Lambda2, Alpha, U0, W0, Umax, Ubcore, Acore, direction, VariableForceGroups)."""
@@ -49,6 +84,9 @@ class ATMMetaForce(_core.ATMMetaForce):
             super().updateParametersInContext(context)
         else:
             context._atm_update_parameters(self)
+
+    def getVariableForceGroups(self):
+        return vectori(super().getVariableForceGroups())
 
     @staticmethod
     def cast(force):

@@ -156,3 +156,32 @@ def test_cpp_impl_test_binary():
         pytest.skip("a GPU is present: tests/test_gpu_facade.py runs the binary in its gpu mode")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "Done" in out.stdout, out.stdout + out.stderr
+
+
+def test_swig_vector_names_and_interface_file():
+    """vectord / vectori (ref: python/atmmetaforceplugin.i:14-17) and the interface file itself: it declares every public
+    member the reference's interface declares."""
+    import os
+    import re
+    import atmmetaforce as atm
+    v = atm.vectori([1, 2])
+    v.push_back(3.0)
+    assert list(v) == [1, 2, 3] and v.size() == 3 and all(type(x) is int for x in v) and not v.empty()
+    d = atm.vectord(2)
+    d[1] = 3
+    d.append(0.5)
+    assert list(d) == [0.0, 3.0, 0.5] and all(type(x) is float for x in d)
+    f = atm.ATMMetaForce(0.1, 0.2, 0.0, 0.0, 0.0, 100.0, 50.0, 0.0625, 1.0, atm.vectori([1, 3]))
+    g = f.getVariableForceGroups()
+    assert isinstance(g, atm.vectori) and list(g) == [1, 3]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "openmm-atmmetaforce-plugin_b200", "python", "atmmetaforceplugin.i")).read()
+    assert "%module atmmetaforce" in text and "%template(vectord) vector<double>" in text and "%template(vectori) vector<int>" in text
+    header = open(os.path.join(root, "openmm-atmmetaforce-plugin_b200", "openmmapi", "include", "ATMMetaForce.h")).read()
+    for name in ("getNumParticles", "addParticle", "setParticleParameters", "getParticleParameters", "updateParametersInContext",
+                 "getPerturbationEnergy", "Lambda1", "Lambda2", "Alpha", "U0", "W0", "Umax", "Ubcore", "Acore", "Direction", "Version",
+                 "getDefaultLambda1", "getDefaultLambda2", "getDefaultAlpha", "getDefaultU0", "getDefaultW0", "getDefaultUmax",
+                 "getDefaultUbcore", "getDefaultAcore", "getDefaultDirection", "getVariableForceGroups", "cast", "isinstance"):
+        assert re.search(r"\b%s\s*\(" % name, text), name
+        if name not in ("cast", "isinstance"):
+            assert re.search(r"\b%s\s*\(" % name, header), name
