@@ -437,7 +437,13 @@ __device__ __forceinline__ int prune_one_list(const NbDev &d, int r, int l, int 
         const float4 p = __ldg(d.xs + rsite + (size_t)A * CL + lane);
         const bool ok = (validA >> lane) & 1;
         const float ax = wrap_delta(p.x - cA.x, L.x, iL.x), ay = wrap_delta(p.y - cA.y, L.y, iL.y), az = wrap_delta(p.z - cA.z, L.z, iL.z);
-        sa[lane] = make_float4(-2.f * ax, -2.f * ay, -2.f * az, ok ? fmaf(az, az, fmaf(ay, ay, ax * ax)) : 1e30f);
+        const float aw = ok ? fmaf(az, az, fmaf(ay, ay, ax * ax)) : 1e30f;
+        sa[lane] = make_float4(-2.f * ax, -2.f * ay, -2.f * az, aw);
+        // packed copy for the f32x2 distance test: pair p = atoms 2p, 2p+1
+        float *q0 = reinterpret_cast<float *>(sa + CL + (lane >> 1)) + (lane & 1);
+        float *q1 = reinterpret_cast<float *>(sa + CL + CL / 2 + (lane >> 1)) + (lane & 1);
+        q0[0] = -2.f * ax; q0[2] = -2.f * ay;
+        q1[0] = -2.f * az; q1[2] = aw;
     }
     __syncwarp();
     const unsigned int *in = d.jlist_outer + li.offset;
@@ -477,9 +483,17 @@ __device__ __forceinline__ int prune_one_list(const NbDev &d, int r, int l, int 
                 const float4 p = pcur[q];
                 const float px = wrap_delta(p.x - cA.x, L.x, iL.x), py = wrap_delta(p.y - cA.y, L.y, iL.y),
                             pz = wrap_delta(p.z - cA.z, L.z, iL.z);
+                // the 8 atoms as 4 packed pairs (fma.rn.f32x2): sp[k] = (-2ax0,-2ax1,-2ay0,-2ay1), sp[k+4] = (-2az0,-2az1,|a0|^2,|a1|^2)
+                const float4 *sp = sa + CL;
                 float d2min = 1e30f;
 #pragma unroll
-                for (int k = 0; k < CL; k++) { const float4 a = sa[k]; d2min = fminf(d2min, fmaf(px, a.x, fmaf(py, a.y, fmaf(pz, a.z, a.w)))); }
+                for (int k = 0; k < CL / 2; k++) {
+                    const float4 u = sp[k], v = sp[k + CL / 2];
+                    const float2 t = __ffma2_rn(make_float2(px, px), make_float2(u.x, u.y),
+                                                __ffma2_rn(make_float2(py, py), make_float2(u.z, u.w),
+                                                           __ffma2_rn(make_float2(pz, pz), make_float2(v.x, v.y), make_float2(v.z, v.w))));
+                    d2min = fminf(d2min, fminf(t.x, t.y));
+                }
                 keep = d2min + fmaf(pz, pz, fmaf(py, py, px * px)) <= rl2;
             }
             const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
@@ -538,7 +552,7 @@ __global__ void __launch_bounds__(32 * PRUNE_WARPS, ATM_PRUNE_MIN_BLOCKS) nl_pru
     const int r = blockIdx.y;
     ListInfo li;
     li.cluster = 0; li.target = TGT_C; li.offset = 0;
-    __shared__ float4 s_atoms[PRUNE_WARPS][CL];
+    __shared__ float4 s_atoms[PRUNE_WARPS][2 * CL];   // per-atom form + the packed-pair form of the same 8 atoms
     const int count = prune_one_list(d, r, l, d.Cmax + d.CLmax, lane, li, s_atoms[w]);
     const int A = li.cluster;
     const int nsteps = (count + 31) >> 5;

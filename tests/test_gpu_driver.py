@@ -18,7 +18,7 @@ def test_driver_writes_samples_checkpoints_and_restarts(tmp_path):
 
     def make(outdir):
         return atm.ReplicaExchangeDriver(s, sched, "job", outdir=str(outdir), temperature=300.0, steps_per_cycle=12, prune_every=5,
-                                         rebuild_every=10, skin=0.1, checkpoint_every=2, seed=5)
+                                         rebuild_every=10, skin=0.1, skin_outer=0.1, checkpoint_every=2, seed=5)
 
     # reference run: 4 cycles in one go
     a = make(tmp_path / "a")
