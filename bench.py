@@ -59,6 +59,10 @@ def parse_args():
                     "concurrent_prune); before: atm_nb_prune on the launching stream before the step (round 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--flush-mode", default="write+read", choices=["write", "write+read"], help="L2 flush between steps (outside "
+                    "the event pairs).  write: a 256 MiB memset -- it leaves the cache full of DIRTY lines whose write-back "
+                    "is then charged to the timed kernels (~20 us per step, measured).  write+read: the memset followed by "
+                    "a read of another 256 MiB buffer, so the cache holds CLEAN lines of unrelated data")
     ap.add_argument("--cpu-steps", type=int, default=200, help="upper bound of the CPU-baseline sample (also capped at ~15 s)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: time budget of the whole run; a step "
                     "covers fewer replicas when K steps of all of them would not fit")
@@ -344,7 +348,20 @@ def run_b200(args):
     force_h = torch.zeros((max(R, 1), 3 * P), dtype=torch.float32 if args.e2e_force == "f32" else torch.int64).pin_memory()
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
-    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    class _Flush:
+        """L2 flush: write a buffer twice the size of L2, then (write+read) read a second one back."""
+
+        def __init__(self):
+            self.w = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+            self.r = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=dev) if args.flush_mode == "write+read" else None
+            self.sink = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def zero_(self):
+            self.w.zero_()
+            if self.r is not None:
+                torch.sum(self.r, out=self.sink[0])
+
+    flush = None if args.no_flush else _Flush()
     device_exchange = not args.host_exchange and total_replicas >= world
     if device_exchange:
         with torch.cuda.stream(stream):
@@ -763,7 +780,8 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 pair math, int64 fixed-point accumulation, f64 scalar stage",
             "data": "synthetic",
             "config": workload_config(args, label, s, max_per_rank, "device" if device_exchange else "host", use_graph, pme_grid,
-                                      "none" if flush is None else "flushed between steps (256 MiB memset outside the per-step event pairs)"),
+                                      "none" if flush is None else ("flushed between steps, outside the per-step event pairs: 256 MiB memset" +
+                                                                  (", then 256 MiB read (clean lines)" if args.flush_mode == "write+read" else ""))),
             "per_replica_ns_day": value / total_replicas, "us_per_replica_step": ms_per_step * 1e3 / max_per_rank,
             "ms_per_step_is": "steady state on the declared cadences: plain step + sum(component ms * per_step), every component "
                               "timed in this run with CUDA events (mean of the plain steps, median of the few maintenance / "

@@ -87,7 +87,11 @@ int atm_create(const atm_config *cfg, atm_handle **out) {
     h->launches = 0;
     h->nb = nullptr;
     cudaDeviceProp prop;
-    ATM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if ((err = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) {
+        set_error("atm_create: cudaGetDeviceProperties failed: %s", cudaGetErrorString(err));
+        atm_destroy(h);   // every failure after `new` releases the handle
+        return ATM_ERR_CUDA;
+    }
     h->num_sms = prop.multiProcessorCount;
     h->params.assign((size_t)h->R * ATM_NUM_PARAMS, 0.0);
     for (int r = 0; r < h->R; r++) h->params[(size_t)r * ATM_NUM_PARAMS + ATM_DIRECTION] = 1.0;
@@ -99,7 +103,11 @@ int atm_create(const atm_config *cfg, atm_handle **out) {
         atm_destroy(h);
         return ATM_ERR_CUDA;
     }
-    ATM_CUDA_CHECK(cudaMemset(h->d_displ, 0, sizeof(float4) * (size_t)std::max(P, 1)));
+    if ((err = cudaMemset(h->d_displ, 0, sizeof(float4) * (size_t)std::max(P, 1))) != cudaSuccess) {
+        set_error("atm_create: cudaMemset failed: %s", cudaGetErrorString(err));
+        atm_destroy(h);
+        return ATM_ERR_CUDA;
+    }
     h->atom_index.resize(h->N);
     for (int i = 0; i < h->N; i++) h->atom_index[i] = i;
     h->displ_by_atom.assign((size_t)h->N * 3, 0.0);

@@ -245,6 +245,14 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
         if (d.capX == 0) d.capX = 32 * (int)ceil(full * 2.0 / 32.0 + 2);
     }
     ATM_REQUIRE((long long)d.Smax < (1ll << 24), ATM_ERR_UNSUPPORTED, "more than 2^24 sites per replica");
+    // work items carry the replica in 8 bits and the list offset in a 32-bit int (atm_nb_lists.cuh, nl_prune_kernel)
+    ATM_REQUIRE(R <= 256, ATM_ERR_UNSUPPORTED, "more than 256 replicas per handle (%d): split them over several handles", R);
+    {
+        const unsigned long long per_replica_entries =
+            (unsigned long long)d.CenvMax * d.capC + (unsigned long long)d.CXmax * d.capX + (unsigned long long)d.CLmax * d.capC;
+        ATM_REQUIRE(per_replica_entries * (unsigned long long)R < (1ull << 31), ATM_ERR_UNSUPPORTED,
+                    "pair-list storage of %llu entries exceeds 2^31: use fewer replicas per handle", per_replica_entries * (unsigned long long)R);
+    }
 
     // static by-atom arrays
     float *qp; float2 *par; int *es, *el, *goa, *ga, *gof, *soa, *aos;

@@ -40,3 +40,16 @@ def abfe():
 @pytest.fixture(scope="session")
 def rbfe():
     return dict(np.load(os.path.join(GOLDEN, "temoa_g1_g4_rbfe.npz")))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU runs leave the measured parity errors behind (gpurun_out/ travels back from the GPU box)."""
+    try:
+        import json
+        from helpers import PARITY_LOG
+        if PARITY_LOG:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "parity_errors.json"), "w") as fh:
+                json.dump(PARITY_LOG, fh, indent=1, sort_keys=True)
+    except Exception:
+        pass

@@ -60,6 +60,9 @@ def _check(r, tol_u=5e-3):
     assert abs(en[E_SP] - sc["sp"]) <= 1e-4
     assert abs(en[E_ENERGY] - sc["energy"]) <= 1e-6 * abs(sc["energy"]) + tol_u
     err = rel_rms(r["f_gpu"], r["f_ref"])
+    from helpers import record
+    record(U1_rel=abs(en[E_U1] - r["e1"]) / abs(r["e1"]), U2_rel=abs(en[E_U2] - r["e2"]) / abs(r["e2"]),
+           u_abs=abs((en[E_U2] - en[E_U1]) - du), usc_abs=abs(en[E_USC] - sc["u_sc"]), sp_abs=abs(en[E_SP] - sc["sp"]), force_rel_rms=err)
     assert err <= 1e-5, err
     return err
 
