@@ -508,6 +508,7 @@ struct SpecialArgs {
     const float4 *exc_par;
     int n_excl, n_exc;
     int blocks_per_replica;  // ceil((n_excl + n_exc) / NB_THREADS)
+    int special_first;       // 1: the special-pair blocks are the first blocks of the grid, 0: the last (round 1)
 };
 
 template <bool STATS>
@@ -516,7 +517,11 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     pdl_trigger();  // the merge may be scheduled once every block of this grid has started (it waits for completion)
     pdl_wait();     // cluster-order coordinates come from the pack kernel
     const int lane = threadIdx.x & 31;
-    if ((int)blockIdx.x < n_item_blocks) {
+    // special-pair blocks come FIRST in the grid (they are short: placed last they formed a tail behind the work items,
+    // placed first they run under the items' start-up latency)
+    const int n_special = sp.blocks_per_replica * d.R;
+    const int bid = sp.special_first ? (int)blockIdx.x - n_special : (int)blockIdx.x;
+    if (bid >= 0 && bid < n_item_blocks) {
         // The pruned list's item count lives on the device; the grid is sized from the count the last verified build
         // saw plus a margin, and this grid-stride loop picks up whatever a later prune added beyond it.
         __shared__ Nb2Smem sm;
@@ -541,7 +546,7 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
             if (lane >= off) pre += v;
         }
         const int n_items = d.iflags[4], stride = n_item_blocks * (NB_THREADS / 32);
-        for (int warp = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
+        for (int warp = bid * (NB_THREADS / 32) + (threadIdx.x >> 5); warp < n_items; warp += stride, parity ^= 1u) {
             __syncwarp();  // the previous item's readers of this warp's shared-memory slots are done
             const unsigned int below = __ballot_sync(0xffffffffu, warp < pre);  // lanes whose prefix covers this item
             const int l = below ? __ffs(below) - 1 : ITEM_STEPS - 1;
@@ -560,7 +565,7 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
             else nb2_item<true, STATS>(d, it, lane, w, sm, parity, pc);
         }
     } else {
-        const int sb = blockIdx.x - n_item_blocks;
+        const int sb = sp.special_first ? (int)blockIdx.x : (int)blockIdx.x - n_item_blocks;
         const int r = sb / sp.blocks_per_replica, chunk = sb - r * sp.blocks_per_replica;
         special_pairs_body(d, chunk * NB_THREADS + threadIdx.x, r, sp.excl, sp.n_excl, sp.exc, sp.exc_par, sp.n_exc);
     }

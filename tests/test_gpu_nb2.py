@@ -1,7 +1,9 @@
 """GPU parity of the fused two-state direct-space path (atm_step) against the CPU oracle.
 
-Tolerances (BASELINE.json north_star): energies <= 1e-6 relative, per-atom forces <= 1e-5 relative RMS, against a
-double-precision evaluation of the SAME float-rounded coordinates.  The reference's only pinned number on this path is
+Bars (BASELINE.json north_star): energies <= 1e-6 relative, per-atom forces <= 1e-5 relative RMS, against a
+double-precision evaluation of the SAME float-rounded coordinates.  The tolerances asserted here are about twice the
+largest error measured on B200 (profiles/r2_parity_errors.md: U1 8.5e-8 relative, forces 3.5e-6 relative RMS, sp 5.8e-7,
+u 3.1e-4 kJ/mol on the reference fixtures and 1.5e-3 on the synthetic 23k system), i.e. tighter than the bars.  The reference's only pinned number on this path is
 u = 58.2 +- 0.1 kJ/mol for the TEMOA-G1 fixture (python/tests/test_abfe.py:148-150).
 """
 import numpy as np
@@ -49,21 +51,21 @@ def _run(s, cutoff, alpha, params, skin=0.1, perm=None, du_ext=0.0, with_ext=Fal
     return dict(en=en, f_gpu=f_gpu, f_ref=f_ref, e1=e1, e2=e2 + du_ext, sc=sc, stats=stats, f1=f1, f2=f2)
 
 
-def _check(r, tol_u=5e-3):
+def _check(r, tol_u=1e-3):
     from helpers import rel_rms
     en, sc = r["en"], r["sc"]
-    assert abs(en[E_U1] - r["e1"]) <= 1e-6 * abs(r["e1"]), (en[E_U1], r["e1"])
-    assert abs(en[E_U2] - r["e2"]) <= 1e-6 * abs(r["e2"])
+    assert abs(en[E_U1] - r["e1"]) <= 2e-7 * abs(r["e1"]), (en[E_U1], r["e1"])
+    assert abs(en[E_U2] - r["e2"]) <= 2e-7 * abs(r["e2"])
     du = r["e2"] - r["e1"]
-    assert abs((en[E_U2] - en[E_U1]) - du) <= max(tol_u, 1e-6 * abs(r["e1"]))
+    assert abs((en[E_U2] - en[E_U1]) - du) <= max(tol_u, 2e-7 * abs(r["e1"]))
     assert abs(en[E_USC] - sc["u_sc"]) <= tol_u
-    assert abs(en[E_SP] - sc["sp"]) <= 1e-4
-    assert abs(en[E_ENERGY] - sc["energy"]) <= 1e-6 * abs(sc["energy"]) + tol_u
+    assert abs(en[E_SP] - sc["sp"]) <= 2e-6
+    assert abs(en[E_ENERGY] - sc["energy"]) <= 2e-7 * abs(sc["energy"]) + tol_u
     err = rel_rms(r["f_gpu"], r["f_ref"])
     from helpers import record
     record(U1_rel=abs(en[E_U1] - r["e1"]) / abs(r["e1"]), U2_rel=abs(en[E_U2] - r["e2"]) / abs(r["e2"]),
            u_abs=abs((en[E_U2] - en[E_U1]) - du), usc_abs=abs(en[E_USC] - sc["u_sc"]), sp_abs=abs(en[E_SP] - sc["sp"]), force_rel_rms=err)
-    assert err <= 1e-5, err
+    assert err <= 7e-6, err
     return err
 
 
@@ -137,7 +139,7 @@ def test_synthetic_systems(maker):
     s = synthetic.config3() if maker == "config3" else synthetic.water_box(20000)
     params = synthetic.atm_schedule_22()[7]
     res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
-    err = _check(res, tol_u=2e-2)
+    err = _check(res, tol_u=5e-3)
     print(maker, "u = %.4f, force rel rms = %.2e, stats %s" % (res["en"][E_U], err, res["stats"]))
 
 
@@ -254,7 +256,7 @@ def test_config4_100k_rbfe():
     assert s["pos"].shape[0] > 90000
     params = synthetic.atm_schedule_22()[5]
     res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
-    err = _check(res, tol_u=2e-2)
+    err = _check(res, tol_u=5e-3)
     assert res["stats"]["groups"] == 2 and res["stats"]["displaced_atoms"] == 80
     print("config4 u = %.4f, force rel rms = %.2e, stats %s" % (res["en"][E_U], err, res["stats"]))
 
@@ -269,7 +271,7 @@ def test_single_atom_ligand_and_graph_replay():
     s["displ"][0] = [1.7, -1.1, 0.9]          # displace the oxygen of the first water only (its exclusions split states)
     params = [0.3, 0.6, 0.02, 20.0, 0.0, 800.0, 400.0, 0.0625, 1.0]
     res = _run(s, s["cutoff"], s["ewald_alpha"], params)
-    _check(res, tol_u=2e-2)
+    _check(res, tol_u=5e-3)
     assert res["stats"]["displaced_atoms"] == 1
     from helpers import make_backend
     be, posq, _ = make_backend(atm, s, s["cutoff"], s["ewald_alpha"], params)
@@ -447,7 +449,7 @@ def test_config5_500k_water_box():
     s = synthetic.water_box(500_000, n_lig=50)
     params = synthetic.atm_schedule_22()[16]          # direction -1 leg
     res = _run(s, s["cutoff"], s["ewald_alpha"], params, skin=0.1)
-    err = _check(res, tol_u=2e-2)
+    err = _check(res, tol_u=5e-3)
     f = res["f_gpu"]
     assert np.abs(f.sum(0)).max() <= 1e-7 * np.abs(f).sum()
     print("500k: N %d u %.4f force rel rms %.2e |sum F|/sum|F| %.1e" % (f.shape[0], res["en"][E_U], err,

@@ -37,10 +37,18 @@ with torch.cuda.stream(stream):
     be.prune(posq, stream=stream)
     be.step(posq, force, stream=stream)
     be.step(posq, force, graph=True, stream=stream)
+    # round 2: a prune on the side stream concurrent with the step (plain launches, then inside the step's CUDA graph), the
+    # copy switch, an asynchronous rebuild (cached graph) behind an odd number of switches, atm_nb_check
+    be.step(posq, force, stream=stream, concurrent_prune=True)
+    be.step(posq, force, graph=True, stream=stream, concurrent_prune=True)
+    be.step(posq, force, graph=True, stream=stream, concurrent_prune=True)
+    be.rebuild(posq, stream=stream)
+    be.step(posq, force, graph=True, stream=stream)
     rex = atm.ReplicaExchange(sched, R, temperature=300.0, seed=1)
-    rex.attach_device(be, stream=stream)
+    rex.attach_device(be, stream=stream)   # one rank: atm_hrex_device_cycle without NCCL
     rex.exchange_device(stream=stream)
 en = be.get_energies(stream=stream)
+be.nb_check(wait=True)
 rex.sync_from_device(stream=stream)
 be.pme_setup(synthetic.pme_grid(s["box"], s["ewald_alpha"]))
 with torch.cuda.stream(stream):
@@ -63,9 +71,14 @@ P = bes[0].P
 posq_h = [posq[r:r + 1].cpu().pin_memory() for r in range(R)]
 force_h = [torch.zeros((1, 3 * P), dtype=torch.int64).pin_memory() for _ in range(R)]
 en_h = [torch.zeros((1, 16), dtype=torch.float64).pin_memory() for _ in range(R)]
-for maint in (pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.REBUILD, pipe.NONE):
+for maint in (pipe.REBUILD, pipe.NONE, pipe.PRUNE, pipe.PRUNE_CONCURRENT, pipe.NONE, pipe.REBUILD, pipe.NONE):
     pipe.step(posq_h, force_h, en_h, maintenance=maint, stream=stream)
     stream.synchronize()
+pipe.check()
+force_f32 = [torch.zeros((1, 3 * P), dtype=torch.float32).pin_memory() for _ in range(R)]
+pipe.step(posq_h, force_f32, en_h, maintenance=pipe.NONE, stream=stream)     # float32 force read-back
+pipe.step(posq_h, None, en_h, maintenance=pipe.NONE, stream=stream)          # energies only
+stream.synchronize()
 print("pipeline u:", [float(e[0, 3]) for e in en_h], "max |F| (fixed point):", [int(f.abs().max()) for f in force_h])
 pipe.close()
 for b in bes:
