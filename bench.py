@@ -69,6 +69,8 @@ def parse_args():
                     "covers fewer replicas when K steps of all of them would not fit")
     ap.add_argument("--skip-two-separate", action="store_true")
     ap.add_argument("--skip-tier1", action="store_true", help="skip the 8M-atom HBM roofline probe of copy-state / hybrid-force")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out (its chunk handles "
+                    "add their own rebuilds and small launches to an ncu launch list)")
     ap.add_argument("--e2e-chunks", type=int, default=6)
     ap.add_argument("--e2e-force", default="f32", choices=["f32", "i64"], help="what the e2e leg reads back: float32 forces "
                     "(12 B per atom) or the 2^32 fixed-point long force buffer (24 B per atom, round 1)")
@@ -632,7 +634,7 @@ def run_b200(args):
     e2e_ms = None
     h2d = d2h = 0
     e2e_chunks = 0
-    if R > 0:
+    if R > 0 and not args.skip_e2e:
         e2e_chunks = max(1, min(args.e2e_chunks, R))
         bounds = [round(i * R / e2e_chunks) for i in range(e2e_chunks + 1)]
         chunks = []

@@ -775,8 +775,10 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
     spa.excl = nb->d_excl_pairs; spa.exc = nb->d_exc_pairs; spa.exc_par = nb->d_exc_par;
     spa.n_excl = nb->n_excl; spa.n_exc = nb->n_exc;
     spa.blocks_per_replica = (nb->n_excl + nb->n_exc + NB_THREADS - 1) / NB_THREADS;
-    {   // ATM_B200_SPECIAL_FIRST=0: special-pair blocks at the end of the grid as in round 1 (A/B switch)
-        static const int first = [] { const char *e = getenv("ATM_B200_SPECIAL_FIRST"); return (e && e[0] == '0') ? 0 : 1; }();
+    {   // ATM_B200_SPECIAL_FIRST=1: special-pair blocks at the START of the grid instead of the end (A/B switch; measured
+        // slower: nb2 0.3296 vs 0.3238 ms at 22 replicas, 0.0550 vs 0.0535 at 3 -- the short blocks delay the first wave
+        // of long work items more than they shorten the tail)
+        static const int first = [] { const char *e = getenv("ATM_B200_SPECIAL_FIRST"); return (e && e[0] == '1') ? 1 : 0; }();
         spa.special_first = first;
     }
     const int nblocks = item_blocks + spa.blocks_per_replica * d.R;

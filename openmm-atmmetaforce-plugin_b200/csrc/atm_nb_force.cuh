@@ -183,13 +183,23 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct __align__(128) Nb2Smem {
     unsigned int el[NB_WARPS][ITEM_STEPS][32];  // the item's list entries (bulk copy destination)
     float4 xj[NB_WARPS][RING][32];
-    float4 pj[NB_WARPS][RING][32];              // .xy = (sigma/2, 2 sqrt(eps)); float4 stride so that ONE offset addresses xj and pj
+#ifdef ATM_NB2_PJ_FLOAT4
+    float4 pj[NB_WARPS][RING][32];              // .xy = (sigma/2, 2 sqrt(eps)); float4 stride so that ONE byte offset addresses xj and pj
+#else
+    float2 pj[NB_WARPS][RING][32];              // (sigma/2, 2 sqrt(eps)): the same ELEMENT offset as xj (8-byte stride: half the
+                                                // shared-memory wavefronts of the float4-strided variant, one more shift)
+#endif
     // cluster atoms in PAIRS (atoms 2p, 2p+1) for the packed f32x2 inner loop: three 128-bit broadcast reads per pair --
     // (x0,x1,y0,y1), (z0,z1,q0,q1), (hs0,hs1,se0,se1)
     float4 ci[NB_WARPS][CL / 2][3];
     unsigned long long bar[NB_WARPS];           // one mbarrier per warp
 };
+#ifdef ATM_NB2_PJ_FLOAT4
 constexpr int PJ_OFF = NB_WARPS * RING * 32;    // float4 elements between a lane's xj slot and its pj slot
+#define ATM_PJ_AT(ring, pring, off) reinterpret_cast<float2 *>((ring) + (off) + PJ_OFF)
+#else
+#define ATM_PJ_AT(ring, pring, off) ((pring) + (off))
+#endif
 
 // Pins a value in a register: the compiler can no longer rematerialise it from kernel arguments / thread ids inside the
 // list-step loop (at 96 registers it re-derived the ring, accumulator and site-array addresses in every step: ~35 of
@@ -273,14 +283,16 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         c[0] = x.x; c[2] = x.y; c[4] = x.z; c[6] = x.w; c[8] = pp.x; c[10] = pp.y;
     }
     const unsigned int *elp = &sm.el[w][0][lane];
-    float4 *ring = &sm.xj[w][0][lane];  // the lane's ring: slot s of xj at ring[32 s], of pj at ring[32 s + PJ_OFF]
+    float4 *ring = &sm.xj[w][0][lane];  // the lane's rings: slot s of xj at ring[32 s], of pj at pring[32 s]
+    float2 *pring = reinterpret_cast<float2 *>(&sm.pj[w][0][lane]);
+    (void)pring;
     mbar_wait(&sm.bar[w], parity);
 #pragma unroll
     for (int q = 0; q < PF_DIST; q++) {
         if (q < it.nst) {
             const unsigned int eq = elp[q * 32] >> 8;
             cp_async16(ring + q * 32, xs_g + (unsigned long long)eq * 16ull);
-            cp_async8(ring + q * 32 + PJ_OFF, par_g + (unsigned long long)eq * 8ull);
+            cp_async8(ATM_PJ_AT(ring, pring, q * 32), par_g + (unsigned long long)eq * 8ull);
         }
         cp_async_commit();
     }
@@ -305,7 +317,7 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
         cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
         const int slot = (st & (RING - 1)) * 32;
         const float4 xjc = ring[slot];
-        const float2 pjc = *reinterpret_cast<const float2 *>(ring + slot + PJ_OFF);
+        const float2 pjc = *ATM_PJ_AT(ring, pring, slot);
         const unsigned int e = elp[st * 32];
         // keep PF_DIST steps in flight
         {
@@ -314,7 +326,7 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
                 const unsigned int e_next = elp[sp * 32] >> 8;
                 const int ps = (sp & (RING - 1)) * 32;
                 cp_async16(ring + ps, xs_g + (unsigned long long)e_next * 16ull);
-                cp_async8(ring + ps + PJ_OFF, par_g + (unsigned long long)e_next * 8ull);
+                cp_async8(ATM_PJ_AT(ring, pring, ps), par_g + (unsigned long long)e_next * 8ull);
             }
             cp_async_commit();
         }
@@ -517,8 +529,7 @@ nb2_kernel(NbDev d, int n_item_blocks, int energy_common, SpecialArgs sp) {
     pdl_trigger();  // the merge may be scheduled once every block of this grid has started (it waits for completion)
     pdl_wait();     // cluster-order coordinates come from the pack kernel
     const int lane = threadIdx.x & 31;
-    // special-pair blocks come FIRST in the grid (they are short: placed last they formed a tail behind the work items,
-    // placed first they run under the items' start-up latency)
+    // the special-pair blocks are the LAST blocks of the grid by default (sp.special_first: A/B switch, measured slower)
     const int n_special = sp.blocks_per_replica * d.R;
     const int bid = sp.special_first ? (int)blockIdx.x - n_special : (int)blockIdx.x;
     if (bid >= 0 && bid < n_item_blocks) {
