@@ -46,11 +46,13 @@ static void drop_graphs(atm_host_pipeline *p) {
         if (p->exec[v]) { cudaGraphExecDestroy(p->exec[v]); p->exec[v] = nullptr; }
 }
 
+namespace atm {
 // force_format 1: the merged fixed-point force as float32 kJ/mol/nm, same [R][3][P] layout: half the D2H bytes
 __global__ void force_to_f32_kernel(const long long *__restrict__ in, float *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)((double)in[i] * (1.0 / 4294967296.0));
 }
+}  // namespace atm
 
 // enqueue one step of every chunk (fork from `stream`, join back into it); capturable
 static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int maintenance, cudaStream_t stream) {
