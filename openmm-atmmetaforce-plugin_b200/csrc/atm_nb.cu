@@ -287,6 +287,18 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     if ((rc = dev_alloc(nb, &d.vals, RU))) return rc;
     if ((rc = dev_alloc(nb, &nb->vals_alt, RU))) return rc;
     if ((rc = dev_alloc(nb, &d.bin_count, (size_t)R * d.nbins))) return rc;
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)R * d.nbins, stream));   // the own sort keeps it zeroed between rebuilds
+    {   // own sort front end: a fixed-capacity segment per bin, sorted inside one warp.  Capacity = twice the mean population
+        // of an environment column (+32), a power of two; beyond 1024 entries (8 KB of shared memory per warp) the CUB
+        // radix sort front end is used instead.  ATM_B200_CUB_SORT=1 forces the CUB path (A/B, bit-identical results).
+        static const bool force_cub = [] { const char *e = getenv("ATM_B200_CUB_SORT"); return e && e[0] == '1'; }();
+        const double mean = (double)d.U / std::max(1, d.ncol);
+        int cap = 64;
+        while (cap < 2.0 * mean + 32.0) cap <<= 1;
+        d.bin_cap = (cap > 1024 || force_cub || nb->use_cub_sort) ? 0 : cap;
+        d.binbuf = nullptr;
+        if (d.bin_cap > 0 && (rc = dev_alloc(nb, &d.binbuf, (size_t)R * d.nbins * d.bin_cap))) return rc;
+    }
     if ((rc = dev_alloc(nb, &d.bin_site_start, (size_t)R * (d.nbins + 1)))) return rc;
     if ((rc = dev_alloc(nb, &d.bin_cluster_start, (size_t)R * (d.nbins + 1)))) return rc;
     if ((rc = dev_alloc(nb, &d.nclusters, R))) return rc;
@@ -298,6 +310,14 @@ static int nb_allocate(atm_handle *h, cudaStream_t stream) {
     if ((rc = dev_alloc(nb, &d.slot_qp, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.xs, RS))) return rc;
     if ((rc = dev_alloc(nb, &d.par, RS))) return rc;
+    // slots the own sort front end does not write (a truncated bin, clusters beyond the last one) must never hold
+    // garbage indices: start from "empty"
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * RS, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * RS, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * RS, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_src, 0, sizeof(int) * RS, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.par, 0, sizeof(float2) * RS, stream));
+    ATM_CUDA_CHECK(cudaMemsetAsync(d.xs, 0, sizeof(float4) * RS, stream));
     if ((rc = dev_alloc(nb, &d.cc, RC))) return rc;
     if ((rc = dev_alloc(nb, &d.ch, RC))) return rc;
     if ((rc = dev_alloc(nb, &d.cmeta, RC))) return rc;
@@ -561,23 +581,33 @@ static int launch_rebuild(atm_handle *h, const float4 *posq, cudaStream_t stream
     const int RU = d.R * d.U;
     nb->cur = 0;   // a rebuild always leaves the pruned list in copy 0 (its cached graph holds that copy's pointers)
     use_inner(d, nb->inner[0]);
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
-    ATM_CUDA_CHECK(cudaMemsetAsync(d.par, 0, sizeof(float2) * (size_t)d.R * d.Smax, stream));  // padding slots are read (masked)
     ATM_CUDA_CHECK(cudaMemsetAsync(d.flags, 0, sizeof(int) * NUM_HOST_FLAGS, stream));
-    nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
-    nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d);
-    size_t tmp_bytes = nb->sort_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
-    nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
-    if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
-    nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq, 1);
-    nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
+    if (d.bin_cap > 0) {
+        // own front end: bin (histogram + scatter) -> scan -> in-warp sort + place -> pack + ghost links + bounding boxes
+        nl_bin_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
+        nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d, 1);
+        nl_sort_place_kernel<<<(d.R * d.nbins + SORT_WARPS - 1) / SORT_WARPS, 32 * SORT_WARPS, sizeof(unsigned long long) * SORT_WARPS * d.bin_cap, stream>>>(d);
+        nl_pack_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d, posq);
+        h->launches += 4;
+    } else {
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.bin_count, 0, sizeof(int) * (size_t)d.R * d.nbins, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_site, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_out, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.slot_ghost, 0xff, sizeof(int) * (size_t)d.R * d.Smax, stream));
+        ATM_CUDA_CHECK(cudaMemsetAsync(d.par, 0, sizeof(float2) * (size_t)d.R * d.Smax, stream));  // padding slots are read (masked)
+        nl_keys_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, posq);
+        nl_scan_kernel<<<d.R, 1024, 0, stream>>>(d, 0);
+        size_t tmp_bytes = nb->sort_tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(nb->sort_tmp, tmp_bytes, d.keys, nb->keys_alt, d.vals, nb->vals_alt, RU, 0, nb->sort_bits, stream);
+        nl_place_kernel<<<(RU + 255) / 256, 256, 0, stream>>>(d, nb->keys_alt, nb->vals_alt);
+        if (d.M > 0) nl_link_ghosts_kernel<<<(d.R * d.M + 127) / 128, 128, 0, stream>>>(d);
+        nb_pack_kernel<<<dim3((d.Smax + 255) / 256, d.R), 256, 0, stream>>>(d, posq, 1);
+        nl_bbox_kernel<<<dim3((d.Cmax + 127) / 128, d.R), 128, 0, stream>>>(d);
+        h->launches += 5 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox
+    }
     const int nlists = d.Cmax + d.CLmax;
     nl_build_kernel<<<dim3((nlists + BUILD_WARPS - 1) / BUILD_WARPS, d.R), 32 * BUILD_WARPS, 0, stream>>>(d);
-    h->launches += 6 + (d.M > 0 ? 1 : 0);  // keys, scan, place, [link], pack, bbox, build
+    h->launches += 1;
     if ((rc = launch_prune(h, stream, d))) return rc;
     ATM_CUDA_CHECK(cudaGetLastError());
     return ATM_OK;
@@ -594,6 +624,12 @@ static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
         set_error("atm_nb_rebuild: a cluster's extent + list radius exceeds half the box; box too small for this build");
         return ATM_ERR_UNSUPPORTED;
     }
+    if (flags[0] & 4) {
+        // a bin outgrew its sort segment (a column more than twice as populous as the mean): the structure is incomplete
+        // (results were poisoned like a list overflow); from now on the CUB radix sort front end is used
+        nb->use_cub_sort = true;
+        *grow = true;
+    }
     if (flags[0] & 1) {
         const int need = flags[1];
         d.capC = std::max(d.capC, 32 * ((int)(need * 1.25) / 32 + 1));
@@ -602,8 +638,8 @@ static int inspect_rebuild_flags(atm_handle *h, const int *flags, bool *grow) {
     } else {
         // head-room: a list within 20 % of its capacity raises that capacity (by half) at the NEXT rebuild, while the
         // lists in use are still complete
-        if (flags[FLAG_MAXLEN_C] > (int)(0.8 * d.capC)) { nb->grow_capC = 32 * ((int)(flags[FLAG_MAXLEN_C] * 1.5) / 32 + 1); nb->grow_pending = true; }
-        if (flags[FLAG_MAXLEN_X] > (int)(0.8 * d.capX)) { nb->grow_capX = 32 * ((int)(flags[FLAG_MAXLEN_X] * 1.5) / 32 + 1); nb->grow_pending = true; }
+        if (!(flags[0] & 4) && flags[FLAG_MAXLEN_C] > (int)(0.8 * d.capC)) { nb->grow_capC = 32 * ((int)(flags[FLAG_MAXLEN_C] * 1.5) / 32 + 1); nb->grow_pending = true; }
+        if (!(flags[0] & 4) && flags[FLAG_MAXLEN_X] > (int)(0.8 * d.capX)) { nb->grow_capX = 32 * ((int)(flags[FLAG_MAXLEN_X] * 1.5) / 32 + 1); nb->grow_pending = true; }
     }
     unsigned long long inner_entries = 0;
     memcpy(&inner_entries, &flags[NUM_HOST_FLAGS + 6], 8);   // the inner-list counters travel behind the rebuild flags

@@ -493,7 +493,7 @@ __device__ double scalar_stage_replica(const NbDev &d, int r, const double *__re
         du += energy_ext[2 * r + 1] - energy_ext[2 * r];
     }
     Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
-    if (d.flags[0] & 3) {
+    if (d.flags[0] & 7) {
         // the pair lists of the last rebuild are incomplete (a list outgrew its capacity, or the box is too small for
         // the list radius): nothing computed from them may look like a result
         const double bad = __longlong_as_double(0x7ff8000000000000ll);

@@ -41,42 +41,194 @@ __global__ void nl_keys_kernel(NbDev d, const float4 *__restrict__ posq) {
     atomicAdd(&d.bin_count[r * d.nbins + bin], 1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Own sort front end (replaces keys -> CUB radix sort -> place -> link -> pack -> bbox: 13 graph nodes become 4).
+// The order produced is exactly the radix sort's: by (replica, bin), then z16, ties by site index -- so clusters, lists
+// and results are bit-identical to the CUB path (which stays as the fallback for bins beyond bin_cap).
+// ------------------------------------------------------------------------------------------------
+// Step 1: every site into its bin's fixed-capacity segment, in arrival order (sorted later, inside the bin).
+__global__ void nl_bin_kernel(NbDev d, const float4 *__restrict__ posq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.R * d.U) return;
+    const int r = t / d.U, u = t - r * d.U;
+    const bool ghost = u >= d.N;
+    const int a = ghost ? d.ghost_atom[u - d.N] : u;
+    const int slot = d.slot_of_atom[a];
+    float4 p = __ldg(posq + (size_t)r * d.P + slot);
+    if (ghost) {
+        const float4 dd = __ldg(d.displ + slot);
+        p.x = __fadd_rn(p.x, dd.x);
+        p.y = __fadd_rn(p.y, dd.y);
+        p.z = __fadd_rn(p.z, dd.z);
+    }
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const float wx = p.x - L.x * floorf(p.x * iL.x), wy = p.y - L.y * floorf(p.y * iL.y), wz = p.z - L.z * floorf(p.z * iL.z);
+    const int g = d.group_of_atom[a];
+    const int cls = g == 0 ? 0 : (ghost ? d.G + g : g);
+    const int ix = min(max((int)(wx * iL.x * d.nx), 0), d.nx - 1);
+    const int iy = min(max((int)(wy * iL.y * d.ny), 0), d.ny - 1);
+    const int bin = cls * d.ncol + ix * d.ny + iy;
+    const int zq = min(max((int)(wz * iL.z * 65536.0f), 0), 65535);
+    const int rb = r * d.nbins + bin;
+    const int rank = atomicAdd(&d.bin_count[rb], 1);
+    if (rank < d.bin_cap) d.binbuf[(size_t)rb * d.bin_cap + rank] = ((unsigned long long)zq << 32) | (unsigned int)u;
+    else atomicOr(&d.flags[0], 4);   // a bin outgrew its segment: the structure is incomplete (poisoned like a list overflow)
+}
+
+// Step 3: one warp per (replica, bin): bitonic sort of the bin's entries in shared memory, then every slot of the bin's
+// clusters is written -- real sites and the padding slots of the last cluster -- so no array needs clearing first.
+constexpr int SORT_WARPS = 4;
+__global__ void __launch_bounds__(32 * SORT_WARPS) nl_sort_place_kernel(NbDev d) {
+    extern __shared__ unsigned long long s_keys[];   // [SORT_WARPS][bin_cap]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rb = blockIdx.x * SORT_WARPS + w;
+    if (rb >= d.R * d.nbins) return;
+    const int r = rb / d.nbins, bin = rb - r * d.nbins;
+    const int start = d.bin_site_start[r * (d.nbins + 1) + bin];
+    const int count = min(d.bin_site_start[r * (d.nbins + 1) + bin + 1] - start, d.bin_cap);
+    if (count == 0) return;
+    unsigned long long *k = s_keys + (size_t)w * d.bin_cap;
+    int n = 2;
+    while (n < count) n <<= 1;
+    for (int i = lane; i < n; i += 32) k[i] = i < count ? d.binbuf[(size_t)rb * d.bin_cap + i] : ~0ull;
+    __syncwarp();
+    for (int kk = 2; kk <= n; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = k[i], b = k[ixj];
+                    if ((a > b) == ((i & kk) == 0)) { k[i] = b; k[ixj] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    const int slot0 = CL * d.bin_cluster_start[r * (d.nbins + 1) + bin];
+    const int nslots = CL * ((count + CL - 1) / CL);
+    for (int rank = lane; rank < nslots; rank += 32) {
+        const size_t rs = (size_t)r * d.Smax + slot0 + rank;
+        if (rank < count) {
+            const int u = (int)(unsigned int)(k[rank] & 0xffffffffull);
+            const bool ghost = u >= d.N;
+            const int a = ghost ? d.ghost_atom[u - d.N] : u;
+            d.slot_site[rs] = u;
+            d.site_slot[(size_t)r * d.U + u] = slot0 + rank;
+            d.slot_src[rs] = (r * d.P + d.slot_of_atom[a]) | (ghost ? 0x80000000 : 0);
+            d.slot_qp[rs] = d.qp_atom[a];
+            d.par[rs] = d.par_atom[a];
+            d.slot_out[rs] = ghost ? -1 : d.slot_of_atom[a];
+        } else {   // padding of the bin's last cluster: read (masked) by the build, the prune and the force kernel
+            d.slot_site[rs] = -1;
+            d.slot_out[rs] = -1;
+            d.par[rs] = make_float2(0.f, 0.f);
+        }
+        d.slot_ghost[rs] = -1;
+    }
+}
+
+// Step 4: one thread per cluster: gathers the cluster's coordinates (as nb_pack_kernel does), links every displaced
+// atom to its ghost site (nl_link_ghosts_kernel) and forms the bounding box (nl_bbox_kernel) in one pass.
+__global__ void nl_pack_bbox_kernel(NbDev d, const float4 *__restrict__ posq) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= d.nclusters[r]) return;
+    const float4 L = d.box[r], iL = d.invbox[r];
+    const size_t base = (size_t)r * d.Smax + (size_t)c * CL;
+    float3 lo = make_float3(0, 0, 0), hi = make_float3(0, 0, 0), x0 = make_float3(0, 0, 0);
+    int valid = 0, cls = 0;
+#pragma unroll
+    for (int k = 0; k < CL; k++) {
+        const int u = d.slot_site[base + k];
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u >= 0) {
+            const int src = d.slot_src[base + k];
+            const int idx = src & 0x7fffffff;
+            p = __ldg(posq + idx);
+            if (src < 0) {
+                const float4 dd = __ldg(d.displ + (idx - r * d.P));
+                p.x = __fadd_rn(p.x, dd.x);
+                p.y = __fadd_rn(p.y, dd.y);
+                p.z = __fadd_rn(p.z, dd.z);
+            }
+            p.w = d.slot_qp[base + k];
+            const int a = u >= d.N ? d.ghost_atom[u - d.N] : u;
+            if (u < d.N) {
+                const int gm = d.ghost_of_atom[a];
+                if (gm >= 0) d.slot_ghost[base + k] = d.site_slot[(size_t)r * d.U + d.N + gm];
+            }
+            if (!valid) {
+                x0 = make_float3(p.x, p.y, p.z);
+                const int g = d.group_of_atom[a];
+                cls = g == 0 ? 0 : (u >= d.N ? d.G + g : g);
+            }
+            const float dx = wrap_delta(p.x - x0.x, L.x, iL.x), dy = wrap_delta(p.y - x0.y, L.y, iL.y),
+                        dz = wrap_delta(p.z - x0.z, L.z, iL.z);
+            lo.x = fminf(lo.x, dx); lo.y = fminf(lo.y, dy); lo.z = fminf(lo.z, dz);
+            hi.x = fmaxf(hi.x, dx); hi.y = fmaxf(hi.y, dy); hi.z = fmaxf(hi.z, dz);
+            valid |= 1 << k;
+        }
+        d.xs[base + k] = p;
+    }
+    const size_t rc = (size_t)r * d.Cmax + c;
+    d.cc[rc] = make_float4(x0.x + 0.5f * (lo.x + hi.x), x0.y + 0.5f * (lo.y + hi.y), x0.z + 0.5f * (lo.z + hi.z), 0.f);
+    d.ch[rc] = make_float4(0.5f * (hi.x - lo.x), 0.5f * (hi.y - lo.y), 0.5f * (hi.z - lo.z), 0.f);
+    d.cmeta[rc] = cls | (valid << 16);
+    const float rl = d.rlist_outer + (d.rlist - sqrtf(d.cutoff2));
+    const float hmax_x = 0.5f * (hi.x - lo.x) + rl, hmax_y = 0.5f * (hi.y - lo.y) + rl, hmax_z = 0.5f * (hi.z - lo.z) + rl;
+    if (hmax_x > 0.5f * L.x || hmax_y > 0.5f * L.y || hmax_z > 0.5f * L.z) atomicOr(&d.flags[0], 2);
+}
+
 // Rebuild step 2: per replica exclusive scans of the bin populations (sites and 8-padded clusters).
-__global__ void nl_scan_kernel(NbDev d) {
+// zero_counts: the histogram is handed back zeroed for the next rebuild (own sort front end; its place step reads the
+// scanned starts only).
+__global__ void nl_scan_kernel(NbDev d, int zero_counts) {
     const int r = blockIdx.x;
-    __shared__ int s_sites[1024], s_clusters[1024];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_sites[1024], s_clusters[1024], s_wsum[2][32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int per = (d.nbins + nt - 1) / nt;
     const int b0 = min(tid * per, d.nbins), b1 = min(b0 + per, d.nbins);
     int ns = 0, nc = 0;
     for (int b = b0; b < b1; b++) {
-        int c = d.bin_count[r * d.nbins + b];
+        const int c = d.bin_count[r * d.nbins + b];
         ns += c;
         nc += (c + CL - 1) / CL;
     }
-    s_sites[tid] = ns;
-    s_clusters[tid] = nc;
+    // block-wide exclusive scan of the per-thread partial sums: warp shuffles, then the warp totals
+    int is = ns, ic = nc;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int vs = __shfl_up_sync(0xffffffffu, is, off), vc = __shfl_up_sync(0xffffffffu, ic, off);
+        if (lane >= off) { is += vs; ic += vc; }
+    }
+    if (lane == 31) { s_wsum[0][wid] = is; s_wsum[1][wid] = ic; }
     __syncthreads();
-    if (tid == 0) {
-        int as = 0, ac = 0;
-        for (int i = 0; i < nt; i++) {
-            int ts = s_sites[i], tc = s_clusters[i];
-            s_sites[i] = as;
-            s_clusters[i] = ac;
-            as += ts;
-            ac += tc;
+    if (wid == 0) {
+        const int nw = nt >> 5;
+        int ws = lane < nw ? s_wsum[0][lane] : 0, wc = lane < nw ? s_wsum[1][lane] : 0;
+        int xs_ = ws, xc_ = wc;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int vs = __shfl_up_sync(0xffffffffu, xs_, off), vc = __shfl_up_sync(0xffffffffu, xc_, off);
+            if (lane >= off) { xs_ += vs; xc_ += vc; }
         }
-        d.nclusters[r] = ac;
-        d.bin_site_start[r * (d.nbins + 1) + d.nbins] = as;
-        d.bin_cluster_start[r * (d.nbins + 1) + d.nbins] = ac;
+        s_wsum[0][lane] = xs_ - ws;   // exclusive prefix of the warp totals
+        s_wsum[1][lane] = xc_ - wc;
+        if (lane == 31) {
+            d.nclusters[r] = xc_;
+            d.bin_site_start[r * (d.nbins + 1) + d.nbins] = xs_;
+            d.bin_cluster_start[r * (d.nbins + 1) + d.nbins] = xc_;
+        }
     }
     __syncthreads();
+    s_sites[tid] = is - ns + s_wsum[0][wid];
+    s_clusters[tid] = ic - nc + s_wsum[1][wid];
     ns = s_sites[tid];
     nc = s_clusters[tid];
     for (int b = b0; b < b1; b++) {
-        int c = d.bin_count[r * d.nbins + b];
+        const int c = d.bin_count[r * d.nbins + b];
         d.bin_site_start[r * (d.nbins + 1) + b] = ns;
         d.bin_cluster_start[r * (d.nbins + 1) + b] = nc;
+        if (zero_counts) d.bin_count[r * d.nbins + b] = 0;
         ns += c;
         nc += (c + CL - 1) / CL;
     }

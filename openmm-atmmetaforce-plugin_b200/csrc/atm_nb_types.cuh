@@ -25,7 +25,7 @@ constexpr int TGT_C = 0, TGT_S1 = 1, TGT_S2 = 2, TGT_SKIP = 3;
 constexpr double ENERGY_SCALE = 4294967296.0;  // 2^32 fixed point for the energy accumulators
 constexpr int ITEM_BUCKET0 = 16;  // flags[ITEM_BUCKET0 + n] = number of work items with n list steps (n = 1..ITEM_STEPS)
 constexpr int NUM_FLAGS = ITEM_BUCKET0 + ITEM_STEPS + 8;   // rebuild flags, then one bucket counter per item length
-// flags[0] bit 0: a list outgrew its capacity, bit 1: box too small; [1] longest overflowing list; [2,3] outer entries
+// flags[0] bit 0: a list outgrew its capacity, bit 1: box too small, bit 2: a bin outgrew its sort segment; [1] longest overflowing list; [2,3] outer entries
 // (64 bit); [4] live work items; [5] outer work items; [6,7] pruned entries (64 bit); [8], [9] longest list of the
 // environment / ligand-ghost capacity class at the last build
 constexpr int FLAG_MAXLEN_C = 8, FLAG_MAXLEN_X = 9;
@@ -53,6 +53,8 @@ struct NbDev {  // everything the kernels need, passed by value
     // per rebuild
     unsigned long long *keys;
     int *vals;
+    unsigned long long *binbuf;   // own sort: [R * nbins][bin_cap] unsorted (z16 << 32 | site) entries of each bin
+    int bin_cap;                  // power of two <= 1024; 0 = the CUB radix-sort front end is used instead
     int *bin_count, *bin_site_start, *bin_cluster_start, *nclusters;
     int *slot_site, *site_slot, *slot_src, *slot_out, *slot_ghost;
     float *slot_qp;
@@ -132,6 +134,7 @@ struct NbState {
     uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
     bool verified = false, needs_realloc = false, flags_pending = false;
     int grow_capC = 0, grow_capX = 0;
+    bool use_cub_sort = false;      // a bin outgrew bin_cap once, or the bins are too populous for the in-warp sort
     bool grow_pending = false;      // a list came within 20 % of its capacity: reallocate (larger) at the next rebuild
     bool overflowed = false;        // the last asynchronous rebuild truncated a list (results since then are NaN-poisoned)
     int *h_flags = nullptr;         // pinned

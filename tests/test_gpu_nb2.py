@@ -585,3 +585,57 @@ def test_async_rebuild_overflow_is_never_silent():
 class _DevView:
     def __init__(self, ptr, shape, typestr):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def test_own_sort_front_end_equals_cub_radix_sort(tmp_path):
+    """The rebuild's own sort front end (bin -> scan -> in-warp bitonic sort + place -> pack + links + boxes) orders the
+    sites exactly as the CUB radix sort it replaces (ties by site index), so clusters, lists, forces and energies are
+    BIT-identical; ATM_B200_CUB_SORT=1 selects the CUB path (read once per process, hence two subprocesses)."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text('''
+import hashlib, os, sys
+import numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, "openmm-atmmetaforce-plugin_b200", "python"))
+import atmmetaforce as atm
+from atmmetaforce import synthetic
+h = hashlib.sha256()
+for name, s, R in (("config3", synthetic.config3(), 3), ("rbfe", dict(np.load(os.path.join(root, "tests", "golden", "temoa_g1_g4_rbfe.npz"))), 1)):
+    if name == "rbfe":
+        s["cutoff"], s["ewald_alpha"] = 1.0, synthetic.ewald_alpha(1.0)
+    n = s["pos"].shape[0]
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=R)
+    be.set_displacements(s["displ"]); be.set_box(s["box"])
+    sched = synthetic.atm_schedule_22()
+    for r in range(R):
+        be.set_parameters(sched[(7 * r + 2) % 22], replica=r)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.05, skin_outer=0.3, exclusions=s["excl"],
+                exception_pairs=s["exc14"], exception_params=s["exc14_par"])
+    rng = np.random.default_rng(4)
+    posq = np.zeros((R, be.P, 4), np.float32)
+    for r in range(R):
+        posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.004, (n, 3)) * (r > 0)
+        posq[r, :n, 3] = s["charge"]
+    posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((R, 3 * be.P), dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        be.rebuild(posq, stream=st); be.step(posq, force, stream=st)
+        posq[:, :n, :3] += 0.01
+        be.rebuild(posq, stream=st); be.step(posq, force, stream=st, graph=True)     # asynchronous (graph) rebuild
+    en = be.get_energies(stream=st)
+    h.update(force.cpu().numpy().tobytes()); h.update(np.ascontiguousarray(en[:, :7]).tobytes())
+    h.update(repr(sorted(be.nb_stats().items())).encode())
+    be.close()
+print("HASH", h.hexdigest())
+''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for cub in ("0", "1"):
+        r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600, env=dict(os.environ, ATM_B200_CUB_SORT=cub))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[cub] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][0]
+    assert out["0"] == out["1"]
