@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out (its chunk handles "
                     "add their own rebuilds and small launches to an ncu launch list)")
     ap.add_argument("--e2e-chunks", type=int, default=6)
+    ap.add_argument("--e2e-posq", default="f3", choices=["f3", "f4"], help="what the e2e leg uploads: packed float3 coordinates "
+                    "(12 B per atom, ATM_POSQ_F3) or OpenMM's float4 posq (16 B per atom)")
     ap.add_argument("--e2e-force", default="f32", choices=["f32", "i64"], help="what the e2e leg reads back: float32 forces "
                     "(12 B per atom) or the 2^32 fixed-point long force buffer (24 B per atom, round 1)")
     ap.add_argument("--pme", action="store_true", help="also evaluate the two-state PME reciprocal space inside the step "
@@ -664,12 +666,15 @@ def run_b200(args):
         # graph launch per step; pair-list maintenance on the same cadence as the device-resident loop
         pipe = atm.HostPipeline([c[0] for c in chunks])
         en_h = torch.zeros((R, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory()
-        pq_c = [posq_h[lo:hi] for _, lo, hi in chunks]
+        # the caller's pinned coordinate buffer: packed float3 (the charges are known to the back-end since nb_setup) or
+        # OpenMM's float4 posq
+        pos_host = (posq_h[:, :, :3].contiguous() if args.e2e_posq == "f3" else posq_h.clone()).pin_memory()
+        pq_c = [pos_host[lo:hi] for _, lo, hi in chunks]
         f_c = [force_h[lo:hi] for _, lo, hi in chunks]
         en_c = [en_h[lo:hi] for _, lo, hi in chunks]
         # per-step jitter of the HOST coordinates: NJ pinned snapshots cycled through (the copy into the caller's pinned
         # buffer happens outside the event pair, like the integrator's position update it stands for)
-        base_h = posq_h.clone()
+        base_h = pos_host.clone()
         snaps = []
         rng_h = np.random.default_rng(3033 + rank)
         for j in range(4):
@@ -693,7 +698,7 @@ def run_b200(args):
             for _ in range(max(0, 3 - seen[kd])):
                 schedule_e += [kd, "plain"]
         for k, kd in enumerate(schedule_e):
-            posq_h.copy_(snaps[k % len(snaps)])
+            pos_host.copy_(snaps[k % len(snaps)])
             with torch.cuda.stream(stream):
                 if flush is not None:
                     flush.zero_()
@@ -718,8 +723,7 @@ def run_b200(args):
             e2e_comp[kd] = {"ms": t_kd, "samples": len(v), "per_step": f_e[kd]}
             e2e_ms += t_kd * f_e[kd]
         e2e_window_ms = sum(a.elapsed_time(b) for _, inw, a, b in ee if inw) / KE
-        posq_h.copy_(base_h)
-        h2d = posq_h.numel() * 4
+        h2d = pos_host.numel() * 4
         d2h = force_h.numel() * force_h.element_size() + R * _capi.NUM_ENERGY_SLOTS * 8
         for bc, *_ in chunks:
             if bc is not be:
@@ -798,7 +802,7 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "window_ms_per_step": e2e_window_ms, "components": e2e_comp, "chunks": e2e_chunks,
-                    "force_format": args.e2e_force,
+                    "force_format": args.e2e_force, "posq_format": args.e2e_posq,
                     "call": "atm_host_pipeline_step (pinned host coordinates in, pinned host forces + energy records out, "
                             "one cached CUDA graph per step; pair-list maintenance on the bench cadence)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,

@@ -281,7 +281,12 @@ typedef struct {
     double *energies_host;     /* [R][ATM_NUM_ENERGY_SLOTS] pinned host memory, or NULL */
     int32_t include_energy;    /* as atm_step_io.include_energy */
     int32_t force_format;      /* ATM_FORCE_I64 (0, default) | ATM_FORCE_F32 | ATM_FORCE_NONE */
+    int32_t posq_format;       /* ATM_POSQ_F4 (0, default): posq_host is [R][P] float4 as above;
+                                  ATM_POSQ_F3: posq_host is [R][P] packed float3 (x, y, z), 12 B per slot instead of 16 -- the
+                                  direct-space path takes the charges from atm_nb_setup, never from posq.w */
+    int32_t reserved;
 } atm_host_io;
+enum { ATM_POSQ_F4 = 0, ATM_POSQ_F3 = 1 };
 
 int atm_host_pipeline_create(int32_t num_handles, atm_handle *const *handles, atm_host_pipeline **out);
 int atm_host_pipeline_destroy(atm_host_pipeline *p);

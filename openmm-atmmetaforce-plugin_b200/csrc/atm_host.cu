@@ -24,6 +24,7 @@ struct Chunk {
     float4 *posq = nullptr;        // device staging [R][P]
     long long *force = nullptr;    // device staging [R][3P]
     float *force_f32 = nullptr;    // device staging [R][3P] for force_format 1 (allocated on first use)
+    float *posq3 = nullptr;        // device staging [R][P][3] for posq_format 1 (allocated on first use)
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     uint64_t generation = 0;       // alloc generation the cached graphs were captured against
@@ -52,6 +53,11 @@ __global__ void force_to_f32_kernel(const long long *__restrict__ in, float *__r
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)((double)in[i] * (1.0 / 4294967296.0));
 }
+// posq_format 1: packed float3 coordinates -> the float4 staging buffer the kernels read (w unused by the Tier-2 path)
+__global__ void posq3_to_posq4_kernel(const float *__restrict__ in, float4 *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.f);
+}
 }  // namespace atm
 
 // enqueue one step of every chunk (fork from `stream`, join back into it); capturable
@@ -63,7 +69,13 @@ static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int mainten
         const size_t np = (size_t)h->R * h->P;
         int rc;
         ATM_CUDA_CHECK(cudaStreamWaitEvent(k.stream, p->fork, 0));
-        ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * np, cudaMemcpyHostToDevice, k.stream));
+        if (ios[c].posq_format == ATM_POSQ_F3) {
+            ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq3, ios[c].posq_host, sizeof(float) * 3 * np, cudaMemcpyHostToDevice, k.stream));
+            posq3_to_posq4_kernel<<<(unsigned)((np + 255) / 256), 256, 0, k.stream>>>(k.posq3, k.posq, np);
+            h->launches++;
+        } else {
+            ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * np, cudaMemcpyHostToDevice, k.stream));
+        }
         ATM_CUDA_CHECK(cudaMemsetAsync(k.force, 0, sizeof(long long) * 3 * np, k.stream));
         if ((rc = nb_host_enqueue(h, k.posq, k.force, ios[c].include_energy, maintenance, k.stream))) return rc;
         if (ios[c].force_format == ATM_FORCE_F32) {
@@ -177,6 +189,7 @@ int atm_host_pipeline_destroy(atm_host_pipeline *p) {
         if (k.posq) cudaFree(k.posq);
         if (k.force) cudaFree(k.force);
         if (k.force_f32) cudaFree(k.force_f32);
+        if (k.posq3) cudaFree(k.posq3);
     }
     if (p->fork) cudaEventDestroy(p->fork);
     delete p;
@@ -199,6 +212,12 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
                     "atm_host_pipeline_step: chunk %d: force_host is required unless force_format is ATM_FORCE_NONE", (int)c);
         ATM_REQUIRE(ios[c].force_format != ATM_FORCE_NONE || ios[c].energies_host, ATM_ERR_INVALID,
                     "atm_host_pipeline_step: chunk %d: nothing to return (no forces, no energies)", (int)c);
+        ATM_REQUIRE(ios[c].posq_format == ATM_POSQ_F4 || ios[c].posq_format == ATM_POSQ_F3, ATM_ERR_INVALID,
+                    "atm_host_pipeline_step: chunk %d: unknown posq_format %d", (int)c, (int)ios[c].posq_format);
+        if (ios[c].posq_format == ATM_POSQ_F3 && !p->chunks[c].posq3) {
+            ATM_CUDA_CHECK(cudaSetDevice(p->device));
+            ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].posq3, sizeof(float) * 3 * (size_t)p->chunks[c].h->R * p->chunks[c].h->P));
+        }
         if (ios[c].force_format == ATM_FORCE_F32 && !p->chunks[c].force_f32) {
             ATM_CUDA_CHECK(cudaSetDevice(p->device));
             ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].force_f32, sizeof(float) * 3 * (size_t)p->chunks[c].h->R * p->chunks[c].h->P));
@@ -216,7 +235,13 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
         // first build (or a capacity change): the synchronous, verified path of atm_nb_rebuild on the staged coordinates
         for (size_t c = 0; c < nc; c++) {
             Chunk &k = p->chunks[c];
-            ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * (size_t)k.h->R * k.h->P, cudaMemcpyHostToDevice, stream));
+            const size_t np = (size_t)k.h->R * k.h->P;
+            if (ios[c].posq_format == ATM_POSQ_F3) {
+                ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq3, ios[c].posq_host, sizeof(float) * 3 * np, cudaMemcpyHostToDevice, stream));
+                posq3_to_posq4_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(k.posq3, k.posq, np);
+            } else {
+                ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * np, cudaMemcpyHostToDevice, stream));
+            }
             if ((rc = atm_nb_rebuild(k.h, k.posq, stream))) return rc;
         }
         maintenance = 0;

@@ -301,6 +301,8 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
     io.energies_host = energyHost;
     io.include_energy = 1;   // the reference always evaluates the inner energies (do_energy = true, :104)
     io.force_format = ATM_FORCE_I64;
+    io.posq_format = ATM_POSQ_F4;
+    io.reserved = 0;
     check(atm_host_pipeline_step(pipeline, &io, maintenance, stream), "ATMMetaForce: evaluating the alchemical force");
     check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
     if (maintenance == 2) {

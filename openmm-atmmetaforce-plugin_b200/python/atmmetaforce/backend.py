@@ -253,7 +253,8 @@ class HostPipeline:
     """atm_host_pipeline_* (include/atm_b200.h): the step with pinned HOST buffers on both sides, for one or more
     back-ends ("chunks") whose copies and kernels overlap; one cached CUDA graph launch per step.
 
-    posq_host  : list of pinned CPU float32 tensors [R_c][P][4]   (this step's coordinates + charges)
+    posq_host  : list of pinned CPU float32 tensors [R_c][P][4] (coordinates + charge, OpenMM's posq layout) or [R_c][P][3]
+                 (packed coordinates, 12 B per slot: the charges come from nb_setup); the last dimension selects the format
     force_host : list of pinned CPU tensors [R_c][3P]: int64 (2^32 fixed point, OpenMM's long force layout) or float32
                  (kJ/mol/nm, half the D2H bytes); the dtype selects the format.  None = energies only
     energies_host : list of pinned CPU float64 tensors [R_c][NUM_ENERGY_SLOTS] or None
@@ -300,7 +301,13 @@ class HostPipeline:
             ios = (_capi.HostIO * n)()
             for c, b in enumerate(self.backends):
                 f = force_host[c]
-                if posq_host[c].numel() != b.R * b.P * 4 or (f is not None and f.numel() != b.R * b.P * 3):
+                if posq_host[c].numel() == b.R * b.P * 4:
+                    pfmt = _capi.POSQ_F4
+                elif posq_host[c].numel() == b.R * b.P * 3:
+                    pfmt = _capi.POSQ_F3
+                else:
+                    raise ATMError(f"HostPipeline.step: chunk {c}: posq_host size does not match [R][P][4] or [R][P][3]")
+                if f is not None and f.numel() != b.R * b.P * 3:
                     raise ATMError(f"HostPipeline.step: chunk {c}: buffer size does not match [R][P]")
                 if f is None:
                     fmt = _capi.FORCE_NONE
@@ -312,7 +319,7 @@ class HostPipeline:
                     raise ATMError("HostPipeline.step: force_host must be int64 (fixed point) or float32")
                 ios[c] = _capi.HostIO(self._hptr(posq_host[c], "posq_host"), self._hptr(f, "force_host"),
                                       self._hptr(energies_host[c], "energies_host") if energies_host is not None else None,
-                                      1 if include_energy else 0, fmt)
+                                      1 if include_energy else 0, fmt, pfmt, 0)
             self._ios, self._key = ios, key
         check(_capi.lib().atm_host_pipeline_step(self._p, self._ios, int(maintenance), _stream_ptr(stream)))
 

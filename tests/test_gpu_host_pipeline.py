@@ -144,6 +144,14 @@ def test_force_formats():
     expect = (f64.numpy().astype(np.float64) / 4294967296.0).astype(np.float32)
     assert np.array_equal(f32.numpy(), expect) and np.abs(expect).max() > 0
     assert np.array_equal(en_a.numpy()[:, :7], en_b.numpy()[:, :7]) and np.array_equal(en_a.numpy()[:, :7], en_c.numpy()[:, :7])
+    # ATM_POSQ_F3: packed float3 coordinates give the same bits as the float4 posq (the charges come from nb_setup)
+    pos3 = posq_h[:, :, :3].contiguous().pin_memory()
+    f64b = torch.zeros_like(f64)
+    pipe.step([pos3], [f64b], [en_b], maintenance=pipe.PRUNE, stream=stream)
+    stream.synchronize()
+    pipe.step([posq_h], [f64], [en_a], maintenance=pipe.PRUNE, stream=stream)
+    stream.synchronize()
+    assert torch.equal(f64, f64b) and np.array_equal(en_a.numpy()[:, :7], en_b.numpy()[:, :7])
     with pytest.raises(atm.ATMError, match="nothing to return"):
         pipe.step([posq_h], None, None, maintenance=pipe.NONE, stream=stream)
     with pytest.raises(atm.ATMError, match="int64"):
