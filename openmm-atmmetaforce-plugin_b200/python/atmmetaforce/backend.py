@@ -231,9 +231,14 @@ class ReplicaComm:
         if self.world > 1:
             if share is None:
                 raise ATMError("ReplicaComm: a `share` callable is needed to distribute the NCCL unique id")
-            if self.rank == 0:
-                check(_capi.lib().atm_re_unique_id(idbuf))
-            raw = share(bytes(idbuf.raw) if self.rank == 0 else None)
+            raw = None
+            if self.rank == 0:   # a failure here (no usable libnccl) is shared too, so that no rank waits for an id that never comes
+                raw = bytes(idbuf.raw) if _capi.lib().atm_re_unique_id(idbuf) == _capi.ATM_OK else b""
+                if raw:
+                    raw = bytes(idbuf.raw)
+            raw = share(raw)
+            if not raw:
+                raise ATMError("ReplicaComm: rank 0 could not create an NCCL unique id: " + (_capi.lib().atm_last_error().decode() or "?"))
             idbuf = (C.c_char * 128).from_buffer_copy(raw)
         check(_capi.lib().atm_re_comm_create(idbuf, self.world, self.rank, int(device), C.byref(self._c)))
 

@@ -88,7 +88,21 @@ class ReplicaExchange:
                 box = [raw]
                 dist.broadcast_object_list(box, src=0, group=self.group)
                 return box[0]
-            self._comm = ReplicaComm(self.rank, self.world, torch.cuda.current_device(), share if self.world > 1 else None)
+            try:
+                self._comm = ReplicaComm(self.rank, self.world, torch.cuda.current_device(), share if self.world > 1 else None)
+                ok = 1
+            except Exception as exc:  # no usable libnccl for the library (e.g. a torch build without NCCL): say so, use torch's
+                import sys
+                print(f"atmmetaforce: library NCCL communicator unavailable ({exc}); using torch.distributed for the all-gather", file=sys.stderr)
+                ok = 0
+            if self.world > 1:   # every rank must take the same path
+                import torch.distributed as dist
+                flag = torch.tensor([ok], device=torch.device("cuda", torch.cuda.current_device()))
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                ok = int(flag.item())
+            if not ok:
+                self._collective = "torch"
+                self._comm = None
         rows = self.world * self.max_per_rank
         gather_slot = np.array([self._slot[g] for g in range(self.num_replicas)], np.int32)
         backend.hrex_setup(self.schedule, self.replica_state, self.mine, gather_slot, rows, self.beta, self.seed, stream=stream)

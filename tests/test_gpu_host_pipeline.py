@@ -146,7 +146,7 @@ def test_force_formats():
     assert np.array_equal(en_a.numpy()[:, :7], en_b.numpy()[:, :7]) and np.array_equal(en_a.numpy()[:, :7], en_c.numpy()[:, :7])
     # ATM_POSQ_F3: packed float3 coordinates give the same bits as the float4 posq (the charges come from nb_setup)
     pos3 = posq_h[:, :, :3].contiguous().pin_memory()
-    f64b = torch.zeros_like(f64)
+    f64b = torch.zeros_like(f64).pin_memory()
     pipe.step([pos3], [f64b], [en_b], maintenance=pipe.PRUNE, stream=stream)
     stream.synchronize()
     pipe.step([posq_h], [f64], [en_a], maintenance=pipe.PRUNE, stream=stream)
