@@ -313,6 +313,10 @@ __device__ __forceinline__ void nb2_item(const NbDev &d, const ItemCtx &it, int 
     const float2 ncA_xy = f2(-cA.x, -cA.y), iL_xy = f2(iL.x, iL.y), L_xy = f2(L.x, L.y);
     const float4 *ci = &sm.ci[w][0][0];
 
+#ifdef ATM_NB2_STEP_UNROLL   // A/B: let ptxas schedule several list steps (independent partners) together
+    constexpr int STEP_UNROLL = ATM_NB2_STEP_UNROLL;
+#pragma unroll STEP_UNROLL
+#endif
     for (int st = 0; st < it.nst; st++) {
         cp_async_wait<PF_DIST - 1>();  // the group of step st has landed (groups retire in order)
         const int slot = (st & (RING - 1)) * 32;
