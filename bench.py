@@ -291,7 +291,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "replica-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle/_ref (the reference compiled in place) is not buildable: OpenMM is absent; kind=port",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 class _DevView:
@@ -808,13 +808,32 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "pair_list": nb_stats, "two_state_vs_two_separate": two_sep,
             "tier1_hbm_roofline": tier1,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # stdout carries the result line and nothing else: whatever libraries print there (NCCL's version banner, ...) is sent
+    # to stderr
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
