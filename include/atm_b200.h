@@ -285,6 +285,13 @@ typedef struct {
                                   ATM_POSQ_F3: posq_host is [R][P] packed float3 (x, y, z), 12 B per slot instead of 16 -- the
                                   direct-space path takes the charges from atm_nb_setup, never from posq.w */
     int32_t reserved;
+    /* optional per-state contributions of OTHER forces of the variable force groups, evaluated by the caller at the state-1
+     * and state-2 coordinates (the reference's inner contexts evaluate every Force in a variable group, ref:
+     * openmmapi/src/ATMMetaForceImpl.cpp:51-65,113-116): uploaded and handed to the step as atm_step_io.force_state{1,2}_ext /
+     * energy_ext.  Pinned host memory; NULL = none. */
+    const int64_t *force_state1_ext_host;   /* [R][3P] 2^32 fixed point, SoA x|y|z blocks per replica */
+    const int64_t *force_state2_ext_host;   /* [R][3P] */
+    const double *energy_ext_host;          /* [R][2] {U1_ext, U2_ext} */
 } atm_host_io;
 enum { ATM_POSQ_F4 = 0, ATM_POSQ_F3 = 1 };
 

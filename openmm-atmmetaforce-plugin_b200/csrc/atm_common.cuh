@@ -121,7 +121,9 @@ void hrex_destroy(atm_handle *h);
 
 // hooks of the host-buffer pipeline (atm_host.cu), implemented in atm_nb.cu
 int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *needs_sync_rebuild);
-int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream);
+int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream,
+                    const long long *force_state1_ext = nullptr, const long long *force_state2_ext = nullptr,
+                    const double *energy_ext = nullptr);
 int nb_host_rebuild_enqueued(atm_handle *h, cudaStream_t stream);
 int nb_host_inner_copy(const atm_handle *h);     // which copy of the pruned list is in use (0 / 1)
 void nb_host_flip_inner(atm_handle *h);          // after a maintenance = 3 step has been enqueued / replayed

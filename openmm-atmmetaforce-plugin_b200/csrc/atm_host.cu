@@ -25,6 +25,8 @@ struct Chunk {
     long long *force = nullptr;    // device staging [R][3P]
     float *force_f32 = nullptr;    // device staging [R][3P] for force_format 1 (allocated on first use)
     float *posq3 = nullptr;        // device staging [R][P][3] for posq_format 1 (allocated on first use)
+    long long *ext[2] = {nullptr, nullptr};   // device staging [R][3P] of force_state{1,2}_ext_host (allocated on first use)
+    double *eext = nullptr;        // device staging [R][2] of energy_ext_host
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     uint64_t generation = 0;       // alloc generation the cached graphs were captured against
@@ -77,7 +79,15 @@ static int enqueue_all(atm_host_pipeline *p, const atm_host_io *ios, int mainten
             ATM_CUDA_CHECK(cudaMemcpyAsync(k.posq, ios[c].posq_host, sizeof(float4) * np, cudaMemcpyHostToDevice, k.stream));
         }
         ATM_CUDA_CHECK(cudaMemsetAsync(k.force, 0, sizeof(long long) * 3 * np, k.stream));
-        if ((rc = nb_host_enqueue(h, k.posq, k.force, ios[c].include_energy, maintenance, k.stream))) return rc;
+        const int64_t *ext_host[2] = {ios[c].force_state1_ext_host, ios[c].force_state2_ext_host};
+        for (int s = 0; s < 2; s++)
+            if (ext_host[s])
+                ATM_CUDA_CHECK(cudaMemcpyAsync(k.ext[s], ext_host[s], sizeof(long long) * 3 * np, cudaMemcpyHostToDevice, k.stream));
+        if (ios[c].energy_ext_host)
+            ATM_CUDA_CHECK(cudaMemcpyAsync(k.eext, ios[c].energy_ext_host, sizeof(double) * 2 * (size_t)h->R, cudaMemcpyHostToDevice, k.stream));
+        if ((rc = nb_host_enqueue(h, k.posq, k.force, ios[c].include_energy, maintenance, k.stream, ext_host[0] ? k.ext[0] : nullptr,
+                                  ext_host[1] ? k.ext[1] : nullptr, ios[c].energy_ext_host ? k.eext : nullptr)))
+            return rc;
         if (ios[c].force_format == ATM_FORCE_F32) {
             force_to_f32_kernel<<<(unsigned)((3 * np + 255) / 256), 256, 0, k.stream>>>(k.force, k.force_f32, 3 * np);
             h->launches++;
@@ -190,6 +200,9 @@ int atm_host_pipeline_destroy(atm_host_pipeline *p) {
         if (k.force) cudaFree(k.force);
         if (k.force_f32) cudaFree(k.force_f32);
         if (k.posq3) cudaFree(k.posq3);
+        if (k.ext[0]) cudaFree(k.ext[0]);
+        if (k.ext[1]) cudaFree(k.ext[1]);
+        if (k.eext) cudaFree(k.eext);
     }
     if (p->fork) cudaEventDestroy(p->fork);
     delete p;
@@ -217,6 +230,16 @@ int atm_host_pipeline_step(atm_host_pipeline *p, const atm_host_io *ios, int32_t
         if (ios[c].posq_format == ATM_POSQ_F3 && !p->chunks[c].posq3) {
             ATM_CUDA_CHECK(cudaSetDevice(p->device));
             ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].posq3, sizeof(float) * 3 * (size_t)p->chunks[c].h->R * p->chunks[c].h->P));
+        }
+        const int64_t *ext_host[2] = {ios[c].force_state1_ext_host, ios[c].force_state2_ext_host};
+        for (int s = 0; s < 2; s++)
+            if (ext_host[s] && !p->chunks[c].ext[s]) {
+                ATM_CUDA_CHECK(cudaSetDevice(p->device));
+                ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].ext[s], sizeof(long long) * 3 * (size_t)p->chunks[c].h->R * p->chunks[c].h->P));
+            }
+        if (ios[c].energy_ext_host && !p->chunks[c].eext) {
+            ATM_CUDA_CHECK(cudaSetDevice(p->device));
+            ATM_CUDA_CHECK(cudaMalloc(&p->chunks[c].eext, sizeof(double) * 2 * (size_t)p->chunks[c].h->R));
         }
         if (ios[c].force_format == ATM_FORCE_F32 && !p->chunks[c].force_f32) {
             ATM_CUDA_CHECK(cudaSetDevice(p->device));

@@ -1133,7 +1133,8 @@ int nb_host_prepare(atm_handle *h, int maintenance, cudaStream_t stream, bool *n
 
 // The device work of one handle for one step on device staging buffers: [rebuild | prune] + the step itself.  No
 // validation, no uploads, no synchronisation: safe inside a stream capture.
-int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream) {
+int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int include_energy, int maintenance, cudaStream_t stream,
+                    const long long *force_state1_ext, const long long *force_state2_ext, const double *energy_ext) {
     NbState *nb = h->nb;
     int rc;
     if (maintenance == 2) {
@@ -1148,6 +1149,9 @@ int nb_host_enqueue(atm_handle *h, const void *posq, long long *force, int inclu
     io.force = (int64_t *)force;
     io.include_energy = include_energy;
     io.concurrent_prune = maintenance == 3;
+    io.force_state1_ext = (const int64_t *)force_state1_ext;
+    io.force_state2_ext = (const int64_t *)force_state2_ext;
+    io.energy_ext = energy_ext;
     return launch_step(h, &io, stream, false);
 }
 

@@ -9,6 +9,9 @@
 // direct-space kernel, the device scalar stage, the merge, D2H of forces and energy record -- one CUDA-graph launch.
 // The NonbondedForce is evaluated as a whole -- direct space, PME reciprocal space of both states and the dispersion
 // correction, as the reference's inner contexts do -- unless its reciprocal space was moved to a non-variable group.
+// Any OTHER Force in a variable force group (OpenMM::HostEvaluatedForce in this build, e.g. HarmonicBondForce) is
+// evaluated at x and at x + d as well and enters the same step through atm_host_io.force_state{1,2}_ext_host /
+// energy_ext_host -- the generic hook for what the reference's inner contexts evaluate besides the NonbondedForce.
 //
 // When the Context's Platform has a "CalcATMMetaForce" kernel registered (libATMMetaForcePluginCUDA.so on the "CUDA"
 // platform), the Impl instead runs the REFERENCE's orchestration, unchanged in structure: every non-ATM Force of the
@@ -92,6 +95,11 @@ private:
     float *posqHost;       // pinned [P][4]
     int64_t *forceHost;    // pinned [3P]
     double *energyHost;    // pinned [ATM_NUM_ENERGY_SLOTS]
+    // the other Forces of the variable force groups (host-evaluated in this build) and their per-state results
+    std::vector<const OpenMM::HostEvaluatedForce *> hostForces;
+    int64_t *extHost[2];   // pinned [3P] each: forces of hostForces at the state-1 / state-2 coordinates, 2^32 fixed point
+    double *energyExtHost; // pinned [2]
+    std::vector<double> displacements;   // [N][3], refreshed with the device table
     int paddedNumAtoms;
     bool displacementsDirty, reciprocalOn;
     unsigned long boxVersionSeen;

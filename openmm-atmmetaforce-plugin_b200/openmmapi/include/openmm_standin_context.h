@@ -97,6 +97,46 @@ private:
     std::vector<int> exceptionPairs;
 };
 
+/** A Force this OpenMM-free build evaluates on the HOST: the stand-in for OpenMM's bonded / custom force kernels, so that
+ *  the variable force groups can hold something besides the NonbondedForce (the reference's inner contexts evaluate
+ *  whatever Force sits in a variable group, ref: openmmapi/src/ATMMetaForceImpl.cpp:51-65,113-116).  Its Impl works on
+ *  every platform (positions come from / forces go to the platform's hooks); the fused ATMMetaForceImpl evaluates it
+ *  at the state-1 and state-2 coordinates and feeds the results to the back-end as the external per-state terms. */
+class HostEvaluatedForce : public Force {
+public:
+    /** Energy (kJ/mol) at `positions`; when forces != NULL the forces (kJ/mol/nm) are ADDED to *forces. */
+    virtual double evaluate(const std::vector<Vec3> &positions, const Vec3 box[3], std::vector<Vec3> *forces) const = 0;
+    ForceImpl *createImpl() const override;
+};
+
+/** OpenMM's HarmonicBondForce: E = 1/2 k (r - r0)^2 per bond. */
+class HarmonicBondForce : public HostEvaluatedForce {
+public:
+    HarmonicBondForce() : periodic(false) {}
+    int addBond(int particle1, int particle2, double length, double k) {
+        bonds.push_back({particle1, particle2, length, k});
+        return (int)bonds.size() - 1;
+    }
+    int getNumBonds() const { return (int)bonds.size(); }
+    void getBondParameters(int index, int &particle1, int &particle2, double &length, double &k) const {
+        ASSERT_VALID_INDEX(index, bonds);
+        particle1 = bonds[index].p1; particle2 = bonds[index].p2; length = bonds[index].length; k = bonds[index].k;
+    }
+    void setBondParameters(int index, int particle1, int particle2, double length, double k) {
+        ASSERT_VALID_INDEX(index, bonds);
+        bonds[index] = {particle1, particle2, length, k};
+    }
+    void setUsesPeriodicBoundaryConditions(bool on) { periodic = on; }
+    bool usesPeriodicBoundaryConditions() const override { return periodic; }
+    Force *clone() const override { return new HarmonicBondForce(*this); }
+    double evaluate(const std::vector<Vec3> &positions, const Vec3 box[3], std::vector<Vec3> *forces) const override;
+
+private:
+    struct Bond { int p1, p2; double length, k; };
+    std::vector<Bond> bonds;
+    bool periodic;
+};
+
 /** Particles (masses), forces (owned), default box. */
 class System {
 public:
@@ -224,6 +264,8 @@ public:
     virtual void beginComputation(ContextImpl &context, bool includeForces, bool includeEnergy, int groups) const;
     virtual double finishComputation(ContextImpl &context, bool includeForces, bool includeEnergy, int groups) const;
     virtual void getForces(ContextImpl &context, std::vector<Vec3> &forces) const;
+    /** Adds host-evaluated forces (atom order, kJ/mol/nm) to the forces of the evaluation in progress. */
+    virtual void addForces(ContextImpl &context, const std::vector<Vec3> &forces) const;
 
 private:
     /** ONE registry per process: defined in openmm_standin_context.cpp, i.e. inside libOpenMMStandin.so, which the API

@@ -108,6 +108,7 @@ public:
     void beginComputation(ContextImpl &context, bool includeForces, bool includeEnergy, int groups) const override;
     double finishComputation(ContextImpl &context, bool includeForces, bool includeEnergy, int groups) const override;
     void getForces(ContextImpl &context, std::vector<Vec3> &forces) const override;
+    void addForces(ContextImpl &context, const std::vector<Vec3> &forces) const override;
     static CudaContext &cudaContext(ContextImpl &context) {
         return *static_cast<PlatformData *>(context.getPlatformData())->contexts[0];
     }

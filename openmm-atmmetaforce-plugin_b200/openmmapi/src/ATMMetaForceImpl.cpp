@@ -33,7 +33,7 @@ ATMMetaForceImpl::ATMMetaForceImpl(const ATMMetaForce &owner)
     : innerIntegrator1(1.0), innerIntegrator2(1.0), hasInitializedInnerContexts(false), owner(owner), nonbonded(nullptr),
       PerturbationEnergy(0.0), variable_force_groups_mask(0), device(-1), skin(0.05),
       skinOuter(0.3), handle(nullptr), pipeline(nullptr), stream(nullptr), posqHost(nullptr), forceHost(nullptr),
-      energyHost(nullptr), paddedNumAtoms(0), displacementsDirty(false), reciprocalOn(false), boxVersionSeen(0),
+      energyHost(nullptr), extHost{nullptr, nullptr}, energyExtHost(nullptr), paddedNumAtoms(0), displacementsDirty(false), reciprocalOn(false), boxVersionSeen(0),
       energyRecord(ATM_NUM_ENERGY_SLOTS, 0.0) {}
 
 ATMMetaForceImpl::~ATMMetaForceImpl() {
@@ -73,8 +73,12 @@ void ATMMetaForceImpl::releaseBackend() {
     if (posqHost) atm_host_free(posqHost);
     if (forceHost) atm_host_free(forceHost);
     if (energyHost) atm_host_free(energyHost);
+    if (extHost[0]) atm_host_free(extHost[0]);
+    if (extHost[1]) atm_host_free(extHost[1]);
+    if (energyExtHost) atm_host_free(energyExtHost);
     if (stream) atm_stream_destroy(stream);
     pipeline = nullptr; handle = nullptr; posqHost = nullptr; forceHost = nullptr; energyHost = nullptr; stream = nullptr;
+    extHost[0] = extHost[1] = nullptr; energyExtHost = nullptr;
 }
 
 void ATMMetaForceImpl::setPairListSkins(double inner_nm, double outer_nm) {
@@ -100,13 +104,18 @@ void ATMMetaForceImpl::initialize(OpenMM::ContextImpl &context) {
     // which Forces the two states evaluate: everything outside the ATM group that sits in a variable force group
     // (ref: copysystem :51-65 clones every non-ATM force; the mask :75-81 selects the variable ones at evaluation time)
     nonbonded = nullptr;
+    hostForces.clear();
     for (int i = 0; i < system.getNumForces(); i++) {
         const OpenMM::Force &f = system.getForce(i);
         if (&f == &owner || f.getForceGroup() == owner.getForceGroup()) continue;
         if (!((variable_force_groups_mask >> f.getForceGroup()) & 1)) continue;
+        if (auto *hf = dynamic_cast<const OpenMM::HostEvaluatedForce *>(&f)) {
+            hostForces.push_back(hf);   // evaluated at both states, fed to the step as the external per-state terms
+            continue;
+        }
         const OpenMM::NonbondedForce *nb = dynamic_cast<const OpenMM::NonbondedForce *>(&f);
         if (!nb) throw OpenMMException("ATMMetaForce: a variable force group holds a Force this OpenMM-free build cannot evaluate "
-                                       "(only NonbondedForce direct space is evaluated by the Blackwell back-end)");
+                                       "(NonbondedForce and host-evaluated forces only)");
         if (nonbonded) throw OpenMMException("ATMMetaForce: more than one NonbondedForce in the variable force groups");
         if (nb->getNumParticles() != system.getNumParticles())
             throw OpenMMException("NonbondedForce must have exactly as many particles as the System it belongs to.");
@@ -146,8 +155,8 @@ void ATMMetaForceImpl::createBackend(OpenMM::ContextImpl &context) {
         check(atm_create(&cfg, &handle), "ATMMetaForce: creating the Blackwell back-end");
         paddedNumAtoms = 32 * ((n + 31) / 32);
         check(atm_stream_create(device, &stream), "ATMMetaForce: stream");
-        std::vector<double> d = owner.getDisplacementArray();
-        check(atm_set_displacements(handle, nullptr, d.data(), stream), "ATMMetaForce: uploading the displacement table");
+        displacements = owner.getDisplacementArray();
+        check(atm_set_displacements(handle, nullptr, displacements.data(), stream), "ATMMetaForce: uploading the displacement table");
         {   // the box goes in before the NonbondedForce description, so that every allocation and upload of the set-up is
             // issued on `stream`
             OpenMM::Vec3 a, b, c;
@@ -200,6 +209,13 @@ void ATMMetaForceImpl::createBackend(OpenMM::ContextImpl &context) {
         check(atm_host_alloc(sizeof(float) * 4 * (size_t)paddedNumAtoms, (void **)&posqHost), "ATMMetaForce: pinned coordinates");
         check(atm_host_alloc(sizeof(int64_t) * 3 * (size_t)paddedNumAtoms, (void **)&forceHost), "ATMMetaForce: pinned forces");
         check(atm_host_alloc(sizeof(double) * ATM_NUM_ENERGY_SLOTS, (void **)&energyHost), "ATMMetaForce: pinned energy record");
+        if (!hostForces.empty()) {
+            for (int s = 0; s < 2; s++) {
+                check(atm_host_alloc(sizeof(int64_t) * 3 * (size_t)paddedNumAtoms, (void **)&extHost[s]), "ATMMetaForce: pinned external forces");
+                std::memset(extHost[s], 0, sizeof(int64_t) * 3 * (size_t)paddedNumAtoms);
+            }
+            check(atm_host_alloc(sizeof(double) * 2, (void **)&energyExtHost), "ATMMetaForce: pinned external energies");
+        }
         std::memset(posqHost, 0, sizeof(float) * 4 * (size_t)paddedNumAtoms);
         for (int i = 0; i < n; i++) posqHost[4 * i + 3] = (float)q[i];
         check(atm_host_pipeline_create(1, &handle, &pipeline), "ATMMetaForce: host pipeline");
@@ -259,8 +275,8 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
     check(atm_set_parameters(handle, 0, p), "ATMMetaForce: parameters");
     bool rebuild = refRebuild.empty();
     if (displacementsDirty) {
-        std::vector<double> d = owner.getDisplacementArray();
-        check(atm_set_displacements(handle, nullptr, d.data(), stream), "ATMMetaForce: uploading the displacement table");
+        displacements = owner.getDisplacementArray();
+        check(atm_set_displacements(handle, nullptr, displacements.data(), stream), "ATMMetaForce: uploading the displacement table");
         displacementsDirty = false;
         rebuild = true;
     }
@@ -303,6 +319,29 @@ double ATMMetaForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl &context, bool 
     io.force_format = ATM_FORCE_I64;
     io.posq_format = ATM_POSQ_F4;
     io.reserved = 0;
+    io.force_state1_ext_host = io.force_state2_ext_host = nullptr;
+    io.energy_ext_host = nullptr;
+    if (!hostForces.empty()) {
+        // the other variable-group Forces at the state-1 (x) and state-2 (x + d) coordinates: what the reference's inner
+        // contexts add to State1Energy / State2Energy and to their force buffers (ref: :113-116)
+        OpenMM::Vec3 box[3];
+        context.getPeriodicBoxVectors(box[0], box[1], box[2]);
+        std::vector<OpenMM::Vec3> statePos(pos), f(n);
+        for (int s = 0; s < 2; s++) {
+            if (s == 1)
+                for (int i = 0; i < n; i++)
+                    for (int c = 0; c < 3; c++) statePos[i][c] = pos[i][c] + displacements[3 * (size_t)i + c];
+            std::fill(f.begin(), f.end(), OpenMM::Vec3());
+            double e = 0.0;
+            for (const OpenMM::HostEvaluatedForce *hf : hostForces) e += hf->evaluate(statePos, box, &f);
+            energyExtHost[s] = e;
+            for (int i = 0; i < n; i++)
+                for (int c = 0; c < 3; c++) extHost[s][(size_t)c * paddedNumAtoms + i] = (int64_t)std::llrint(f[i][c] * 4294967296.0);
+        }
+        io.force_state1_ext_host = extHost[0];
+        io.force_state2_ext_host = extHost[1];
+        io.energy_ext_host = energyExtHost;
+    }
     check(atm_host_pipeline_step(pipeline, &io, maintenance, stream), "ATMMetaForce: evaluating the alchemical force");
     check(atm_stream_synchronize(stream), "ATMMetaForce: waiting for the step");
     if (maintenance == 2) {

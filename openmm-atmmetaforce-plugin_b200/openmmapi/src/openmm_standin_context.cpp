@@ -18,6 +18,11 @@ void Platform::beginComputation(ContextImpl &context, bool, bool, int) const {
 }
 double Platform::finishComputation(ContextImpl &, bool, bool, int) const { return 0.0; }
 void Platform::getForces(ContextImpl &context, std::vector<Vec3> &forces) const { forces = context.getForces(); }
+void Platform::addForces(ContextImpl &context, const std::vector<Vec3> &forces) const {
+    std::vector<Vec3> &f = context.getForces();
+    for (size_t i = 0; i < forces.size(); i++)
+        for (int c = 0; c < 3; c++) f[i][c] += forces[i][c];
+}
 
 std::vector<std::unique_ptr<Platform>> &Platform::registry() {
     static std::vector<std::unique_ptr<Platform>> r;
@@ -107,6 +112,57 @@ private:
 }  // namespace
 
 ForceImpl *NonbondedForce::createImpl() const { return new NonbondedForceImpl(*this); }
+
+// ---- host-evaluated forces ---------------------------------------------------------------------------------------
+namespace {
+class HostEvaluatedForceImpl : public ForceImpl {
+public:
+    explicit HostEvaluatedForceImpl(const HostEvaluatedForce &owner) : owner(owner) {}
+    void initialize(ContextImpl &) override {}
+    double calcForcesAndEnergy(ContextImpl &context, bool includeForces, bool includeEnergy, int groups) override {
+        if ((groups & (1 << owner.getForceGroup())) == 0) return 0.0;
+        std::vector<Vec3> pos;
+        context.getPositions(pos);
+        Vec3 box[3];
+        context.getPeriodicBoxVectors(box[0], box[1], box[2]);
+        std::vector<Vec3> f;
+        if (includeForces) f.assign(pos.size(), Vec3());
+        const double e = owner.evaluate(pos, box, includeForces ? &f : nullptr);
+        if (includeForces) context.getPlatform().addForces(context, f);
+        return includeEnergy ? e : 0.0;
+    }
+    std::map<std::string, double> getDefaultParameters() override { return {}; }
+    std::vector<std::string> getKernelNames() override { return {}; }
+
+private:
+    const HostEvaluatedForce &owner;
+};
+}  // namespace
+
+ForceImpl *HostEvaluatedForce::createImpl() const { return new HostEvaluatedForceImpl(*this); }
+
+double HarmonicBondForce::evaluate(const std::vector<Vec3> &positions, const Vec3 box[3], std::vector<Vec3> *forces) const {
+    double energy = 0.0;
+    for (const Bond &b : bonds) {
+        if (b.p1 < 0 || b.p2 < 0 || b.p1 >= (int)positions.size() || b.p2 >= (int)positions.size())
+            throw OpenMMException("HarmonicBondForce: Illegal particle index for a bond");
+        double d[3];
+        for (int c = 0; c < 3; c++) d[c] = positions[b.p2][c] - positions[b.p1][c];
+        if (periodic)   // rectangular boxes only, like the rest of this build
+            for (int c = 0; c < 3; c++) d[c] -= box[c][c] * std::floor(d[c] / box[c][c] + 0.5);
+        const double r = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const double dr = r - b.length;
+        energy += 0.5 * b.k * dr * dr;
+        if (forces && r > 0.0) {
+            const double s = b.k * dr / r;   // dE/dr / r
+            for (int c = 0; c < 3; c++) {
+                (*forces)[b.p1][c] += s * d[c];
+                (*forces)[b.p2][c] -= s * d[c];
+            }
+        }
+    }
+    return energy;
+}
 
 void pmeGridDimensions(double alpha, double tolerance, const Vec3 box[3], int grid[3]) {
     for (int k = 0; k < 3; k++) {

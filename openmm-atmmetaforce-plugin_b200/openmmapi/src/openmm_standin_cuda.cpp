@@ -282,7 +282,42 @@ void CudaPlatform::setPositions(ContextImpl &context, const std::vector<Vec3> &p
     if (cu.getUseMixedPrecision()) cu.getPosqCorrection().upload(corr.data());
 }
 
-void CudaPlatform::getPositions(const ContextImpl &context, std::vector<Vec3> &positions) const { positions = context.positionsRef(); }
+// What the device holds (an inner context's coordinates are written there by the ATM kernel's copyState, never by
+// setPositions): posq (+ the correction in mixed precision), slot order -> atom order.
+void CudaPlatform::getPositions(const ContextImpl &context, std::vector<Vec3> &positions) const {
+    CudaContext &cu = cudaContext(const_cast<ContextImpl &>(context));
+    ContextSelector selector(cu);
+    cu.synchronize();
+    const int P = cu.getPaddedNumAtoms(), n = cu.getNumAtoms();
+    const std::vector<int> &order = cu.getAtomIndex();
+    positions.assign(n, Vec3());
+    if (cu.getUseDoublePrecision()) {
+        std::vector<double> p(4 * (size_t)P);
+        cu.getPosq().download(p.data());
+        for (int s = 0; s < n; s++)
+            for (int c = 0; c < 3; c++) positions[order[s]][c] = p[4 * (size_t)s + c];
+        return;
+    }
+    std::vector<float> p(4 * (size_t)P), corr(4 * (size_t)P, 0.f);
+    cu.getPosq().download(p.data());
+    if (cu.getUseMixedPrecision()) cu.getPosqCorrection().download(corr.data());
+    for (int s = 0; s < n; s++)
+        for (int c = 0; c < 3; c++) positions[order[s]][c] = (double)p[4 * (size_t)s + c] + (double)corr[4 * (size_t)s + c];
+}
+
+// Host-evaluated forces enter the long force buffer the way every OpenMM kernel's do: 2^32 fixed point, slot order.
+void CudaPlatform::addForces(ContextImpl &context, const std::vector<Vec3> &forces) const {
+    CudaContext &cu = cudaContext(context);
+    ContextSelector selector(cu);
+    cu.synchronize();
+    const int P = cu.getPaddedNumAtoms(), n = cu.getNumAtoms();
+    std::vector<long long> f(3 * (size_t)P);
+    cu.getLongForceBuffer().download(f.data());
+    const std::vector<int> &order = cu.getAtomIndex();
+    for (int s = 0; s < n; s++)
+        for (int c = 0; c < 3; c++) f[(size_t)c * P + s] += (long long)std::llrint(forces[order[s]][c] * 4294967296.0);
+    cu.getLongForceBuffer().upload(f.data());
+}
 
 void CudaPlatform::beginComputation(ContextImpl &context, bool, bool, int) const {
     CudaContext &cu = cudaContext(context);

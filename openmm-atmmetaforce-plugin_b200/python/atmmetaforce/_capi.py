@@ -57,7 +57,8 @@ class StepIO(C.Structure):
 
 class HostIO(C.Structure):
     _fields_ = [("posq_host", C.c_void_p), ("force_host", C.c_void_p), ("energies_host", C.c_void_p),
-                ("include_energy", C.c_int32), ("force_format", C.c_int32), ("posq_format", C.c_int32), ("reserved", C.c_int32)]
+                ("include_energy", C.c_int32), ("force_format", C.c_int32), ("posq_format", C.c_int32), ("reserved", C.c_int32),
+                ("force_state1_ext_host", C.c_void_p), ("force_state2_ext_host", C.c_void_p), ("energy_ext_host", C.c_void_p)]
 
 
 FORCE_I64, FORCE_F32, FORCE_NONE = 0, 1, 2

@@ -293,15 +293,29 @@ class HostPipeline:
             raise ATMError(f"{what}: expected a contiguous pinned host tensor")
         return t.data_ptr()
 
-    def step(self, posq_host, force_host, energies_host=None, maintenance=0, include_energy=True, stream=None):
+    def step(self, posq_host, force_host, energies_host=None, maintenance=0, include_energy=True, stream=None,
+             f1_ext_host=None, f2_ext_host=None, energy_ext_host=None):
+        """f1_ext_host / f2_ext_host ([R][3P] int64 fixed point) and energy_ext_host ([R][2] float64), one pinned tensor
+        per back-end: contributions of other variable-group forces evaluated by the caller at the state-1 / state-2
+        coordinates (atm_host_io.force_state{1,2}_ext_host / energy_ext_host)."""
         n = len(self.backends)
         import torch
         if force_host is None:
             force_host = [None] * n
         if len(posq_host) != n or len(force_host) != n or (energies_host is not None and len(energies_host) != n):
             raise ATMError("HostPipeline.step: one buffer per back-end is required")
+        ext = (f1_ext_host, f2_ext_host, energy_ext_host)
+        for e, dt, per in zip(ext, (torch.int64, torch.int64, torch.float64), (None, None, 2)):
+            if e is None:
+                continue
+            if len(e) != n:
+                raise ATMError("HostPipeline.step: one external buffer per back-end is required")
+            for c, b in enumerate(self.backends):
+                if e[c].dtype != dt or e[c].numel() != (b.R * per if per else b.R * b.P * 3):
+                    raise ATMError(f"HostPipeline.step: chunk {c}: external buffer has the wrong dtype or size")
         key = (tuple(t.data_ptr() for t in posq_host), tuple(t.data_ptr() if t is not None else 0 for t in force_host),
-               tuple(t.data_ptr() for t in energies_host) if energies_host is not None else None, bool(include_energy))
+               tuple(t.data_ptr() for t in energies_host) if energies_host is not None else None, bool(include_energy),
+               tuple(tuple(t.data_ptr() for t in e) if e is not None else None for e in ext))
         if key != self._key:
             ios = (_capi.HostIO * n)()
             for c, b in enumerate(self.backends):
@@ -324,7 +338,8 @@ class HostPipeline:
                     raise ATMError("HostPipeline.step: force_host must be int64 (fixed point) or float32")
                 ios[c] = _capi.HostIO(self._hptr(posq_host[c], "posq_host"), self._hptr(f, "force_host"),
                                       self._hptr(energies_host[c], "energies_host") if energies_host is not None else None,
-                                      1 if include_energy else 0, fmt, pfmt, 0)
+                                      1 if include_energy else 0, fmt, pfmt, 0,
+                                      *[self._hptr(e[c], "external buffer") if e is not None else None for e in ext])
             self._ios, self._key = ios, key
         check(_capi.lib().atm_host_pipeline_step(self._p, self._ios, int(maintenance), _stream_ptr(stream)))
 

@@ -118,6 +118,21 @@ PYBIND11_MODULE(_atmmetaforce_core, m) {
         }, py::arg("charge"), py::arg("sigma"), py::arg("epsilon"), py::arg("exceptionPairs"), py::arg("exceptionParams"),
            py::arg("cutoff"), py::arg("ewaldTolerance") = 5e-4, py::arg("forceGroup") = 0, py::arg("reciprocalSpaceForceGroup") = -1,
            py::arg("useDispersionCorrection") = true)
+        .def("addHarmonicBondForce", [](OpenMM::System &s, const std::vector<int> &particle1, const std::vector<int> &particle2,
+                                        const std::vector<double> &length, const std::vector<double> &k, int group, bool periodic) {
+            if (particle1.size() != particle2.size() || particle1.size() != length.size() || particle1.size() != k.size())
+                throw OpenMM::OpenMMException("addHarmonicBondForce: inconsistent array lengths");
+            auto *hb = new OpenMM::HarmonicBondForce();
+            for (size_t b = 0; b < particle1.size(); b++) {
+                if (particle1[b] < 0 || particle2[b] < 0 || particle1[b] >= s.getNumParticles() || particle2[b] >= s.getNumParticles())
+                    throw OpenMM::OpenMMException("HarmonicBondForce: Illegal particle index for a bond");
+                hb->addBond(particle1[b], particle2[b], length[b], k[b]);
+            }
+            hb->setForceGroup(group);
+            hb->setUsesPeriodicBoundaryConditions(periodic);
+            return s.addForce(hb);
+        }, py::arg("particle1"), py::arg("particle2"), py::arg("length"), py::arg("k"), py::arg("forceGroup") = 0,
+           py::arg("usesPeriodicBoundaryConditions") = false)
         .def("addATMMetaForce", [](OpenMM::System &s, const ATMMetaForce &f) {
             auto *copy = new ATMMetaForce(f);     // the System owns its forces
             s.addForce(copy);

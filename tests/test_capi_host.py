@@ -76,7 +76,7 @@ def test_host_pipeline_rejects_bad_arguments_before_touching_the_device():
     assert L.atm_host_pipeline_create(1, handles, C.byref(p)) != _capi.ATM_OK and not p.value
     assert L.atm_host_pipeline_step(None, None, 0, None) != _capi.ATM_OK
     assert L.atm_host_pipeline_destroy(None) == _capi.ATM_OK      # destroying nothing is not an error
-    assert C.sizeof(_capi.HostIO) == 40                           # 3 pointers + 4 int32, as declared in the header
+    assert C.sizeof(_capi.HostIO) == 64                           # 3 pointers + 4 int32 + 3 pointers, as declared in the header
 
 
 # ------------------------------------------------------------------ replica exchange decisions (host, deterministic)

@@ -185,3 +185,50 @@ def test_swig_vector_names_and_interface_file():
         assert re.search(r"\b%s\s*\(" % name, text), name
         if name not in ("cast", "isinstance"):
             assert re.search(r"\b%s\s*\(" % name, header), name
+
+
+def _bond_energy_forces(pos, bonds, box=None):
+    e, f = 0.0, np.zeros_like(pos)
+    for a, b, r0, k in bonds:
+        d = pos[b] - pos[a]
+        if box is not None:
+            d -= box * np.floor(d / box + 0.5)
+        r = np.linalg.norm(d)
+        e += 0.5 * k * (r - r0) ** 2
+        f[a] += k * (r - r0) * d / r
+        f[b] -= k * (r - r0) * d / r
+    return e, f
+
+
+def test_host_evaluated_force_standin_and_variable_group_acceptance():
+    """The OpenMM-free build's HarmonicBondForce (a HostEvaluatedForce: the stand-in for OpenMM's bonded kernels) against
+    numpy on the kernel-less platform, with and without the minimum-image rule, force groups honoured; and
+    ATMMetaForceImpl::initialize accepts it in a variable force group next to the NonbondedForce (the generic
+    variable-force hook; ref: openmmapi/src/ATMMetaForceImpl.cpp:51-65 clones every Force)."""
+    from atmmetaforce import _atmmetaforce_core as core
+    rng = np.random.default_rng(5)
+    n = 40
+    pos = rng.uniform(0, 3.0, (n, 3))
+    bonds = [(int(a), int(b), float(r0), float(k)) for a, b, r0, k in
+             zip(rng.integers(0, n // 2, 12), rng.integers(n // 2, n, 12), rng.uniform(0.1, 0.3, 12), rng.uniform(1e3, 3e5, 12))]
+    for periodic in (False, True):
+        s = core.System()
+        for _ in range(n):
+            s.addParticle(12.0)
+        s.setDefaultPeriodicBoxVectors([3.0, 0, 0], [0, 3.0, 0], [0, 0, 3.0])
+        s.addHarmonicBondForce([b[0] for b in bonds], [b[1] for b in bonds], [b[2] for b in bonds], [b[3] for b in bonds],
+                               forceGroup=4, usesPeriodicBoundaryConditions=periodic)
+        ctx = core.Context(s)
+        ctx.setPositions(pos)
+        e, f = ctx.calcForcesAndEnergy(True, True, 1 << 4)
+        e_ref, f_ref = _bond_energy_forces(pos, bonds, np.full(3, 3.0) if periodic else None)
+        assert abs(e - e_ref) <= 1e-12 * abs(e_ref) and np.allclose(f, f_ref, rtol=1e-12, atol=1e-9)
+        e0, f0 = ctx.calcForcesAndEnergy(True, True, 1 << 3)       # another group: nothing
+        assert e0 == 0.0 and not f0.any()
+    with pytest.raises(atm.OpenMMException, match="Illegal particle index"):
+        core.System().addHarmonicBondForce([0], [1], [0.1], [1.0])
+
+    core, s, f = _cpp_system()          # NonbondedForce in group 1, ATM in group 3, variable groups (1,)
+    s.addHarmonicBondForce([0, 1], [5, 6], [0.2, 0.2], [1000.0, 1000.0], forceGroup=1)
+    ctx = core.Context(s)               # accepted: no "cannot evaluate" error
+    assert not ctx.usesPlatformKernel(f)

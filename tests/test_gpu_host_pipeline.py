@@ -181,3 +181,68 @@ def test_pipeline_errors():
         pipe.step([posq_h], [force_h], maintenance=5, stream=stream)
     pipe.close()
     be.close()
+
+
+def test_external_state_terms_through_the_host_path():
+    """atm_host_io.force_state{1,2}_ext_host / energy_ext_host (the generic hook for other variable-group forces evaluated by
+    the caller): bit-identical to atm_step with the same arrays as device buffers, over two chunks; and the merged force
+    differs from the run without them by exactly sp * F2_ext + (1 - sp) * F1_ext at equal sp."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic, _capi
+    s = synthetic.water_box(12000)
+    sched = synthetic.atm_schedule_22()
+    rows = [sched[4], sched[11], sched[17]]
+    ref = _setup(atm, s, rows, 3)
+    P, n = ref.P, s["pos"].shape[0]
+    bes = [_setup(atm, s, rows[:2], 2), _setup(atm, s, rows[2:], 1)]
+    pipe = atm.HostPipeline(bes)
+    rng = np.random.default_rng(8)
+    x = _coords(s, P, 3, seed=21, sigma=0.003)
+    ext = np.zeros((2, 3, 3, P))
+    ext[:, :, :, :n] = rng.normal(0, 300.0, (2, 3, 3, n))
+    ext_fixed = np.rint(ext * 4294967296.0).astype(np.int64).reshape(2, 3, 3 * P)
+    e_ext = rng.normal(0, 20.0, (3, 2))
+    stream = torch.cuda.Stream()
+    xd = torch.from_numpy(x).cuda()
+    force = torch.zeros((3, 3 * P), dtype=torch.int64, device="cuda")
+    with torch.cuda.stream(stream):
+        ref.rebuild(xd, stream=stream)
+        ref.step(xd, force, f1_ext=torch.from_numpy(ext_fixed[0]).cuda(), f2_ext=torch.from_numpy(ext_fixed[1]).cuda(),
+                 energy_ext=torch.from_numpy(e_ext).cuda(), include_energy=True, stream=stream)
+    en_ref = ref.get_energies(stream=stream)
+    split = (slice(0, 2), slice(2, 3))
+    posq_h = [torch.from_numpy(x[c]).pin_memory() for c in split]
+    force_h = [torch.zeros((k, 3 * P), dtype=torch.int64).pin_memory() for k in (2, 1)]
+    en_h = [torch.zeros((k, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory() for k in (2, 1)]
+    f1_h = [torch.from_numpy(ext_fixed[0][c].copy()).pin_memory() for c in split]
+    f2_h = [torch.from_numpy(ext_fixed[1][c].copy()).pin_memory() for c in split]
+    ee_h = [torch.from_numpy(e_ext[c].copy()).pin_memory() for c in split]
+    pipe.step(posq_h, force_h, en_h, maintenance=pipe.REBUILD, stream=stream, f1_ext_host=f1_h, f2_ext_host=f2_h, energy_ext_host=ee_h)
+    stream.synchronize()
+    pipe.step(posq_h, force_h, en_h, maintenance=pipe.NONE, stream=stream, f1_ext_host=f1_h, f2_ext_host=f2_h, energy_ext_host=ee_h)
+    stream.synchronize()
+    assert torch.equal(torch.cat(force_h, 0), force.cpu())
+    got_e = torch.cat(en_h, 0).numpy()
+    assert np.array_equal(got_e[:, :7], en_ref[:, :7])
+    # the same step without the external energies but with the external forces: sp is unchanged by the forces, so the
+    # difference to a plain step is the sp-weighted mix of the two external force sets
+    plain_f = [torch.zeros((k, 3 * P), dtype=torch.int64).pin_memory() for k in (2, 1)]
+    pipe.step(posq_h, plain_f, en_h, maintenance=pipe.NONE, stream=stream)
+    stream.synchronize()
+    sp = torch.cat(en_h, 0).numpy()[:, _capi.E_SP]
+    only_f = [torch.zeros((k, 3 * P), dtype=torch.int64).pin_memory() for k in (2, 1)]
+    pipe.step(posq_h, only_f, en_h, maintenance=pipe.NONE, stream=stream, f1_ext_host=f1_h, f2_ext_host=f2_h)
+    stream.synchronize()
+    assert np.array_equal(torch.cat(en_h, 0).numpy()[:, _capi.E_SP], sp)
+    diff = (torch.cat(only_f, 0) - torch.cat(plain_f, 0)).numpy() / 4294967296.0
+    want = sp[:, None] * ext[1].reshape(3, 3 * P) + (1.0 - sp[:, None]) * ext[0].reshape(3, 3 * P)
+    assert np.abs(diff - want).max() <= 1e-6
+    # argument checks
+    with pytest.raises(atm.ATMError, match="wrong dtype or size"):
+        pipe.step(posq_h, force_h, en_h, stream=stream, energy_ext_host=[torch.zeros(3).pin_memory(), torch.zeros(2).pin_memory()])
+    with pytest.raises(atm.ATMError, match="pinned"):
+        pipe.step(posq_h, force_h, en_h, stream=stream, energy_ext_host=[torch.zeros(4, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)])
+    pipe.close()
+    for b in bes + [ref]:
+        b.close()

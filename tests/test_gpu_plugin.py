@@ -175,6 +175,102 @@ def test_fused_host_path_and_kernel_path_agree(abfe):
     assert abs((u_fused - u_direct) - (r2 - r1)) <= 5e-3
 
 
+def _bonded_system(core, abfe, params, k_bond, var_groups):
+    """NonbondedForce (group 1) + a HarmonicBondForce tying ligand atoms to host atoms (group 3) + ATMMetaForce (group 2)."""
+    import atmmetaforce as atm
+    n = abfe["pos"].shape[0]
+    s = core.System()
+    for m in abfe["mass"]:
+        s.addParticle(float(m))
+    L = abfe["box"]
+    s.setDefaultPeriodicBoxVectors([L[0], 0, 0], [0, L[1], 0], [0, 0, L[2]])
+    exc = {(int(a), int(b)): (0.0, 0.3, 0.0) for a, b in abfe["excl"]}
+    for (a, b), p in zip(abfe["exc14"], abfe["exc14_par"]):
+        exc[(int(a), int(b))] = tuple(float(x) for x in p)
+    s.addNonbondedForce(abfe["charge"].tolist(), abfe["sigma"].tolist(), abfe["epsilon"].tolist(), [x for ab in exc for x in ab],
+                        [x for ab in exc for x in exc[ab]], cutoff=1.0, ewaldTolerance=5e-4, forceGroup=1)
+    lig = [int(i) for i in abfe["lig1"][:3]]
+    host = [5, 60, 130]
+    bonds = [(a, b, 0.8 * float(np.linalg.norm(abfe["pos"][b] - abfe["pos"][a])), k_bond) for a, b in zip(lig, host)]
+    if k_bond is not None:
+        s.addHarmonicBondForce([b[0] for b in bonds], [b[1] for b in bonds], [b[2] for b in bonds], [b[3] for b in bonds], forceGroup=3)
+    f = atm.ATMMetaForce(*params, list(var_groups))
+    for i in range(n):
+        f.addParticle(i, *abfe["displ"][i])
+    f.setForceGroup(2)
+    return s, s.addATMMetaForce(f), bonds
+
+
+def _bonds_numpy(pos, bonds):
+    e, f = 0.0, np.zeros_like(pos)
+    for a, b, r0, k in bonds:
+        d = pos[b] - pos[a]
+        r = np.linalg.norm(d)
+        e += 0.5 * k * (r - r0) ** 2
+        f[a] += k * (r - r0) * d / r
+        f[b] -= k * (r - r0) * d / r
+    return e, f
+
+
+def test_generic_variable_force_through_both_impl_modes(abfe):
+    """A second Force in the variable force groups (HarmonicBondForce between the displaced ligand and the host): the
+    fused Impl evaluates it at x and x + d on the host and feeds force_state{1,2}_ext / energy_ext through
+    atm_host_pipeline_step; the reference orchestration clones it into the two inner contexts (ref:
+    openmmapi/src/ATMMetaForceImpl.cpp:51-65,113-116).  Both must give U1 + E_bond(x), U2 + E_bond(x + d), the same
+    u_sc / energy / forces; at lambda1 == lambda2 (sp = 1/2 below the soft-core threshold) the force changes by exactly
+    (F_bond(x) + F_bond(x + d)) / 2."""
+    from atmmetaforce import _atmmetaforce_core as core, _capi
+    from helpers import rel_rms
+    if "CUDA" not in core.getPlatformNames():
+        core.registerCudaPlatform()
+    core.loadPluginLibrary(PLUGIN)
+    kcal = 4.184
+    pos, displ = abfe["pos"], abfe["displ"]
+    for params, k_bond in (((0.5, 0.5, 0.0, 0.0, 0.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0), 2.0),
+                           ((0.2, 0.7, 0.05, 30.0, 1.0, 200.0 * kcal, 100.0 * kcal, 0.0625, 1.0), 25.0)):
+        s0, fc0, _ = _bonded_system(core, abfe, params, None, (1,))
+        h0 = core.Context(s0)
+        h0.setPositions(pos)
+        _, f0 = h0.calcForcesAndEnergy(True, True, 1 << 2)
+        rec0 = np.array(h0.getEnergyRecord(fc0))
+        s, fc, bonds = _bonded_system(core, abfe, params, k_bond, (1, 3))
+        e1b, f1b = _bonds_numpy(pos, bonds)
+        e2b, f2b = _bonds_numpy(pos + displ, bonds)
+        assert e2b - e1b > 10.0                                        # the bonds do see the displacement
+        host = core.Context(s)
+        host.setPositions(pos)
+        e_h, f_h = host.calcForcesAndEnergy(True, True, 1 << 2)
+        rec = np.array(host.getEnergyRecord(fc))
+        assert abs(rec[_capi.E_U1] - rec0[_capi.E_U1] - e1b) <= 1e-9 * abs(rec0[_capi.E_U1]) + 1e-9
+        assert abs(rec[_capi.E_U2] - rec0[_capi.E_U2] - e2b) <= 1e-9 * abs(rec0[_capi.E_U2]) + 1e-9
+        assert abs(rec[_capi.E_U] - rec0[_capi.E_U] - (e2b - e1b)) <= 1e-9 * abs(rec0[_capi.E_U]) + 1e-7
+        sc = atm_softcore(params, rec[_capi.E_U])
+        assert abs(rec[_capi.E_USC] - sc["u_sc"]) <= 1e-9 * abs(sc["u_sc"]) and abs(rec[_capi.E_SP] - sc["sp"]) <= 1e-12
+        if params[0] == params[1]:
+            assert rec[_capi.E_SP] == 0.5 == rec0[_capi.E_SP]
+            assert np.abs((f_h - f0) - 0.5 * (f1b + f2b)).max() <= 1e-6
+        else:
+            assert abs(rec[_capi.E_SP] - rec0[_capi.E_SP]) > 1e-3     # the bond energies moved the soft-plus weight
+        # only group 3: the bond force on its own, through its own Impl
+        e3, f3 = host.calcForcesAndEnergy(True, True, 1 << 3)
+        assert abs(e3 - e1b) <= 1e-12 * abs(e1b) and np.allclose(f3, f1b, rtol=1e-12, atol=1e-9)
+        # the reference orchestration: two inner contexts evaluate NonbondedForce + HarmonicBondForce
+        cu = core.Context(s, "CUDA", {"Precision": "mixed"})
+        assert cu.usesPlatformKernel(fc)
+        cu.setPositions(pos)
+        e_k, f_k = cu.calcForcesAndEnergy(True, True, 1 << 2)
+        rec_k = np.array(cu.getEnergyRecord(fc))
+        assert abs(rec_k[_capi.E_U1] - rec[_capi.E_U1]) <= 1e-6 * abs(rec[_capi.E_U1])
+        assert abs(rec_k[_capi.E_USC] - rec[_capi.E_USC]) <= 5e-3
+        assert abs(e_k - e_h) <= 1e-5 * abs(e_h) + 1e-3
+        assert rel_rms(f_k, f_h) <= 1e-5
+
+
+def atm_softcore(params, u):
+    import atmmetaforce as atm
+    return atm.softcore_softplus(params, 0.0, u if params[8] > 0 else -u)
+
+
 def test_example_scripts_agree_across_the_three_paths():
     """example/abfe and example/rbfe single-point scripts (ref: example/abfe/abfe.py, example/rbfe/rbfe.py): the Python
     Context, the C++ fused Impl and the plugin-glue path print the same sample line (u to 1e-3 kcal/mol), and the ABFE
