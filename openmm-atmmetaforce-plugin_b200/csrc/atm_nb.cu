@@ -82,6 +82,40 @@ static void launch_pme_spread(const NbDev &d, cudaStream_t stream) {
     }
 }
 
+static void launch_pme_spread_tile(const NbDev &d, size_t smem, cudaStream_t stream) {
+    const dim3 grid(d.pme_ntx * d.pme_nty, d.R);
+    switch (d.pme_order) {
+        case 4: pme_spread_tile_kernel<4><<<grid, PME_SPREAD_THREADS, smem, stream>>>(d); break;
+        case 5: pme_spread_tile_kernel<5><<<grid, PME_SPREAD_THREADS, smem, stream>>>(d); break;
+        case 6: pme_spread_tile_kernel<6><<<grid, PME_SPREAD_THREADS, smem, stream>>>(d); break;
+        case 7: pme_spread_tile_kernel<7><<<grid, PME_SPREAD_THREADS, smem, stream>>>(d); break;
+        default: pme_spread_tile_kernel<8><<<grid, PME_SPREAD_THREADS, smem, stream>>>(d); break;
+    }
+}
+
+static cudaError_t pme_spread_tile_smem_attr(int order, size_t smem) {
+    const void *fn;
+    switch (order) {
+        case 4: fn = (const void *)pme_spread_tile_kernel<4>; break;
+        case 5: fn = (const void *)pme_spread_tile_kernel<5>; break;
+        case 6: fn = (const void *)pme_spread_tile_kernel<6>; break;
+        case 7: fn = (const void *)pme_spread_tile_kernel<7>; break;
+        default: fn = (const void *)pme_spread_tile_kernel<8>; break;
+    }
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+static void launch_pme_gather_f(const NbDev &d, cudaStream_t stream) {
+    const dim3 grid((d.Smax + 127) / 128, d.R);
+    switch (d.pme_order) {
+        case 4: pme_gather_f_kernel<4><<<grid, 128, 0, stream>>>(d); break;
+        case 5: pme_gather_f_kernel<5><<<grid, 128, 0, stream>>>(d); break;
+        case 6: pme_gather_f_kernel<6><<<grid, 128, 0, stream>>>(d); break;
+        case 7: pme_gather_f_kernel<7><<<grid, 128, 0, stream>>>(d); break;
+        default: pme_gather_f_kernel<8><<<grid, 128, 0, stream>>>(d); break;
+    }
+}
+
 static void launch_pme_gather(const NbDev &d, cudaStream_t stream) {
     const dim3 grid((d.Smax + 127) / 128, d.R);
     switch (d.pme_order) {
@@ -840,7 +874,19 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         }
         if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
     }
-    if (d.pme_on) {
+    if (d.pme_on && d.pme_f32) {
+        const size_t nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
+        launch_pme_spread_tile(d, nb->pme_tile_smem, stream);
+        ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
+        ATM_REQUIRE(cufftExecR2C(nb->pme_plan_fwd, d.pme_gridf, (cufftComplex *)d.pme_specf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
+                    "cufftExecR2C failed");
+        pme_convolve_f_kernel<<<dim3((unsigned)((nspec + 255) / 256), d.R), 256, 0, stream>>>(d);
+        ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
+        ATM_REQUIRE(cufftExecC2R(nb->pme_plan_bwd, (cufftComplex *)d.pme_specf, d.pme_gridf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
+                    "cufftExecC2R failed");
+        launch_pme_gather_f(d, stream);
+        h->launches += 3;  // own kernels (the FFTs are cuFFT library code)
+    } else if (d.pme_on) {
         const size_t ng = (size_t)d.gx * d.gy * d.gz, nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
         launch_pme_spread(d, stream);
         pme_finalize_kernel<<<dim3((unsigned)((ng / 2 + 256) / 256), d.R), 256, 0, stream>>>(d);
@@ -1054,13 +1100,33 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
     };
     int rc;
     void *p;
-    if ((rc = alloc(&p, sizeof(unsigned long long) * 2 * ng * R))) return rc;
-    d.pme_acc = (unsigned long long *)p;
-    ATM_CUDA_CHECK(cudaMemset(d.pme_acc, 0, sizeof(unsigned long long) * 2 * ng * R));
-    if ((rc = alloc(&p, sizeof(double) * 2 * ng * R))) return rc;
-    d.pme_grid = (double *)p;
-    if ((rc = alloc(&p, sizeof(double2) * 2 * nspec * R))) return rc;
-    d.pme_spec = (double2 *)p;
+    // ATM_B200_PME_F64=1: the double-precision mesh pipeline of round 1 (global fixed-point spread, D2Z / Z2D) for A/B runs
+    static const bool f64 = [] { const char *e = getenv("ATM_B200_PME_F64"); return e && e[0] == '1'; }();
+    d.pme_f32 = f64 ? 0 : 1;
+    d.pme_acc = nullptr; d.pme_grid = nullptr; d.pme_spec = nullptr; d.pme_gridf = nullptr; d.pme_specf = nullptr;
+    if (d.pme_f32) {
+        if ((rc = alloc(&p, sizeof(float) * 2 * ng * R))) return rc;
+        d.pme_gridf = (float *)p;
+        if ((rc = alloc(&p, sizeof(float2) * 2 * nspec * R))) return rc;
+        d.pme_specf = (float2 *)p;
+        // spread tiles: about 12 x 12 cells in xy (all of z), smaller when the z extent would not fit in shared memory
+        int T = 12;
+        while (T > 4 && sizeof(int) * (size_t)T * T * nz > 160 * 1024) T--;
+        d.pme_ntx = (nx + T - 1) / T;
+        d.pme_nty = (ny + T - 1) / T;
+        const int tw = (nx + d.pme_ntx - 1) / d.pme_ntx, th = (ny + d.pme_nty - 1) / d.pme_nty;
+        nb->pme_tile_smem = sizeof(int) * (size_t)tw * th * nz;
+        ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
+        ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, nb->pme_tile_smem));
+    } else {
+        if ((rc = alloc(&p, sizeof(unsigned long long) * 2 * ng * R))) return rc;
+        d.pme_acc = (unsigned long long *)p;
+        ATM_CUDA_CHECK(cudaMemset(d.pme_acc, 0, sizeof(unsigned long long) * 2 * ng * R));
+        if ((rc = alloc(&p, sizeof(double) * 2 * ng * R))) return rc;
+        d.pme_grid = (double *)p;
+        if ((rc = alloc(&p, sizeof(double2) * 2 * nspec * R))) return rc;
+        d.pme_spec = (double2 *)p;
+    }
     std::vector<double> mods, m1;
     for (int n : {nx, ny, nz}) {
         pme_moduli(n, order, m1);
@@ -1070,9 +1136,9 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
     ATM_CUDA_CHECK(cudaMemcpy(p, mods.data(), sizeof(double) * mods.size(), cudaMemcpyHostToDevice));
     d.pme_mod = (const double *)p;
     int dims[3] = {nx, ny, nz};
-    ATM_REQUIRE(cufftPlanMany(&nb->pme_plan_fwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, 2 * R) == CUFFT_SUCCESS, ATM_ERR_CUDA,
-                "atm_pme_setup: cufftPlanMany(D2Z) failed");
-    if (cufftPlanMany(&nb->pme_plan_bwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, 2 * R) != CUFFT_SUCCESS) {
+    ATM_REQUIRE(cufftPlanMany(&nb->pme_plan_fwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, d.pme_f32 ? CUFFT_R2C : CUFFT_D2Z, 2 * R) == CUFFT_SUCCESS,
+                ATM_ERR_CUDA, "atm_pme_setup: cufftPlanMany(forward) failed");
+    if (cufftPlanMany(&nb->pme_plan_bwd, 3, dims, nullptr, 1, 0, nullptr, 1, 0, d.pme_f32 ? CUFFT_C2R : CUFFT_Z2D, 2 * R) != CUFFT_SUCCESS) {
         cufftDestroy(nb->pme_plan_fwd);
         set_error("atm_pme_setup: cufftPlanMany(Z2D) failed");
         return ATM_ERR_CUDA;

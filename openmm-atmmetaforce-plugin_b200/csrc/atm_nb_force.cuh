@@ -497,9 +497,10 @@ __device__ double scalar_stage_replica(const NbDev &d, int r, const double *__re
         du += energy_ext[2 * r + 1] - energy_ext[2 * r];
     }
     Scalars s = scalar_stage(d.params + (size_t)r * ATM_NUM_PARAMS, U1, U2, du);
-    if (d.flags[0] & 7) {
+    if (d.flags[0] & 15) {
         // the pair lists of the last rebuild are incomplete (a list outgrew its capacity, or the box is too small for
-        // the list radius): nothing computed from them may look like a result
+        // the list radius), or a site has moved further since that rebuild than the structure tolerates (bit 3, set by
+        // the PME gather): nothing computed from them may look like a result
         const double bad = __longlong_as_double(0x7ff8000000000000ll);
         U1 = U2 = bad;
         s.u = s.usc = s.ebias = s.energy = s.sp = bad;

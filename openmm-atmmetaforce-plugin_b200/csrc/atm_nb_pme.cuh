@@ -19,29 +19,29 @@ constexpr int PME_MAX_ORDER = 8;
 
 // cardinal B-spline weights theta[k] and derivatives dtheta[k], k = 0..ORDER-1, for fractional offset w (Essmann 1995);
 // ORDER is a compile-time constant so that everything stays in registers
-template <int ORDER>
-__device__ __forceinline__ void pme_bspline(double w, double (&theta)[ORDER], double (&dtheta)[ORDER]) {
+template <int ORDER, typename T>
+__device__ __forceinline__ void pme_bspline(T w, T (&theta)[ORDER], T (&dtheta)[ORDER]) {
 #pragma unroll
-    for (int k = 0; k < ORDER; k++) theta[k] = 0.0;
+    for (int k = 0; k < ORDER; k++) theta[k] = T(0);
     theta[1] = w;
-    theta[0] = 1.0 - w;
+    theta[0] = T(1) - w;
 #pragma unroll
     for (int k = 3; k < ORDER; k++) {
-        const double div = 1.0 / (k - 1.0);
+        const T div = T(1) / T(k - 1);
         theta[k - 1] = div * w * theta[k - 2];
 #pragma unroll
-        for (int j = 1; j <= k - 2; j++) theta[k - j - 1] = div * ((w + j) * theta[k - j - 2] + (k - j - w) * theta[k - j - 1]);
-        theta[0] = div * (1.0 - w) * theta[0];
+        for (int j = 1; j <= k - 2; j++) theta[k - j - 1] = div * ((w + T(j)) * theta[k - j - 2] + (T(k - j) - w) * theta[k - j - 1]);
+        theta[0] = div * (T(1) - w) * theta[0];
     }
     dtheta[0] = -theta[0];
 #pragma unroll
     for (int k = 1; k < ORDER; k++) dtheta[k] = theta[k - 1] - theta[k];
-    const double div = 1.0 / (ORDER - 1.0);
+    const T div = T(1) / T(ORDER - 1);
     theta[ORDER - 1] = div * w * theta[ORDER - 2];
 #pragma unroll
     for (int j = 1; j <= ORDER - 2; j++)
-        theta[ORDER - j - 1] = div * ((w + j) * theta[ORDER - j - 2] + (ORDER - j - w) * theta[ORDER - j - 1]);
-    theta[0] = div * (1.0 - w) * theta[0];
+        theta[ORDER - j - 1] = div * ((w + T(j)) * theta[ORDER - j - 2] + (T(ORDER - j) - w) * theta[ORDER - j - 1]);
+    theta[0] = div * (T(1) - w) * theta[0];
 }
 
 template <int ORDER>
@@ -59,7 +59,7 @@ __device__ __forceinline__ void pme_site_setup(const NbDev &d, const float4 &x, 
         double u = (xr[c] - floor(xr[c])) * n[c];
         int fl = (int)floor(u);
         if (fl >= n[c]) fl = n[c] - 1;
-        pme_bspline<ORDER>(u - fl, ps.th[c], ps.dth[c]);
+        pme_bspline<ORDER, double>(u - fl, ps.th[c], ps.dth[c]);
         ps.k0[c] = fl - ORDER + 1;
     }
 }
@@ -224,6 +224,258 @@ __global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
         atomicAdd(buf2 + s, (unsigned long long)__double2ll_rn(sx * f2x * FORCE_SCALE));
         atomicAdd(buf2 + cs + s, (unsigned long long)__double2ll_rn(sy * f2y * FORCE_SCALE));
         atomicAdd(buf2 + 2 * cs + s, (unsigned long long)__double2ll_rn(sz * f2z * FORCE_SCALE));
+    }
+}
+
+// ================================================================================================
+// Single-precision mesh pipeline (default; the double kernels above stay selectable with ATM_B200_PME_F64=1):
+//   pme_spread_tile_kernel   one block OWNS a brick of mesh cells (a tile of xy cells, all z): it scans the sites of the
+//                            xy columns that can reach the brick (sites are stored column by column), accumulates their
+//                            contributions in a shared-memory tile with 32-bit fixed-point atomics (deterministic), and
+//                            stores the brick as floats straight into the transform input -- no global atomics, no
+//                            accumulator to clear, no separate conversion pass.  Two passes per block: Q1 (environment +
+//                            displaced atoms) and dQ = Q2 - Q1 (ghosts - displaced atoms).
+//   cuFFT R2C (float), batched over both meshes of every replica
+//   pme_convolve_f_kernel    influence function in double per mode; E1 = 1/2 sum G |Q1^|^2 and, by linearity of the
+//                            transform, E2 - E1 = sum G (Re(conj(Q1^) dQ^) + 1/2 |dQ^|^2), both accumulated in double:
+//                            the rounding noise of the big mesh never enters the DIFFERENCE as a difference of two sums
+//   cuFFT C2R (float): phi1 and dphi = phi2 - phi1
+//   pme_gather_f_kernel      F1 from phi1, F2 from phi1 + dphi, float weights, row sums over z first
+// Positions -> mesh coordinates stay in double (the float coordinate is the exact input; its fractional mesh offset
+// would lose five digits in float); weights, meshes and transforms are float.
+// ================================================================================================
+constexpr float PME_TILE_SCALE = 16777216.0f;   // 2^24 fixed point of the shared-memory tile (|cell charge| < 128 sqrt(k_e) e)
+constexpr int PME_SPREAD_THREADS = 256;
+
+template <int ORDER, bool WANT_D>
+__device__ __forceinline__ void pme_site_setup_f(const NbDev &d, const float4 &x, const float4 &L, int (&fl)[3], float (&th)[3][ORDER],
+                                                 float (&dth)[3][ORDER]) {
+    const int n[3] = {d.gx, d.gy, d.gz};
+    const double xr[3] = {(double)x.x / (double)L.x, (double)x.y / (double)L.y, (double)x.z / (double)L.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double u = (xr[c] - floor(xr[c])) * n[c];
+        int f = (int)u;
+        if (f >= n[c]) f = n[c] - 1;
+        fl[c] = f;
+        pme_bspline<ORDER, float>((float)(u - f), th[c], dth[c]);
+    }
+}
+
+__device__ __forceinline__ int pme_mod(int i, int n) {   // any i >= -n
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+template <int ORDER>
+__device__ __forceinline__ void pme_spread_site(const NbDev &d, const float4 &x, const float4 &L, float sign, int x0, int tw, int y0, int th_,
+                                                int *s_tile) {
+    int fl[3];
+    float th[3][ORDER], dth[3][ORDER];
+    pme_site_setup_f<ORDER, false>(d, x, L, fl, th, dth);
+    // tile-relative x / y cell of each spline point, or -1 when the point belongs to another block's brick
+    int ra[ORDER], rb[ORDER];
+    bool anyx = false, anyy = false;
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+        int t = pme_wrap(pme_wrap(fl[0] - (ORDER - 1) + a, d.gx) - x0, d.gx);
+        ra[a] = t < tw ? t : -1;
+        anyx |= t < tw;
+        t = pme_wrap(pme_wrap(fl[1] - (ORDER - 1) + a, d.gy) - y0, d.gy);
+        rb[a] = t < th_ ? t : -1;
+        anyy |= t < th_;
+    }
+    if (!anyx || !anyy) return;
+    int iz[ORDER];
+#pragma unroll
+    for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
+    const float q = sign * x.w * PME_TILE_SCALE;
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+        if (ra[a] < 0) continue;
+#pragma unroll
+        for (int b = 0; b < ORDER; b++) {
+            if (rb[b] < 0) continue;
+            const float qab = q * th[0][a] * th[1][b];
+            int *row = s_tile + (ra[a] * th_ + rb[b]) * d.gz;
+#pragma unroll
+            for (int c = 0; c < ORDER; c++) atomicAdd(row + iz[c], __float2int_rn(qab * th[2][c]));
+        }
+    }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbDev d) {
+    extern __shared__ int s_tile[];   // [tw][th][gz]
+    const int r = blockIdx.y;
+    const int tx = blockIdx.x / d.pme_nty, ty = blockIdx.x - tx * d.pme_nty;
+    const int x0 = (int)((long long)tx * d.gx / d.pme_ntx), x1 = (int)((long long)(tx + 1) * d.gx / d.pme_ntx);
+    const int y0 = (int)((long long)ty * d.gy / d.pme_nty), y1 = (int)((long long)(ty + 1) * d.gy / d.pme_nty);
+    const int tw = x1 - x0, th_ = y1 - y0, gz = d.gz;
+    const int ncell = tw * th_ * gz;
+    for (int i = threadIdx.x; i < ncell; i += PME_SPREAD_THREADS) s_tile[i] = 0;
+    const float4 L = d.box[r];
+    // xy columns whose sites can reach the brick: a site at mesh coordinate u touches cells floor(u) - (ORDER - 1) .. floor(u),
+    // and sits within `margin` of the column it was sorted into at the last rebuild (checked by the gather kernel)
+    const float hx = L.x / d.gx, hy = L.y / d.gy, wx = L.x / d.nx, wy = L.y / d.ny;
+    const float margin = 0.5f * (d.rlist_outer - sqrtf(d.cutoff2));
+    const int cx_lo = (int)floorf((x0 * hx - margin - hx) / wx), cx_hi = (int)floorf(((x1 + ORDER - 1) * hx + margin + hx) / wx);
+    const int cy_lo = (int)floorf((y0 * hy - margin - hy) / wy), cy_hi = (int)floorf(((y1 + ORDER - 1) * hy + margin + hy) / wy);
+    const int ncx = min(cx_hi - cx_lo + 1, d.nx), ncy = min(cy_hi - cy_lo + 1, d.ny);
+    const size_t ng = (size_t)d.gx * d.gy * gz;
+    float *out = d.pme_gridf + (size_t)r * 2 * ng;
+    const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
+    const float4 *xs = d.xs + (size_t)r * d.Smax;
+    const int *slot_site = d.slot_site + (size_t)r * d.Smax;
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+        // pass 0: Q1 = environment (class 0) + displaced atoms (classes 1..G); pass 1: dQ = ghosts (G+1..2G) - displaced atoms
+        const int cls_lo = pass == 0 ? 0 : 1, cls_hi = pass == 0 ? d.G : 2 * d.G;
+        for (int cls = cls_lo; cls <= cls_hi; cls++) {
+            const float sign = (pass == 1 && cls <= d.G) ? -1.f : 1.f;
+            for (int icx = 0; icx < ncx; icx++) {
+                const int cx = pme_mod(cx_lo + icx, d.nx);
+                int cya = pme_mod(cy_lo, d.ny), remaining = ncy;
+                while (remaining > 0) {   // the y range is one or two runs of consecutive bins (periodic wrap)
+                    const int seg = min(remaining, d.ny - cya);
+                    const int b0 = cls * d.ncol + cx * d.ny + cya;
+                    const int s0 = CL * bcs[b0], s1 = CL * bcs[b0 + seg];
+                    for (int s = s0 + threadIdx.x; s < s1; s += PME_SPREAD_THREADS)
+                        if (slot_site[s] >= 0) pme_spread_site<ORDER>(d, xs[s], L, sign, x0, tw, y0, th_, s_tile);
+                    remaining -= seg;
+                    cya = 0;
+                }
+            }
+        }
+        __syncthreads();
+        float *o = out + (size_t)pass * ng;
+        for (int i = threadIdx.x; i < ncell; i += PME_SPREAD_THREADS) {
+            const int iz = i % gz, t = i / gz;
+            const int rb = t % th_, ra = t / th_;
+            o[((size_t)(x0 + ra) * d.gy + (y0 + rb)) * gz + iz] = (float)s_tile[i] * (1.0f / PME_TILE_SCALE);
+            s_tile[i] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// Influence function and energies on the float spectra of Q1 and dQ (see the header comment of this section).
+__global__ void __launch_bounds__(256) pme_convolve_f_kernel(NbDev d) {
+    const int nzh = d.gz / 2 + 1;
+    const size_t nspec = (size_t)d.gx * d.gy * nzh;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double e1 = 0.0, de = 0.0;
+    if (i < nspec) {
+        const int c = (int)(i % nzh), b = (int)((i / nzh) % d.gy), a = (int)(i / ((size_t)nzh * d.gy));
+        float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec, *sd = s1 + nspec;
+        if (a == 0 && b == 0 && c == 0) {
+            s1[i] = make_float2(0.f, 0.f);
+            sd[i] = make_float2(0.f, 0.f);
+        } else {
+            const float4 L = d.box[r];
+            const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y,
+                         mc = (double)c / (double)L.z;
+            const double m2 = ma * ma + mb * mb + mc * mc;
+            const double V = (double)L.x * (double)L.y * (double)L.z;
+            const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
+            const double eterm = exp(-fac * m2) / (3.141592653589793 * V * m2 * d.pme_mod[a] * d.pme_mod[d.gx + b] * d.pme_mod[d.gx + d.gy + c]);
+            float2 v1 = s1[i], vd = sd[i];
+            const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
+            const double x1 = v1.x, y1 = v1.y, xd = vd.x, yd = vd.y;
+            e1 = 0.5 * w * eterm * (x1 * x1 + y1 * y1);
+            de = w * eterm * (x1 * xd + y1 * yd + 0.5 * (xd * xd + yd * yd));
+            const float g = (float)eterm;
+            s1[i] = make_float2(v1.x * g, v1.y * g);
+            sd[i] = make_float2(vd.x * g, vd.y * g);
+        }
+    }
+    __shared__ double red[2][256 / 32];
+    for (int off = 16; off > 0; off >>= 1) {
+        e1 += __shfl_xor_sync(0xffffffffu, e1, off);
+        de += __shfl_xor_sync(0xffffffffu, de, off);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = e1; red[1][threadIdx.x >> 5] = de; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, td = 0.0;
+        for (int k = 0; k < 256 / 32; k++) { t1 += red[0][k]; td += red[1][k]; }
+        const long long f1 = __double2ll_rn(t1 * ENERGY_SCALE), fd = __double2ll_rn(td * ENERGY_SCALE);
+        atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 6, (unsigned long long)f1);
+        atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 7, (unsigned long long)(f1 + fd));   // E2 = E1 + (E2 - E1), exactly
+    }
+}
+
+// one thread per site: row sums over z first (2 FMA per mesh point and mesh), then the xy weights
+template <int ORDER>
+__global__ void __launch_bounds__(128) pme_gather_f_kernel(NbDev d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (s >= CL * d.nclusters[r]) return;
+    const size_t rs = (size_t)r * d.Smax + s;
+    if (d.slot_site[rs] < 0) return;
+    const size_t rc = (size_t)r * d.Cmax + (s >> 3);
+    const int kind = class_kind(d.cmeta[rc] & 0xffff, d.G);
+    const float4 x = d.xs[rs];
+    const float4 L = d.box[r], iL = d.invbox[r];
+    {   // the spread kernel found this site through the xy column it was sorted into at the last rebuild: that holds while
+        // no site has left its cluster's bounding box of that time by more than half the outer skin -- the same movement
+        // the pair list tolerates.  Beyond it the step is poisoned like a list overflow (flags bit 3).
+        const float4 cc = d.cc[rc], ch = d.ch[rc];
+        const float margin = 0.5f * (d.rlist_outer - sqrtf(d.cutoff2));
+        if (fabsf(wrap_delta(x.x - cc.x, L.x, iL.x)) - ch.x > margin || fabsf(wrap_delta(x.y - cc.y, L.y, iL.y)) - ch.y > margin)
+            atomicOr(&d.flags[0], 8);
+    }
+    int fl[3];
+    float th[3][ORDER], dth[3][ORDER];
+    pme_site_setup_f<ORDER, true>(d, x, L, fl, th, dth);
+    const size_t ng = (size_t)d.gx * d.gy * d.gz;
+    const float *phi1 = d.pme_gridf + (size_t)r * 2 * ng, *phid = phi1 + ng;
+    int iz[ORDER];
+#pragma unroll
+    for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
+    float f1x = 0.f, f1y = 0.f, f1z = 0.f, fdx = 0.f, fdy = 0.f, fdz = 0.f;
+    const bool wantd = kind != 1;   // displaced atoms exist in state 1 only
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+        const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+#pragma unroll
+        for (int b = 0; b < ORDER; b++) {
+            const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
+            const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
+            float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
+#pragma unroll
+            for (int c = 0; c < ORDER; c++) {
+                const float p = __ldg(phi1 + row + iz[c]);
+                s0 = fmaf(th[2][c], p, s0);
+                sz = fmaf(dth[2][c], p, sz);
+            }
+            if (wantd) {
+#pragma unroll
+                for (int c = 0; c < ORDER; c++) {
+                    const float p = __ldg(phid + row + iz[c]);
+                    d0 = fmaf(th[2][c], p, d0);
+                    dz = fmaf(dth[2][c], p, dz);
+                }
+            }
+            const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
+            f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
+            fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
+        }
+    }
+    const double q = (double)x.w;
+    const double sx = -q * d.gx / (double)L.x * FORCE_SCALE, sy = -q * d.gy / (double)L.y * FORCE_SCALE, sz_ = -q * d.gz / (double)L.z * FORCE_SCALE;
+    const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
+    unsigned long long *buf1 = d.buf + 3 * cs + rsite, *buf2 = d.buf + 6 * cs + rsite;
+    if (kind != 2) {   // this thread is the only writer of its site's slots at this point of the step
+        buf1[s] += (unsigned long long)__double2ll_rn(sx * (double)f1x);
+        buf1[cs + s] += (unsigned long long)__double2ll_rn(sy * (double)f1y);
+        buf1[2 * cs + s] += (unsigned long long)__double2ll_rn(sz_ * (double)f1z);
+    }
+    if (kind != 1) {
+        buf2[s] += (unsigned long long)__double2ll_rn(sx * ((double)f1x + (double)fdx));
+        buf2[cs + s] += (unsigned long long)__double2ll_rn(sy * ((double)f1y + (double)fdy));
+        buf2[2 * cs + s] += (unsigned long long)__double2ll_rn(sz_ * ((double)f1z + (double)fdz));
     }
 }
 

@@ -78,6 +78,10 @@ struct NbDev {  // everything the kernels need, passed by value
     double *pme_grid;              // [R][2][ng] real charge grids of the two states (overwritten by the potentials)
     double2 *pme_spec;             // [R][2][gx][gy][gz/2+1]
     const double *pme_mod;         // |b(m)|^2 moduli: gx + gy + gz doubles
+    // single-precision mesh pipeline (default): Q1 and dQ = Q2 - Q1 / phi1 and dphi as floats, see atm_nb_pme.cuh
+    int pme_f32, pme_ntx, pme_nty; // tiles of mesh cells in x and y owned by one spread block each
+    float *pme_gridf;              // [R][2][ng]
+    float2 *pme_specf;             // [R][2][gx][gy][gz/2+1]
     double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms
     double pme_qtot2;              // (sum of q sqrt(ke))^2: neutralising-background term -pi Q^2 / (2 V alpha^2)
     double disp_coeff;             // long-range dispersion correction = disp_coeff / V (0 = off)
@@ -130,6 +134,7 @@ struct NbState {
     std::vector<void *> pme_owned;
     cufftHandle pme_plan_fwd = 0, pme_plan_bwd = 0;
     bool pme_plans = false;
+    size_t pme_tile_smem = 0;       // dynamic shared memory of one spread tile
     uint64_t generation = 0;        // bumped by every rebuild
     uint64_t alloc_generation = 0;  // bumped by every (re)allocation: buffers and grid bounds change, graphs are stale
     bool verified = false, needs_realloc = false, flags_pending = false;
