@@ -875,12 +875,12 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         if (profile) ATM_CUDA_CHECK(cudaEventRecord(e1, stream));
     }
     if (d.pme_on && d.pme_f32) {
-        const size_t nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
         launch_pme_spread_tile(d, nb->pme_tile_smem, stream);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecR2C(nb->pme_plan_fwd, d.pme_gridf, (cufftComplex *)d.pme_specf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecR2C failed");
-        pme_convolve_f_kernel<<<dim3((unsigned)((nspec + 255) / 256), d.R), 256, 0, stream>>>(d);
+        pme_convolve_f_kernel<<<dim3((unsigned)((d.gx * d.gy + PME_CONV_ROWS - 1) / PME_CONV_ROWS), d.R), 32 * PME_CONV_ROWS,
+                                sizeof(double) * (d.gz / 2 + 1 + 2 * PME_CONV_ROWS), stream>>>(d);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecC2R(nb->pme_plan_bwd, (cufftComplex *)d.pme_specf, d.pme_gridf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecC2R failed");
@@ -1115,7 +1115,8 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         d.pme_ntx = (nx + T - 1) / T;
         d.pme_nty = (ny + T - 1) / T;
         const int tw = (nx + d.pme_ntx - 1) / d.pme_ntx, th = (ny + d.pme_nty - 1) / d.pme_nty;
-        nb->pme_tile_smem = sizeof(int) * (size_t)tw * th * nz;
+        d.pme_tile_cells = tw * th * nz;
+        nb->pme_tile_smem = sizeof(int) * ((size_t)d.pme_tile_cells + PME_LIST_CAP);
         ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
         ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, nb->pme_tile_smem));
     } else {

@@ -247,18 +247,26 @@ __global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
 constexpr float PME_TILE_SCALE = 16777216.0f;   // 2^24 fixed point of the shared-memory tile (|cell charge| < 128 sqrt(k_e) e)
 constexpr int PME_SPREAD_THREADS = 256;
 
+// mesh coordinate of one component: cell index in [0, n) and the fractional offset inside the cell
+__device__ __forceinline__ int pme_cell(float x, double invL, int n, double &w) {
+    const double xr = (double)x * invL;
+    const double u = (xr - floor(xr)) * n;
+    int f = (int)u;
+    if (f >= n) f = n - 1;
+    w = u - f;
+    return f;
+}
+
 template <int ORDER, bool WANT_D>
-__device__ __forceinline__ void pme_site_setup_f(const NbDev &d, const float4 &x, const float4 &L, int (&fl)[3], float (&th)[3][ORDER],
+__device__ __forceinline__ void pme_site_setup_f(const NbDev &d, const float4 &x, const double (&invL)[3], int (&fl)[3], float (&th)[3][ORDER],
                                                  float (&dth)[3][ORDER]) {
     const int n[3] = {d.gx, d.gy, d.gz};
-    const double xr[3] = {(double)x.x / (double)L.x, (double)x.y / (double)L.y, (double)x.z / (double)L.z};
+    const float xc[3] = {x.x, x.y, x.z};
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const double u = (xr[c] - floor(xr[c])) * n[c];
-        int f = (int)u;
-        if (f >= n[c]) f = n[c] - 1;
-        fl[c] = f;
-        pme_bspline<ORDER, float>((float)(u - f), th[c], dth[c]);
+        double w;
+        fl[c] = pme_cell(xc[c], invL[c], n[c], w);
+        pme_bspline<ORDER, float>((float)w, th[c], dth[c]);
     }
 }
 
@@ -267,25 +275,28 @@ __device__ __forceinline__ int pme_mod(int i, int n) {   // any i >= -n
     return i < 0 ? i + n : i;
 }
 
+// Does the spline support of mesh coordinate (flx, fly) touch the brick [x0, x0 + tw) x [y0, y0 + th)?
 template <int ORDER>
-__device__ __forceinline__ void pme_spread_site(const NbDev &d, const float4 &x, const float4 &L, float sign, int x0, int tw, int y0, int th_,
-                                                int *s_tile) {
+__device__ __forceinline__ bool pme_touches(const NbDev &d, int flx, int fly, int x0, int tw, int y0, int th_) {
+    // cells flx - (ORDER - 1) .. flx  <=>  the brick-relative index of the LAST cell is below tw + ORDER - 1
+    return pme_wrap(flx - x0, d.gx) < tw + ORDER - 1 && pme_wrap(fly - y0, d.gy) < th_ + ORDER - 1;
+}
+
+template <int ORDER>
+__device__ __forceinline__ void pme_spread_site(const NbDev &d, const float4 &x, const double (&invL)[3], float sign, int x0, int tw, int y0,
+                                                int th_, int *s_tile) {
     int fl[3];
     float th[3][ORDER], dth[3][ORDER];
-    pme_site_setup_f<ORDER, false>(d, x, L, fl, th, dth);
+    pme_site_setup_f<ORDER, false>(d, x, invL, fl, th, dth);
     // tile-relative x / y cell of each spline point, or -1 when the point belongs to another block's brick
     int ra[ORDER], rb[ORDER];
-    bool anyx = false, anyy = false;
 #pragma unroll
     for (int a = 0; a < ORDER; a++) {
         int t = pme_wrap(pme_wrap(fl[0] - (ORDER - 1) + a, d.gx) - x0, d.gx);
         ra[a] = t < tw ? t : -1;
-        anyx |= t < tw;
         t = pme_wrap(pme_wrap(fl[1] - (ORDER - 1) + a, d.gy) - y0, d.gy);
         rb[a] = t < th_ ? t : -1;
-        anyy |= t < th_;
     }
-    if (!anyx || !anyy) return;
     int iz[ORDER];
 #pragma unroll
     for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
@@ -304,17 +315,24 @@ __device__ __forceinline__ void pme_spread_site(const NbDev &d, const float4 &x,
     }
 }
 
+constexpr int PME_SCAN_ROUND = 4 * PME_SPREAD_THREADS;   // candidate slots examined between two looks at the list
+constexpr int PME_LIST_CAP = 3 * PME_SCAN_ROUND;          // contributing slots collected before they are spread
+
 template <int ORDER>
 __global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbDev d) {
-    extern __shared__ int s_tile[];   // [tw][th][gz]
+    extern __shared__ int s_tile[];   // [tw][th][gz], then the list of contributing slots (bit 31: negative sign)
+    __shared__ int s_count;
     const int r = blockIdx.y;
     const int tx = blockIdx.x / d.pme_nty, ty = blockIdx.x - tx * d.pme_nty;
     const int x0 = (int)((long long)tx * d.gx / d.pme_ntx), x1 = (int)((long long)(tx + 1) * d.gx / d.pme_ntx);
     const int y0 = (int)((long long)ty * d.gy / d.pme_nty), y1 = (int)((long long)(ty + 1) * d.gy / d.pme_nty);
     const int tw = x1 - x0, th_ = y1 - y0, gz = d.gz;
     const int ncell = tw * th_ * gz;
+    unsigned int *s_list = reinterpret_cast<unsigned int *>(s_tile + d.pme_tile_cells);
     for (int i = threadIdx.x; i < ncell; i += PME_SPREAD_THREADS) s_tile[i] = 0;
+    if (threadIdx.x == 0) s_count = 0;
     const float4 L = d.box[r];
+    const double invL[3] = {1.0 / (double)L.x, 1.0 / (double)L.y, 1.0 / (double)L.z};
     // xy columns whose sites can reach the brick: a site at mesh coordinate u touches cells floor(u) - (ORDER - 1) .. floor(u),
     // and sits within `margin` of the column it was sorted into at the last rebuild (checked by the gather kernel)
     const float hx = L.x / d.gx, hy = L.y / d.gy, wx = L.x / d.nx, wy = L.y / d.ny;
@@ -327,12 +345,23 @@ __global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbD
     const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
     const float4 *xs = d.xs + (size_t)r * d.Smax;
     const int *slot_site = d.slot_site + (size_t)r * d.Smax;
+    // spread what the list holds, every lane busy (integer accumulation: the order of the list does not matter)
+    auto flush = [&]() {
+        const int n = s_count;
+        for (int i = threadIdx.x; i < n; i += PME_SPREAD_THREADS) {
+            const unsigned int e = s_list[i];
+            pme_spread_site<ORDER>(d, xs[e & 0x7fffffffu], invL, (e >> 31) ? -1.f : 1.f, x0, tw, y0, th_, s_tile);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+    };
     __syncthreads();
     for (int pass = 0; pass < 2; pass++) {
         // pass 0: Q1 = environment (class 0) + displaced atoms (classes 1..G); pass 1: dQ = ghosts (G+1..2G) - displaced atoms
         const int cls_lo = pass == 0 ? 0 : 1, cls_hi = pass == 0 ? d.G : 2 * d.G;
         for (int cls = cls_lo; cls <= cls_hi; cls++) {
-            const float sign = (pass == 1 && cls <= d.G) ? -1.f : 1.f;
+            const unsigned int neg = (pass == 1 && cls <= d.G) ? 0x80000000u : 0u;
             for (int icx = 0; icx < ncx; icx++) {
                 const int cx = pme_mod(cx_lo + icx, d.nx);
                 int cya = pme_mod(cy_lo, d.ny), remaining = ncy;
@@ -340,75 +369,104 @@ __global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbD
                     const int seg = min(remaining, d.ny - cya);
                     const int b0 = cls * d.ncol + cx * d.ny + cya;
                     const int s0 = CL * bcs[b0], s1 = CL * bcs[b0 + seg];
-                    for (int s = s0 + threadIdx.x; s < s1; s += PME_SPREAD_THREADS)
-                        if (slot_site[s] >= 0) pme_spread_site<ORDER>(d, xs[s], L, sign, x0, tw, y0, th_, s_tile);
+                    for (int base = s0; base < s1; base += PME_SCAN_ROUND) {
+                        for (int s = base + threadIdx.x; s < min(s1, base + PME_SCAN_ROUND); s += PME_SPREAD_THREADS) {
+                            if (slot_site[s] < 0) continue;
+                            const float4 x = xs[s];
+                            double w;
+                            const int flx = pme_cell(x.x, invL[0], d.gx, w), fly = pme_cell(x.y, invL[1], d.gy, w);
+                            if (pme_touches<ORDER>(d, flx, fly, x0, tw, y0, th_)) s_list[atomicAdd(&s_count, 1)] = (unsigned int)s | neg;
+                        }
+                        __syncthreads();
+                        const int filled = s_count;
+                        __syncthreads();   // every thread has read the count before the next round appends to the list
+                        if (filled > PME_LIST_CAP - PME_SCAN_ROUND) flush();
+                    }
                     remaining -= seg;
                     cya = 0;
                 }
             }
         }
         __syncthreads();
+        flush();
         float *o = out + (size_t)pass * ng;
-        for (int i = threadIdx.x; i < ncell; i += PME_SPREAD_THREADS) {
-            const int iz = i % gz, t = i / gz;
-            const int rb = t % th_, ra = t / th_;
-            o[((size_t)(x0 + ra) * d.gy + (y0 + rb)) * gz + iz] = (float)s_tile[i] * (1.0f / PME_TILE_SCALE);
-            s_tile[i] = 0;
+        for (int row = threadIdx.x >> 5; row < tw * th_; row += PME_SPREAD_THREADS / 32) {   // a warp per (x, y) row, lanes along z
+            const int ra = row / th_, rb = row - ra * th_;
+            float *orow = o + ((size_t)(x0 + ra) * d.gy + (y0 + rb)) * gz;
+            int *trow = s_tile + row * gz;
+            for (int iz = threadIdx.x & 31; iz < gz; iz += 32) {
+                orow[iz] = (float)trow[iz] * (1.0f / PME_TILE_SCALE);
+                trow[iz] = 0;
+            }
         }
         __syncthreads();
     }
 }
 
-// Influence function and energies on the float spectra of Q1 and dQ (see the header comment of this section).
-__global__ void __launch_bounds__(256) pme_convolve_f_kernel(NbDev d) {
+// Influence function on the float spectra of Q1 and dQ, and E1 = 1/2 sum G |Q1^|^2 in double.  One warp per (a, b) row of
+// the half spectrum, lanes over c: G(m) = Ta(a) Tb(b) Tc(c) / (pi V m^2) with T(k) = exp(-pi^2 m_k^2 / alpha^2) / |b(k)|^2 --
+// the row factors once per warp, the column factors once per block in shared memory.
+constexpr int PME_CONV_ROWS = 8;
+__global__ void __launch_bounds__(32 * PME_CONV_ROWS) pme_convolve_f_kernel(NbDev d) {
+    extern __shared__ double s_tc[];   // [nzh] factors along z, then the block reduction
     const int nzh = d.gz / 2 + 1;
-    const size_t nspec = (size_t)d.gx * d.gy * nzh;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = blockIdx.y, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const float4 L = d.box[r];
+    const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
+    for (int c = threadIdx.x; c < nzh; c += 32 * PME_CONV_ROWS) {
+        const double mc = (double)c / (double)L.z;
+        s_tc[c] = exp(-fac * mc * mc) / d.pme_mod[d.gx + d.gy + c];
+    }
+    __syncthreads();
+    const int row = blockIdx.x * PME_CONV_ROWS + wrp;   // a * gy + b
     double e1 = 0.0, de = 0.0;
-    if (i < nspec) {
-        const int c = (int)(i % nzh), b = (int)((i / nzh) % d.gy), a = (int)(i / ((size_t)nzh * d.gy));
-        float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec, *sd = s1 + nspec;
-        if (a == 0 && b == 0 && c == 0) {
-            s1[i] = make_float2(0.f, 0.f);
-            sd[i] = make_float2(0.f, 0.f);
-        } else {
-            const float4 L = d.box[r];
-            const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y,
-                         mc = (double)c / (double)L.z;
-            const double m2 = ma * ma + mb * mb + mc * mc;
-            const double V = (double)L.x * (double)L.y * (double)L.z;
-            const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
-            const double eterm = exp(-fac * m2) / (3.141592653589793 * V * m2 * d.pme_mod[a] * d.pme_mod[d.gx + b] * d.pme_mod[d.gx + d.gy + c]);
-            float2 v1 = s1[i], vd = sd[i];
+    if (row < d.gx * d.gy) {
+        const int a = row / d.gy, b = row - a * d.gy;
+        const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y;
+        const double mab2 = ma * ma + mb * mb;
+        const double tab = exp(-fac * mab2) / (3.141592653589793 * (double)L.x * (double)L.y * (double)L.z * d.pme_mod[a] * d.pme_mod[d.gx + b]);
+        const size_t nspec = (size_t)d.gx * d.gy * nzh;
+        float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh, *sd = s1 + nspec;
+        for (int c = lane; c < nzh; c += 32) {
+            if (row == 0 && c == 0) {
+                s1[0] = make_float2(0.f, 0.f);
+                sd[0] = make_float2(0.f, 0.f);
+                continue;
+            }
+            const double mc = (double)c / (double)L.z;
+            const double eterm = tab * s_tc[c] / (mab2 + mc * mc);
+            const float2 v1 = s1[c], vd = sd[c];
             const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
             const double x1 = v1.x, y1 = v1.y, xd = vd.x, yd = vd.y;
-            e1 = 0.5 * w * eterm * (x1 * x1 + y1 * y1);
-            de = w * eterm * (x1 * xd + y1 * yd + 0.5 * (xd * xd + yd * yd));
+            e1 += 0.5 * w * eterm * (x1 * x1 + y1 * y1);
+            de += w * eterm * (x1 * xd + y1 * yd + 0.5 * (xd * xd + yd * yd));   // E2 - E1 by linearity of the transform
             const float g = (float)eterm;
-            s1[i] = make_float2(v1.x * g, v1.y * g);
-            sd[i] = make_float2(vd.x * g, vd.y * g);
+            s1[c] = make_float2(v1.x * g, v1.y * g);
+            sd[c] = make_float2(vd.x * g, vd.y * g);
         }
     }
-    __shared__ double red[2][256 / 32];
+    double *red = s_tc + nzh;
     for (int off = 16; off > 0; off >>= 1) {
         e1 += __shfl_xor_sync(0xffffffffu, e1, off);
         de += __shfl_xor_sync(0xffffffffu, de, off);
     }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = e1; red[1][threadIdx.x >> 5] = de; }
+    if (lane == 0) { red[wrp] = e1; red[PME_CONV_ROWS + wrp] = de; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double t1 = 0.0, td = 0.0;
-        for (int k = 0; k < 256 / 32; k++) { t1 += red[0][k]; td += red[1][k]; }
+        for (int k = 0; k < PME_CONV_ROWS; k++) { t1 += red[k]; td += red[PME_CONV_ROWS + k]; }
         const long long f1 = __double2ll_rn(t1 * ENERGY_SCALE), fd = __double2ll_rn(td * ENERGY_SCALE);
         atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 6, (unsigned long long)f1);
         atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 7, (unsigned long long)(f1 + fd));   // E2 = E1 + (E2 - E1), exactly
     }
 }
 
-// one thread per site: row sums over z first (2 FMA per mesh point and mesh), then the xy weights
+// one thread per site: row sums over z first (2 FMA per mesh point and mesh), then the xy weights.  When the z extent of
+// the mesh is a multiple of 4 and the site's z support does not wrap, a row is read as NV aligned float4s and the z
+// weights are shifted onto that window instead (zeros outside): 2-3 load instructions per row instead of ORDER.
 template <int ORDER>
 __global__ void __launch_bounds__(128) pme_gather_f_kernel(NbDev d) {
+    constexpr int NV = ORDER <= 5 ? 2 : 3;   // float4s that cover ORDER consecutive floats at any 4-byte alignment
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (s >= CL * d.nclusters[r]) return;
@@ -422,45 +480,88 @@ __global__ void __launch_bounds__(128) pme_gather_f_kernel(NbDev d) {
         // no site has left its cluster's bounding box of that time by more than half the outer skin -- the same movement
         // the pair list tolerates.  Beyond it the step is poisoned like a list overflow (flags bit 3).
         const float4 cc = d.cc[rc], ch = d.ch[rc];
-        const float margin = 0.5f * (d.rlist_outer - sqrtf(d.cutoff2));
+        const float margin = 0.5f * (d.rlist_outer - sqrtf(d.cutoff2)) + 1e-4f;   // + rounding of the box arithmetic
         if (fabsf(wrap_delta(x.x - cc.x, L.x, iL.x)) - ch.x > margin || fabsf(wrap_delta(x.y - cc.y, L.y, iL.y)) - ch.y > margin)
             atomicOr(&d.flags[0], 8);
     }
     int fl[3];
     float th[3][ORDER], dth[3][ORDER];
-    pme_site_setup_f<ORDER, true>(d, x, L, fl, th, dth);
+    const double invL[3] = {1.0 / (double)L.x, 1.0 / (double)L.y, 1.0 / (double)L.z};
+    pme_site_setup_f<ORDER, true>(d, x, invL, fl, th, dth);
     const size_t ng = (size_t)d.gx * d.gy * d.gz;
     const float *phi1 = d.pme_gridf + (size_t)r * 2 * ng, *phid = phi1 + ng;
-    int iz[ORDER];
-#pragma unroll
-    for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
     float f1x = 0.f, f1y = 0.f, f1z = 0.f, fdx = 0.f, fdy = 0.f, fdz = 0.f;
-    const bool wantd = kind != 1;   // displaced atoms exist in state 1 only
+    const int iz0 = fl[2] - (ORDER - 1);
+    const int zb = iz0 & ~3, sh = iz0 & 3;
+    if ((d.gz & 3) == 0 && iz0 >= 0 && zb + 4 * NV <= d.gz) {
+        float wz[4 * NV], wdz[4 * NV];
 #pragma unroll
-    for (int a = 0; a < ORDER; a++) {
-        const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+        for (int k = 0; k < 4 * NV; k++) {   // wz[k] = th[2][k - sh], zero outside the support (compile-time register indices)
+            float t = 0.f, u = 0.f;
 #pragma unroll
-        for (int b = 0; b < ORDER; b++) {
-            const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
-            const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
-            float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
+            for (int q = 0; q < 4; q++)
+                if (k - q >= 0 && k - q < ORDER) {
+                    t = sh == q ? th[2][k - q] : t;
+                    u = sh == q ? dth[2][k - q] : u;
+                }
+            wz[k] = t;
+            wdz[k] = u;
+        }
 #pragma unroll
-            for (int c = 0; c < ORDER; c++) {
-                const float p = __ldg(phi1 + row + iz[c]);
-                s0 = fmaf(th[2][c], p, s0);
-                sz = fmaf(dth[2][c], p, sz);
+        for (int a = 0; a < ORDER; a++) {
+            const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+#pragma unroll
+            for (int b = 0; b < ORDER; b++) {
+                const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
+                const size_t row = ((size_t)ia * d.gy + ib) * d.gz + zb;
+                float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
+                const float4 *p = reinterpret_cast<const float4 *>(phi1 + row);
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const float4 t = __ldg(p + v);
+                    s0 = fmaf(wz[4 * v], t.x, s0); s0 = fmaf(wz[4 * v + 1], t.y, s0); s0 = fmaf(wz[4 * v + 2], t.z, s0); s0 = fmaf(wz[4 * v + 3], t.w, s0);
+                    sz = fmaf(wdz[4 * v], t.x, sz); sz = fmaf(wdz[4 * v + 1], t.y, sz); sz = fmaf(wdz[4 * v + 2], t.z, sz); sz = fmaf(wdz[4 * v + 3], t.w, sz);
+                }
+                const float4 *pd = reinterpret_cast<const float4 *>(phid + row);
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const float4 t = __ldg(pd + v);
+                    d0 = fmaf(wz[4 * v], t.x, d0); d0 = fmaf(wz[4 * v + 1], t.y, d0); d0 = fmaf(wz[4 * v + 2], t.z, d0); d0 = fmaf(wz[4 * v + 3], t.w, d0);
+                    dz = fmaf(wdz[4 * v], t.x, dz); dz = fmaf(wdz[4 * v + 1], t.y, dz); dz = fmaf(wdz[4 * v + 2], t.z, dz); dz = fmaf(wdz[4 * v + 3], t.w, dz);
+                }
+                const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
+                f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
+                fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
             }
-            if (wantd) {
+        }
+    } else {
+        int iz[ORDER];
+#pragma unroll
+        for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(iz0 + c, d.gz);
+#pragma unroll
+        for (int a = 0; a < ORDER; a++) {
+            const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+#pragma unroll
+            for (int b = 0; b < ORDER; b++) {
+                const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
+                const size_t row = ((size_t)ia * d.gy + ib) * d.gz;   // (general path: any mesh extent, supports that wrap in z)
+                float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
+#pragma unroll
+                for (int c = 0; c < ORDER; c++) {
+                    const float p = __ldg(phi1 + row + iz[c]);
+                    s0 = fmaf(th[2][c], p, s0);
+                    sz = fmaf(dth[2][c], p, sz);
+                }
 #pragma unroll
                 for (int c = 0; c < ORDER; c++) {
                     const float p = __ldg(phid + row + iz[c]);
                     d0 = fmaf(th[2][c], p, d0);
                     dz = fmaf(dth[2][c], p, dz);
                 }
+                const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
+                f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
+                fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
             }
-            const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
-            f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
-            fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
         }
     }
     const double q = (double)x.w;

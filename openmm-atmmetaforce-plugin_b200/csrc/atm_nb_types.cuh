@@ -80,6 +80,7 @@ struct NbDev {  // everything the kernels need, passed by value
     const double *pme_mod;         // |b(m)|^2 moduli: gx + gy + gz doubles
     // single-precision mesh pipeline (default): Q1 and dQ = Q2 - Q1 / phi1 and dphi as floats, see atm_nb_pme.cuh
     int pme_f32, pme_ntx, pme_nty; // tiles of mesh cells in x and y owned by one spread block each
+    int pme_tile_cells;            // ints of shared memory reserved for a tile (the list of contributing sites follows)
     float *pme_gridf;              // [R][2][ng]
     float2 *pme_specf;             // [R][2][gx][gy][gz/2+1]
     double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms

@@ -54,7 +54,7 @@ def test_abfe_pin_fully_on_gpu(abfe):
         en[E_USC], en[E_UREC1], r["r1"], en[E_UREC2] - en[E_UREC1], r["r2"] - r["r1"], en[E_U1], r["U1"], rel_rms(r["f_gpu"], r["f_ref"])))
     assert abs(en[E_USC] - 58.2) <= 0.1
     assert abs(en[E_UREC1] - r["r1"]) <= 1e-6 * abs(r["r1"]) + 1e-4
-    assert abs((en[E_UREC2] - en[E_UREC1]) - (r["r2"] - r["r1"])) <= 1e-4
+    assert abs((en[E_UREC2] - en[E_UREC1]) - (r["r2"] - r["r1"])) <= 1e-3    # float meshes (measured 4.7e-4): DESIGN.md section 3.4
     assert abs(en[E_USELF] - r["self_e"]) <= 1e-6 * abs(r["self_e"])
     assert abs(en[E_U1] - r["U1"]) <= 1e-6 * abs(r["U1"])
     assert abs(en[E_USC] - r["sc"]["u_sc"]) <= 5e-3
@@ -121,3 +121,113 @@ def test_pme_order_and_odd_grid():
     assert abs(en[E_UREC1] - r["r1"]) <= 1e-6 * abs(r["r1"]) + 1e-4
     assert abs((en[E_UREC2] - en[E_UREC1]) - (r["r2"] - r["r1"])) <= 1e-4
     assert rel_rms(r["f_gpu"], r["f_ref"]) <= 1e-5
+
+
+def test_pme_order6_replicas_shifted_coordinates():
+    """Spline order 6 on a mesh with a z extent divisible by 4 (the 128-bit row loads with three float4s), two replicas, the
+    second with every coordinate shifted by whole box lengths and a fraction (unwrapped input, tiles that wrap around the
+    periodic boundary): the replica results agree with the oracle and, up to the float rounding of the shifted coordinates,
+    with each other."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic
+    from helpers import oracle_system, make_backend, force_from_fixed, rel_rms
+    s = synthetic.water_box(6000, n_lig=15, seed=9)
+    params = synthetic.atm_schedule_22()[7]
+    grid, order = [32, 36, 40], 6
+    n = s["pos"].shape[0]
+    be, posq, _ = make_backend(atm, s, s["cutoff"], s["ewald_alpha"], params, skin=0.1, replicas=2)
+    be.set_parameters(params, replica=1)
+    shift = np.array([2.0, -1.0, 3.0]) * s["box"] + np.array([0.37, 0.11, 0.05])
+    posq[1, :n, :3] += torch.from_numpy(shift.astype(np.float32)).cuda()
+    be.pme_setup(grid, order)
+    be.rebuild(posq)
+    force = torch.zeros((2, 3 * be.P), dtype=torch.int64, device="cuda")
+    be.step(posq, force)
+    en = be.get_energies()
+    S = oracle_system(O, s, s["cutoff"], s["ewald_alpha"])
+    x = posq.cpu().numpy()
+    for r in range(2):
+        pos1 = x[r, :n, :3].astype(np.float64)
+        pos2 = (x[r, :n, :3] + s["displ"].astype(np.float32)).astype(np.float64)
+        e1, _, f1 = S.nb_direct(pos1)
+        e2, _, f2 = S.nb_direct(pos2)
+        r1, g1 = S.pme_recip(pos1, grid, order, want_force=True)
+        r2, g2 = S.pme_recip(pos2, grid, order, want_force=True)
+        assert abs(en[r][E_UREC1] - r1) <= 1e-6 * abs(r1) + 1e-4
+        assert abs((en[r][E_UREC2] - en[r][E_UREC1]) - (r2 - r1)) <= 1e-3
+        sc = O.scalars(params, e1 + r1, e2 + r2)
+        f_ref = O.merge_ref(np.zeros_like(f1), f1 + g1, f2 + g2, sc["sp_ref"], params[8])
+        assert rel_rms(force_from_fixed(force.cpu().numpy()[r], n, be.P), f_ref) <= 1e-5
+    assert abs(en[0][E_UREC1] - en[1][E_UREC1]) <= 1e-5 * abs(en[0][E_UREC1])
+    be.close()
+
+
+def test_pme_float_and_double_mesh_pipelines_agree(tmp_path):
+    """ATM_B200_PME_F64=1 selects the double-precision mesh pipeline of round 1 (global fixed-point spread, D2Z / Z2D); the
+    default single-precision pipeline must give the same energies and forces to float-mesh accuracy."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pme_case.py"
+    script.write_text('''
+import json, sys, numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, root + "/openmm-atmmetaforce-plugin_b200/python"); sys.path.insert(0, root + "/tests")
+import atmmetaforce as atm
+from atmmetaforce import synthetic
+from helpers import make_backend
+s = synthetic.water_box(9000, n_lig=20, seed=4)
+be, posq, _ = make_backend(atm, s, s["cutoff"], s["ewald_alpha"], synthetic.atm_schedule_22()[9], skin=0.1)
+be.pme_setup([40, 40, 40], 5)
+be.rebuild(posq)
+force = torch.zeros((1, 3 * be.P), dtype=torch.int64, device="cuda")
+be.step(posq, force)
+en = be.get_energies()[0]
+f = force.cpu().numpy()[0].astype(np.float64) / 4294967296.0
+np.save(sys.argv[2], f)
+print(json.dumps([float(v) for v in en]))
+''')
+    res = {}
+    for f64 in ("0", "1"):
+        out = str(tmp_path / f"f_{f64}.npy")
+        p = subprocess.run([sys.executable, str(script), root, out], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, ATM_B200_PME_F64=f64))
+        assert p.returncode == 0, p.stdout + p.stderr
+        res[f64] = (np.array(json.loads(p.stdout.strip().splitlines()[-1])), np.load(out))
+    (e32, f32), (e64, f64_) = res["0"], res["1"]
+    assert abs(e32[E_UREC1] - e64[E_UREC1]) <= 1e-6 * abs(e64[E_UREC1]) + 1e-4
+    assert abs((e32[E_UREC2] - e32[E_UREC1]) - (e64[E_UREC2] - e64[E_UREC1])) <= 1e-3
+    assert abs(e32[E_USC] - e64[E_USC]) <= 1e-3
+    assert np.sqrt(((f32 - f64_) ** 2).sum() / (f64_ ** 2).sum()) <= 5e-6
+
+
+def test_pme_site_drift_beyond_the_skin_poisons_the_step():
+    """The tile-owned spread finds sites through the xy column they were sorted into at the last rebuild.  A site that has
+    moved further since then than the structure tolerates (half the outer skin beyond its cluster's bounding box) must
+    not be silently dropped from the mesh: the step returns NaN energies until the next rebuild."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic
+    from helpers import make_backend
+    s = synthetic.water_box(9000, n_lig=20, seed=4)
+    be, posq, _ = make_backend(atm, s, s["cutoff"], s["ewald_alpha"], synthetic.atm_schedule_22()[9], skin=0.1)
+    be.pme_setup([40, 40, 40], 5)
+    be.rebuild(posq)
+    force = torch.zeros((1, 3 * be.P), dtype=torch.int64, device="cuda")
+    be.step(posq, force)
+    assert np.isfinite(be.get_energies()[0][:7]).all()
+    moved = posq.clone()
+    moved[0, 100, 0] += 0.04                       # within half the skin (0.05 nm here): still fine
+    be.step(moved, force)
+    assert np.isfinite(be.get_energies()[0][:7]).all()
+    moved[0, 100, 0] += 1.0                        # far outside
+    be.step(moved, force)
+    assert np.isnan(be.get_energies()[0][E_U1]) and np.isnan(be.get_energies()[0][E_USC])
+    be.rebuild(moved)                              # the rebuild re-sorts the site: results again
+    be.step(moved, force)
+    assert np.isfinite(be.get_energies()[0][:7]).all()
+    be.close()

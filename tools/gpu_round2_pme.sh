@@ -21,3 +21,5 @@ for r in rows[2:]:
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     v.sort(); print(f"{k:60s} n={len(v):4d} median={v[len(v)//2]/1000:9.1f} us")
 PY
+bash tools/gpu_session.sh ncu_kernel r2q_pme_spread pme_spread_tile 6 --pme
+bash tools/gpu_session.sh ncu_kernel r2q_pme_gather pme_gather_f 6 --pme
