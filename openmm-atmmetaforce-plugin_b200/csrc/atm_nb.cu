@@ -879,8 +879,8 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_fwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecR2C(nb->pme_plan_fwd, d.pme_gridf, (cufftComplex *)d.pme_specf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecR2C failed");
-        pme_convolve_f_kernel<<<dim3((unsigned)((d.gx * d.gy + PME_CONV_ROWS - 1) / PME_CONV_ROWS), d.R), 32 * PME_CONV_ROWS,
-                                sizeof(double) * (d.gz / 2 + 1 + 2 * PME_CONV_ROWS), stream>>>(d);
+        pme_convolve_f_kernel<<<dim3((unsigned)((d.gx * d.gy + PME_CONV_ROWS - 1) / PME_CONV_ROWS), d.R), 32 * PME_CONV_WARPS,
+                                sizeof(double) * (d.gz / 2 + 1 + 2 * PME_CONV_WARPS), stream>>>(d);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecC2R(nb->pme_plan_bwd, (cufftComplex *)d.pme_specf, d.pme_gridf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecC2R failed");
@@ -1089,7 +1089,7 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
     nb->alloc_generation++;  // cached graphs are stale
     if (nx == 0 && ny == 0 && nz == 0) return ATM_OK;  // switched off
     ATM_REQUIRE(order >= 4 && order <= PME_MAX_ORDER, ATM_ERR_INVALID, "atm_pme_setup: spline order must be 4..%d", PME_MAX_ORDER);
-    ATM_REQUIRE(nx >= order && ny >= order && nz >= order, ATM_ERR_INVALID, "atm_pme_setup: grid smaller than the spline order");
+    ATM_REQUIRE(nx >= order && ny >= order && nz >= std::max(order, 8), ATM_ERR_INVALID, "atm_pme_setup: grid smaller than the spline order (or fewer than 8 points along z)");
     ATM_REQUIRE(nb->desc.ewald_alpha > 0, ATM_ERR_INVALID, "atm_pme_setup: needs ewald_alpha > 0");
     const size_t ng = (size_t)nx * ny * nz, nspec = (size_t)nx * ny * (nz / 2 + 1);
     const int R = h->R;
@@ -1111,11 +1111,12 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         d.pme_specf = (float2 *)p;
         // spread tiles: about 12 x 12 cells in xy (all of z), smaller when the z extent would not fit in shared memory
         int T = 12;
-        while (T > 4 && sizeof(int) * (size_t)T * T * nz > 160 * 1024) T--;
+        const int nzp = pme_tile_stride(nz, order);   // a tile row: padding for supports that start below z = 0, then the column
+        while (T > 4 && sizeof(int) * (size_t)T * T * nzp > 160 * 1024) T--;
         d.pme_ntx = (nx + T - 1) / T;
         d.pme_nty = (ny + T - 1) / T;
         const int tw = (nx + d.pme_ntx - 1) / d.pme_ntx, th = (ny + d.pme_nty - 1) / d.pme_nty;
-        d.pme_tile_cells = tw * th * nz;
+        d.pme_tile_cells = tw * th * nzp;
         nb->pme_tile_smem = sizeof(int) * ((size_t)d.pme_tile_cells + PME_LIST_CAP);
         ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
         ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, nb->pme_tile_smem));

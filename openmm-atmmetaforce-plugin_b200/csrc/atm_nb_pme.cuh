@@ -282,52 +282,68 @@ __device__ __forceinline__ bool pme_touches(const NbDev &d, int flx, int fly, in
     return pme_wrap(flx - x0, d.gx) < tw + ORDER - 1 && pme_wrap(fly - y0, d.gy) < th_ + ORDER - 1;
 }
 
+// Tile layout: one row per (x, y) column of the brick, `zpad` cells (a multiple of 4, >= ORDER - 1) in front of the gz cells
+// of the column for supports that start below z = 0 (folded onto the top of the column when the brick is written out), so
+// that the z cells of a site are always consecutive; the row stride is a multiple of 4 cells (128-bit write-out) with an odd
+// number of 16-byte units (rows of equal z fall into different banks).
+__host__ __device__ inline int pme_tile_zpad(int order) { return order <= 5 ? 4 : 8; }
+__host__ __device__ inline int pme_tile_stride(int gz, int order) {
+    int st = (gz + pme_tile_zpad(order) + 3) & ~3;
+    return (st & 4) ? st : st + 4;
+}
+
 template <int ORDER>
 __device__ __forceinline__ void pme_spread_site(const NbDev &d, const float4 &x, const double (&invL)[3], float sign, int x0, int tw, int y0,
-                                                int th_, int *s_tile) {
+                                                int th_, int stride, int *s_tile) {
     int fl[3];
     float th[3][ORDER], dth[3][ORDER];
     pme_site_setup_f<ORDER, false>(d, x, invL, fl, th, dth);
-    // tile-relative x / y cell of each spline point, or -1 when the point belongs to another block's brick
-    int ra[ORDER], rb[ORDER];
-#pragma unroll
-    for (int a = 0; a < ORDER; a++) {
-        int t = pme_wrap(pme_wrap(fl[0] - (ORDER - 1) + a, d.gx) - x0, d.gx);
-        ra[a] = t < tw ? t : -1;
-        t = pme_wrap(pme_wrap(fl[1] - (ORDER - 1) + a, d.gy) - y0, d.gy);
-        rb[a] = t < th_ ? t : -1;
-    }
-    int iz[ORDER];
-#pragma unroll
-    for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
+    // brick-relative index of the first spline cell in x and y (the following ones are consecutive modulo the mesh extent)
+    const int tx0 = pme_wrap(pme_wrap(fl[0] - (ORDER - 1), d.gx) - x0, d.gx), ty0 = pme_wrap(pme_wrap(fl[1] - (ORDER - 1), d.gy) - y0, d.gy);
+    int yo[ORDER];   // element offset of each y row inside the tile (-1: the row belongs to another block's brick)
+    float qz[ORDER];
     const float q = sign * x.w * PME_TILE_SCALE;
 #pragma unroll
+    for (int c = 0; c < ORDER; c++) {
+        qz[c] = q * th[2][c];
+        int rb = ty0 + c;
+        rb -= rb >= d.gy ? d.gy : 0;
+        yo[c] = rb < th_ ? rb * stride : -1;
+    }
+    int *base = s_tile + (pme_tile_zpad(ORDER) - (ORDER - 1)) + fl[2];   // cell fl - (ORDER - 1) + c of the column lives at zpad + that
+#pragma unroll
     for (int a = 0; a < ORDER; a++) {
-        if (ra[a] < 0) continue;
+        int ra = tx0 + a;
+        ra -= ra >= d.gx ? d.gx : 0;
+        if (ra >= tw) continue;
+        int *rowa = base + ra * th_ * stride;
 #pragma unroll
         for (int b = 0; b < ORDER; b++) {
-            if (rb[b] < 0) continue;
-            const float qab = q * th[0][a] * th[1][b];
-            int *row = s_tile + (ra[a] * th_ + rb[b]) * d.gz;
+            if (yo[b] < 0) continue;
+            const float wab = th[0][a] * th[1][b];
+            int *row = rowa + yo[b];
 #pragma unroll
-            for (int c = 0; c < ORDER; c++) atomicAdd(row + iz[c], __float2int_rn(qab * th[2][c]));
+            for (int c = 0; c < ORDER; c++) atomicAdd(row + c, __float2int_rn(wab * qz[c]));
         }
     }
 }
 
 constexpr int PME_SCAN_ROUND = 4 * PME_SPREAD_THREADS;   // candidate slots examined between two looks at the list
 constexpr int PME_LIST_CAP = 3 * PME_SCAN_ROUND;          // contributing slots collected before they are spread
+constexpr int PME_MAX_RUNS = 256;                         // runs of candidate slots tabulated at a time
 
 template <int ORDER>
-__global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbDev d) {
-    extern __shared__ int s_tile[];   // [tw][th][gz], then the list of contributing slots (bit 31: negative sign)
+__global__ void __launch_bounds__(PME_SPREAD_THREADS, 4) pme_spread_tile_kernel(NbDev d) {
+    extern __shared__ int s_tile[];   // [tw][th][stride], then the list of contributing slots (bit 31: negative sign)
     __shared__ int s_count;
+    __shared__ int s_run_begin[PME_MAX_RUNS], s_run_end[PME_MAX_RUNS];   // end | bit 31: negative sign
     const int r = blockIdx.y;
     const int tx = blockIdx.x / d.pme_nty, ty = blockIdx.x - tx * d.pme_nty;
     const int x0 = (int)((long long)tx * d.gx / d.pme_ntx), x1 = (int)((long long)(tx + 1) * d.gx / d.pme_ntx);
     const int y0 = (int)((long long)ty * d.gy / d.pme_nty), y1 = (int)((long long)(ty + 1) * d.gy / d.pme_nty);
     const int tw = x1 - x0, th_ = y1 - y0, gz = d.gz;
-    const int ncell = tw * th_ * gz;
+    const int stride = pme_tile_stride(gz, ORDER), zpad = pme_tile_zpad(ORDER);
+    const int ncell = tw * th_ * stride;
     unsigned int *s_list = reinterpret_cast<unsigned int *>(s_tile + d.pme_tile_cells);
     for (int i = threadIdx.x; i < ncell; i += PME_SPREAD_THREADS) s_tile[i] = 0;
     if (threadIdx.x == 0) s_count = 0;
@@ -340,65 +356,102 @@ __global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbD
     const int cx_lo = (int)floorf((x0 * hx - margin - hx) / wx), cx_hi = (int)floorf(((x1 + ORDER - 1) * hx + margin + hx) / wx);
     const int cy_lo = (int)floorf((y0 * hy - margin - hy) / wy), cy_hi = (int)floorf(((y1 + ORDER - 1) * hy + margin + hy) / wy);
     const int ncx = min(cx_hi - cx_lo + 1, d.nx), ncy = min(cy_hi - cy_lo + 1, d.ny);
+    const int cya = pme_mod(cy_lo, d.ny), seg0 = min(ncy, d.ny - cya);   // the y range: [cya, cya + seg0) and, wrapped, [0, ncy - seg0)
     const size_t ng = (size_t)d.gx * d.gy * gz;
     float *out = d.pme_gridf + (size_t)r * 2 * ng;
     const int *bcs = d.bin_cluster_start + (size_t)r * (d.nbins + 1);
     const float4 *xs = d.xs + (size_t)r * d.Smax;
     const int *slot_site = d.slot_site + (size_t)r * d.Smax;
-    // spread what the list holds, every lane busy (integer accumulation: the order of the list does not matter)
-    auto flush = [&]() {
-        const int n = s_count;
-        for (int i = threadIdx.x; i < n; i += PME_SPREAD_THREADS) {
-            const unsigned int e = s_list[i];
-            pme_spread_site<ORDER>(d, xs[e & 0x7fffffffu], invL, (e >> 31) ? -1.f : 1.f, x0, tw, y0, th_, s_tile);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-    };
     __syncthreads();
     for (int pass = 0; pass < 2; pass++) {
-        // pass 0: Q1 = environment (class 0) + displaced atoms (classes 1..G); pass 1: dQ = ghosts (G+1..2G) - displaced atoms
-        const int cls_lo = pass == 0 ? 0 : 1, cls_hi = pass == 0 ? d.G : 2 * d.G;
-        for (int cls = cls_lo; cls <= cls_hi; cls++) {
-            const unsigned int neg = (pass == 1 && cls <= d.G) ? 0x80000000u : 0u;
-            for (int icx = 0; icx < ncx; icx++) {
-                const int cx = pme_mod(cx_lo + icx, d.nx);
-                int cya = pme_mod(cy_lo, d.ny), remaining = ncy;
-                while (remaining > 0) {   // the y range is one or two runs of consecutive bins (periodic wrap)
-                    const int seg = min(remaining, d.ny - cya);
-                    const int b0 = cls * d.ncol + cx * d.ny + cya;
-                    const int s0 = CL * bcs[b0], s1 = CL * bcs[b0 + seg];
-                    for (int base = s0; base < s1; base += PME_SCAN_ROUND) {
-                        for (int s = base + threadIdx.x; s < min(s1, base + PME_SCAN_ROUND); s += PME_SPREAD_THREADS) {
-                            if (slot_site[s] < 0) continue;
-                            const float4 x = xs[s];
-                            double w;
-                            const int flx = pme_cell(x.x, invL[0], d.gx, w), fly = pme_cell(x.y, invL[1], d.gy, w);
-                            if (pme_touches<ORDER>(d, flx, fly, x0, tw, y0, th_)) s_list[atomicAdd(&s_count, 1)] = (unsigned int)s | neg;
+        // pass 0: Q1 = environment (class 0) + displaced atoms (classes 1..G); pass 1: dQ = ghosts (G+1..2G) - displaced atoms.
+        // Runs of candidate slots: one per class, x column and contiguous part of the y range (consecutive bins hold
+        // consecutive clusters).  They are tabulated by the threads, then walked by the whole block: slots whose support
+        // touches the brick go into the list, and the list is spread -- every lane busy, integer accumulation, so its
+        // order does not matter -- before it can overflow and at the end.
+        const int cls_lo = pass == 0 ? 0 : 1, ncls = pass == 0 ? d.G + 1 : 2 * d.G;
+        const int nruns = ncls * ncx * 2;
+        int pending = 0;
+        for (int run0 = 0; run0 < nruns; run0 += PME_MAX_RUNS) {
+            const int nr = min(PME_MAX_RUNS, nruns - run0);
+            if (threadIdx.x < nr) {
+                const int t = run0 + threadIdx.x, half = t & 1, ci = t >> 1;
+                const int icx = ci % ncx, cls = cls_lo + ci / ncx;
+                const int b0 = cls * d.ncol + pme_mod(cx_lo + icx, d.nx) * d.ny + (half ? 0 : cya);
+                const int nb = half ? ncy - seg0 : seg0;
+                s_run_begin[threadIdx.x] = CL * bcs[b0];
+                s_run_end[threadIdx.x] = (CL * bcs[b0 + nb]) | ((pass == 1 && cls <= d.G) ? 0x80000000 : 0);
+            }
+            __syncthreads();
+            for (int k = 0; k < nr; k++) {
+                const int begin = s_run_begin[k], e = s_run_end[k];
+                const int end = e & 0x7fffffff;
+                const unsigned int neg = (unsigned int)e & 0x80000000u;
+                for (int base = begin; base < end; base += PME_SCAN_ROUND) {
+                    const int len = min(end - base, PME_SCAN_ROUND);
+                    if (pending + len > PME_SCAN_ROUND) {   // uniform: look at the list before it can overflow
+                        __syncthreads();
+                        const int n = s_count;
+                        if (n > PME_LIST_CAP - PME_SCAN_ROUND) {
+                            for (int i = threadIdx.x; i < n; i += PME_SPREAD_THREADS) {
+                                const unsigned int en = s_list[i];
+                                pme_spread_site<ORDER>(d, xs[en & 0x7fffffffu], invL, (en >> 31) ? -1.f : 1.f, x0, tw, y0, th_, stride, s_tile);
+                            }
+                            __syncthreads();
+                            if (threadIdx.x == 0) s_count = 0;
                         }
                         __syncthreads();
-                        const int filled = s_count;
-                        __syncthreads();   // every thread has read the count before the next round appends to the list
-                        if (filled > PME_LIST_CAP - PME_SCAN_ROUND) flush();
+                        pending = 0;
                     }
-                    remaining -= seg;
-                    cya = 0;
+                    for (int s = base + threadIdx.x; s < base + len; s += PME_SPREAD_THREADS) {
+                        if (slot_site[s] < 0) continue;
+                        const float4 x = xs[s];
+                        double w;
+                        const int flx = pme_cell(x.x, invL[0], d.gx, w), fly = pme_cell(x.y, invL[1], d.gy, w);
+                        if (pme_touches<ORDER>(d, flx, fly, x0, tw, y0, th_)) s_list[atomicAdd(&s_count, 1)] = (unsigned int)s | neg;
+                    }
+                    pending += len;
                 }
+            }
+            __syncthreads();   // the table is rewritten by the next chunk of runs
+        }
+        {
+            const int n = s_count;
+            for (int i = threadIdx.x; i < n; i += PME_SPREAD_THREADS) {
+                const unsigned int en = s_list[i];
+                pme_spread_site<ORDER>(d, xs[en & 0x7fffffffu], invL, (en >> 31) ? -1.f : 1.f, x0, tw, y0, th_, stride, s_tile);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_count = 0;
+        }
+        // write the brick out and clear the tile for the next pass
+        float *o = out + (size_t)pass * ng + ((size_t)x0 * d.gy + y0) * gz;
+        if ((gz & 3) == 0) {   // 128-bit: thread per 4 cells
+            const int nv = gz >> 2, foldv = (gz - zpad) >> 2, nrow = tw * th_;
+            for (int i = threadIdx.x; i < nrow * nv; i += PME_SPREAD_THREADS) {
+                const int row = i / nv, v = i - row * nv;
+                const int ra = row / th_, rb = row - ra * th_;
+                int4 *trow = reinterpret_cast<int4 *>(s_tile + row * stride);
+                int4 t = trow[(zpad >> 2) + v];
+                if (v >= foldv) {   // supports that started below z = 0
+                    const int4 u = trow[v - foldv];
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                const float sc = 1.0f / PME_TILE_SCALE;
+                reinterpret_cast<float4 *>(o + ((size_t)ra * d.gy + rb) * gz)[v] = make_float4((float)t.x * sc, (float)t.y * sc, (float)t.z * sc, (float)t.w * sc);
+            }
+        } else {
+            for (int i = threadIdx.x; i < tw * th_ * gz; i += PME_SPREAD_THREADS) {
+                const int row = i / gz, iz = i - row * gz;
+                const int ra = row / th_, rb = row - ra * th_;
+                const int *trow = s_tile + row * stride;
+                int v = trow[zpad + iz];
+                if (iz >= gz - (ORDER - 1)) v += trow[zpad + iz - gz];
+                o[((size_t)ra * d.gy + rb) * gz + iz] = (float)v * (1.0f / PME_TILE_SCALE);
             }
         }
         __syncthreads();
-        flush();
-        float *o = out + (size_t)pass * ng;
-        for (int row = threadIdx.x >> 5; row < tw * th_; row += PME_SPREAD_THREADS / 32) {   // a warp per (x, y) row, lanes along z
-            const int ra = row / th_, rb = row - ra * th_;
-            float *orow = o + ((size_t)(x0 + ra) * d.gy + (y0 + rb)) * gz;
-            int *trow = s_tile + row * gz;
-            for (int iz = threadIdx.x & 31; iz < gz; iz += 32) {
-                orow[iz] = (float)trow[iz] * (1.0f / PME_TILE_SCALE);
-                trow[iz] = 0;
-            }
-        }
+        for (int i = threadIdx.x; i < ncell >> 2; i += PME_SPREAD_THREADS) reinterpret_cast<int4 *>(s_tile)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
     }
 }
@@ -406,43 +459,57 @@ __global__ void __launch_bounds__(PME_SPREAD_THREADS) pme_spread_tile_kernel(NbD
 // Influence function on the float spectra of Q1 and dQ, and E1 = 1/2 sum G |Q1^|^2 in double.  One warp per (a, b) row of
 // the half spectrum, lanes over c: G(m) = Ta(a) Tb(b) Tc(c) / (pi V m^2) with T(k) = exp(-pi^2 m_k^2 / alpha^2) / |b(k)|^2 --
 // the row factors once per warp, the column factors once per block in shared memory.
-constexpr int PME_CONV_ROWS = 8;
-__global__ void __launch_bounds__(32 * PME_CONV_ROWS) pme_convolve_f_kernel(NbDev d) {
+constexpr int PME_CONV_WARPS = 8, PME_CONV_RPW = 4, PME_CONV_ROWS = PME_CONV_WARPS * PME_CONV_RPW;   // rows per block
+__global__ void __launch_bounds__(32 * PME_CONV_WARPS) pme_convolve_f_kernel(NbDev d) {
     extern __shared__ double s_tc[];   // [nzh] factors along z, then the block reduction
     const int nzh = d.gz / 2 + 1;
     const int r = blockIdx.y, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const float4 L = d.box[r];
     const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
-    for (int c = threadIdx.x; c < nzh; c += 32 * PME_CONV_ROWS) {
+    for (int c = threadIdx.x; c < nzh; c += 32 * PME_CONV_WARPS) {
         const double mc = (double)c / (double)L.z;
         s_tc[c] = exp(-fac * mc * mc) / d.pme_mod[d.gx + d.gy + c];
     }
     __syncthreads();
-    const int row = blockIdx.x * PME_CONV_ROWS + wrp;   // a * gy + b
+    const size_t nspec = (size_t)d.gx * d.gy * nzh;
+    const double piV = 3.141592653589793 * (double)L.x * (double)L.y * (double)L.z;
     double e1 = 0.0, de = 0.0;
-    if (row < d.gx * d.gy) {
-        const int a = row / d.gy, b = row - a * d.gy;
-        const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y;
-        const double mab2 = ma * ma + mb * mb;
-        const double tab = exp(-fac * mab2) / (3.141592653589793 * (double)L.x * (double)L.y * (double)L.z * d.pme_mod[a] * d.pme_mod[d.gx + b]);
-        const size_t nspec = (size_t)d.gx * d.gy * nzh;
-        float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh, *sd = s1 + nspec;
-        for (int c = lane; c < nzh; c += 32) {
+    for (int c0 = 0; c0 < nzh; c0 += 32) {
+        const int c = c0 + lane;
+        // the RPW rows of this warp: all loads first, then the arithmetic
+        float2 v1[PME_CONV_RPW], vd[PME_CONV_RPW];
+#pragma unroll
+        for (int k = 0; k < PME_CONV_RPW; k++) {
+            const int row = (blockIdx.x * PME_CONV_WARPS + wrp) * PME_CONV_RPW + k;   // a * gy + b
+            if (row < d.gx * d.gy && c < nzh) {
+                const float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh;
+                v1[k] = s1[c];
+                vd[k] = s1[nspec + c];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PME_CONV_RPW; k++) {
+            const int row = (blockIdx.x * PME_CONV_WARPS + wrp) * PME_CONV_RPW + k;
+            if (row >= d.gx * d.gy || c >= nzh) continue;
+            float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh, *sd = s1 + nspec;
             if (row == 0 && c == 0) {
                 s1[0] = make_float2(0.f, 0.f);
                 sd[0] = make_float2(0.f, 0.f);
                 continue;
             }
+            const int a = row / d.gy, b = row - a * d.gy;
+            const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y;
+            const double mab2 = ma * ma + mb * mb;
+            const double tab = exp(-fac * mab2) / (piV * d.pme_mod[a] * d.pme_mod[d.gx + b]);
             const double mc = (double)c / (double)L.z;
             const double eterm = tab * s_tc[c] / (mab2 + mc * mc);
-            const float2 v1 = s1[c], vd = sd[c];
             const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
-            const double x1 = v1.x, y1 = v1.y, xd = vd.x, yd = vd.y;
+            const double x1 = v1[k].x, y1 = v1[k].y, xd = vd[k].x, yd = vd[k].y;
             e1 += 0.5 * w * eterm * (x1 * x1 + y1 * y1);
             de += w * eterm * (x1 * xd + y1 * yd + 0.5 * (xd * xd + yd * yd));   // E2 - E1 by linearity of the transform
             const float g = (float)eterm;
-            s1[c] = make_float2(v1.x * g, v1.y * g);
-            sd[c] = make_float2(vd.x * g, vd.y * g);
+            s1[c] = make_float2(v1[k].x * g, v1[k].y * g);
+            sd[c] = make_float2(vd[k].x * g, vd[k].y * g);
         }
     }
     double *red = s_tc + nzh;
@@ -450,11 +517,11 @@ __global__ void __launch_bounds__(32 * PME_CONV_ROWS) pme_convolve_f_kernel(NbDe
         e1 += __shfl_xor_sync(0xffffffffu, e1, off);
         de += __shfl_xor_sync(0xffffffffu, de, off);
     }
-    if (lane == 0) { red[wrp] = e1; red[PME_CONV_ROWS + wrp] = de; }
+    if (lane == 0) { red[wrp] = e1; red[PME_CONV_WARPS + wrp] = de; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double t1 = 0.0, td = 0.0;
-        for (int k = 0; k < PME_CONV_ROWS; k++) { t1 += red[k]; td += red[PME_CONV_ROWS + k]; }
+        for (int k = 0; k < PME_CONV_WARPS; k++) { t1 += red[k]; td += red[PME_CONV_WARPS + k]; }
         const long long f1 = __double2ll_rn(t1 * ENERGY_SCALE), fd = __double2ll_rn(td * ENERGY_SCALE);
         atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 6, (unsigned long long)f1);
         atomicAdd(d.eacc + (size_t)r * EACC_SLOTS + 7, (unsigned long long)(f1 + fd));   // E2 = E1 + (E2 - E1), exactly
@@ -464,8 +531,11 @@ __global__ void __launch_bounds__(32 * PME_CONV_ROWS) pme_convolve_f_kernel(NbDe
 // one thread per site: row sums over z first (2 FMA per mesh point and mesh), then the xy weights.  When the z extent of
 // the mesh is a multiple of 4 and the site's z support does not wrap, a row is read as NV aligned float4s and the z
 // weights are shifted onto that window instead (zeros outside): 2-3 load instructions per row instead of ORDER.
+#ifndef ATM_PME_GATHER_MINB
+#define ATM_PME_GATHER_MINB 4
+#endif
 template <int ORDER>
-__global__ void __launch_bounds__(128) pme_gather_f_kernel(NbDev d) {
+__global__ void __launch_bounds__(128, ATM_PME_GATHER_MINB) pme_gather_f_kernel(NbDev d) {
     constexpr int NV = ORDER <= 5 ? 2 : 3;   // float4s that cover ORDER consecutive floats at any 4-byte alignment
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
