@@ -93,6 +93,19 @@ static void launch_pme_spread_tile(const NbDev &d, size_t smem, cudaStream_t str
     }
 }
 
+// the gather kernel lives on L1 hits of the two potential meshes and uses no shared memory: ask for the largest L1
+static cudaError_t pme_gather_prefer_l1(int order) {
+    const void *fn;
+    switch (order) {
+        case 4: fn = (const void *)pme_gather_f_kernel<4>; break;
+        case 5: fn = (const void *)pme_gather_f_kernel<5>; break;
+        case 6: fn = (const void *)pme_gather_f_kernel<6>; break;
+        case 7: fn = (const void *)pme_gather_f_kernel<7>; break;
+        default: fn = (const void *)pme_gather_f_kernel<8>; break;
+    }
+    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+}
+
 static cudaError_t pme_spread_tile_smem_attr(int order, size_t smem) {
     const void *fn;
     switch (order) {
@@ -884,8 +897,10 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecC2R(nb->pme_plan_bwd, (cufftComplex *)d.pme_specf, d.pme_gridf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecC2R failed");
+        pme_blend_kernel<<<dim3((unsigned)(((size_t)d.gx * d.gy * (pme_blend_stride(d.gz, d.pme_order) / 4) + 255) / 256), d.R), 256, 0, stream>>>(
+            d, io->energy_ext, (int)io->include_energy);
         launch_pme_gather_f(d, stream);
-        h->launches += 3;  // own kernels (the FFTs are cuFFT library code)
+        h->launches += 4;  // own kernels (the FFTs are cuFFT library code)
     } else if (d.pme_on) {
         const size_t ng = (size_t)d.gx * d.gy * d.gz, nspec = (size_t)d.gx * d.gy * (d.gz / 2 + 1);
         launch_pme_spread(d, stream);
@@ -1103,12 +1118,14 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
     // ATM_B200_PME_F64=1: the double-precision mesh pipeline of round 1 (global fixed-point spread, D2Z / Z2D) for A/B runs
     static const bool f64 = [] { const char *e = getenv("ATM_B200_PME_F64"); return e && e[0] == '1'; }();
     d.pme_f32 = f64 ? 0 : 1;
-    d.pme_acc = nullptr; d.pme_grid = nullptr; d.pme_spec = nullptr; d.pme_gridf = nullptr; d.pme_specf = nullptr;
+    d.pme_acc = nullptr; d.pme_grid = nullptr; d.pme_spec = nullptr; d.pme_gridf = nullptr; d.pme_specf = nullptr; d.pme_blend = nullptr;
     if (d.pme_f32) {
         if ((rc = alloc(&p, sizeof(float) * 2 * ng * R))) return rc;
         d.pme_gridf = (float *)p;
         if ((rc = alloc(&p, sizeof(float2) * 2 * nspec * R))) return rc;
         d.pme_specf = (float2 *)p;
+        if ((rc = alloc(&p, sizeof(float) * (size_t)R * nx * ny * pme_blend_stride(nz, order)))) return rc;
+        d.pme_blend = (float *)p;
         // spread tiles: about 12 x 12 cells in xy (all of z), smaller when the z extent would not fit in shared memory
         int T = 12;
         const int nzp = pme_tile_stride(nz, order);   // a tile row: padding for supports that start below z = 0, then the column
@@ -1120,6 +1137,7 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         nb->pme_tile_smem = sizeof(int) * ((size_t)d.pme_tile_cells + PME_LIST_CAP);
         ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
         ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, nb->pme_tile_smem));
+        ATM_CUDA_CHECK(pme_gather_prefer_l1(order));
     } else {
         if ((rc = alloc(&p, sizeof(unsigned long long) * 2 * ng * R))) return rc;
         d.pme_acc = (unsigned long long *)p;

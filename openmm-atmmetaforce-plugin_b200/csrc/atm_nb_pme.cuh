@@ -4,6 +4,7 @@
 
 #include "atm_common.cuh"
 #include "atm_nb_types.cuh"
+#include "atm_nb_force.cuh"   // scalar_stage_replica (the blend kernel forms sp before the inverse transform)
 
 namespace atm {
 
@@ -528,11 +529,83 @@ __global__ void __launch_bounds__(32 * PME_CONV_WARPS) pme_convolve_f_kernel(NbD
     }
 }
 
-// one thread per site: row sums over z first (2 FMA per mesh point and mesh), then the xy weights.  When the z extent of
-// the mesh is a multiple of 4 and the site's z support does not wrap, a row is read as NV aligned float4s and the z
-// weights are shifted onto that window instead (zeros outside): 2-3 load instructions per row instead of ORDER.
+// The merged force is F1 + sp (F2 - F1) and both are linear in the potentials, so the environment -- almost every site --
+// needs only the blended potential phi_b = phi1 + sp dphi: once the reciprocal energies are known (after the convolve
+// kernel; the direct-space energies are complete since nb2) the scalar stage gives sp, this kernel writes the blended
+// mesh, and the gather reads ONE mesh per environment site instead of two.  The blended mesh has its own row layout,
+// made for the gather: every (x, y) row is `zpad` cells (copies of the top of the column) followed by the gz cells of the
+// column, in a stride that is a multiple of 4 floats (zero filled), so that the z support of ANY site is a run of
+// consecutive floats inside two or three aligned float4s.  The few displaced atoms / ghosts read phi1 and dphi themselves.
+// (an odd number of 16-byte units, like the spread tile: rows that start 256 bytes apart would share their L1 sets)
+__host__ __device__ inline int pme_blend_stride(int gz, int order) { return pme_tile_stride(gz, order); }
+
+__global__ void __launch_bounds__(256) pme_blend_kernel(NbDev d, const double *__restrict__ energy_ext, int include_energy) {
+    __shared__ float s_sp;
+    const int r = blockIdx.y;
+    if (threadIdx.x == 0) s_sp = (float)scalar_stage_replica(d, r, energy_ext, include_energy, false);   // same inputs as the merge kernel's
+    __syncthreads();
+    const float sp = s_sp;
+    const int gz = d.gz, zpad = pme_tile_zpad(d.pme_order), st = pme_blend_stride(gz, d.pme_order), nv = st >> 2;
+    const size_t ng = (size_t)d.gx * d.gy * gz;
+    const float *p1 = d.pme_gridf + (size_t)r * 2 * ng, *pd = p1 + ng;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of a padded row
+    if (i >= d.gx * d.gy * nv) return;
+    const int row = i / nv, v = i - row * nv;
+    const float *q1 = p1 + (size_t)row * gz, *qd = pd + (size_t)row * gz;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int z = 4 * v + k - zpad;   // padded element 4 v + k holds cell z (z < 0: cell gz + z)
+        const int zz = z < 0 ? z + gz : z;
+        o[k] = z < gz ? fmaf(sp, __ldg(qd + zz), __ldg(q1 + zz)) : 0.f;
+    }
+    reinterpret_cast<float4 *>(d.pme_blend + ((size_t)r * d.gx * d.gy + row) * st)[v] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// A displaced atom (kind 1: F1 from phi1) or a ghost (kind 2: F2 from phi1 + dphi): plain loops (a few dozen sites).
+template <int ORDER>
+__device__ __forceinline__ void pme_gather_special(const NbDev &d, int r, int s, const float4 &x, const float4 &L, int kind) {
+    const double invL[3] = {1.0 / (double)L.x, 1.0 / (double)L.y, 1.0 / (double)L.z};
+    int fl[3];
+    float th[3][ORDER], dth[3][ORDER];   // indexed by loop counters below: these live in local memory, on this rare path only
+    pme_site_setup_f<ORDER, true>(d, x, invL, fl, th, dth);
+    const size_t ng = (size_t)d.gx * d.gy * d.gz;
+    const float *phi1 = d.pme_gridf + (size_t)r * 2 * ng, *phid = phi1 + ng;
+    const float wd = kind == 1 ? 0.f : 1.f;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < ORDER; a++) {
+        const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+#pragma unroll 1
+        for (int b = 0; b < ORDER; b++) {
+            const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
+            const size_t row = ((size_t)ia * d.gy + ib) * d.gz;
+            float s0 = 0.f, sz = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < ORDER; c++) {
+                const int ic = pme_wrap(fl[2] - (ORDER - 1) + c, d.gz);
+                const float p = fmaf(wd, __ldg(phid + row + ic), __ldg(phi1 + row + ic));
+                s0 = fmaf(th[2][c], p, s0);
+                sz = fmaf(dth[2][c], p, sz);
+            }
+            fx = fmaf(dth[0][a] * th[1][b], s0, fx);
+            fy = fmaf(th[0][a] * dth[1][b], s0, fy);
+            fz = fmaf(th[0][a] * th[1][b], sz, fz);
+        }
+    }
+    const double q = (double)x.w;
+    const size_t cs = (size_t)d.R * d.Smax;
+    unsigned long long *buf = d.buf + (kind == 1 ? 3 : 6) * cs + (size_t)r * d.Smax;   // S1 / S2 accumulators
+    buf[s] += (unsigned long long)__double2ll_rn(-q * d.gx / (double)L.x * FORCE_SCALE * (double)fx);
+    buf[cs + s] += (unsigned long long)__double2ll_rn(-q * d.gy / (double)L.y * FORCE_SCALE * (double)fy);
+    buf[2 * cs + s] += (unsigned long long)__double2ll_rn(-q * d.gz / (double)L.z * FORCE_SCALE * (double)fz);
+}
+
+// one thread per site.  Environment sites read the blended potential only and add their force to the COMMON accumulator
+// (the merge adds it with weight one): per (x, y) row NV aligned float4s that contain the z support, the z weights
+// shifted onto that window (zeros outside), row sums first (2 FMA per loaded float), then the xy weights.
 #ifndef ATM_PME_GATHER_MINB
-#define ATM_PME_GATHER_MINB 4
+#define ATM_PME_GATHER_MINB 5
 #endif
 template <int ORDER>
 __global__ void __launch_bounds__(128, ATM_PME_GATHER_MINB) pme_gather_f_kernel(NbDev d) {
@@ -541,113 +614,75 @@ __global__ void __launch_bounds__(128, ATM_PME_GATHER_MINB) pme_gather_f_kernel(
     const int r = blockIdx.y;
     if (s >= CL * d.nclusters[r]) return;
     const size_t rs = (size_t)r * d.Smax + s;
-    if (d.slot_site[rs] < 0) return;
     const size_t rc = (size_t)r * d.Cmax + (s >> 3);
-    const int kind = class_kind(d.cmeta[rc] & 0xffff, d.G);
+    const size_t cs = (size_t)d.R * d.Smax;
+    unsigned long long *bufC = d.buf + (size_t)r * d.Smax;
+    // every load that does not depend on another one first
+    const int site = d.slot_site[rs];
+    const int cm = d.cmeta[rc];
     const float4 x = d.xs[rs];
+    const float4 cc = d.cc[rc], ch = d.ch[rc];
     const float4 L = d.box[r], iL = d.invbox[r];
+    const unsigned long long c0 = bufC[s], c1 = bufC[cs + s], c2 = bufC[2 * cs + s];   // this thread is the only writer of these at this point of the step
+    if (site < 0) return;
+    const int kind = class_kind(cm & 0xffff, d.G);
     {   // the spread kernel found this site through the xy column it was sorted into at the last rebuild: that holds while
         // no site has left its cluster's bounding box of that time by more than half the outer skin -- the same movement
         // the pair list tolerates.  Beyond it the step is poisoned like a list overflow (flags bit 3).
-        const float4 cc = d.cc[rc], ch = d.ch[rc];
         const float margin = 0.5f * (d.rlist_outer - sqrtf(d.cutoff2)) + 1e-4f;   // + rounding of the box arithmetic
         if (fabsf(wrap_delta(x.x - cc.x, L.x, iL.x)) - ch.x > margin || fabsf(wrap_delta(x.y - cc.y, L.y, iL.y)) - ch.y > margin)
             atomicOr(&d.flags[0], 8);
+    }
+    if (kind != 0) {
+        pme_gather_special<ORDER>(d, r, s, x, L, kind);
+        return;
     }
     int fl[3];
     float th[3][ORDER], dth[3][ORDER];
     const double invL[3] = {1.0 / (double)L.x, 1.0 / (double)L.y, 1.0 / (double)L.z};
     pme_site_setup_f<ORDER, true>(d, x, invL, fl, th, dth);
-    const size_t ng = (size_t)d.gx * d.gy * d.gz;
-    const float *phi1 = d.pme_gridf + (size_t)r * 2 * ng, *phid = phi1 + ng;
-    float f1x = 0.f, f1y = 0.f, f1z = 0.f, fdx = 0.f, fdy = 0.f, fdz = 0.f;
-    const int iz0 = fl[2] - (ORDER - 1);
-    const int zb = iz0 & ~3, sh = iz0 & 3;
-    if ((d.gz & 3) == 0 && iz0 >= 0 && zb + 4 * NV <= d.gz) {
-        float wz[4 * NV], wdz[4 * NV];
+    const int st = pme_blend_stride(d.gz, ORDER);
+    const float *phib = d.pme_blend + (size_t)r * d.gx * d.gy * st;
+    const int p0 = fl[2] - (ORDER - 1) + pme_tile_zpad(ORDER);   // first element of the z support in a padded row: >= 0
+    const int zb = p0 & ~3, sh = p0 & 3;
+    float wz[4 * NV], wdz[4 * NV];
 #pragma unroll
-        for (int k = 0; k < 4 * NV; k++) {   // wz[k] = th[2][k - sh], zero outside the support (compile-time register indices)
-            float t = 0.f, u = 0.f;
+    for (int k = 0; k < 4 * NV; k++) {   // wz[k] = th[2][k - sh], zero outside the support (compile-time register indices)
+        float t = 0.f, u = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (k - q >= 0 && k - q < ORDER) {
-                    t = sh == q ? th[2][k - q] : t;
-                    u = sh == q ? dth[2][k - q] : u;
-                }
-            wz[k] = t;
-            wdz[k] = u;
-        }
-#pragma unroll
-        for (int a = 0; a < ORDER; a++) {
-            const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
-#pragma unroll
-            for (int b = 0; b < ORDER; b++) {
-                const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
-                const size_t row = ((size_t)ia * d.gy + ib) * d.gz + zb;
-                float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
-                const float4 *p = reinterpret_cast<const float4 *>(phi1 + row);
-#pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    const float4 t = __ldg(p + v);
-                    s0 = fmaf(wz[4 * v], t.x, s0); s0 = fmaf(wz[4 * v + 1], t.y, s0); s0 = fmaf(wz[4 * v + 2], t.z, s0); s0 = fmaf(wz[4 * v + 3], t.w, s0);
-                    sz = fmaf(wdz[4 * v], t.x, sz); sz = fmaf(wdz[4 * v + 1], t.y, sz); sz = fmaf(wdz[4 * v + 2], t.z, sz); sz = fmaf(wdz[4 * v + 3], t.w, sz);
-                }
-                const float4 *pd = reinterpret_cast<const float4 *>(phid + row);
-#pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    const float4 t = __ldg(pd + v);
-                    d0 = fmaf(wz[4 * v], t.x, d0); d0 = fmaf(wz[4 * v + 1], t.y, d0); d0 = fmaf(wz[4 * v + 2], t.z, d0); d0 = fmaf(wz[4 * v + 3], t.w, d0);
-                    dz = fmaf(wdz[4 * v], t.x, dz); dz = fmaf(wdz[4 * v + 1], t.y, dz); dz = fmaf(wdz[4 * v + 2], t.z, dz); dz = fmaf(wdz[4 * v + 3], t.w, dz);
-                }
-                const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
-                f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
-                fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
+        for (int q = 0; q < 4; q++)
+            if (k - q >= 0 && k - q < ORDER) {
+                t = sh == q ? th[2][k - q] : t;
+                u = sh == q ? dth[2][k - q] : u;
             }
-        }
-    } else {
-        int iz[ORDER];
+        wz[k] = t;
+        wdz[k] = u;
+    }
+    float fx = 0.f, fy = 0.f, fz = 0.f;
 #pragma unroll
-        for (int c = 0; c < ORDER; c++) iz[c] = pme_wrap(iz0 + c, d.gz);
+    for (int a = 0; a < ORDER; a++) {
+        const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
 #pragma unroll
-        for (int a = 0; a < ORDER; a++) {
-            const int ia = pme_wrap(fl[0] - (ORDER - 1) + a, d.gx);
+        for (int b = 0; b < ORDER; b++) {
+            const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
+            const float4 *p = reinterpret_cast<const float4 *>(phib + ((size_t)ia * d.gy + ib) * st + zb);
+            float s0 = 0.f, sz = 0.f;
 #pragma unroll
-            for (int b = 0; b < ORDER; b++) {
-                const int ib = pme_wrap(fl[1] - (ORDER - 1) + b, d.gy);
-                const size_t row = ((size_t)ia * d.gy + ib) * d.gz;   // (general path: any mesh extent, supports that wrap in z)
-                float s0 = 0.f, sz = 0.f, d0 = 0.f, dz = 0.f;
-#pragma unroll
-                for (int c = 0; c < ORDER; c++) {
-                    const float p = __ldg(phi1 + row + iz[c]);
-                    s0 = fmaf(th[2][c], p, s0);
-                    sz = fmaf(dth[2][c], p, sz);
-                }
-#pragma unroll
-                for (int c = 0; c < ORDER; c++) {
-                    const float p = __ldg(phid + row + iz[c]);
-                    d0 = fmaf(th[2][c], p, d0);
-                    dz = fmaf(dth[2][c], p, dz);
-                }
-                const float wxy = th[0][a] * th[1][b], wdx = dth[0][a] * th[1][b], wdy = th[0][a] * dth[1][b];
-                f1x = fmaf(wdx, s0, f1x); f1y = fmaf(wdy, s0, f1y); f1z = fmaf(wxy, sz, f1z);
-                fdx = fmaf(wdx, d0, fdx); fdy = fmaf(wdy, d0, fdy); fdz = fmaf(wxy, dz, fdz);
+            for (int v = 0; v < NV; v++) {
+                if (NV == 3 && v == 2 && zb + 8 >= st) break;   // the third float4 would lie beyond the row: its weights are zero
+                const float4 t = __ldg(p + v);
+                s0 = fmaf(wz[4 * v], t.x, s0); s0 = fmaf(wz[4 * v + 1], t.y, s0); s0 = fmaf(wz[4 * v + 2], t.z, s0); s0 = fmaf(wz[4 * v + 3], t.w, s0);
+                sz = fmaf(wdz[4 * v], t.x, sz); sz = fmaf(wdz[4 * v + 1], t.y, sz); sz = fmaf(wdz[4 * v + 2], t.z, sz); sz = fmaf(wdz[4 * v + 3], t.w, sz);
             }
+            fx = fmaf(dth[0][a] * th[1][b], s0, fx);
+            fy = fmaf(th[0][a] * dth[1][b], s0, fy);
+            fz = fmaf(th[0][a] * th[1][b], sz, fz);
         }
     }
     const double q = (double)x.w;
-    const double sx = -q * d.gx / (double)L.x * FORCE_SCALE, sy = -q * d.gy / (double)L.y * FORCE_SCALE, sz_ = -q * d.gz / (double)L.z * FORCE_SCALE;
-    const size_t cs = (size_t)d.R * d.Smax, rsite = (size_t)r * d.Smax;
-    unsigned long long *buf1 = d.buf + 3 * cs + rsite, *buf2 = d.buf + 6 * cs + rsite;
-    if (kind != 2) {   // this thread is the only writer of its site's slots at this point of the step
-        buf1[s] += (unsigned long long)__double2ll_rn(sx * (double)f1x);
-        buf1[cs + s] += (unsigned long long)__double2ll_rn(sy * (double)f1y);
-        buf1[2 * cs + s] += (unsigned long long)__double2ll_rn(sz_ * (double)f1z);
-    }
-    if (kind != 1) {
-        buf2[s] += (unsigned long long)__double2ll_rn(sx * ((double)f1x + (double)fdx));
-        buf2[cs + s] += (unsigned long long)__double2ll_rn(sy * ((double)f1y + (double)fdy));
-        buf2[2 * cs + s] += (unsigned long long)__double2ll_rn(sz_ * ((double)f1z + (double)fdz));
-    }
+    bufC[s] = c0 + (unsigned long long)__double2ll_rn(-q * d.gx / (double)L.x * FORCE_SCALE * (double)fx);
+    bufC[cs + s] = c1 + (unsigned long long)__double2ll_rn(-q * d.gy / (double)L.y * FORCE_SCALE * (double)fy);
+    bufC[2 * cs + s] = c2 + (unsigned long long)__double2ll_rn(-q * d.gz / (double)L.z * FORCE_SCALE * (double)fz);
 }
 
 }  // namespace atm

@@ -83,6 +83,7 @@ struct NbDev {  // everything the kernels need, passed by value
     int pme_tile_cells;            // ints of shared memory reserved for a tile (the list of contributing sites follows)
     float *pme_gridf;              // [R][2][ng]
     float2 *pme_specf;             // [R][2][gx][gy][gz/2+1]
+    float *pme_blend;              // [R][gx][gy][stride] blended potential phi1 + sp dphi in the gather's padded row layout
     double pme_self_sum;           // sum of (q sqrt(ke))^2 over all atoms
     double pme_qtot2;              // (sum of q sqrt(ke))^2: neutralising-background term -pi Q^2 / (2 V alpha^2)
     double disp_coeff;             // long-range dispersion correction = disp_coeff / V (0 = off)

@@ -22,5 +22,3 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     if 'at::' in k or 'nl_' in k or 'hrex' in k: continue
     v.sort(); print(f"{k:60s} n={len(v):4d} median={v[len(v)//2]/1000:9.1f} us")
 PY
-bash tools/gpu_session.sh ncu_kernel r2r_pme_spread pme_spread_tile 6 --pme
-bash tools/gpu_session.sh ncu_kernel r2r_pme_gather pme_gather_f 6 --pme
