@@ -1,5 +1,6 @@
 """Small two-replica case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): rebuild, prune, two plain
-steps with statistics, one CUDA-graph step (programmatic dependent launches inside), PME on for the last step, the
+steps with statistics, one CUDA-graph step (programmatic dependent launches inside), PME on for the last step (tile-owned
+shared-memory spread, float transforms, blend, gather), the
 on-device replica exchange, energies read back; then the host-buffer pipeline (two handles forked / joined inside one
 captured graph) through its rebuild / prune / plain variants.
 
@@ -78,6 +79,11 @@ pipe.check()
 force_f32 = [torch.zeros((1, 3 * P), dtype=torch.float32).pin_memory() for _ in range(R)]
 pipe.step(posq_h, force_f32, en_h, maintenance=pipe.NONE, stream=stream)     # float32 force read-back
 pipe.step(posq_h, None, en_h, maintenance=pipe.NONE, stream=stream)          # energies only
+# external per-state forces / energies of other variable-group forces (atm_host_io.force_state{1,2}_ext_host, energy_ext_host)
+f1_ext = [torch.randint(-2 ** 36, 2 ** 36, (1, 3 * P), dtype=torch.int64).pin_memory() for _ in range(R)]
+f2_ext = [torch.randint(-2 ** 36, 2 ** 36, (1, 3 * P), dtype=torch.int64).pin_memory() for _ in range(R)]
+e_ext = [torch.tensor([[1.5, -2.5]], dtype=torch.float64).pin_memory() for _ in range(R)]
+pipe.step(posq_h, force_h, en_h, maintenance=pipe.NONE, stream=stream, f1_ext_host=f1_ext, f2_ext_host=f2_ext, energy_ext_host=e_ext)
 stream.synchronize()
 print("pipeline u:", [float(e[0, 3]) for e in en_h], "max |F| (fixed point):", [int(f.abs().max()) for f in force_h])
 pipe.close()
