@@ -161,9 +161,14 @@ typedef struct {
 int atm_nb_setup(atm_handle *h, const atm_nonbonded_desc *desc, void *stream);
 
 /* Optional: evaluate the PME reciprocal space of BOTH states inside atm_step as well (smooth PME,
- * B-splines of `order` (OpenMM: 5), mesh nx*ny*nz, double precision, cuFFT for the transforms; the environment charge
+ * B-splines of `order` 4..8 (OpenMM: 5), mesh nx*ny*nz with nz >= 8, cuFFT for the transforms; the environment charge
  * is spread once for the two states).  U1/U2 then contain direct + reciprocal + self energy, i.e. the complete
  * NonbondedForce of both inner contexts (the long-range dispersion correction: atm_nb_set_dispersion_correction).  nx = ny = nz = 0 switches it off.
+ * Meshes and transforms are single precision, energies double (the environment variable ATM_B200_PME_F64=1, read at
+ * the first set-up, selects the double-precision mesh pipeline instead).  The spread finds sites through the pair-list
+ * structure of the last atm_nb_rebuild: a site that has since moved further than half the outer skin beyond its cluster
+ * makes the step return NaN energies (like a pair-list overflow) until the next rebuild -- the same movement invalidates
+ * the pair list itself.
  * Call after atm_nb_setup.  SYNCHRONISES the device. */
 int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t order);
 

@@ -893,7 +893,7 @@ static int launch_step(atm_handle *h, const atm_step_io *io, cudaStream_t stream
         ATM_REQUIRE(cufftExecR2C(nb->pme_plan_fwd, d.pme_gridf, (cufftComplex *)d.pme_specf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecR2C failed");
         pme_convolve_f_kernel<<<dim3((unsigned)((d.gx * d.gy + PME_CONV_ROWS - 1) / PME_CONV_ROWS), d.R), 32 * PME_CONV_WARPS,
-                                sizeof(double) * (d.gz / 2 + 1 + 2 * PME_CONV_WARPS), stream>>>(d);
+                                sizeof(double) * (d.gz / 2 + 1), stream>>>(d);
         ATM_REQUIRE(cufftSetStream(nb->pme_plan_bwd, stream) == CUFFT_SUCCESS, ATM_ERR_CUDA, "cufftSetStream failed");
         ATM_REQUIRE(cufftExecC2R(nb->pme_plan_bwd, (cufftComplex *)d.pme_specf, d.pme_gridf) == CUFFT_SUCCESS, ATM_ERR_CUDA,
                     "cufftExecC2R failed");

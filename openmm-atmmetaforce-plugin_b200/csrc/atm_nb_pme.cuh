@@ -457,13 +457,14 @@ __global__ void __launch_bounds__(PME_SPREAD_THREADS, 4) pme_spread_tile_kernel(
     }
 }
 
-// Influence function on the float spectra of Q1 and dQ, and E1 = 1/2 sum G |Q1^|^2 in double.  One warp per (a, b) row of
-// the half spectrum, lanes over c: G(m) = Ta(a) Tb(b) Tc(c) / (pi V m^2) with T(k) = exp(-pi^2 m_k^2 / alpha^2) / |b(k)|^2 --
-// the row factors once per warp, the column factors once per block in shared memory.
+// Influence function on the float spectra of Q1 and dQ, and the two reciprocal energies in double.  A warp per four (a, b)
+// rows of the half spectrum, lanes over c: G(m) = Ta(a) Tb(b) Tc(c) / (pi V m^2) with T(k) = exp(-pi^2 m_k^2 / alpha^2) / |b(k)|^2;
+// the row factors and the z factors are formed once per block in shared memory (one exp per row / per c, not per mode).
 constexpr int PME_CONV_WARPS = 8, PME_CONV_RPW = 4, PME_CONV_ROWS = PME_CONV_WARPS * PME_CONV_RPW;   // rows per block
-__global__ void __launch_bounds__(32 * PME_CONV_WARPS) pme_convolve_f_kernel(NbDev d) {
-    extern __shared__ double s_tc[];   // [nzh] factors along z, then the block reduction
-    const int nzh = d.gz / 2 + 1;
+__global__ void __launch_bounds__(32 * PME_CONV_WARPS, 4) pme_convolve_f_kernel(NbDev d) {
+    extern __shared__ double s_tc[];   // [nzh] factors along z
+    __shared__ double s_tab[PME_CONV_ROWS], s_m2[PME_CONV_ROWS], red[2 * PME_CONV_WARPS];
+    const int nzh = d.gz / 2 + 1, nrows = d.gx * d.gy;
     const int r = blockIdx.y, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const float4 L = d.box[r];
     const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
@@ -471,49 +472,54 @@ __global__ void __launch_bounds__(32 * PME_CONV_WARPS) pme_convolve_f_kernel(NbD
         const double mc = (double)c / (double)L.z;
         s_tc[c] = exp(-fac * mc * mc) / d.pme_mod[d.gx + d.gy + c];
     }
-    __syncthreads();
-    const size_t nspec = (size_t)d.gx * d.gy * nzh;
-    const double piV = 3.141592653589793 * (double)L.x * (double)L.y * (double)L.z;
-    double e1 = 0.0, de = 0.0;
-    for (int c0 = 0; c0 < nzh; c0 += 32) {
-        const int c = c0 + lane;
-        // the RPW rows of this warp: all loads first, then the arithmetic
-        float2 v1[PME_CONV_RPW], vd[PME_CONV_RPW];
-#pragma unroll
-        for (int k = 0; k < PME_CONV_RPW; k++) {
-            const int row = (blockIdx.x * PME_CONV_WARPS + wrp) * PME_CONV_RPW + k;   // a * gy + b
-            if (row < d.gx * d.gy && c < nzh) {
-                const float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh;
-                v1[k] = s1[c];
-                vd[k] = s1[nspec + c];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < PME_CONV_RPW; k++) {
-            const int row = (blockIdx.x * PME_CONV_WARPS + wrp) * PME_CONV_RPW + k;
-            if (row >= d.gx * d.gy || c >= nzh) continue;
-            float2 *s1 = d.pme_specf + (size_t)r * 2 * nspec + (size_t)row * nzh, *sd = s1 + nspec;
-            if (row == 0 && c == 0) {
-                s1[0] = make_float2(0.f, 0.f);
-                sd[0] = make_float2(0.f, 0.f);
-                continue;
-            }
+    if (threadIdx.x < PME_CONV_ROWS) {
+        const int row = blockIdx.x * PME_CONV_ROWS + threadIdx.x;   // a * gy + b
+        if (row < nrows) {
             const int a = row / d.gy, b = row - a * d.gy;
             const double ma = (double)(a <= d.gx / 2 ? a : a - d.gx) / (double)L.x, mb = (double)(b <= d.gy / 2 ? b : b - d.gy) / (double)L.y;
             const double mab2 = ma * ma + mb * mb;
-            const double tab = exp(-fac * mab2) / (piV * d.pme_mod[a] * d.pme_mod[d.gx + b]);
-            const double mc = (double)c / (double)L.z;
-            const double eterm = tab * s_tc[c] / (mab2 + mc * mc);
-            const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
+            s_m2[threadIdx.x] = mab2;
+            s_tab[threadIdx.x] = exp(-fac * mab2) / (3.141592653589793 * (double)L.x * (double)L.y * (double)L.z * d.pme_mod[a] * d.pme_mod[d.gx + b]);
+        }
+    }
+    __syncthreads();
+    const size_t nspec = (size_t)nrows * nzh;
+    float2 *spec = d.pme_specf + (size_t)r * 2 * nspec;
+    const int row0 = blockIdx.x * PME_CONV_ROWS + wrp * PME_CONV_RPW;
+    double e1 = 0.0, de = 0.0;
+    for (int c0 = 0; c0 < nzh; c0 += 32) {
+        const int c = c0 + lane;
+        if (c >= nzh) break;
+        // the RPW rows of this warp: all loads first, then the arithmetic
+        float2 v1[PME_CONV_RPW], vd[PME_CONV_RPW];
+#pragma unroll
+        for (int k = 0; k < PME_CONV_RPW; k++)
+            if (row0 + k < nrows) {
+                v1[k] = spec[(size_t)(row0 + k) * nzh + c];
+                vd[k] = spec[nspec + (size_t)(row0 + k) * nzh + c];
+            }
+        const double mc = (double)c / (double)L.z;
+        const double tc = s_tc[c], mc2 = mc * mc;
+        const double w = (c == 0 || (2 * c == d.gz)) ? 1.0 : 2.0;  // half spectrum: the conjugate half counts too
+#pragma unroll
+        for (int k = 0; k < PME_CONV_RPW; k++) {
+            const int row = row0 + k;
+            if (row >= nrows) break;
+            float2 *s1 = spec + (size_t)row * nzh + c, *sd = s1 + nspec;
+            if (row == 0 && c == 0) {
+                *s1 = make_float2(0.f, 0.f);
+                *sd = make_float2(0.f, 0.f);
+                continue;
+            }
+            const double eterm = s_tab[wrp * PME_CONV_RPW + k] * tc / (s_m2[wrp * PME_CONV_RPW + k] + mc2);
             const double x1 = v1[k].x, y1 = v1[k].y, xd = vd[k].x, yd = vd[k].y;
             e1 += 0.5 * w * eterm * (x1 * x1 + y1 * y1);
             de += w * eterm * (x1 * xd + y1 * yd + 0.5 * (xd * xd + yd * yd));   // E2 - E1 by linearity of the transform
             const float g = (float)eterm;
-            s1[c] = make_float2(v1[k].x * g, v1[k].y * g);
-            sd[c] = make_float2(vd[k].x * g, vd[k].y * g);
+            *s1 = make_float2(v1[k].x * g, v1[k].y * g);
+            *sd = make_float2(vd[k].x * g, vd[k].y * g);
         }
     }
-    double *red = s_tc + nzh;
     for (int off = 16; off > 0; off >>= 1) {
         e1 += __shfl_xor_sync(0xffffffffu, e1, off);
         de += __shfl_xor_sync(0xffffffffu, de, off);
