@@ -72,6 +72,10 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out (its chunk handles "
                     "add their own rebuilds and small launches to an ncu launch list)")
     ap.add_argument("--e2e-chunks", type=int, default=6)
+    ap.add_argument("--e2e-split", default="equal",
+                    help="replicas per chunk of the e2e leg: 'equal' (--e2e-chunks equal chunks, the default: measured best or "
+                         "within 4 %% of the best at 22 / 11 / 6 / 3 replicas, profiles/r2u_e2e_split_sweep.log), an explicit list "
+                         "such as '1,2,4,8,5,2', or 'graded' (small first and last chunks, larger ones in between)")
     ap.add_argument("--e2e-posq", default="f3", choices=["f3", "f4"], help="what the e2e leg uploads: packed float3 coordinates "
                     "(12 B per atom, ATM_POSQ_F3) or OpenMM's float4 posq (16 B per atom)")
     ap.add_argument("--e2e-force", default="f32", choices=["f32", "i64"], help="what the e2e leg reads back: float32 forces "
@@ -230,6 +234,23 @@ def tier1_hbm_probe(torch, atm, dev, flush, atoms=8_000_000):
         out[name] = {"bytes": bpa * n, "ms": ms, "GBps": bpa * n / (ms * 1e-3) / 1e9, "frac": bpa * n / (ms * 1e-3) / 1e9 / peak}
     be.close()
     return out
+
+
+def e2e_split(spec, R, nchunks):
+    """Replicas per chunk of the e2e leg (see --e2e-split)."""
+    if spec not in ("graded", "equal"):
+        sizes = [int(x) for x in spec.split(",")]
+        if sum(sizes) != R or min(sizes) < 1:
+            raise SystemExit(f"--e2e-split {spec}: the chunk sizes must be positive and add up to the {R} replicas of this rank")
+        return sizes
+    k = max(1, min(nchunks, R))
+    if spec == "equal" or R < 8:
+        b = [round(i * R / k) for i in range(k + 1)]
+        return [b[i + 1] - b[i] for i in range(k)]
+    # graded: about R/11 replicas in the first and last chunk, twice that next to them, the rest in two central chunks
+    e = max(1, R // 11)
+    rest = R - 6 * e
+    return [e, 2 * e, rest - rest // 2, rest // 2, 2 * e, e] if rest >= 2 else [round((i + 1) * R / k) - round(i * R / k) for i in range(k)]
 
 
 def workload_config(args, label, s, replicas_per_rank, exchange, use_graph, pme_grid, flush_note):
@@ -642,8 +663,9 @@ def run_b200(args):
     h2d = d2h = 0
     e2e_chunks = 0
     if R > 0 and not args.skip_e2e:
-        e2e_chunks = max(1, min(args.e2e_chunks, R))
-        bounds = [round(i * R / e2e_chunks) for i in range(e2e_chunks + 1)]
+        sizes = e2e_split(args.e2e_split, R, args.e2e_chunks)
+        e2e_chunks = len(sizes)
+        bounds = [sum(sizes[:i]) for i in range(e2e_chunks + 1)]
         chunks = []
         for c in range(e2e_chunks):
             lo, hi = bounds[c], bounds[c + 1]
@@ -801,7 +823,7 @@ def run_b200(args):
             "components": comp, "window_ms_per_step": window_ms_per_step,
             "clocks": clocks, "gpu_launches": int(launches), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "replica-ns/day", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "window_ms_per_step": e2e_window_ms, "components": e2e_comp, "chunks": e2e_chunks,
+                    "ms_per_step": e2e_ms, "window_ms_per_step": e2e_window_ms, "components": e2e_comp, "chunks": e2e_chunks, "chunk_replicas": sizes,
                     "force_format": args.e2e_force, "posq_format": args.e2e_posq,
                     "call": "atm_host_pipeline_step (pinned host coordinates in, pinned host forces + energy records out, "
                             "one cached CUDA graph per step; pair-list maintenance on the bench cadence)"},

@@ -1135,8 +1135,9 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         const int tw = (nx + d.pme_ntx - 1) / d.pme_ntx, th = (ny + d.pme_nty - 1) / d.pme_nty;
         d.pme_tile_cells = tw * th * nzp;
         nb->pme_tile_smem = sizeof(int) * ((size_t)d.pme_tile_cells + PME_LIST_CAP);
-        ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
-        ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, nb->pme_tile_smem));
+        ATM_REQUIRE(nb->pme_tile_smem <= 200 * 1024 + sizeof(int) * PME_LIST_CAP, ATM_ERR_UNSUPPORTED, "atm_pme_setup: %d mesh points along z do not fit a shared-memory tile", nz);
+        // the opt-in limit is per kernel and device, not per handle: always the largest tile a handle may ask for
+        ATM_CUDA_CHECK(pme_spread_tile_smem_attr(order, (size_t)200 * 1024 + sizeof(int) * PME_LIST_CAP));
         ATM_CUDA_CHECK(pme_gather_prefer_l1(order));
     } else {
         if ((rc = alloc(&p, sizeof(unsigned long long) * 2 * ng * R))) return rc;
