@@ -468,11 +468,13 @@ __global__ void __launch_bounds__(32 * PME_CONV_WARPS, 4) pme_convolve_f_kernel(
     const int r = blockIdx.y, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const float4 L = d.box[r];
     const double fac = 9.869604401089358 / ((double)d.alpha * (double)d.alpha);  // pi^2 / alpha^2
-    for (int c = threadIdx.x; c < nzh; c += 32 * PME_CONV_WARPS) {
-        const double mc = (double)c / (double)L.z;
-        s_tc[c] = exp(-fac * mc * mc) / d.pme_mod[d.gx + d.gy + c];
-    }
-    if (threadIdx.x < PME_CONV_ROWS) {
+    // warp 0 forms the row factors while the other warps form the z factors
+    if (threadIdx.x >= PME_CONV_ROWS) {
+        for (int c = (int)threadIdx.x - PME_CONV_ROWS; c < nzh; c += 32 * PME_CONV_WARPS - PME_CONV_ROWS) {
+            const double mc = (double)c / (double)L.z;
+            s_tc[c] = exp(-fac * mc * mc) / d.pme_mod[d.gx + d.gy + c];
+        }
+    } else {
         const int row = blockIdx.x * PME_CONV_ROWS + threadIdx.x;   // a * gy + b
         if (row < nrows) {
             const int a = row / d.gy, b = row - a * d.gy;
