@@ -198,6 +198,8 @@ int atm_nb_rebuild(atm_handle *h, const void *posq, void *stream);
  * returned NaN energies and NaN-poisoned forces (never silently truncated sums); atm_nb_rebuild again reallocates
  * with larger capacities (synchronously) and the caller repeats those steps.  A list that merely came within 20 % of
  * its capacity makes the NEXT atm_nb_rebuild reallocate ahead of time; that is not an error.
+ * With the PME option on, wait != 0 also synchronises the device and reports (ATM_ERR_STATE) when a site has moved
+ * further since the last rebuild than the structure tolerates (see atm_pme_setup): the steps since then returned NaN.
  * No reference counterpart: OpenMM's own neighbour list handles this inside its inner contexts. */
 int atm_nb_check(atm_handle *h, int32_t wait);
 

@@ -724,7 +724,21 @@ int atm_nb_check(atm_handle *h, int32_t wait) {
         set_error("the pair lists of the last atm_nb_rebuild are incomplete (capacity overflow): call atm_nb_rebuild again");
         return ATM_ERR_STATE;
     }
-    return check_pending_rebuild(h, wait != 0);
+    int rc = check_pending_rebuild(h, wait != 0);
+    if (rc || !wait || !h->nb->d.pme_on || !h->nb->d.pme_f32 || !h->nb->list_valid) return rc;
+    // the PME spread relies on no site having left its place in the structure by more than half the outer skin; the
+    // gather kernel raises flag bit 3 when one has (the steps since then returned NaN)
+    ATM_CUDA_CHECK(cudaSetDevice(h->device));
+    ATM_CUDA_CHECK(cudaDeviceSynchronize());
+    int f0 = 0;
+    ATM_CUDA_CHECK(cudaMemcpy(&f0, h->nb->d.flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f0 & 8) {
+        set_error("a site has moved further since the last atm_nb_rebuild than half the outer skin (%.3f nm) beyond its cluster: the "
+                  "energies and forces of the steps since then are NaN -- call atm_nb_rebuild and repeat them",
+                  0.5 * std::max(h->nb->desc.skin, h->nb->desc.skin_outer));
+        return ATM_ERR_STATE;
+    }
+    return ATM_OK;
 }
 
 int atm_nb_rebuild(atm_handle *h, const void *posq_, void *stream_) {

@@ -230,7 +230,10 @@ def test_pme_site_drift_beyond_the_skin_poisons_the_step():
     moved[0, 100, 0] += 1.0                        # far outside
     be.step(moved, force)
     assert np.isnan(be.get_energies()[0][E_U1]) and np.isnan(be.get_energies()[0][E_USC])
+    with pytest.raises(atm.ATMError, match="moved further"):
+        be.nb_check(wait=True)                     # the waiting check names the cause
     be.rebuild(moved)                              # the rebuild re-sorts the site: results again
+    be.nb_check(wait=True)
     be.step(moved, force)
     assert np.isfinite(be.get_energies()[0][:7]).all()
     be.close()
