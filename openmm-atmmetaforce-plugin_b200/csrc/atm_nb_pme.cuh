@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(128, 4) pme_gather_kernel(NbDev d) {
 //                            transform, E2 - E1 = sum G (Re(conj(Q1^) dQ^) + 1/2 |dQ^|^2), both accumulated in double:
 //                            the rounding noise of the big mesh never enters the DIFFERENCE as a difference of two sums
 //   cuFFT C2R (float): phi1 and dphi = phi2 - phi1
-//   pme_gather_f_kernel      F1 from phi1, F2 from phi1 + dphi, float weights, row sums over z first
+//   pme_blend_kernel         sp is known by now (scalar stage on the complete energies): phi_b = phi1 + sp dphi, written in
+//                            a padded row layout in which every z support is a run inside aligned float4s
+//   pme_gather_f_kernel      environment sites: ONE mesh (phi_b), force into the common accumulator; displaced atoms /
+//                            ghosts: phi1 / phi1 + dphi into the state accumulators.  Float weights, row sums over z first
 // Positions -> mesh coordinates stay in double (the float coordinate is the exact input; its fractional mesh offset
 // would lose five digits in float); weights, meshes and transforms are float.
 // ================================================================================================
