@@ -662,6 +662,7 @@ def run_b200(args):
     e2e_ms = None
     h2d = d2h = 0
     e2e_chunks = 0
+    sizes = []
     if R > 0 and not args.skip_e2e:
         sizes = e2e_split(args.e2e_split, R, args.e2e_chunks)
         e2e_chunks = len(sizes)

@@ -1142,6 +1142,10 @@ int atm_pme_setup(atm_handle *h, int32_t nx, int32_t ny, int32_t nz, int32_t ord
         d.pme_blend = (float *)p;
         // spread tiles: about 12 x 12 cells in xy (all of z), smaller when the z extent would not fit in shared memory
         int T = 12;
+        {   // ATM_B200_PME_TILE=t: edge of a spread brick in mesh cells (experiment; 12 measured best, profiles/r2x_pme_tile_ab.log)
+            static const int t_env = [] { const char *e = getenv("ATM_B200_PME_TILE"); return e ? atoi(e) : 0; }();
+            if (t_env >= 4 && t_env <= 32) T = t_env;
+        }
         const int nzp = pme_tile_stride(nz, order);   // a tile row: padding for supports that start below z = 0, then the column
         while (T > 4 && sizeof(int) * (size_t)T * T * nzp > 160 * 1024) T--;
         d.pme_ntx = (nx + T - 1) / T;
