@@ -616,7 +616,7 @@ __device__ __forceinline__ void pme_gather_special(const NbDev &d, int r, int s,
 // (the merge adds it with weight one): per (x, y) row NV aligned float4s that contain the z support, the z weights
 // shifted onto that window (zeros outside), row sums first (2 FMA per loaded float), then the xy weights.
 #ifndef ATM_PME_GATHER_MINB
-#define ATM_PME_GATHER_MINB 5
+#define ATM_PME_GATHER_MINB 6
 #endif
 template <int ORDER>
 __global__ void __launch_bounds__(128, ATM_PME_GATHER_MINB) pme_gather_f_kernel(NbDev d) {
