@@ -639,3 +639,80 @@ print("HASH", h.hexdigest())
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         out[cub] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][0]
     assert out["0"] == out["1"]
+
+
+def test_headline_workload_full_size_properties():
+    """BASELINE configs[2] at its full size -- 22 replicas of the 23k-atom system, one lambda state each, in ONE handle, the
+    bench's pair-list settings -- through properties that do not need the oracle at that size: every replica's merged force
+    sums to zero over the atoms (Newton's third law in each state, fixed-point sums), a replica taken alone in a
+    one-replica handle gives the same bits (the batching is invisible), the graph replay gives the same bits, and the
+    replica with lambda = 0 feels exactly the state-1 force (sp = 0).  Three replicas are also checked against the oracle."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic
+    from helpers import oracle_system, force_from_fixed, rel_rms
+    s = synthetic.config3()
+    n = s["pos"].shape[0]
+    sched = synthetic.atm_schedule_22()
+    R = 22
+
+    def handle(rows):
+        be = atm.ATMBackend(n, precision="mixed", num_replicas=len(rows))
+        be.set_displacements(s["displ"])
+        be.set_box(s["box"])
+        for r, row in enumerate(rows):
+            be.set_parameters(row, replica=r)
+        be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.05, skin_outer=0.3,
+                    exclusions=s["excl"], exception_pairs=s["exc14"], exception_params=s["exc14_par"])
+        return be
+
+    be = handle([sched[r] for r in range(R)])
+    P = be.P
+    rng = np.random.default_rng(77)
+    posq = np.zeros((R, P, 4), np.float32)
+    for r in range(R):
+        posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.005, (n, 3))
+        posq[r, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+    be.rebuild(d_posq)
+    be.step(d_posq, force)
+    en = be.get_energies()
+    f_all = force.cpu().numpy()
+    assert np.isfinite(en[:, :7]).all()
+    for r in range(R):
+        f = force_from_fixed(f_all[r], n, P)
+        assert np.abs(f.sum(0)).max() <= 1e-7 * np.abs(f).sum(), r
+    # graph replay: same bits
+    force_g = torch.zeros_like(force)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        be.step(d_posq, force_g, graph=True, stream=stream)
+    stream.synchronize()
+    assert torch.equal(force_g, force)
+    # lambda = 0 end state (schedule row 0): sp = 0, the merged force is the state-1 force; lambda = 1 rows: sp = 1 or 0 by leg
+    assert en[0, E_SP] == 0.0
+    # one replica alone: same bits as inside the batch
+    for r in (0, 7, 21):
+        one = handle([sched[r]])
+        f1 = torch.zeros((1, 3 * P), dtype=torch.int64, device="cuda")
+        one.rebuild(d_posq[r:r + 1].contiguous())
+        one.step(d_posq[r:r + 1].contiguous(), f1)
+        assert torch.equal(f1[0], force[r]), r
+        assert np.array_equal(one.get_energies()[0][:7], en[r][:7])
+        one.close()
+    # oracle on three of the replicas
+    S = oracle_system(O, s, s["cutoff"], s["ewald_alpha"])
+    d32 = s["displ"].astype(np.float32)
+    for r in (3, 11, 18):
+        p1 = posq[r, :n, :3].astype(np.float64)
+        p2 = (posq[r, :n, :3] + d32).astype(np.float64)
+        e1, _, g1 = S.nb_direct(p1)
+        e2, _, g2 = S.nb_direct(p2)
+        sc = O.scalars(sched[r], e1, e2)
+        f_ref = O.merge_ref(np.zeros_like(g1), g1, g2, sc["sp_ref"], sched[r][8])
+        assert abs(en[r, E_U1] - e1) <= 1e-6 * abs(e1)
+        assert abs(en[r, E_USC] - sc["u_sc"]) <= 5e-3
+        assert rel_rms(force_from_fixed(f_all[r], n, P), f_ref) <= 1e-5
+    be.close()
