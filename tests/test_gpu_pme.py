@@ -237,3 +237,60 @@ def test_pme_site_drift_beyond_the_skin_poisons_the_step():
     be.step(moved, force)
     assert np.isfinite(be.get_energies()[0][:7]).all()
     be.close()
+
+
+def test_pme_headline_size_batch_is_invisible():
+    """The bench's --pme workload at full size (22 replicas x 23k atoms, 60^3 mesh, one lambda state each): every replica of
+    the batch agrees with the same replica evaluated alone (the transforms are batched differently, so agreement is to
+    float-mesh accuracy, not to the bit), and a second step gives the same bits (fixed-point tiles, deterministic)."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic
+    s = synthetic.config3()
+    n = s["pos"].shape[0]
+    sched = synthetic.atm_schedule_22()
+    grid = synthetic.pme_grid(s["box"], s["ewald_alpha"])
+
+    def handle(rows):
+        be = atm.ATMBackend(n, precision="mixed", num_replicas=len(rows))
+        be.set_displacements(s["displ"])
+        be.set_box(s["box"])
+        for r, row in enumerate(rows):
+            be.set_parameters(row, replica=r)
+        be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.05, skin_outer=0.3,
+                    exclusions=s["excl"], exception_pairs=s["exc14"], exception_params=s["exc14_par"])
+        be.pme_setup(grid)
+        return be
+
+    R = 22
+    be = handle([sched[r] for r in range(R)])
+    P = be.P
+    rng = np.random.default_rng(5)
+    posq = np.zeros((R, P, 4), np.float32)
+    for r in range(R):
+        posq[r, :n, :3] = s["pos"] + rng.normal(0, 0.005, (n, 3))
+        posq[r, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((R, 3 * P), dtype=torch.int64, device="cuda")
+    be.rebuild(d_posq)
+    be.step(d_posq, force)
+    en = be.get_energies()
+    assert np.isfinite(en[:, :14]).all() and (np.abs(en[:, E_UREC1]) > 1.0).all()
+    force2 = torch.zeros_like(force)
+    be.step(d_posq, force2)
+    torch.cuda.synchronize()
+    assert torch.equal(force, force2) and np.array_equal(be.get_energies()[:, :14], en[:, :14])
+    for r in (2, 13):
+        one = handle([sched[r]])
+        f1 = torch.zeros((1, 3 * P), dtype=torch.int64, device="cuda")
+        x = d_posq[r:r + 1].contiguous()
+        one.rebuild(x)
+        one.step(x, f1)
+        e1 = one.get_energies()[0]
+        assert abs(e1[E_UREC1] - en[r, E_UREC1]) <= 1e-6 * abs(en[r, E_UREC1])
+        assert abs(e1[E_USC] - en[r, E_USC]) <= 1e-3
+        a = f1[0].cpu().numpy().astype(np.float64)
+        b = force[r].cpu().numpy().astype(np.float64)
+        assert np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()) <= 2e-6
+        one.close()
+    be.close()
