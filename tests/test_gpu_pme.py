@@ -294,3 +294,58 @@ def test_pme_headline_size_batch_is_invisible():
         assert np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()) <= 2e-6
         one.close()
     be.close()
+
+
+def test_pme_per_replica_boxes():
+    """Two replicas in ONE handle, the second in a 2 % larger box (barostat) with molecules translated by whole box vectors:
+    the spread's column scan, the influence function, the blend and the gather all use the replica's own box."""
+    import torch
+    import atmmetaforce as atm
+    import oracle_py as O
+    from atmmetaforce import synthetic
+    from helpers import force_from_fixed, rel_rms
+    s = synthetic.water_box(9000, n_lig=30, seed=33)
+    n = s["pos"].shape[0]
+    sched = synthetic.atm_schedule_22()
+    rng = np.random.default_rng(5)
+    lig = np.nonzero(np.abs(s["displ"]).sum(1) > 0)[0]
+    mol = np.full(n, -1)
+    mol[lig] = 0
+    rest = np.nonzero(mol < 0)[0]
+    mol[rest] = 1 + np.arange(rest.size) // 3
+    shifts = rng.integers(-1, 2, (mol.max() + 1, 3)).astype(np.float64)
+    scale = [1.0, 1.02]
+    grid, order = [40, 40, 40], 5
+    be = atm.ATMBackend(n, precision="mixed", num_replicas=2)
+    P = be.P
+    be.set_displacements(s["displ"])
+    for r in range(2):
+        be.set_box(s["box"] * scale[r], replica=r)
+        be.set_parameters(sched[4 + 11 * r], replica=r)
+    be.nb_setup(s["charge"], s["sigma"], s["epsilon"], s["cutoff"], s["ewald_alpha"], skin=0.1, exclusions=s["excl"])
+    be.pme_setup(grid, order)
+    posq = np.zeros((2, P, 4), np.float32)
+    for r in range(2):
+        posq[r, :n, :3] = s["pos"] * scale[r] + shifts[mol] * (s["box"] * scale[r])
+        posq[r, :n, 3] = s["charge"]
+    d_posq = torch.from_numpy(posq).cuda()
+    force = torch.zeros((2, 3 * P), dtype=torch.int64, device="cuda")
+    be.rebuild(d_posq)
+    be.step(d_posq, force)
+    en = be.get_energies()
+    d32 = s["displ"].astype(np.float32)
+    for r in range(2):
+        S = O.System(s["charge"], s["sigma"], s["epsilon"], s["box"] * scale[r], s["cutoff"], s["ewald_alpha"], s["excl"])
+        p1 = posq[r, :n, :3].astype(np.float64)
+        p2 = (posq[r, :n, :3] + d32).astype(np.float64)
+        e1, _, f1 = S.nb_direct(p1)
+        e2, _, f2 = S.nb_direct(p2)
+        r1, g1 = S.pme_recip(p1, grid, order, want_force=True)
+        r2, g2 = S.pme_recip(p2, grid, order, want_force=True)
+        prm = sched[4 + 11 * r]
+        sc = O.scalars(prm, e1 + r1, e2 + r2)
+        f_ref = O.merge_ref(np.zeros_like(f1), f1 + g1, f2 + g2, sc["sp_ref"], prm[8])
+        assert abs(en[r, E_UREC1] - r1) <= 1e-6 * abs(r1) + 1e-4, (r, en[r, E_UREC1], r1)
+        assert abs((en[r, E_UREC2] - en[r, E_UREC1]) - (r2 - r1)) <= 1e-3
+        assert rel_rms(force_from_fixed(force.cpu().numpy()[r], n, P), f_ref) <= 1e-5, r
+    be.close()
