@@ -246,3 +246,57 @@ def test_external_state_terms_through_the_host_path():
     pipe.close()
     for b in bes + [ref]:
         b.close()
+
+
+def test_pipeline_with_pme():
+    """The host path with the two-state PME inside the step: one chunk holding both replicas is bit-identical to atm_step
+    on device buffers (same kernels, same transform batch); two one-replica chunks agree to float-mesh accuracy (their
+    transforms are batched differently)."""
+    import torch
+    import atmmetaforce as atm
+    from atmmetaforce import synthetic, _capi
+    s = synthetic.water_box(12000)
+    sched = synthetic.atm_schedule_22()
+    rows = [sched[6], sched[15]]
+    grid = synthetic.pme_grid(s["box"], s["ewald_alpha"])
+
+    def setup(rr):
+        be = _setup(atm, s, rr, len(rr))
+        be.pme_setup(grid)
+        return be
+
+    ref = setup(rows)
+    P = ref.P
+    x = _coords(s, P, 2, seed=11, sigma=0.003)
+    xd = torch.from_numpy(x).cuda()
+    force = torch.zeros((2, 3 * P), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ref.rebuild(xd, stream=stream)
+        ref.step(xd, force, include_energy=True, stream=stream)
+    en_ref = ref.get_energies(stream=stream)
+    for split in ((2,), (1, 1)):
+        bounds = np.cumsum((0,) + split)
+        bes = [setup(rows[bounds[c]:bounds[c + 1]]) for c in range(len(split))]
+        pipe = atm.HostPipeline(bes)
+        posq_h = [torch.from_numpy(x[bounds[c]:bounds[c + 1]]).pin_memory() for c in range(len(split))]
+        force_h = [torch.zeros((k, 3 * P), dtype=torch.int64).pin_memory() for k in split]
+        en_h = [torch.zeros((k, _capi.NUM_ENERGY_SLOTS), dtype=torch.float64).pin_memory() for k in split]
+        pipe.step(posq_h, force_h, en_h, maintenance=pipe.REBUILD, stream=stream)
+        stream.synchronize()
+        pipe.check()
+        pipe.step(posq_h, force_h, en_h, maintenance=pipe.NONE, stream=stream)
+        stream.synchronize()
+        got_f, got_e = torch.cat(force_h, 0), torch.cat(en_h, 0).numpy()
+        if split == (2,):
+            assert torch.equal(got_f, force.cpu())
+            assert np.array_equal(got_e[:, :14], en_ref[:, :14])
+        else:
+            a, b = got_f.numpy().astype(np.float64), force.cpu().numpy().astype(np.float64)
+            assert np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()) <= 2e-6
+            assert np.abs(got_e[:, _capi.E_USC] - en_ref[:, _capi.E_USC]).max() <= 1e-3
+            assert np.abs(got_e[:, 11] / en_ref[:, 11] - 1.0).max() <= 1e-6
+        pipe.close()
+        for b in bes:
+            b.close()
+    ref.close()
