@@ -72,10 +72,11 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out (its chunk handles "
                     "add their own rebuilds and small launches to an ncu launch list)")
     ap.add_argument("--e2e-chunks", type=int, default=6)
-    ap.add_argument("--e2e-split", default="equal",
-                    help="replicas per chunk of the e2e leg: 'equal' (--e2e-chunks equal chunks, the default: measured best or "
-                         "within 4 %% of the best at 22 / 11 / 6 / 3 replicas, profiles/r2u_e2e_split_sweep.log), an explicit list "
-                         "such as '1,2,4,8,5,2', or 'graded' (small first and last chunks, larger ones in between)")
+    ap.add_argument("--e2e-split", default="auto",
+                    help="replicas per chunk of the e2e leg: 'equal' (--e2e-chunks equal chunks), 'graded' (seven chunks 1:2:3:6:6:3:1, "
+                         "small first and last chunks because their upload / download is not hidden), an explicit list such as "
+                         "'1,2,4,8,5,2', or 'auto' (default): graded from 16 replicas per rank, equal below -- measured "
+                         "3 %% faster than equal at 22 replicas and slower at 11 / 6 / 3 (profiles/r2u_e2e_split_sweep.log)")
     ap.add_argument("--e2e-posq", default="f3", choices=["f3", "f4"], help="what the e2e leg uploads: packed float3 coordinates "
                     "(12 B per atom, ATM_POSQ_F3) or OpenMM's float4 posq (16 B per atom)")
     ap.add_argument("--e2e-force", default="f32", choices=["f32", "i64"], help="what the e2e leg reads back: float32 forces "
@@ -238,19 +239,29 @@ def tier1_hbm_probe(torch, atm, dev, flush, atoms=8_000_000):
 
 def e2e_split(spec, R, nchunks):
     """Replicas per chunk of the e2e leg (see --e2e-split)."""
-    if spec not in ("graded", "equal"):
+    if spec not in ("auto", "graded", "equal"):
         sizes = [int(x) for x in spec.split(",")]
         if sum(sizes) != R or min(sizes) < 1:
             raise SystemExit(f"--e2e-split {spec}: the chunk sizes must be positive and add up to the {R} replicas of this rank")
         return sizes
     k = max(1, min(nchunks, R))
-    if spec == "equal" or R < 8:
+    if spec == "equal" or (spec == "auto" and R < 16) or R < 7:
         b = [round(i * R / k) for i in range(k + 1)]
         return [b[i + 1] - b[i] for i in range(k)]
-    # graded: about R/11 replicas in the first and last chunk, twice that next to them, the rest in two central chunks
-    e = max(1, R // 11)
-    rest = R - 6 * e
-    return [e, 2 * e, rest - rest // 2, rest // 2, 2 * e, e] if rest >= 2 else [round((i + 1) * R / k) - round(i * R / k) for i in range(k)]
+    # graded: seven chunks in the proportions 1 : 2 : 3 : 6 : 6 : 3 : 1 -- the first upload and the last download are not
+    # hidden behind any compute, so those chunks are small; the central ones are large for per-launch efficiency
+    w = [1, 2, 3, 6, 6, 3, 1]
+    sizes = [max(1, (x * R) // 22) for x in w]
+    rest = R - sum(sizes)
+    i = 0
+    while rest != 0:                       # the remainder goes to (or comes from) the two central chunks
+        j = 3 + (i & 1)
+        step = 1 if rest > 0 else -1
+        if sizes[j] + step >= 1:
+            sizes[j] += step
+            rest -= step
+        i += 1
+    return sizes
 
 
 def workload_config(args, label, s, replicas_per_rank, exchange, use_graph, pme_grid, flush_note):

@@ -104,7 +104,7 @@ def test_standin_harmonic_bond_force_properties(seed, periodic, shift):
     assert abs(fd - f[i, c]) <= 1e-4 * (1.0 + np.abs(f).max())
 
 
-@given(R=st.integers(1, 64), k=st.integers(1, 12), mode=st.sampled_from(["equal", "graded"]))
+@given(R=st.integers(1, 64), k=st.integers(1, 12), mode=st.sampled_from(["equal", "graded", "auto"]))
 def test_bench_chunk_split_partitions_the_replicas(R, k, mode):
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
