@@ -379,7 +379,7 @@ constexpr int TBL_CAP = 160;  // exclusion partners of one cluster kept in share
 // OUTER list: every site inside (cutoff + outer skin) of the cluster's bounding box, with exclusion masks.
 // Built rarely; the per-step work uses the pruned INNER list (nl_prune_kernel).
 __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
-    __shared__ int s_pass[BUILD_WARPS][32];
+    __shared__ int s_pass[BUILD_WARPS][36];   // queue of clusters that passed stage 1: a batch of up to 32 behind up to 3 waiting ones
     __shared__ int2 s_tbl[BUILD_WARPS][TBL_CAP];
     __shared__ int s_tn[BUILD_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -449,6 +449,59 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
     else if (iy_lo < 0) { seg_lo[0] = 0; seg_hi[0] = iy_hi; seg_lo[1] = iy_lo + d.ny; seg_hi[1] = d.ny - 1; nseg = 2; }
     else { seg_lo[0] = iy_lo; seg_hi[0] = d.ny - 1; seg_lo[1] = 0; seg_hi[1] = iy_hi - d.ny; nseg = 2; }
 
+    // stage 2 of the search, one candidate SITE per lane: the sites of up to four clusters of the queue (from entry q) are
+    // tested against the bounding box of A, masked by the exclusions, and appended to the list in queue order
+    auto sweep = [&](int q, int nq) {
+        const int g = q + (lane >> 3), k = lane & 7;
+        bool take = false;
+        unsigned int entry = 0;
+        if ((lane >> 3) < nq) {
+            const int B2 = s_pass[w][g];
+            const int j = B2 * CL + k;
+            const int u = d.slot_site[rsite + j];
+            if (u >= 0) {
+                const float4 p = __ldg(d.xs + rsite + j);
+                const float bx = fmaxf(fabsf(wrap_delta(p.x - cA.x, L.x, iL.x)) - hA.x, 0.f);
+                const float by = fmaxf(fabsf(wrap_delta(p.y - cA.y, L.y, iL.y)) - hA.y, 0.f);
+                const float bz = fmaxf(fabsf(wrap_delta(p.z - cA.z, L.z, iL.z)) - hA.z, 0.f);
+                if (bx * bx + by * by + bz * bz <= rl2) {
+                    unsigned int m = (~validA) & 0xff;
+                    if (B2 == A) m |= (0xffu << k) & 0xff;  // within a cluster: pairs (i<j) once
+                    if (tbl_ok) {
+                        if ((bloom >> (B2 & 63)) & 1ull) {
+                            for (int t = 0; t < T; t++) {
+                                const int2 te = s_tbl[w][t];
+                                if (te.x == j) m |= te.y;
+                            }
+                        }
+                    } else {  // rare: a cluster with more exclusion partners than the table holds
+                        const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
+                        for (int e = d.excl_start[aj]; e < d.excl_start[aj + 1]; e++) {
+                            const int b = d.excl_list[e];
+                            const int s_real = d.site_slot[(size_t)r * d.U + b];
+                            if ((s_real >> 3) == A) m |= 1u << (s_real & 7);
+                            const int gm = d.ghost_of_atom[b];
+                            if (gm >= 0) {
+                                const int s_gh = d.site_slot[(size_t)r * d.U + d.N + gm];
+                                if ((s_gh >> 3) == A) m |= 1u << (s_gh & 7);
+                            }
+                        }
+                    }
+                    if (m != 0xff) {
+                        take = true;
+                        entry = ((unsigned int)j << 8) | m;
+                    }
+                }
+            }
+        }
+        const unsigned int tmask = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const int pos = count + __popc(tmask & ((1u << lane) - 1));
+            if (pos < li.cap) out[pos] = entry;
+        }
+        count += __popc(tmask);
+    };
+    int npend = 0;   // clusters that passed stage 1 and wait in the queue for a FULL sweep of four
     const int n_ranges = n_ix * nseg + 1;
     for (int rg = 0; rg < n_ranges; rg++) {
         int c_begin, c_end;
@@ -483,62 +536,22 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
             const unsigned int cmask = __ballot_sync(0xffffffffu, pass);
             const int npass = __popc(cmask);
             if (npass == 0) continue;
-            if (pass) s_pass[w][__popc(cmask & ((1u << lane) - 1))] = B;
+            if (pass) s_pass[w][npend + __popc(cmask & ((1u << lane) - 1))] = B;
+            npend += npass;
             __syncwarp();
-            // stage 2: one candidate SITE per lane (four clusters per sweep)
-            for (int q = 0; q < npass; q += 4) {
-                const int g = q + (lane >> 3), k = lane & 7;
-                bool take = false;
-                unsigned int entry = 0;
-                if (g < npass) {
-                    const int B2 = s_pass[w][g];
-                    const int j = B2 * CL + k;
-                    const int u = d.slot_site[rsite + j];
-                    if (u >= 0) {
-                        const float4 p = __ldg(d.xs + rsite + j);
-                        const float bx = fmaxf(fabsf(wrap_delta(p.x - cA.x, L.x, iL.x)) - hA.x, 0.f);
-                        const float by = fmaxf(fabsf(wrap_delta(p.y - cA.y, L.y, iL.y)) - hA.y, 0.f);
-                        const float bz = fmaxf(fabsf(wrap_delta(p.z - cA.z, L.z, iL.z)) - hA.z, 0.f);
-                        if (bx * bx + by * by + bz * bz <= rl2) {
-                            unsigned int m = (~validA) & 0xff;
-                            if (B2 == A) m |= (0xffu << k) & 0xff;  // within a cluster: pairs (i<j) once
-                            if (tbl_ok) {
-                                if ((bloom >> (B2 & 63)) & 1ull) {
-                                    for (int t = 0; t < T; t++) {
-                                        const int2 te = s_tbl[w][t];
-                                        if (te.x == j) m |= te.y;
-                                    }
-                                }
-                            } else {  // rare: a cluster with more exclusion partners than the table holds
-                                const int aj = u >= d.N ? d.ghost_atom[u - d.N] : u;
-                                for (int e = d.excl_start[aj]; e < d.excl_start[aj + 1]; e++) {
-                                    const int b = d.excl_list[e];
-                                    const int s_real = d.site_slot[(size_t)r * d.U + b];
-                                    if ((s_real >> 3) == A) m |= 1u << (s_real & 7);
-                                    const int gm = d.ghost_of_atom[b];
-                                    if (gm >= 0) {
-                                        const int s_gh = d.site_slot[(size_t)r * d.U + d.N + gm];
-                                        if ((s_gh >> 3) == A) m |= 1u << (s_gh & 7);
-                                    }
-                                }
-                            }
-                            if (m != 0xff) {
-                                take = true;
-                                entry = ((unsigned int)j << 8) | m;
-                            }
-                        }
-                    }
-                }
-                const unsigned int tmask = __ballot_sync(0xffffffffu, take);
-                if (take) {
-                    const int pos = count + __popc(tmask & ((1u << lane) - 1));
-                    if (pos < li.cap) out[pos] = entry;
-                }
-                count += __popc(tmask);
-            }
+            // full sweeps only; the remainder (< 4 clusters) stays at the front of the queue for the next batch, so that
+            // every sweep but the very last one of a list has all 32 lanes on candidate sites (same order of entries)
+            int q = 0;
+            for (; q + 4 <= npend; q += 4) sweep(q, 4);
+            const int rem = npend - q;
+            const int keep = lane < rem ? s_pass[w][q + lane] : 0;
+            __syncwarp();
+            if (lane < rem) s_pass[w][lane] = keep;
+            npend = rem;
             __syncwarp();
         }
     }
+    if (npend > 0) sweep(0, npend);
     // longest list of each capacity class, every build: the host grows a capacity BEFORE a list can outgrow it
     if (lane == 0) atomicMax(&d.flags[li.cap == d.capC ? FLAG_MAXLEN_C : FLAG_MAXLEN_X], count);
     if (count > li.cap) {
