@@ -515,13 +515,27 @@ __global__ void __launch_bounds__(32 * BUILD_WARPS) nl_build_kernel(NbDev d) {
             c_begin = nenv;
             c_end = ncl;
         }
-        for (int base = c_begin; base < c_end; base += 32) {
+        // An environment cluster A owns, among the environment clusters of a range, those below it with the parity of A,
+        // itself, and those above it with the other parity (the ownership rule below): enumerate exactly those -- half
+        // the candidates, every lane on a cluster A can own, same ascending order.
+        const bool by_parity = clsA == 0 && rg < n_ix * nseg;
+        int n_cand = c_end - c_begin, lo0 = 0, n_lo = 0, n_self = 0, hi0 = 0;
+        if (by_parity) {
+            const int lo_end = min(c_end, A), hi_begin = max(c_begin, A + 1);
+            lo0 = c_begin + ((c_begin ^ A) & 1);
+            n_lo = lo_end > lo0 ? (lo_end - lo0 + 1) >> 1 : 0;
+            n_self = (A >= c_begin && A < c_end) ? 1 : 0;
+            hi0 = hi_begin + (1 - ((hi_begin ^ A) & 1));
+            n_cand = n_lo + n_self + (c_end > hi0 ? (c_end - hi0 + 1) >> 1 : 0);
+        }
+        for (int base = 0; base < n_cand; base += 32) {
             // stage 1: one candidate cluster per lane, box-box distance; passing clusters compacted (in order) to smem
-            const int B = base + lane;
+            const int t = base + lane;
+            const int B = !by_parity ? c_begin + t : (t < n_lo ? lo0 + 2 * t : (t < n_lo + n_self ? A : hi0 + 2 * (t - n_lo - n_self)));
             bool pass = false;
-            if (B < c_end) {
+            if (t < n_cand) {
                 const size_t rcB = (size_t)r * d.Cmax + B;
-                const int clsB = d.cmeta[rcB] & 0xffff;
+                const int clsB = by_parity ? 0 : d.cmeta[rcB] & 0xffff;
                 bool owner;
                 if (clsA == clsB) owner = (A == B) || (((A + B) & 1) ? (A < B) : (A > B));
                 else owner = clsA > clsB;
